@@ -1,0 +1,204 @@
+/*
+ * moegan_sm100.h - C ABI of libmoegan_sm100.so: the B200 (sm_100a) hot path of MoE-GAN's
+ * Bayesian-routed Mixture-of-Experts block (forward + backward).
+ *
+ * The reference (shmurthy08/MoE-GAN_CPSC541) is pure Python/PyTorch and has no FFI; the boundary it
+ * offers for this path is the nn.Module `SparseMoE` (moegan/t2i_moe_gan.py:426-491).  Each entry point
+ * below replaces one cluster of eager torch ops inside that module; the citation after "replaces:"
+ * is the reference code it stands in for (paths relative to the reference root).  INTEGRATION.md shows
+ * the ctypes binding and the two-line swap a reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless it says "host".
+ *  - The caller owns all memory (including workspaces); the library never allocates or frees device
+ *    memory and keeps no state besides the last error string and cached device attributes.
+ *  - Every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *    synchronising.  Return value: 0 = success, negative = moegan_status.  Nothing throws or exits.
+ *  - Tokens are "token-major": x is [T, d] row-major with T = B * tokens_per_sample, token order
+ *    (b, h, w) - exactly `x.permute(0,2,3,1).contiguous().view(-1, C)` (t2i_moe_gan.py:455).
+ *  - precision: 0 = bf16 operands / fp32 accumulate on tcgen05;  1 = "fp32": every operand is split
+ *    into bf16 hi + lo halves and each GEMM runs three tcgen05 passes (hi*hi + hi*lo + lo*hi),
+ *    accurate to ~2^-16 relative - this is the mode that meets the 1e-4 fp32 parity bar.
+ *    "bf16 operand" buffers are [rows, S*cols] bf16 with S = 1 (precision 0) or 2 (hi | lo halves).
+ *  - Row-permuted ("dispatched") buffers have m_cap rows (moegan_m_cap()).  Each expert's rows are
+ *    contiguous, in ascending token order, and start at a multiple of 128 rows; padding rows are zero.
+ */
+#ifndef MOEGAN_SM100_H
+#define MOEGAN_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+#define MOEGAN_ABI_VERSION 1
+#define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
+#define MOEGAN_MAX_EXPERTS 32
+#define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
+#define MOEGAN_CHUNK 32       /* tokens per router CTA / permutation chunk */
+#define MOEGAN_KL_PARTS 256   /* scratch partial sums behind kl_out */
+#define MOEGAN_KL_OUT_FLOATS (2 + MOEGAN_KL_PARTS)
+
+typedef enum {
+    MOEGAN_OK = 0,
+    MOEGAN_ERR_BAD_SHAPE = -1,
+    MOEGAN_ERR_NULL_POINTER = -2,
+    MOEGAN_ERR_MISALIGNED = -3,
+    MOEGAN_ERR_UNSUPPORTED = -4,
+    MOEGAN_ERR_CUDA = -5,
+    MOEGAN_ERR_DRIVER = -6
+} moegan_status;
+
+typedef struct {
+    int32_t T;                 /* tokens = B * tokens_per_sample */
+    int32_t d;                 /* feature dim (multiple of 128) */
+    int32_t Dt;                /* text / style dim (multiple of 32) */
+    int32_t E;                 /* experts, <= MOEGAN_MAX_EXPERTS */
+    int32_t k;                 /* experts per token; k == E in dense mode, 1 in hard mode */
+    int32_t B;                 /* samples */
+    int32_t tokens_per_sample; /* H * W */
+    int32_t precision;         /* 0 bf16, 1 fp32 (3-pass bf16 split) */
+    int32_t dense;             /* 1: all experts see all tokens, gate = prob (reference training path, :465-470) */
+    int32_t hard;              /* 1: eval path, one-hot probs, top-1, gate 1.0 (:392-400, :471-483) */
+    int32_t m_cap;             /* row capacity of dispatched buffers, = moegan_m_cap() */
+} moegan_shape;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int moegan_version(void);
+const char* moegan_last_error_string(void); /* host string, valid until the next failing call on this thread */
+/* rows to allocate for dispatched buffers: dense E*ceil128(T); sparse ceil128(T*k) + 128*E */
+int64_t moegan_m_cap(int32_t T, int32_t E, int32_t k, int32_t dense);
+/* int32 elements of the dispatch plan array */
+int64_t moegan_plan_ints(int32_t m_cap);
+/* bytes of scratch moegan_router_bwd needs */
+int64_t moegan_router_bwd_workspace_bytes(const moegan_shape* s);
+
+/* ---- router --------------------------------------------------------------------------------- */
+/* replaces: BayesianRouter.reparameterize x3 (t2i_moe_gan.py:302-333, called :354-356) and
+ * BayesianRouter.kl_divergence (:405-423).  sampling=0 copies mu (eval, :357-361).
+ * Wf [d,128], Wt [Dt,128], Wc [256,E] fp32.  Wf_op [d, S*128], Wt_op [Dt, S*128] (bf16 operand copies
+ * for the backward GEMMs; may be NULL).  kl_out [MOEGAN_KL_OUT_FLOATS]: [0] = nan_to_num+clamp[0,120] value,
+ * [1] = raw sum, [2..] scratch partials. */
+int moegan_router_sample_kl_fwd(const moegan_shape* s,
+                                const float* mu_f, const float* rho_f, const float* eps_f,
+                                const float* mu_t, const float* rho_t, const float* eps_t,
+                                const float* mu_c, const float* rho_c, const float* eps_c,
+                                int32_t sampling, float* Wf, float* Wt, float* Wc,
+                                void* Wf_op, void* Wt_op, float* kl_out, void* stream);
+
+/* replaces: text half of the projections (t2i_moe_gan.py:365,368,371) computed ONCE PER SAMPLE instead
+ * of on the materialised [T,Dt] expansion (:456).  tp [B,128] = nan_to_num(w) @ Wt;  tl [B,E] = tp @ Wc[128:]. */
+int moegan_router_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc,
+                           float* tp, float* tl, void* stream);
+
+/* replaces: BayesianRouter.forward projections, temperature, clamps, softmax, clamp+renorm, eval one-hot
+ * (t2i_moe_gan.py:338-402) plus top-k gating and the per-chunk expert histogram / prob column sums.
+ * fp [T,128] (may be NULL when no backward is needed), raw [T,E] logits before temperature,
+ * probs [T,E] (one-hot when s->hard), topk_idx [T,k] int32 (descending prob, ties -> lowest index),
+ * gates [T,k], chunk_counts [ceil(T/32), E] int32, chunk_colsum [ceil(T/32), E] fp32 (soft probs). */
+int moegan_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
+                      const float* temperature, float annealing_factor,
+                      float* fp, float* raw, float* probs, int32_t* topk_idx, float* gates,
+                      int32_t* chunk_counts, float* chunk_colsum, void* stream);
+
+/* ---- dispatch ------------------------------------------------------------------------------- */
+/* replaces: `expert_indices == i` masks / torch.any host syncs (t2i_moe_gan.py:473-479) with a device-side
+ * histogram + exclusive scan.  plan: see DESIGN.md (block->expert map, padded expert offsets, counts).
+ * chunk_base [ceil(T/32), E] int32: first row (relative to the expert segment) of each chunk.
+ * load [E] = column sums of the soft probs (input of moe_balance_loss, t2i_moe_gan.py:973). */
+int moegan_dispatch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float* chunk_colsum,
+                         int32_t* plan, int32_t* chunk_base, float* load, void* stream);
+
+/* replaces: boolean-mask gather `x_reshaped[mask]` (t2i_moe_gan.py:481).  Stable permutation.
+ * x_op [m_cap, S*d] gathered bf16 operand rows; x_copy [T, S*d] un-permuted operand copy (may be NULL);
+ * row_token [m_cap] (-1 on padding rows), row_gate [m_cap], token_rows [T,k]. */
+int moegan_dispatch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates,
+                           const int32_t* plan, const int32_t* chunk_base,
+                           void* x_op, void* x_copy, int32_t* row_token, float* row_gate, int32_t* token_rows,
+                           void* stream);
+
+/* dense mode: no permutation, only fp32 -> bf16 operand conversion.  x_copy [T, S*d]. */
+int moegan_convert_tokens(const moegan_shape* s, const float* x, void* x_copy, void* stream);
+
+/* replaces: the per-call autocast weight casts of nn.Linear (t2i_moe_gan.py:257,259).  Host arrays of E
+ * device pointers to the per-expert fp32 parameters (state_dict layout) -> stacked operands
+ * W1_op [E*4d, S*d], W2_op [E*d, S*4d] and stacked fp32 biases b1s [E,4d], b2s [E,d]. */
+int moegan_prep_weights(const moegan_shape* s, const float* const* w1_host_ptrs, const float* const* b1_host_ptrs,
+                        const float* const* w2_host_ptrs, const float* const* b2_host_ptrs,
+                        void* W1_op, float* b1s, void* W2_op, float* b2s, void* stream);
+
+/* ---- experts -------------------------------------------------------------------------------- */
+/* replaces: SparseExpertFFN.forward for all experts (t2i_moe_gan.py:262-263, loops :467-468 / :476-482):
+ * two grouped GEMMs on tcgen05.  a_op = x_op (sparse) or x_copy (dense: shared by all experts).
+ * pre [m_cap,4d] (bf16, or fp32 when precision==1), h_op [m_cap, S*4d], y [m_cap,d] (bf16 / fp32). */
+int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const float* b1s,
+                   const void* W2_op, const float* b2s, void* pre, void* h_op, void* y, void* stream);
+
+/* replaces: `combined_output += probs[:, i:i+1] * expert_output` (t2i_moe_gan.py:462,470) and
+ * `combined_output[mask] = expert_output` (:483).  out [T,d] fp32. */
+int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows,
+                       float* out, void* stream);
+
+/* ---- backward ------------------------------------------------------------------------------- */
+/* autograd of the combine: dy_op[r] = gate * dout[token(r)] (zero on padding rows),
+ * dgate_row[r] = <dout[token(r)], y[r]>.  gates: [T,k] (dense: the probs, k == E). */
+int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y,
+                       const int32_t* row_token, const float* row_gate, const float* gates,
+                       void* dy_op, float* dgate_row, void* stream);
+
+/* autograd of the experts (B2): dgrad + wgrad grouped GEMMs and bias column sums.
+ * dpre_op [m_cap, S*4d], dx_rows [m_cap,d] (bf16 / fp32), dW1 [E,4d,d], db1 [E,4d], dW2 [E,d,4d], db2 [E,d] fp32. */
+int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
+                   const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
+                   float* dW1, float* db1, float* dW2, float* db2, void* stream);
+
+/* un-permute + sum of the k expert contributions per token, plus the router's dx:  dx [T,d] fp32. */
+int moegan_uncombine_bwd(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows,
+                         const float* dx_router, float* dx, void* stream);
+
+/* autograd of the router (B3-B6): gates/probs -> logits -> projections -> sampled weights -> (mu, rho),
+ * temperature, x and w; plus the KL gradient.  dprobs_ext [T,E] and dload [E] may be NULL.
+ * grads: dmu/drho x3, dtemperature[1], dx_router [T,d], dw [B,Dt].  x_copy [T,S*d], Wf_op, Wt_op as above. */
+int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
+                      const float* Wf, const float* Wt, const float* Wc, const void* Wf_op, const void* Wt_op,
+                      const float* fp, const float* tp, const float* raw, const int32_t* topk_idx,
+                      const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
+                      const float* temperature, float annealing_factor, int32_t sampled,
+                      const float* mu_f, const float* rho_f, const float* eps_f,
+                      const float* mu_t, const float* rho_t, const float* eps_t,
+                      const float* mu_c, const float* rho_c, const float* eps_c,
+                      const float* kl_out, const float* dkl,
+                      float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c,
+                      float* dtemperature, float* dx_router, float* dw,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* replaces: AuroraGANLoss.moe_balance_loss on the fused column sums (t2i_moe_gan.py:973-1000).
+ * fwd: loss[0] = bw * nan_to_num(clamp(E * std(frac)/(mean(frac)+1e-6), 0, 10)), frac = (load+1e-6)/T.
+ * bwd: dload [E] = dloss * d(loss)/d(load). */
+int moegan_balance_loss_fwd(const float* load, int32_t E, int32_t T, float balance_weight, float* loss, void* stream);
+int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balance_weight, const float* dloss,
+                            float* dload, void* stream);
+
+/* ---- test / bench hook ---------------------------------------------------------------------- */
+/* Plain (ungrouped) GEMM on the same tcgen05 kernel, fp32 out:  C[M,N] = op(A) * op(B).
+ * kind 0: A [M,S*K] K-major, B [N,S*K] K-major.   kind 1: A [M,S*K] K-major, B [K,S*N] (N contiguous).
+ * kind 2: A [K,S*M] (M contiguous), B [K,S*N].    precision as above.  Used by tests and bench only. */
+int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K,
+                     const void* A, const void* B, float* C, void* stream);
+/* debug: override the MN-major shared-memory descriptor parameters of the GEMM (0 = built-in defaults) */
+int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes);
+/* fp32 [rows, cols] -> bf16 operand [rows, S*cols] */
+int moegan_to_operand(const float* src, int64_t rows, int64_t cols, int32_t precision, void* dst, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOEGAN_SM100_H */

@@ -1,0 +1,463 @@
+// extern "C" boundary of libmoegan_sm100.so (declared in include/moegan_sm100.h).
+#include "kernels.cuh"
+#include "umma_gemm.cuh"
+
+#include <cstring>
+
+namespace moegan {
+
+// ---- error plumbing --------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return MOEGAN_ERR_CUDA;
+}
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+int validate_shape(const moegan_shape* s) {
+    MOEGAN_REQUIRE(s != nullptr, MOEGAN_ERR_NULL_POINTER, "shape is NULL");
+    MOEGAN_REQUIRE(s->T >= 0 && s->B >= 0 && s->tokens_per_sample > 0 && (int64_t)s->B * s->tokens_per_sample == s->T,
+                   MOEGAN_ERR_BAD_SHAPE, "T (%d) must equal B (%d) * tokens_per_sample (%d)", s->T, s->B, s->tokens_per_sample);
+    MOEGAN_REQUIRE(s->d >= 128 && s->d % 128 == 0 && s->d <= 1024, MOEGAN_ERR_BAD_SHAPE, "d (%d) must be a multiple of 128 in [128, 1024]", s->d);
+    MOEGAN_REQUIRE(s->Dt >= 64 && s->Dt % 64 == 0, MOEGAN_ERR_BAD_SHAPE, "Dt (%d) must be a positive multiple of 64", s->Dt);
+    MOEGAN_REQUIRE(s->E >= 1 && s->E <= MOEGAN_MAX_EXPERTS, MOEGAN_ERR_BAD_SHAPE, "E (%d) must be in [1, %d]", s->E, MOEGAN_MAX_EXPERTS);
+    MOEGAN_REQUIRE(s->precision == 0 || s->precision == 1, MOEGAN_ERR_UNSUPPORTED, "precision (%d) must be 0 (bf16) or 1 (fp32 3-pass)", s->precision);
+    if (s->dense) {
+        MOEGAN_REQUIRE(s->k == s->E && !s->hard, MOEGAN_ERR_BAD_SHAPE, "dense mode needs k == E (k=%d, E=%d) and hard == 0", s->k, s->E);
+    } else {
+        MOEGAN_REQUIRE(s->k >= 1 && s->k <= MOEGAN_MAX_TOPK && s->k < s->E + (s->E == 1), MOEGAN_ERR_BAD_SHAPE,
+                       "sparse mode needs 1 <= k (%d) <= %d and k < E (%d); use dense mode for k == E", s->k, MOEGAN_MAX_TOPK, s->E);
+        MOEGAN_REQUIRE(!s->hard || s->k == 1, MOEGAN_ERR_BAD_SHAPE, "hard (eval) routing is top-1 (k=%d)", s->k);
+    }
+    MOEGAN_REQUIRE(s->m_cap == moegan_m_cap(s->T, s->E, s->k, s->dense), MOEGAN_ERR_BAD_SHAPE,
+                   "m_cap (%d) must equal moegan_m_cap() = %lld", s->m_cap, (long long)moegan_m_cap(s->T, s->E, s->k, s->dense));
+    return MOEGAN_OK;
+}
+
+static int g_mn_lbo = 0, g_mn_sbo = 0, g_mn_kadv = 0;   // debug overrides (0 = kernel defaults)
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct RouterBwdWs {
+    size_t draw, dfp_op, dtau_part, dtl, dwc_part, dWc, dtp, dtp_op, w_op, dWf, dWt, total;
+};
+static RouterBwdWs router_bwd_layout(const moegan_shape* s) {
+    const size_t S = s->precision == 1 ? 2 : 1;
+    const size_t H = MOEGAN_ROUTER_HID;
+    RouterBwdWs w;
+    size_t o = 0;
+    w.draw = o;      o = align256(o + (size_t)s->T * s->E * 4);
+    w.dfp_op = o;    o = align256(o + (size_t)s->T * S * H * 2);
+    w.dtau_part = o; o = align256(o + (size_t)router_bwd_logits_blocks(s) * 4 + 4);
+    w.dtl = o;       o = align256(o + (size_t)s->B * s->E * 4);
+    w.dwc_part = o;  o = align256(o + (size_t)router_bwd_dwc_parts(s) * H * s->E * 4 + 4);
+    w.dWc = o;       o = align256(o + 2 * H * s->E * 4);
+    w.dtp = o;       o = align256(o + (size_t)s->B * H * 4);
+    w.dtp_op = o;    o = align256(o + (size_t)s->B * S * H * 2);
+    w.w_op = o;      o = align256(o + (size_t)s->B * S * s->Dt * 2);
+    w.dWf = o;       o = align256(o + (size_t)s->d * H * 4);
+    w.dWt = o;       o = align256(o + (size_t)s->Dt * H * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace moegan
+
+using namespace moegan;
+
+#define REQ_PTR(p) MOEGAN_REQUIRE((p) != nullptr, MOEGAN_ERR_NULL_POINTER, "%s: argument '%s' is NULL", __func__, #p)
+#define CHECK_SHAPE(s)                                        \
+    do {                                                      \
+        int _rc = validate_shape(s);                          \
+        if (_rc != MOEGAN_OK) return _rc;                     \
+    } while (0)
+#define RUN(expr)                                             \
+    do {                                                      \
+        int _rc = (expr);                                     \
+        if (_rc != MOEGAN_OK) return _rc;                     \
+    } while (0)
+
+extern "C" {
+
+int moegan_version(void) { return MOEGAN_ABI_VERSION; }
+const char* moegan_last_error_string(void) { return g_err; }
+
+int64_t moegan_m_cap(int32_t T, int32_t E, int32_t k, int32_t dense) {
+    if (dense) return (int64_t)E * (((int64_t)T + 127) / 128 * 128);
+    return (((int64_t)T * k + 127) / 128 * 128) + 128LL * E;
+}
+int64_t moegan_plan_ints(int32_t m_cap) { return PLAN_BLK + m_cap / 128 + 8; }
+int64_t moegan_router_bwd_workspace_bytes(const moegan_shape* s) {
+    if (s == nullptr) return 0;
+    return (int64_t)router_bwd_layout(s).total;
+}
+int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes) {
+    g_mn_lbo = lbo_bytes; g_mn_sbo = sbo_bytes; g_mn_kadv = kadv_bytes;
+    return MOEGAN_OK;
+}
+
+// ---- router ----------------------------------------------------------------------------------------
+int moegan_router_sample_kl_fwd(const moegan_shape* s, const float* mu_f, const float* rho_f, const float* eps_f,
+                                const float* mu_t, const float* rho_t, const float* eps_t,
+                                const float* mu_c, const float* rho_c, const float* eps_c,
+                                int32_t sampling, float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(mu_f); REQ_PTR(rho_f); REQ_PTR(mu_t); REQ_PTR(rho_t); REQ_PTR(mu_c); REQ_PTR(rho_c);
+    REQ_PTR(Wf); REQ_PTR(Wt); REQ_PTR(Wc); REQ_PTR(kl_out);
+    if (sampling) { REQ_PTR(eps_f); REQ_PTR(eps_t); REQ_PTR(eps_c); }
+    return launch_sample_kl(s, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampling, Wf, Wt, Wc, Wf_op, Wt_op, kl_out,
+                            (cudaStream_t)stream);
+}
+
+int moegan_router_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->B == 0) return MOEGAN_OK;
+    REQ_PTR(w); REQ_PTR(Wt); REQ_PTR(Wc); REQ_PTR(tp); REQ_PTR(tl);
+    return launch_text_fwd(s, w, Wt, Wc, tp, tl, (cudaStream_t)stream);
+}
+
+int moegan_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
+                      const float* temperature, float annealing_factor, float* fp, float* raw, float* probs, int32_t* topk_idx,
+                      float* gates, int32_t* chunk_counts, float* chunk_colsum, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(x); REQ_PTR(Wf); REQ_PTR(Wc); REQ_PTR(tl); REQ_PTR(temperature); REQ_PTR(raw); REQ_PTR(probs);
+    REQ_PTR(topk_idx); REQ_PTR(gates); REQ_PTR(chunk_counts); REQ_PTR(chunk_colsum);
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wf) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                   "router_fwd: x / Wf must be 16-byte aligned");
+    return launch_router_fwd(s, x, Wf, Wc, tl, temperature, annealing_factor, fp, raw, probs, topk_idx, gates, chunk_counts,
+                             chunk_colsum, (cudaStream_t)stream);
+}
+
+// ---- dispatch --------------------------------------------------------------------------------------
+int moegan_dispatch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float* chunk_colsum, int32_t* plan,
+                         int32_t* chunk_base, float* load, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(chunk_counts); REQ_PTR(chunk_colsum); REQ_PTR(plan); REQ_PTR(chunk_base); REQ_PTR(load);
+    return launch_plan(s, chunk_counts, chunk_colsum, plan, chunk_base, load, (cudaStream_t)stream);
+}
+
+int moegan_dispatch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates, const int32_t* plan,
+                           const int32_t* chunk_base, void* x_op, void* x_copy, int32_t* row_token, float* row_gate,
+                           int32_t* token_rows, void* stream) {
+    CHECK_SHAPE(s);
+    MOEGAN_REQUIRE(!s->dense, MOEGAN_ERR_UNSUPPORTED, "dispatch_gather is for sparse mode; dense mode uses convert_tokens");
+    REQ_PTR(x); REQ_PTR(topk_idx); REQ_PTR(gates); REQ_PTR(plan); REQ_PTR(chunk_base); REQ_PTR(x_op); REQ_PTR(row_token);
+    REQ_PTR(row_gate); REQ_PTR(token_rows);
+    return launch_gather(s, x, topk_idx, gates, plan, chunk_base, x_op, x_copy, row_token, row_gate, token_rows, (cudaStream_t)stream);
+}
+
+int moegan_convert_tokens(const moegan_shape* s, const float* x, void* x_copy, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(x); REQ_PTR(x_copy);
+    return launch_to_operand(x, s->T, s->d, s->precision == 1, 0, x_copy, (cudaStream_t)stream);
+}
+
+int moegan_prep_weights(const moegan_shape* s, const float* const* w1, const float* const* b1, const float* const* w2,
+                        const float* const* b2, void* W1_op, float* b1s, void* W2_op, float* b2s, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(w1); REQ_PTR(b1); REQ_PTR(w2); REQ_PTR(b2); REQ_PTR(W1_op); REQ_PTR(b1s); REQ_PTR(W2_op); REQ_PTR(b2s);
+    for (int e = 0; e < s->E; ++e) {
+        MOEGAN_REQUIRE(w1[e] && b1[e] && w2[e] && b2[e], MOEGAN_ERR_NULL_POINTER, "prep_weights: NULL parameter pointer for expert %d", e);
+        MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(w1[e]) | reinterpret_cast<uintptr_t>(w2[e])) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                       "prep_weights: expert %d weights not 16-byte aligned", e);
+    }
+    return launch_prep_weights(s, w1, b1, w2, b2, W1_op, b1s, W2_op, b2s, (cudaStream_t)stream);
+}
+
+// ---- experts ---------------------------------------------------------------------------------------
+static GemmParams base_params(const moegan_shape* s, const int32_t* plan) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.passes = s->precision == 1 ? 3 : 1;
+    p.m_blocks_host = -1;
+    p.k_rows_host = -1;
+    p.plan = plan;
+    p.E = s->E;
+    p.out_rows_valid = s->m_cap;
+    p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo; p.mn_kadv = g_mn_kadv;
+    return p;
+}
+
+int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const float* b1s,
+                   const void* W2_op, const float* b2s, void* pre, void* h_op, void* y, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(b1s); REQ_PTR(W2_op); REQ_PTR(b2s); REQ_PTR(pre); REQ_PTR(h_op); REQ_PTR(y);
+    const uint64_t S = s->precision == 1 ? 2 : 1;
+    const int d = s->d, hid = 4 * s->d;
+    const int T_pad = ceil_div(s->T, 128) * 128;
+    const long long m_blocks = s->m_cap / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    {   // GEMM1: pre = x W1^T + b1, h = gelu(pre)   (t2i_moe_gan.py:257-258)
+        GemmOperand A{a_op, S * d, (uint64_t)(s->dense ? s->T : s->m_cap), S * d};
+        GemmOperand B{W1_op, S * d, (uint64_t)s->E * hid, S * d};
+        GemmParams p = base_params(s, plan);
+        p.N = hid; p.K = d; p.a_lo_off = d; p.b_lo_off = d;
+        p.a_mod = s->dense ? T_pad / 128 : 0;
+        p.b_rows_per_expert = hid;
+        p.epi = s->precision == 1 ? EPI_GELU_X3 : EPI_GELU_BF16;
+        p.out0 = h_op; p.ld_out0 = (long long)S * hid; p.out_split_off = hid;
+        p.out1 = pre;  p.ld_out1 = hid;
+        p.bias = b1s;
+        RUN(launch_umma_gemm(GEMM_ROWS_BK, 256, A, B, p, m_blocks * (hid / 256), st));
+    }
+    {   // GEMM2: y = h W2^T + b2   (:259)
+        GemmOperand A{h_op, S * hid, (uint64_t)s->m_cap, S * hid};
+        GemmOperand B{W2_op, S * hid, (uint64_t)s->E * d, S * hid};
+        GemmParams p = base_params(s, plan);
+        const int BN = d % 256 == 0 ? 256 : 128;
+        p.N = d; p.K = hid; p.a_lo_off = hid; p.b_lo_off = hid;
+        p.b_rows_per_expert = d;
+        p.epi = s->precision == 1 ? EPI_BIAS_F32 : EPI_BIAS_BF16;
+        p.out0 = y; p.ld_out0 = d;
+        p.bias = b2s;
+        RUN(launch_umma_gemm(GEMM_ROWS_BK, BN, A, B, p, m_blocks * (d / BN), st));
+    }
+    return MOEGAN_OK;
+}
+
+int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(y); REQ_PTR(gates); REQ_PTR(out);
+    if (!s->dense) REQ_PTR(token_rows);
+    return launch_combine_fwd(s, y, gates, token_rows, out, (cudaStream_t)stream);
+}
+
+// ---- backward --------------------------------------------------------------------------------------
+int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(plan); REQ_PTR(dout); REQ_PTR(y); REQ_PTR(dy_op); REQ_PTR(dgate_row);
+    if (s->dense) { REQ_PTR(gates); } else { REQ_PTR(row_token); REQ_PTR(row_gate); }
+    return launch_combine_bwd(s, plan, dout, y, row_token, row_gate, gates, dy_op, dgate_row, (cudaStream_t)stream);
+}
+
+int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
+                   const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
+                   float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(W2_op); REQ_PTR(pre); REQ_PTR(h_op); REQ_PTR(dy_op); REQ_PTR(dpre_op);
+    REQ_PTR(dx_rows); REQ_PTR(dW1); REQ_PTR(db1); REQ_PTR(dW2); REQ_PTR(db2);
+    const uint64_t S = s->precision == 1 ? 2 : 1;
+    const int d = s->d, hid = 4 * s->d;
+    const long long m_blocks = s->m_cap / 128;
+    const int BNd = d % 256 == 0 ? 256 : 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->T == 0) {
+        MOEGAN_CHECK_CUDA(cudaMemsetAsync(dW1, 0, (size_t)s->E * hid * d * 4, st));
+        MOEGAN_CHECK_CUDA(cudaMemsetAsync(dW2, 0, (size_t)s->E * hid * d * 4, st));
+        MOEGAN_CHECK_CUDA(cudaMemsetAsync(db1, 0, (size_t)s->E * hid * 4, st));
+        MOEGAN_CHECK_CUDA(cudaMemsetAsync(db2, 0, (size_t)s->E * d * 4, st));
+        return MOEGAN_OK;
+    }
+    {   // dgrad2 + GELU':  dpre = (dy W2) * gelu'(pre)
+        GemmOperand A{dy_op, S * d, (uint64_t)s->m_cap, S * d};
+        GemmOperand B{W2_op, S * hid, (uint64_t)s->E * d, S * hid};
+        GemmParams p = base_params(s, plan);
+        p.N = hid; p.K = d; p.a_lo_off = d; p.b_lo_off = hid;
+        p.b_rows_per_expert = d;
+        p.epi = s->precision == 1 ? EPI_DGELU_X3 : EPI_DGELU_BF16;
+        p.aux = pre; p.ld_aux = hid;
+        p.out0 = dpre_op; p.ld_out0 = (long long)S * hid; p.out_split_off = hid;
+        RUN(launch_umma_gemm(GEMM_ROWS_BMN, 256, A, B, p, m_blocks * (hid / 256), st));
+    }
+    RUN(launch_colsum_grouped(s, plan, dy_op, d, db2, st));
+    RUN(launch_colsum_grouped(s, plan, dpre_op, hid, db1, st));
+    {   // dgrad1: dx_rows = dpre W1
+        GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
+        GemmOperand B{W1_op, S * d, (uint64_t)s->E * hid, S * d};
+        GemmParams p = base_params(s, plan);
+        p.N = d; p.K = hid; p.a_lo_off = hid; p.b_lo_off = d;
+        p.b_rows_per_expert = hid;
+        p.epi = s->precision == 1 ? EPI_F32 : EPI_BF16;
+        p.out0 = dx_rows; p.ld_out0 = d;
+        RUN(launch_umma_gemm(GEMM_ROWS_BMN, BNd, A, B, p, m_blocks * (d / BNd), st));
+    }
+    {   // wgrad2: dW2[e] = dy_e^T h_e   [d, 4d]
+        GemmOperand A{dy_op, S * d, (uint64_t)s->m_cap, S * d};
+        GemmOperand B{h_op, S * hid, (uint64_t)s->m_cap, S * hid};
+        GemmParams p = base_params(s, plan);
+        p.N = hid; p.dimA = d; p.a_lo_off = d; p.b_lo_off = hid;
+        p.epi = EPI_F32; p.out0 = dW2; p.ld_out0 = hid;
+        RUN(launch_umma_gemm(GEMM_WGRAD, 256, A, B, p, (long long)s->E * (d / 128) * (hid / 256), st));
+    }
+    {   // wgrad1: dW1[e] = dpre_e^T x_e   [4d, d]
+        GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
+        GemmOperand B{a_op, S * d, (uint64_t)(s->dense ? s->T : s->m_cap), S * d};
+        GemmParams p = base_params(s, plan);
+        p.N = d; p.dimA = hid; p.a_lo_off = hid; p.b_lo_off = d;
+        p.b_rel = s->dense ? 1 : 0;
+        p.epi = EPI_F32; p.out0 = dW1; p.ld_out0 = d;
+        RUN(launch_umma_gemm(GEMM_WGRAD, BNd, A, B, p, (long long)s->E * (hid / 128) * (d / BNd), st));
+    }
+    return MOEGAN_OK;
+}
+
+int moegan_uncombine_bwd(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
+                         void* stream) {
+    CHECK_SHAPE(s);
+    if (s->T == 0) return MOEGAN_OK;
+    REQ_PTR(dx_rows); REQ_PTR(dx);
+    if (!s->dense) REQ_PTR(token_rows);
+    return launch_uncombine(s, dx_rows, token_rows, dx_router, dx, (cudaStream_t)stream);
+}
+
+int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w, const float* Wf, const float* Wt, const float* Wc,
+                      const void* Wf_op, const void* Wt_op, const float* fp, const float* tp, const float* raw,
+                      const int32_t* topk_idx, const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext,
+                      const float* dload, const float* temperature, float annealing_factor, int32_t sampled,
+                      const float* mu_f, const float* rho_f, const float* eps_f, const float* mu_t, const float* rho_t,
+                      const float* eps_t, const float* mu_c, const float* rho_c, const float* eps_c,
+                      const float* kl_out, const float* dkl,
+                      float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c,
+                      float* dtemperature, float* dx_router, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+    CHECK_SHAPE(s);
+    MOEGAN_REQUIRE(!s->hard, MOEGAN_ERR_UNSUPPORTED, "router_bwd: hard (eval) routing has no gradient");
+    MOEGAN_REQUIRE(s->T > 0, MOEGAN_ERR_BAD_SHAPE, "router_bwd: T must be positive");
+    REQ_PTR(x_copy); REQ_PTR(w); REQ_PTR(Wf); REQ_PTR(Wt); REQ_PTR(Wc); REQ_PTR(Wf_op); REQ_PTR(Wt_op); REQ_PTR(fp); REQ_PTR(tp);
+    REQ_PTR(raw); REQ_PTR(dgate_row); REQ_PTR(temperature);
+    REQ_PTR(mu_f); REQ_PTR(rho_f); REQ_PTR(mu_t); REQ_PTR(rho_t); REQ_PTR(mu_c); REQ_PTR(rho_c);
+    REQ_PTR(dmu_f); REQ_PTR(drho_f); REQ_PTR(dmu_t); REQ_PTR(drho_t); REQ_PTR(dmu_c); REQ_PTR(drho_c);
+    REQ_PTR(dtemperature); REQ_PTR(dx_router); REQ_PTR(dw); REQ_PTR(workspace);
+    if (!s->dense) { REQ_PTR(topk_idx); REQ_PTR(token_rows); }
+    if (sampled) { REQ_PTR(eps_f); REQ_PTR(eps_t); REQ_PTR(eps_c); }
+    const RouterBwdWs L = router_bwd_layout(s);
+    MOEGAN_REQUIRE(workspace_bytes >= (int64_t)L.total, MOEGAN_ERR_BAD_SHAPE, "router_bwd: workspace %lld < required %lld bytes",
+                   (long long)workspace_bytes, (long long)L.total);
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MOEGAN_ERR_MISALIGNED, "router_bwd: workspace must be 256-byte aligned");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    float* draw = reinterpret_cast<float*>(ws + L.draw);
+    void* dfp_op = ws + L.dfp_op;
+    float* dtau_part = reinterpret_cast<float*>(ws + L.dtau_part);
+    float* dtl = reinterpret_cast<float*>(ws + L.dtl);
+    float* dwc_part = reinterpret_cast<float*>(ws + L.dwc_part);
+    float* dWc = reinterpret_cast<float*>(ws + L.dWc);
+    float* dtp = reinterpret_cast<float*>(ws + L.dtp);
+    void* dtp_op = ws + L.dtp_op;
+    void* w_op = ws + L.w_op;
+    float* dWf = reinterpret_cast<float*>(ws + L.dWf);
+    float* dWt = reinterpret_cast<float*>(ws + L.dWt);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t S = s->precision == 1 ? 2 : 1;
+    const uint64_t H = MOEGAN_ROUTER_HID;
+    const int d = s->d, Dt = s->Dt;
+
+    RUN(launch_router_bwd_logits(s, raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, annealing_factor,
+                                 draw, dfp_op, dtau_part, st));
+    RUN(launch_router_bwd_small(s, fp, draw, tp, Wc, dtau_part, temperature, annealing_factor, dtl, dwc_part, dWc, dtp, dtp_op,
+                                dtemperature, st));
+    RUN(launch_to_operand(w, s->B, Dt, s->precision == 1, 1, w_op, st));
+
+    GemmParams base;
+    memset(&base, 0, sizeof(base));
+    base.passes = s->precision == 1 ? 3 : 1;
+    base.m_blocks_host = -1; base.k_rows_host = -1; base.E = 1; base.epi = EPI_F32;
+    base.mn_lbo = g_mn_lbo; base.mn_sbo = g_mn_sbo; base.mn_kadv = g_mn_kadv;
+    {   // dx_router [T, d] = dfp [T,128] * Wf[d,128]^T
+        GemmOperand A{dfp_op, S * H, (uint64_t)s->T, S * H};
+        GemmOperand B{Wf_op, S * H, (uint64_t)d, S * H};
+        GemmParams p = base;
+        const int BN = d % 256 == 0 ? 256 : 128;
+        p.N = d; p.K = (int)H; p.a_lo_off = (int)H; p.b_lo_off = (int)H; p.b_rows_per_expert = d;
+        p.m_blocks_host = ceil_div(s->T, 128); p.out_rows_valid = s->T;
+        p.out0 = dx_router; p.ld_out0 = d;
+        RUN(launch_umma_gemm(GEMM_ROWS_BK, BN, A, B, p, (long long)p.m_blocks_host * (d / BN), st));
+    }
+    {   // dWf [d, 128] = x^T dfp
+        GemmOperand A{x_copy, S * d, (uint64_t)s->T, S * d};
+        GemmOperand B{dfp_op, S * H, (uint64_t)s->T, S * H};
+        GemmParams p = base;
+        p.N = (int)H; p.dimA = d; p.a_lo_off = d; p.b_lo_off = (int)H; p.k_rows_host = s->T;
+        p.out0 = dWf; p.ld_out0 = (long long)H;
+        RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)(d / 128), st));
+    }
+    {   // dw [B, Dt] = dtp [B,128] * Wt[Dt,128]^T
+        GemmOperand A{dtp_op, S * H, (uint64_t)s->B, S * H};
+        GemmOperand B{Wt_op, S * H, (uint64_t)Dt, S * H};
+        GemmParams p = base;
+        p.N = Dt; p.K = (int)H; p.a_lo_off = (int)H; p.b_lo_off = (int)H; p.b_rows_per_expert = Dt;
+        p.m_blocks_host = ceil_div(s->B, 128); p.out_rows_valid = s->B;
+        p.out0 = dw; p.ld_out0 = Dt;
+        RUN(launch_umma_gemm(GEMM_ROWS_BK, 128, A, B, p, (long long)p.m_blocks_host * ceil_div(Dt, 128), st));
+    }
+    {   // dWt [Dt, 128] = w^T dtp
+        GemmOperand A{w_op, S * Dt, (uint64_t)s->B, S * Dt};
+        GemmOperand B{dtp_op, S * H, (uint64_t)s->B, S * H};
+        GemmParams p = base;
+        p.N = (int)H; p.dimA = Dt; p.a_lo_off = Dt; p.b_lo_off = (int)H; p.k_rows_host = s->B;
+        p.out0 = dWt; p.ld_out0 = (long long)H;
+        RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)ceil_div(Dt, 128), st));
+    }
+    RUN(launch_reparam_kl_bwd(s, dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampled, kl_out, dkl,
+                              dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c, st));
+    return MOEGAN_OK;
+}
+
+int moegan_balance_loss_fwd(const float* load, int32_t E, int32_t T, float balance_weight, float* loss, void* stream) {
+    REQ_PTR(load); REQ_PTR(loss);
+    MOEGAN_REQUIRE(E >= 1 && E <= MOEGAN_MAX_EXPERTS && T > 0, MOEGAN_ERR_BAD_SHAPE, "balance_loss: bad E (%d) or T (%d)", E, T);
+    return launch_balance_loss(load, E, T, balance_weight, nullptr, loss, nullptr, (cudaStream_t)stream);
+}
+int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balance_weight, const float* dloss, float* dload, void* stream) {
+    REQ_PTR(load); REQ_PTR(dloss); REQ_PTR(dload);
+    MOEGAN_REQUIRE(E >= 1 && E <= MOEGAN_MAX_EXPERTS && T > 0, MOEGAN_ERR_BAD_SHAPE, "balance_loss: bad E (%d) or T (%d)", E, T);
+    return launch_balance_loss(load, E, T, balance_weight, dloss, nullptr, dload, (cudaStream_t)stream);
+}
+
+// ---- test / bench hooks ----------------------------------------------------------------------------
+int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* C, void* stream) {
+    REQ_PTR(A); REQ_PTR(B); REQ_PTR(C);
+    MOEGAN_REQUIRE(M > 0 && N > 0 && K > 0 && N % 32 == 0 && M % 8 == 0 && K % 8 == 0, MOEGAN_ERR_BAD_SHAPE, "umma_gemm: bad M/N/K %d/%d/%d", M, N, K);
+    const uint64_t S = precision == 1 ? 2 : 1;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.passes = precision == 1 ? 3 : 1;
+    p.m_blocks_host = -1; p.k_rows_host = -1; p.E = 1; p.epi = EPI_F32;
+    p.out0 = C; p.ld_out0 = N; p.N = N;
+    p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo; p.mn_kadv = g_mn_kadv;
+    const int BN = N % 256 == 0 ? 256 : 128;
+    const long long n_blocks = ceil_div(N, BN);
+    if (kind == 0 || kind == 1) {
+        MOEGAN_REQUIRE(K % 64 == 0, MOEGAN_ERR_BAD_SHAPE, "umma_gemm: K (%d) must be a multiple of 64 for kinds 0/1", K);
+        GemmOperand a{A, S * K, (uint64_t)M, S * K};
+        GemmOperand b = kind == 0 ? GemmOperand{B, S * K, (uint64_t)N, S * K} : GemmOperand{B, S * N, (uint64_t)K, S * N};
+        p.K = K; p.a_lo_off = K; p.b_lo_off = kind == 0 ? K : N;
+        p.b_rows_per_expert = kind == 0 ? N : K;
+        p.m_blocks_host = ceil_div(M, 128); p.out_rows_valid = M;
+        return launch_umma_gemm(kind == 0 ? GEMM_ROWS_BK : GEMM_ROWS_BMN, BN, a, b, p, (long long)p.m_blocks_host * n_blocks, (cudaStream_t)stream);
+    }
+    if (kind == 2) {
+        GemmOperand a{A, S * M, (uint64_t)K, S * M};
+        GemmOperand b{B, S * N, (uint64_t)K, S * N};
+        p.dimA = M; p.a_lo_off = M; p.b_lo_off = N; p.k_rows_host = K;
+        return launch_umma_gemm(GEMM_WGRAD, BN, a, b, p, (long long)ceil_div(M, 128) * n_blocks, (cudaStream_t)stream);
+    }
+    set_error("umma_gemm: unknown kind %d", kind);
+    return MOEGAN_ERR_UNSUPPORTED;
+}
+
+int moegan_to_operand(const float* src, int64_t rows, int64_t cols, int32_t precision, void* dst, void* stream) {
+    REQ_PTR(src); REQ_PTR(dst);
+    return launch_to_operand(src, rows, cols, precision == 1, 0, dst, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Shared host/device helpers for libmoegan_sm100.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/moegan_sm100.h"
+
+namespace moegan {
+
+// ---- plan array layout (int32) -------------------------------------------------------------------
+// [0] number of 128-row blocks in use   [1] rows in use (= 128 * [0])   [2] T_pad (dense) or 0
+// [PLAN_OFF .. PLAN_OFF+E]  padded row offset of each expert segment (E+1 entries)
+// [PLAN_CNT .. PLAN_CNT+E)  real rows per expert
+// [PLAN_BLK .. )            expert id of each 128-row block
+constexpr int PLAN_OFF = 8;
+constexpr int PLAN_CNT = 48;
+constexpr int PLAN_BLK = 88;
+
+// ---- error plumbing ------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int num_sms();
+
+#define MOEGAN_CHECK_CUDA(expr)                                   \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return ::moegan::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define MOEGAN_CHECK_LAUNCH(name)                                     \
+    do {                                                              \
+        cudaError_t _e = cudaGetLastError();                          \
+        if (_e != cudaSuccess) return ::moegan::cuda_fail(_e, name);  \
+    } while (0)
+
+#define MOEGAN_REQUIRE(cond, status, ...)      \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::moegan::set_error(__VA_ARGS__);  \
+            return (status);                   \
+        }                                      \
+    } while (0)
+
+int validate_shape(const moegan_shape* s);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// torch.nan_to_num(v, nan=0, posinf=1, neginf=-1) - identity on finite input (t2i_moe_gan.py:340,344)
+__device__ __forceinline__ float nan_to_num_router(float v) {
+    if (v != v) return 0.0f;
+    if (isinf(v)) return v > 0.0f ? 1.0f : -1.0f;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// v = hi + lo + O(2^-17 |v|), both representable in bf16
+__device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
+    hi = __bfloat162float(__float2bfloat16_rn(v));
+    lo = v - hi;
+}
+__device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+// erf, Abramowitz-Stegun 7.1.26: |abs err| <= 1.5e-7.  Used by the bf16-precision epilogues where the
+// GEMM epilogue must stay under the tensor-pipe time; the fp32 (3-pass) mode uses erff().
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float r = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+    return copysignf(r, x);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU(approximate='none'), t2i_moe_gan.py:258
+    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
+    return 0.5f * x * (1.0f + e);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
+    const float pdf = (PRECISE ? expf(-0.5f * x * x) : __expf(-0.5f * x * x)) * 0.39894228040143268f;
+    return fmaf(x, pdf, 0.5f * (1.0f + e));
+}
+#endif  // __CUDACC__
+
+}  // namespace moegan

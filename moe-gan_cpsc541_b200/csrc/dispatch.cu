@@ -1,0 +1,445 @@
+// Token permutation / expert dispatch, weighted combine and their backward kernels.  All of these are
+// HBM-bandwidth-bound byte movers: one warp per token row, 8/16-byte vector accesses, fully coalesced on
+// the contiguous side of every gather / scatter.
+//
+// Reference semantics: SparseMoE.forward expert loops (moegan/t2i_moe_gan.py:462-483).
+#include "kernels.cuh"
+
+namespace moegan {
+
+namespace {
+
+constexpr int MAX_SEG = 8;   // d <= 1024: a warp covers 128 columns per segment (32 lanes x 4)
+
+// =====================================================================================================
+// plan: histogram totals -> padded expert offsets, block->expert map, per-chunk bases, balance load
+// =====================================================================================================
+__global__ void __launch_bounds__(1024)
+plan_kernel(const int* __restrict__ chunk_counts, const float* __restrict__ chunk_colsum, int nchunks, int T, int E, int dense,
+            int m_cap, int* __restrict__ plan, int* __restrict__ chunk_base, float* __restrict__ load) {
+    __shared__ int warp_tot[32];
+    __shared__ float fred[32];
+    __shared__ int tot_e[MOEGAN_MAX_EXPERTS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // ---- balance load: deterministic column sums of the soft probs over chunks ----
+    for (int e = 0; e < E; ++e) {
+        float acc = 0.0f;
+        for (int c = tid; c < nchunks; c += 1024) acc += chunk_colsum[(size_t)c * E + e];
+        acc = warp_sum(acc);
+        if (lane == 0) fred[wid] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.0f;
+            for (int w = 0; w < 32; ++w) s += fred[w];
+            load[e] = s;
+        }
+        __syncthreads();
+    }
+
+    if (dense) {
+        const int T_pad = (T + 127) / 128 * 128;
+        const int bpe = T_pad / 128;
+        if (tid <= E) plan[PLAN_OFF + tid] = tid * T_pad;
+        if (tid < E) plan[PLAN_CNT + tid] = T;
+        for (int i = tid; i < E * bpe; i += 1024) plan[PLAN_BLK + i] = i / bpe;
+        if (tid == 0) { plan[0] = E * bpe; plan[1] = E * T_pad; plan[2] = T_pad; }
+        return;
+    }
+
+    // ---- sparse: per-expert exclusive scan of the chunk histograms ----
+    const int ipt = (nchunks + 1023) / 1024;   // consecutive chunks per thread
+    const int c0 = tid * ipt;
+    for (int e = 0; e < E; ++e) {
+        int local = 0;
+        for (int i = 0; i < ipt; ++i) { const int c = c0 + i; if (c < nchunks) local += chunk_counts[(size_t)c * E + e]; }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_tot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+            warp_tot[lane] = wi - w;             // exclusive warp offsets
+            if (lane == 31) tot_e[e] = wi;
+        }
+        __syncthreads();
+        int run = warp_tot[wid] + incl - local;
+        for (int i = 0; i < ipt; ++i) {
+            const int c = c0 + i;
+            if (c < nchunks) { chunk_base[(size_t)c * E + e] = run; run += chunk_counts[(size_t)c * E + e]; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int off = 0;
+        for (int e = 0; e < E; ++e) {
+            plan[PLAN_OFF + e] = off;
+            plan[PLAN_CNT + e] = tot_e[e];
+            off += (tot_e[e] + 127) / 128 * 128;
+        }
+        if (off > m_cap) off = m_cap;            // cannot happen (m_cap is an upper bound); guards the buffers
+        plan[PLAN_OFF + E] = off;
+        plan[0] = off / 128; plan[1] = off; plan[2] = 0;
+    }
+    __syncthreads();
+    for (int e = 0; e < E; ++e) {
+        const int b0 = plan[PLAN_OFF + e] / 128, b1 = plan[PLAN_OFF + e + 1] / 128;
+        for (int i = b0 + tid; i < b1; i += 1024) plan[PLAN_BLK + i] = e;
+    }
+}
+
+// =====================================================================================================
+// gather: stable permutation of token rows into expert-contiguous order, fp32 -> bf16 operand
+// =====================================================================================================
+__device__ __forceinline__ void store_operand4(__nv_bfloat16* dst, int lo_off, bool split, float4 v) {
+    float h0, h1, h2, h3, l0, l1, l2, l3;
+    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    if (split) *reinterpret_cast<uint2*>(dst + lo_off) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const float* __restrict__ x, const int* __restrict__ topk_idx, const float* __restrict__ gates,
+              const int* __restrict__ plan, const int* __restrict__ chunk_base, int nchunks, int T, int d, int E, int k, int split,
+              __nv_bfloat16* __restrict__ x_op, __nv_bfloat16* __restrict__ x_copy,
+              int* __restrict__ row_token, float* __restrict__ row_gate, int* __restrict__ token_rows) {
+    __shared__ int dst_row[MOEGAN_CHUNK * MOEGAN_MAX_TOPK];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ld = split ? 2 * d : d;
+    if ((int)blockIdx.x >= nchunks) {
+        // ---- padding rows of expert e: zero operand rows, row_token = -1 ----
+        const int e = blockIdx.x - nchunks;
+        const int r0 = plan[PLAN_OFF + e] + plan[PLAN_CNT + e], r1 = plan[PLAN_OFF + e + 1];
+        for (int r = r0 + wid; r < r1; r += 8) {
+            uint2* row = reinterpret_cast<uint2*>(x_op + (size_t)r * ld);
+            for (int i = lane; i < ld / 4; i += 32) row[i] = make_uint2(0u, 0u);
+            if (lane == 0) { row_token[r] = -1; row_gate[r] = 0.0f; }
+        }
+        return;
+    }
+    const int chunk = blockIdx.x;
+    if (wid == 0) {
+        const int t = chunk * MOEGAN_CHUNK + lane;
+        const bool valid = t < T;
+        int idx[MOEGAN_MAX_TOPK], rows[MOEGAN_MAX_TOPK];
+#pragma unroll
+        for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) { idx[j] = (valid && j < k) ? topk_idx[(size_t)t * k + j] : -1; rows[j] = -1; }
+        for (int e = 0; e < E; ++e) {
+            bool has = false;
+#pragma unroll
+            for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) has |= (idx[j] == e);
+            const unsigned b = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int rank = __popc(b & ((1u << lane) - 1u));       // tokens before me in this chunk (stable)
+                const int row = plan[PLAN_OFF + e] + chunk_base[(size_t)chunk * E + e] + rank;
+#pragma unroll
+                for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) if (idx[j] == e) rows[j] = row;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) {
+            if (j < k) {
+                dst_row[lane * k + j] = rows[j];
+                if (valid) {
+                    token_rows[(size_t)t * k + j] = rows[j];
+                    row_token[rows[j]] = t;
+                    row_gate[rows[j]] = gates[(size_t)t * k + j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int tok = wid; tok < MOEGAN_CHUNK; tok += 8) {
+        const int t = chunk * MOEGAN_CHUNK + tok;
+        if (t >= T) break;
+        for (int seg = 0; seg < d / 128; ++seg) {
+            const int col = seg * 128 + lane * 4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)t * d + col));
+            for (int j = 0; j < k; ++j)
+                store_operand4(x_op + (size_t)dst_row[tok * k + j] * ld + col, d, split, v);
+            if (x_copy != nullptr) store_operand4(x_copy + (size_t)t * ld + col, d, split, v);
+        }
+    }
+}
+
+// fp32 [rows, cols] -> bf16 operand [rows, S*cols]
+__global__ void __launch_bounds__(256)
+to_operand_kernel(const float* __restrict__ src, long long rows, int cols, int split, int sanitize, __nv_bfloat16* __restrict__ dst) {
+    const long long n4 = rows * (cols / 4);
+    const int c4 = cols / 4;
+    const int ld = split ? 2 * cols : cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        float4 v = __ldg(reinterpret_cast<const float4*>(src + r * cols + c));
+        if (sanitize) { v.x = nan_to_num_router(v.x); v.y = nan_to_num_router(v.y); v.z = nan_to_num_router(v.z); v.w = nan_to_num_router(v.w); }
+        store_operand4(dst + r * ld + c, cols, split, v);
+    }
+}
+
+// per-expert fp32 parameters (state_dict layout) -> stacked operands + stacked biases
+struct WeightPtrs {
+    const float* w1[MOEGAN_MAX_EXPERTS];
+    const float* b1[MOEGAN_MAX_EXPERTS];
+    const float* w2[MOEGAN_MAX_EXPERTS];
+    const float* b2[MOEGAN_MAX_EXPERTS];
+};
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const WeightPtrs ptrs, int E, int d, int split, __nv_bfloat16* __restrict__ W1_op, float* __restrict__ b1s,
+                    __nv_bfloat16* __restrict__ W2_op, float* __restrict__ b2s) {
+    const int hid = 4 * d;
+    const long long per = (long long)hid * d / 4;          // float4 per weight matrix
+    const long long total = 2 * per * E;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int which = (int)(i / (per * E));            // 0: W1 [4d, d], 1: W2 [d, 4d]
+        const long long r = i - (long long)which * per * E;
+        const int e = (int)(r / per);
+        const long long q = r - (long long)e * per;
+        const int cols = which == 0 ? d : hid, rows = which == 0 ? hid : d;
+        const int c4 = cols / 4;
+        const int row = (int)(q / c4), c = (int)(q - (long long)row * c4) * 4;
+        const float* src = (which == 0 ? ptrs.w1[e] : ptrs.w2[e]) + (long long)row * cols + c;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        __nv_bfloat16* dst = (which == 0 ? W1_op : W2_op) + ((long long)e * rows + row) * (split ? 2 * cols : cols) + c;
+        store_operand4(dst, cols, split, v);
+    }
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gsz = gridDim.x * blockDim.x;
+    for (int i = gtid; i < E * hid; i += gsz) b1s[i] = ptrs.b1[i / hid][i % hid];
+    for (int i = gtid; i < E * d; i += gsz) b2s[i] = ptrs.b2[i / d][i % d];
+}
+
+// =====================================================================================================
+// combine forward: out[t] = sum_j gate_j * y[row(t, j)]      (t2i_moe_gan.py:470 / :483)
+// =====================================================================================================
+template <bool Y_F32>
+__device__ __forceinline__ float4 load_row4(const void* base, size_t elem_off) {
+    if (Y_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+    return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
+}
+
+template <bool Y_F32>
+__global__ void __launch_bounds__(256)
+combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, const int* __restrict__ token_rows,
+                   int T, int T_pad, int d, int k, int dense, float* __restrict__ out) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int nseg = d / 128;
+    float4 acc[MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < k; ++j) {                     // slot order == expert order in dense mode (:467)
+        const int row = dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j);
+        const float g = __ldg(gates + (size_t)t * k + j);
+#pragma unroll
+        for (int s = 0; s < MAX_SEG; ++s) {
+            if (s < nseg) {
+                const float4 v = load_row4<Y_F32>(y, (size_t)row * d + s * 128 + lane * 4);
+                acc[s].x = fmaf(g, v.x, acc[s].x); acc[s].y = fmaf(g, v.y, acc[s].y);
+                acc[s].z = fmaf(g, v.z, acc[s].z); acc[s].w = fmaf(g, v.w, acc[s].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s)
+        if (s < nseg) *reinterpret_cast<float4*>(out + (size_t)t * d + s * 128 + lane * 4) = acc[s];
+}
+
+// combine backward: one warp per dispatched row
+template <bool Y_F32>
+__global__ void __launch_bounds__(256)
+combine_bwd_kernel(const int* __restrict__ plan, const float* __restrict__ dout, const void* __restrict__ y,
+                   const int* __restrict__ row_token, const float* __restrict__ row_gate, const float* __restrict__ gates,
+                   int T, int T_pad, int d, int E, int dense, int split,
+                   __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= __ldg(plan + 1)) return;                  // rows in use
+    const int ld = split ? 2 * d : d;
+    int t; float g;
+    if (dense) {
+        const int e = r / T_pad; t = r - e * T_pad;
+        if (t >= T) t = -1;
+        g = t >= 0 ? __ldg(gates + (size_t)t * E + e) : 0.0f;
+    } else {
+        t = __ldg(row_token + r);
+        g = t >= 0 ? __ldg(row_gate + r) : 0.0f;
+    }
+    __nv_bfloat16* dst = dy_op + (size_t)r * ld;
+    if (t < 0) {                                       // padding row: zero (the wgrad GEMMs sum over it)
+        for (int i = lane; i < ld / 4; i += 32) reinterpret_cast<uint2*>(dst)[i] = make_uint2(0u, 0u);
+        if (lane == 0) dgate_row[r] = 0.0f;
+        return;
+    }
+    float dot = 0.0f;
+    for (int s = 0; s < d / 128; ++s) {
+        const int col = s * 128 + lane * 4;
+        const float4 go = __ldg(reinterpret_cast<const float4*>(dout + (size_t)t * d + col));
+        const float4 yv = load_row4<Y_F32>(y, (size_t)r * d + col);
+        dot = fmaf(go.x, yv.x, fmaf(go.y, yv.y, fmaf(go.z, yv.z, fmaf(go.w, yv.w, dot))));
+        store_operand4(dst + col, d, split != 0, make_float4(g * go.x, g * go.y, g * go.z, g * go.w));
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) dgate_row[r] = dot;
+}
+
+// dx[t] = sum_j dx_rows[row(t, j)] (+ dx_router[t])
+template <bool R_F32>
+__global__ void __launch_bounds__(256)
+uncombine_kernel(const void* __restrict__ dx_rows, const int* __restrict__ token_rows, const float* __restrict__ dx_router,
+                 int T, int T_pad, int d, int k, int dense, float* __restrict__ dx) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int nseg = d / 128;
+    float4 acc[MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) {
+        acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < nseg && dx_router != nullptr) acc[s] = __ldg(reinterpret_cast<const float4*>(dx_router + (size_t)t * d + s * 128 + lane * 4));
+    }
+    for (int j = 0; j < k; ++j) {
+        const int row = dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j);
+#pragma unroll
+        for (int s = 0; s < MAX_SEG; ++s) {
+            if (s < nseg) {
+                const float4 v = load_row4<R_F32>(dx_rows, (size_t)row * d + s * 128 + lane * 4);
+                acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s)
+        if (s < nseg) *reinterpret_cast<float4*>(dx + (size_t)t * d + s * 128 + lane * 4) = acc[s];
+}
+
+// bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c]
+__global__ void __launch_bounds__(256)
+colsum_grouped_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restrict__ src, int cols, int split, int T, int dense,
+                      float* __restrict__ out) {
+    __shared__ float red[8][64];
+    const int e = blockIdx.y;
+    const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+    const int wid = threadIdx.x >> 5;
+    const int ld = split ? 2 * cols : cols;
+    const int r0 = __ldg(plan + PLAN_OFF + e);
+    const int r1 = r0 + (dense ? T : __ldg(plan + PLAN_CNT + e));
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int r = r0 + wid; r < r1; r += 8) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + c));
+        a0 += bf16_lo_to_float(u); a1 += bf16_hi_to_float(u);
+        if (split) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + cols + c));
+            a0 += bf16_lo_to_float(v); a1 += bf16_hi_to_float(v);
+        }
+    }
+    red[wid][(threadIdx.x & 31) * 2] = a0;
+    red[wid][(threadIdx.x & 31) * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        out[(size_t)e * cols + blockIdx.x * 64 + threadIdx.x] = s;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// host launchers
+// =====================================================================================================
+int launch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float* chunk_colsum, int32_t* plan,
+                int32_t* chunk_base, float* load, cudaStream_t st) {
+    plan_kernel<<<1, 1024, 0, st>>>(chunk_counts, chunk_colsum, ceil_div(s->T, MOEGAN_CHUNK), s->T, s->E, s->dense, s->m_cap, plan,
+                                    chunk_base, load);
+    MOEGAN_CHECK_LAUNCH("plan_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates, const int32_t* plan,
+                  const int32_t* chunk_base, void* x_op, void* x_copy, int32_t* row_token, float* row_gate, int32_t* token_rows,
+                  cudaStream_t st) {
+    const int nchunks = ceil_div(s->T, MOEGAN_CHUNK);
+    gather_kernel<<<nchunks + s->E, 256, 0, st>>>(x, topk_idx, gates, plan, chunk_base, nchunks, s->T, s->d, s->E, s->k,
+                                                  s->precision == 1, reinterpret_cast<__nv_bfloat16*>(x_op),
+                                                  reinterpret_cast<__nv_bfloat16*>(x_copy), row_token, row_gate, token_rows);
+    MOEGAN_CHECK_LAUNCH("gather_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_to_operand(const float* src, int64_t rows, int64_t cols, int split, int sanitize, void* dst, cudaStream_t st) {
+    if (rows * cols == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(cols % 4 == 0, MOEGAN_ERR_BAD_SHAPE, "to_operand: cols (%lld) must be a multiple of 4", (long long)cols);
+    const long long n4 = rows * cols / 4;
+    long long blocks = ceil_div64(n4, 256);
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    to_operand_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, (int)cols, split, sanitize, reinterpret_cast<__nv_bfloat16*>(dst));
+    MOEGAN_CHECK_LAUNCH("to_operand_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_prep_weights(const moegan_shape* s, const float* const* w1, const float* const* b1, const float* const* w2,
+                        const float* const* b2, void* W1_op, float* b1s, void* W2_op, float* b2s, cudaStream_t st) {
+    WeightPtrs p;
+    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) {
+        const int q = e < s->E ? e : 0;
+        p.w1[e] = w1[q]; p.b1[e] = b1[q]; p.w2[e] = w2[q]; p.b2[e] = b2[q];
+    }
+    const long long total = 2LL * s->E * 4 * s->d * s->d / 4;
+    long long blocks = ceil_div64(total, 256);
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    prep_weights_kernel<<<(int)blocks, 256, 0, st>>>(p, s->E, s->d, s->precision == 1, reinterpret_cast<__nv_bfloat16*>(W1_op), b1s,
+                                                     reinterpret_cast<__nv_bfloat16*>(W2_op), b2s);
+    MOEGAN_CHECK_LAUNCH("prep_weights_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, cudaStream_t st) {
+    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int blocks = ceil_div(s->T, 8);
+    if (s->precision == 1) combine_fwd_kernel<true><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
+    else                   combine_fwd_kernel<false><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
+    MOEGAN_CHECK_LAUNCH("combine_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, cudaStream_t st) {
+    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int blocks = ceil_div(s->m_cap, 8);
+    __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
+    if (s->precision == 1)
+        combine_bwd_kernel<true><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 1, dy, dgate_row);
+    else
+        combine_bwd_kernel<false><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 0, dy, dgate_row);
+    MOEGAN_CHECK_LAUNCH("combine_bwd_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
+                     cudaStream_t st) {
+    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int blocks = ceil_div(s->T, 8);
+    if (s->precision == 1) uncombine_kernel<true><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);
+    else                   uncombine_kernel<false><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);
+    MOEGAN_CHECK_LAUNCH("uncombine_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* out, cudaStream_t st) {
+    dim3 grid(cols / 64, s->E);
+    colsum_grouped_kernel<<<grid, 256, 0, st>>>(plan, reinterpret_cast<const __nv_bfloat16*>(src_op), cols, s->precision == 1, s->T,
+                                                s->dense, out);
+    MOEGAN_CHECK_LAUNCH("colsum_grouped_kernel");
+    return MOEGAN_OK;
+}
+
+}  // namespace moegan

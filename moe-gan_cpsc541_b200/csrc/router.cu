@@ -1,0 +1,643 @@
+// Bayesian router kernels (forward + backward) and the balance-loss scalar kernels.
+//
+// Reference semantics: BayesianRouter (moegan/t2i_moe_gan.py:265-423).  All router math is fp32 on the
+// CUDA cores on purpose: expert assignment has to be bit-exact against the reference (north_star), so
+// the 128-wide projections are NOT sent through the bf16 tensor pipe in the forward pass.
+#include "kernels.cuh"
+
+namespace moegan {
+
+namespace {
+
+constexpr int HID = MOEGAN_ROUTER_HID;
+
+// =====================================================================================================
+// K1: sample the three weight matrices from (mu, rho, eps) + KL reduction  (t2i_moe_gan.py:302-333, 405-423)
+// =====================================================================================================
+__device__ __forceinline__ float softplus_ref(float x) { return log1pf(expf(x)); }   // log1p(exp(x)) as written at :316
+
+__global__ void __launch_bounds__(256)
+sample_kl_kernel(const float* __restrict__ mu_f, const float* __restrict__ rho_f, const float* __restrict__ eps_f,
+                 const float* __restrict__ mu_t, const float* __restrict__ rho_t, const float* __restrict__ eps_t,
+                 const float* __restrict__ mu_c, const float* __restrict__ rho_c, const float* __restrict__ eps_c,
+                 int n_f, int n_t, int n_c, int sampling, int split,
+                 float* __restrict__ Wf, float* __restrict__ Wt, float* __restrict__ Wc,
+                 __nv_bfloat16* __restrict__ Wf_op, __nv_bfloat16* __restrict__ Wt_op, float* __restrict__ kl_part) {
+    const int n = n_f + n_t + n_c;
+    float kl = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *mu, *rho, *eps; float* W; __nv_bfloat16* op; int j;
+        if (i < n_f)            { j = i;             mu = mu_f; rho = rho_f; eps = eps_f; W = Wf; op = Wf_op; }
+        else if (i < n_f + n_t) { j = i - n_f;       mu = mu_t; rho = rho_t; eps = eps_t; W = Wt; op = Wt_op; }
+        else                    { j = i - n_f - n_t; mu = mu_c; rho = rho_c; eps = eps_c; W = Wc; op = nullptr; }
+        const float m = mu[j], r = rho[j];
+        float w;
+        if (sampling) {
+            const float sigma = clampf(softplus_ref(clampf(r, -8.0f, 4.0f)), 1e-6f, 10.0f);
+            w = clampf(m, -10.0f, 10.0f) + sigma * clampf(eps[j], -2.0f, 2.0f);
+        } else {
+            w = m;   // eval: raw mu, no clamp (:357-361)
+        }
+        W[j] = w;
+        if (op != nullptr) {   // bf16 operand copy [rows, S*128] for the backward GEMMs
+            const int row = j / HID, col = j - row * HID;
+            float hi, lo;
+            split_bf16(w, hi, lo);
+            if (split) {
+                op[(size_t)row * (2 * HID) + col] = __float2bfloat16_rn(hi);
+                op[(size_t)row * (2 * HID) + HID + col] = __float2bfloat16_rn(lo);
+            } else {
+                op[(size_t)row * HID + col] = __float2bfloat16_rn(hi);
+            }
+        }
+        // KL term uses the UNclamped rho (:408-415)
+        const float sp = softplus_ref(r);
+        const float log_var = 2.0f * logf(sp);
+        kl += 0.5f * (expf(log_var) + m * m - 1.0f - log_var);
+    }
+    __shared__ float red[8];
+    kl = warp_sum(kl);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        kl_part[blockIdx.x] = s;
+    }
+}
+
+__global__ void kl_finalize_kernel(const float* __restrict__ kl_part, int nparts, float* __restrict__ kl_out) {
+    // single warp, fixed order -> deterministic
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < nparts; i += 32) s += kl_part[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+        kl_out[1] = s;
+        float v = s;
+        if (v != v) v = 0.0f;                          // nan_to_num(nan=0, posinf=200, neginf=0)  (:419)
+        else if (isinf(v)) v = v > 0.0f ? 200.0f : 0.0f;
+        kl_out[0] = clampf(v, 0.0f, 120.0f);           // (:420)
+    }
+}
+
+// =====================================================================================================
+// K2a: text half of the router, once per sample  (t2i_moe_gan.py:365, text rows of :371)
+// =====================================================================================================
+__global__ void __launch_bounds__(HID)
+text_fwd_kernel(const float* __restrict__ w, const float* __restrict__ Wt, const float* __restrict__ Wc,
+                int Dt, int E, float* __restrict__ tp, float* __restrict__ tl) {
+    extern __shared__ float sm[];
+    float* ws = sm;            // [Dt]
+    float* tps = sm + Dt;      // [128]
+    const int b = blockIdx.x, j = threadIdx.x;
+    for (int k = j; k < Dt; k += HID) ws[k] = nan_to_num_router(w[(size_t)b * Dt + k]);
+    __syncthreads();
+    float acc = 0.0f;
+    for (int k = 0; k < Dt; ++k) acc = fmaf(ws[k], Wt[(size_t)k * HID + j], acc);
+    tp[(size_t)b * HID + j] = acc;
+    tps[j] = acc;
+    __syncthreads();
+    if (j < E) {
+        float s = 0.0f;
+        for (int i = 0; i < HID; ++i) s = fmaf(tps[i], Wc[(size_t)(HID + i) * E + j], s);
+        tl[(size_t)b * E + j] = s;
+    }
+}
+
+// =====================================================================================================
+// K2: fused router forward.  CTA = 32 tokens (one permutation chunk), 4 warps x 8 tokens, lane owns 4 of
+// the 128 projection columns.  Wf streams through shared memory in 32-row chunks (cp.async, double
+// buffered); the epilogue is warp-per-token: logits, temperature, clamps, softmax, clamp+renorm, top-k.
+// =====================================================================================================
+constexpr int RT_TOK = MOEGAN_CHUNK;   // 32 tokens per CTA
+constexpr int RT_KC = 32;              // k rows per smem chunk
+constexpr int RT_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+    const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(RT_THREADS)
+router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, const float* __restrict__ Wc,
+                  const float* __restrict__ tl, const float* __restrict__ temperature, float af,
+                  int T, int d, int E, int k, int tps, int dense, int hard,
+                  float* __restrict__ fp, float* __restrict__ raw, float* __restrict__ probs,
+                  int* __restrict__ topk_idx, float* __restrict__ gates,
+                  int* __restrict__ chunk_counts, float* __restrict__ chunk_colsum) {
+    extern __shared__ __align__(16) uint8_t rsm[];
+    float* Ws = reinterpret_cast<float*>(rsm);                    // [2][RT_KC][128]
+    float* xs = Ws + 2 * RT_KC * HID;                             // [2][RT_TOK][RT_KC]
+    float* WcT = xs + 2 * RT_TOK * RT_KC;                         // [E][128]
+    float* colsum_s = WcT + E * HID;                              // [4][32]
+    int* cnt_s = reinterpret_cast<int*>(colsum_s + 4 * 32);       // [32]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = blockIdx.x;
+    const int t0 = chunk * RT_TOK;
+
+    for (int i = tid; i < HID * E; i += RT_THREADS) {   // WcT[e][j] = Wc[j][e], top 128 rows only
+        const int j = i / E, e = i - j * E;
+        WcT[e * HID + j] = Wc[i];
+    }
+    if (tid < 32) cnt_s[tid] = 0;
+
+    auto load_chunk = [&](int c, int buf) {
+        const int k0 = c * RT_KC;
+        float* wdst = Ws + buf * RT_KC * HID;
+#pragma unroll
+        for (int i = 0; i < (RT_KC * HID / 4) / RT_THREADS; ++i) {     // 8 x 16 B per thread
+            const int idx = tid + i * RT_THREADS;
+            cp_async16(wdst + idx * 4, Wf + (size_t)k0 * HID + idx * 4, true);
+        }
+        float* xdst = xs + buf * RT_TOK * RT_KC;
+#pragma unroll
+        for (int i = 0; i < (RT_TOK * RT_KC / 4) / RT_THREADS; ++i) {  // 2 x 16 B per thread
+            const int idx = tid + i * RT_THREADS;
+            const int tok = idx >> 3, q4 = idx & 7;
+            const bool ok = (t0 + tok) < T;
+            const float* src = x + (size_t)(ok ? (t0 + tok) : 0) * d + k0 + q4 * 4;
+            cp_async16(xdst + tok * RT_KC + q4 * 4, src, ok);
+        }
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
+
+    const int nchunks = d / RT_KC;
+    load_chunk(0, 0);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) { load_chunk(c + 1, buf ^ 1); cp_async_commit(); cp_async_wait<1>(); }
+        else                 { cp_async_wait<0>(); }
+        {   // nan_to_num on the x elements this thread staged (identity on finite input, :338-340)
+            float* xdst = xs + buf * RT_TOK * RT_KC;
+#pragma unroll
+            for (int i = 0; i < (RT_TOK * RT_KC / 4) / RT_THREADS; ++i) {
+                const int idx = tid + i * RT_THREADS;
+                float4* p4 = reinterpret_cast<float4*>(xdst + (idx >> 3) * RT_KC + (idx & 7) * 4);
+                float4 v = *p4;
+                v.x = nan_to_num_router(v.x); v.y = nan_to_num_router(v.y);
+                v.z = nan_to_num_router(v.z); v.w = nan_to_num_router(v.w);
+                *p4 = v;
+            }
+        }
+        __syncthreads();
+        const float* wsrc = Ws + buf * RT_KC * HID;
+        const float* xsrc = xs + buf * RT_TOK * RT_KC + (wid * 8) * RT_KC;
+        float part[8][4];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) { part[a][0] = part[a][1] = part[a][2] = part[a][3] = 0.0f; }
+#pragma unroll
+        for (int kq = 0; kq < RT_KC / 4; ++kq) {
+            float4 xv[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) xv[a] = *reinterpret_cast<const float4*>(xsrc + a * RT_KC + kq * 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 wv = *reinterpret_cast<const float4*>(wsrc + (kq * 4 + kk) * HID + lane * 4);
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const float xk = kk == 0 ? xv[a].x : kk == 1 ? xv[a].y : kk == 2 ? xv[a].z : xv[a].w;
+                    part[a][0] = fmaf(xk, wv.x, part[a][0]);
+                    part[a][1] = fmaf(xk, wv.y, part[a][1]);
+                    part[a][2] = fmaf(xk, wv.z, part[a][2]);
+                    part[a][3] = fmaf(xk, wv.w, part[a][3]);
+                }
+            }
+        }
+        // blocked summation: per-chunk partials are added once -> error grows with sqrt(#chunks), not K
+#pragma unroll
+        for (int a = 0; a < 8; ++a) { acc[a][0] += part[a][0]; acc[a][1] += part[a][1]; acc[a][2] += part[a][2]; acc[a][3] += part[a][3]; }
+        __syncthreads();
+    }
+
+    // ------------------------------- warp-per-token epilogue -------------------------------
+    const float tau = clampf(__ldg(temperature) * af, 0.5f, 5.0f);   // (:375)
+    float my_colsum = 0.0f;
+#pragma unroll 1
+    for (int a = 0; a < 8; ++a) {
+        const int t = t0 + wid * 8 + a;
+        if (t >= T) break;   // warp-uniform
+        float f0, f1, f2, f3;
+        // select acc[a] without dynamic register indexing
+        f0 = f1 = f2 = f3 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q == a) { f0 = acc[q][0]; f1 = acc[q][1]; f2 = acc[q][2]; f3 = acc[q][3]; }
+        if (fp != nullptr) *reinterpret_cast<float4*>(fp + (size_t)t * HID + lane * 4) = make_float4(f0, f1, f2, f3);
+        float my_raw = 0.0f;
+        for (int e = 0; e < E; ++e) {
+            const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+            float part = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
+            part = warp_sum(part);
+            if (lane == e) my_raw = part;
+        }
+        const bool act = lane < E;
+        if (act) my_raw += __ldg(tl + (size_t)(t / tps) * E + lane);
+        const float z = my_raw / tau;                              // (:378)
+        const float l = clampf(z, -20.0f, 20.0f);                  // (:381)
+        const float m = warp_max(act ? l : -INFINITY);
+        const float ex = act ? expf(l - m) : 0.0f;
+        const float s = ex / warp_sum(ex);                         // (:384)
+        const float cl = act ? clampf(s, 1e-6f, 1.0f) : 0.0f;      // (:387)
+        const float p = cl / warp_sum(cl);                         // (:389)
+        my_colsum += act ? p : 0.0f;
+        if (act) raw[(size_t)t * E + lane] = my_raw;
+        if (dense) {
+            if (act) {
+                probs[(size_t)t * E + lane] = p;
+                gates[(size_t)t * E + lane] = p;
+                topk_idx[(size_t)t * E + lane] = lane;
+            }
+        } else {
+            bool taken = false;
+            int sel_i[MOEGAN_MAX_TOPK]; float sel_p[MOEGAN_MAX_TOPK];
+            float gsum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) {
+                if (j < k) {
+                    float bv = (act && !taken) ? p : -1.0f;
+                    int bi = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == bi) taken = true;
+                    sel_i[j] = bi; sel_p[j] = bv;
+                    gsum += bv;
+                } else { sel_i[j] = 0; sel_p[j] = 0.0f; }
+            }
+#pragma unroll
+            for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) {
+                if (j < k && lane == j) {
+                    topk_idx[(size_t)t * k + j] = sel_i[j];
+                    gates[(size_t)t * k + j] = hard ? 1.0f : sel_p[j] / gsum;
+                    atomicAdd(&cnt_s[sel_i[j]], 1);
+                }
+            }
+            if (act) probs[(size_t)t * E + lane] = hard ? (lane == sel_i[0] ? 1.0f : 0.0f) : p;   // (:392-400)
+        }
+    }
+    colsum_s[wid * 32 + lane] = my_colsum;
+    __syncthreads();
+    if (tid < E) {
+        chunk_colsum[(size_t)chunk * E + tid] = (colsum_s[tid] + colsum_s[32 + tid]) + (colsum_s[64 + tid] + colsum_s[96 + tid]);
+        chunk_counts[(size_t)chunk * E + tid] = cnt_s[tid];
+    }
+}
+
+// =====================================================================================================
+// B3: gates/probs -> raw logits gradient, dfp operand, dtau partials (warp per token)
+// =====================================================================================================
+constexpr int RB_THREADS = 256;
+constexpr int RB_TOK = 64;   // tokens per CTA
+
+__global__ void __launch_bounds__(RB_THREADS)
+router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict__ Wc, const int* __restrict__ topk_idx,
+                         const int* __restrict__ token_rows, const float* __restrict__ dgate_row,
+                         const float* __restrict__ dprobs_ext, const float* __restrict__ dload,
+                         const float* __restrict__ temperature, float af,
+                         int T, int T_pad, int E, int k, int dense, int split,
+                         float* __restrict__ draw, __nv_bfloat16* __restrict__ dfp_op, float* __restrict__ dtau_part) {
+    extern __shared__ __align__(16) float bsm[];
+    float* WcT = bsm;                 // [E][128]
+    float* red = bsm + E * HID;       // [8]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < HID * E; i += RB_THREADS) {
+        const int j = i / E, e = i - j * E;
+        WcT[e * HID + j] = Wc[i];
+    }
+    __syncthreads();
+    const float tau = clampf(__ldg(temperature) * af, 0.5f, 5.0f);
+    const bool act = lane < E;
+    const float dl_add = (act && dload != nullptr) ? __ldg(dload + lane) : 0.0f;
+    float dtau_acc = 0.0f;
+    const int ldop = split ? 2 * HID : HID;
+    for (int a = wid; a < RB_TOK; a += RB_THREADS / 32) {
+        const int t = blockIdx.x * RB_TOK + a;
+        if (t >= T) break;
+        // recompute the forward chain exactly as router_fwd_kernel does
+        const float r = act ? raw[(size_t)t * E + lane] : 0.0f;
+        const float z = r / tau;
+        const float l = clampf(z, -20.0f, 20.0f);
+        const float m = warp_max(act ? l : -INFINITY);
+        const float ex = act ? expf(l - m) : 0.0f;
+        const float s = ex / warp_sum(ex);
+        const float cl = act ? clampf(s, 1e-6f, 1.0f) : 0.0f;
+        const float S = warp_sum(cl);
+        const float p = cl / S;
+        float dp = dl_add;
+        if (act && dprobs_ext != nullptr) dp += dprobs_ext[(size_t)t * E + lane];
+        if (dense) {
+            if (act) dp += dgate_row[(size_t)lane * T_pad + t];         // gate == prob (:470)
+        } else {
+            bool in = false; float dg = 0.0f;
+            for (int j = 0; j < k; ++j) {
+                const int e = __ldg(topk_idx + (size_t)t * k + j);
+                if (e == lane) { in = true; dg = __ldg(dgate_row + __ldg(token_rows + (size_t)t * k + j)); }
+            }
+            const float G = warp_sum(in ? p : 0.0f);
+            const float g = in ? p / G : 0.0f;
+            const float dot = warp_sum(dg * g);
+            if (in) dp += (dg - dot) / G;                                // g_i = p_i / sum_topk p
+        }
+        const float dc = (dp - warp_sum(act ? dp * p : 0.0f)) / S;      // p = c / S
+        const float ds = (act && s >= 1e-6f && s <= 1.0f) ? dc : 0.0f;   // clamp mask
+        const float dlg = s * (ds - warp_sum(ds * s));                   // softmax
+        const float dz = (act && z >= -20.0f && z <= 20.0f) ? dlg : 0.0f;
+        const float dr = dz / tau;
+        dtau_acc += dz * z;                                              // dtau = -sum(dz*z)/tau
+        if (act) draw[(size_t)t * E + lane] = dr;
+        // dfp[t, j] = sum_e draw[e] * Wc[j, e]
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = 0; e < E; ++e) {
+            const float de = __shfl_sync(0xffffffffu, dr, e);
+            const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+            o.x = fmaf(de, wc.x, o.x); o.y = fmaf(de, wc.y, o.y); o.z = fmaf(de, wc.z, o.z); o.w = fmaf(de, wc.w, o.w);
+        }
+        __nv_bfloat16* dst = dfp_op + (size_t)t * ldop + lane * 4;
+        float h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        if (split) *reinterpret_cast<uint2*>(dst + HID) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+    dtau_acc = warp_sum(dtau_acc);
+    if (lane == 0) red[wid] = dtau_acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < RB_THREADS / 32; ++w) s += red[w];
+        dtau_part[blockIdx.x] = s;
+    }
+}
+
+// dtl[b, e] = sum over the sample's tokens of draw[t, e]  (one CTA per sample, deterministic)
+__global__ void __launch_bounds__(256)
+router_bwd_dtl_kernel(const float* __restrict__ draw, int tps, int E, float* __restrict__ dtl) {
+    __shared__ float red[8][32];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float acc = 0.0f;
+    if (lane < E)
+        for (int i = wid; i < tps; i += 8) acc += draw[((size_t)b * tps + i) * E + lane];
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0 && lane < E) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][lane];
+        dtl[(size_t)b * E + lane] = s;
+    }
+}
+
+// dWc[0:128] partials: part[blk][j][e] = sum over 256 tokens of fp[t, j] * draw[t, e]
+constexpr int WC_TOK = 256;
+__global__ void __launch_bounds__(HID)
+router_bwd_dwc_part_kernel(const float* __restrict__ fp, const float* __restrict__ draw, int T, int E, float* __restrict__ part) {
+    __shared__ float ds[64 * 32];
+    const int j = threadIdx.x;
+    const int tbeg = blockIdx.x * WC_TOK;
+    float acc[MOEGAN_MAX_EXPERTS];
+#pragma unroll
+    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) acc[e] = 0.0f;
+    for (int t0 = tbeg; t0 < min(tbeg + WC_TOK, T); t0 += 64) {
+        const int nt = min(64, T - t0);
+        __syncthreads();
+        for (int i = j; i < nt * E; i += HID) ds[i] = draw[(size_t)t0 * E + i];
+        __syncthreads();
+        for (int tt = 0; tt < nt; ++tt) {
+            const float f = fp[(size_t)(t0 + tt) * HID + j];
+#pragma unroll
+            for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e)
+                if (e < E) acc[e] = fmaf(f, ds[tt * E + e], acc[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e)
+        if (e < E) part[((size_t)blockIdx.x * HID + j) * E + e] = acc[e];
+}
+
+// Finishes the small router reductions: dWc (top from partials, bottom from tp/dtl), dtp (+ operand copy),
+// dtemperature.  grid = 1 + B blocks:  block 0 -> dWc + dtemperature;  block 1+b -> dtp[b].
+__global__ void __launch_bounds__(256)
+router_bwd_small_kernel(const float* __restrict__ dwc_part, int nparts, const float* __restrict__ tp, const float* __restrict__ dtl,
+                        const float* __restrict__ Wc, const float* __restrict__ dtau_part, int ntau,
+                        const float* __restrict__ temperature, float af, int B, int E, int split,
+                        float* __restrict__ dWc, float* __restrict__ dtp, __nv_bfloat16* __restrict__ dtp_op,
+                        float* __restrict__ dtemperature) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < HID * E; i += 256) {            // top rows
+            float s = 0.0f;
+            for (int pz = 0; pz < nparts; ++pz) s += dwc_part[(size_t)pz * HID * E + i];
+            dWc[i] = s;
+        }
+        for (int i = tid; i < HID * E; i += 256) {            // bottom rows: sum_b tp[b, j] * dtl[b, e]
+            const int j = i / E, e = i - j * E;
+            float s = 0.0f;
+            for (int b = 0; b < B; ++b) s = fmaf(tp[(size_t)b * HID + j], dtl[(size_t)b * E + e], s);
+            dWc[HID * E + i] = s;
+        }
+        if (tid < 32) {
+            float s = 0.0f;
+            for (int i = tid; i < ntau; i += 32) s += dtau_part[i];
+            s = warp_sum(s);
+            if (tid == 0) {
+                const float ta = __ldg(temperature) * af;
+                const float tau = clampf(ta, 0.5f, 5.0f);
+                const float dtau = -s / tau;
+                dtemperature[0] = (ta >= 0.5f && ta <= 5.0f) ? dtau * af : 0.0f;   // clamp mask (:375)
+            }
+        }
+    } else {
+        const int b = blockIdx.x - 1;
+        if (tid < HID) {
+            float s = 0.0f;
+            for (int e = 0; e < E; ++e) s = fmaf(dtl[(size_t)b * E + e], Wc[(size_t)(HID + tid) * E + e], s);
+            dtp[(size_t)b * HID + tid] = s;
+            float hi, lo;
+            split_bf16(s, hi, lo);
+            const int ld = split ? 2 * HID : HID;
+            dtp_op[(size_t)b * ld + tid] = __float2bfloat16_rn(hi);
+            if (split) dtp_op[(size_t)b * ld + HID + tid] = __float2bfloat16_rn(lo);
+        }
+    }
+}
+
+// B5 + B6: dW -> (dmu, drho) through the reparameterisation clamps, plus the KL gradient.
+__global__ void __launch_bounds__(256)
+reparam_kl_bwd_kernel(const float* __restrict__ dWf, const float* __restrict__ dWt, const float* __restrict__ dWc,
+                      const float* __restrict__ mu_f, const float* __restrict__ rho_f, const float* __restrict__ eps_f,
+                      const float* __restrict__ mu_t, const float* __restrict__ rho_t, const float* __restrict__ eps_t,
+                      const float* __restrict__ mu_c, const float* __restrict__ rho_c, const float* __restrict__ eps_c,
+                      int n_f, int n_t, int n_c, int sampled, const float* __restrict__ kl_out, const float* __restrict__ dkl,
+                      float* __restrict__ dmu_f, float* __restrict__ drho_f, float* __restrict__ dmu_t, float* __restrict__ drho_t,
+                      float* __restrict__ dmu_c, float* __restrict__ drho_c) {
+    const int n = n_f + n_t + n_c;
+    float gkl = 0.0f;
+    if (dkl != nullptr && kl_out != nullptr) {
+        const float rawkl = kl_out[1];
+        // clamp(nan_to_num(raw), 0, 120) passes gradient only for finite raw in [0, 120]
+        if (rawkl == rawkl && !isinf(rawkl) && rawkl >= 0.0f && rawkl <= 120.0f) gkl = dkl[0];
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *dW, *mu, *rho, *eps; float *dmu, *drho; int j;
+        if (i < n_f)            { j = i;             dW = dWf; mu = mu_f; rho = rho_f; eps = eps_f; dmu = dmu_f; drho = drho_f; }
+        else if (i < n_f + n_t) { j = i - n_f;       dW = dWt; mu = mu_t; rho = rho_t; eps = eps_t; dmu = dmu_t; drho = drho_t; }
+        else                    { j = i - n_f - n_t; dW = dWc; mu = mu_c; rho = rho_c; eps = eps_c; dmu = dmu_c; drho = drho_c; }
+        const float g = dW[j], m = mu[j], r = rho[j];
+        float gm, gr;
+        if (sampled) {
+            const float rc = clampf(r, -8.0f, 4.0f);
+            const float sp = softplus_ref(rc);
+            const float sig = 1.0f / (1.0f + expf(-rc));
+            gm = (m >= -10.0f && m <= 10.0f) ? g : 0.0f;
+            const bool pass = (r >= -8.0f && r <= 4.0f) && (sp >= 1e-6f && sp <= 10.0f);
+            gr = pass ? g * clampf(eps[j], -2.0f, 2.0f) * sig : 0.0f;
+        } else {
+            gm = g; gr = 0.0f;
+        }
+        if (gkl != 0.0f) {
+            const float sp = softplus_ref(r);
+            const float sig = 1.0f / (1.0f + expf(-r));
+            gm = fmaf(gkl, m, gm);
+            gr = fmaf(gkl, (sp - 1.0f / sp) * sig, gr);
+        }
+        dmu[j] = gm; drho[j] = gr;
+    }
+}
+
+// =====================================================================================================
+// balance loss on the fused column sums (t2i_moe_gan.py:973-1000): single warp
+// =====================================================================================================
+__global__ void balance_loss_kernel(const float* __restrict__ load, int E, int T, float bw,
+                                    const float* __restrict__ dloss, float* __restrict__ loss, float* __restrict__ dload) {
+    const int lane = threadIdx.x;
+    const bool act = lane < E;
+    const float frac = act ? (load[lane] + 1e-6f) / (float)T : 0.0f;        // (:973,:976)
+    const float mean = warp_sum(frac) / (float)E;                            // (:987)
+    const float dev = act ? frac - mean : 0.0f;
+    const float var = warp_sum(dev * dev) / (float)(E - 1);                  // unbiased (:988); E == 1 -> nan
+    const float sd = sqrtf(var);
+    const float cv = sd / (mean + 1e-6f);                                    // (:989)
+    const float v = (float)E * cv;                                           // (:992)
+    if (loss != nullptr && lane == 0) {
+        float c = fminf(fmaxf(v, 0.0f), 10.0f);                              // (:995)
+        if (v != v) c = 0.0f;                                                // nan_to_num (:998)
+        loss[0] = bw * c;
+    }
+    if (dload != nullptr && act) {
+        float g = 0.0f;
+        if (v == v && v >= 0.0f && v <= 10.0f && sd > 0.0f) {
+            const float dstd = dev / ((float)(E - 1) * sd);
+            const float dcv = dstd / (mean + 1e-6f) - sd / ((mean + 1e-6f) * (mean + 1e-6f)) / (float)E;
+            g = dloss[0] * bw * (float)E * dcv / (float)T;
+        }
+        dload[lane] = g;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// host launchers (called from api.cu)
+// =====================================================================================================
+int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_f, const float* eps_f,
+                     const float* mu_t, const float* rho_t, const float* eps_t,
+                     const float* mu_c, const float* rho_c, const float* eps_c, int sampling,
+                     float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out, cudaStream_t st) {
+    const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
+    const int n = n_f + n_t + n_c;
+    int blocks = ceil_div(n, 256 * 4);
+    if (blocks > MOEGAN_KL_PARTS) blocks = MOEGAN_KL_PARTS;
+    sample_kl_kernel<<<blocks, 256, 0, st>>>(mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, n_f, n_t, n_c,
+                                             sampling, s->precision == 1, Wf, Wt, Wc,
+                                             reinterpret_cast<__nv_bfloat16*>(Wf_op), reinterpret_cast<__nv_bfloat16*>(Wt_op), kl_out + 2);
+    MOEGAN_CHECK_LAUNCH("sample_kl_kernel");
+    kl_finalize_kernel<<<1, 32, 0, st>>>(kl_out + 2, blocks, kl_out);
+    MOEGAN_CHECK_LAUNCH("kl_finalize_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, cudaStream_t st) {
+    text_fwd_kernel<<<s->B, HID, (s->Dt + HID) * sizeof(float), st>>>(w, Wt, Wc, s->Dt, s->E, tp, tl);
+    MOEGAN_CHECK_LAUNCH("text_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+static size_t router_fwd_smem(int E) {
+    return (size_t)(2 * RT_KC * HID + 2 * RT_TOK * RT_KC + E * HID + 4 * 32) * sizeof(float) + 32 * sizeof(int);
+}
+
+int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
+                      const float* temperature, float af, float* fp, float* raw, float* probs, int32_t* topk_idx, float* gates,
+                      int32_t* chunk_counts, float* chunk_colsum, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(router_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)router_fwd_smem(MOEGAN_MAX_EXPERTS)));
+        attr = true;
+    }
+    const int chunks = ceil_div(s->T, RT_TOK);
+    router_fwd_kernel<<<chunks, RT_THREADS, router_fwd_smem(s->E), st>>>(x, Wf, Wc, tl, temperature, af, s->T, s->d, s->E, s->k,
+                                                                        s->tokens_per_sample, s->dense, s->hard, fp, raw, probs,
+                                                                        topk_idx, gates, chunk_counts, chunk_colsum);
+    MOEGAN_CHECK_LAUNCH("router_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const float* Wc, const int32_t* topk_idx,
+                             const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
+                             const float* temperature, float af, float* draw, void* dfp_op, float* dtau_part, cudaStream_t st) {
+    const int blocks = ceil_div(s->T, RB_TOK);
+    const int T_pad = ceil_div(s->T, 128) * 128;
+    router_bwd_logits_kernel<<<blocks, RB_THREADS, (s->E * HID + 8) * sizeof(float), st>>>(
+        raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, af, s->T, T_pad, s->E, s->k, s->dense,
+        s->precision == 1, draw, reinterpret_cast<__nv_bfloat16*>(dfp_op), dtau_part);
+    MOEGAN_CHECK_LAUNCH("router_bwd_logits_kernel");
+    return MOEGAN_OK;
+}
+int router_bwd_logits_blocks(const moegan_shape* s) { return ceil_div(s->T, RB_TOK); }
+int router_bwd_dwc_parts(const moegan_shape* s) { return ceil_div(s->T, WC_TOK); }
+
+int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,
+                            const float* dtau_part, const float* temperature, float af,
+                            float* dtl, float* dwc_part, float* dWc, float* dtp, void* dtp_op, float* dtemperature, cudaStream_t st) {
+    router_bwd_dtl_kernel<<<s->B, 256, 0, st>>>(draw, s->tokens_per_sample, s->E, dtl);
+    MOEGAN_CHECK_LAUNCH("router_bwd_dtl_kernel");
+    const int nparts = router_bwd_dwc_parts(s);
+    router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_part);
+    MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
+    router_bwd_small_kernel<<<1 + s->B, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
+                                                     temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
+                                                     reinterpret_cast<__nv_bfloat16*>(dtp_op), dtemperature);
+    MOEGAN_CHECK_LAUNCH("router_bwd_small_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* dWt, const float* dWc,
+                          const float* mu_f, const float* rho_f, const float* eps_f,
+                          const float* mu_t, const float* rho_t, const float* eps_t,
+                          const float* mu_c, const float* rho_c, const float* eps_c, int sampled,
+                          const float* kl_out, const float* dkl,
+                          float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c, cudaStream_t st) {
+    const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
+    const int blocks = ceil_div(n_f + n_t + n_c, 256 * 2);
+    reparam_kl_bwd_kernel<<<blocks, 256, 0, st>>>(dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c,
+                                                  n_f, n_t, n_c, sampled, kl_out, dkl, dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c);
+    MOEGAN_CHECK_LAUNCH("reparam_kl_bwd_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_balance_loss(const float* load, int E, int T, float bw, const float* dloss, float* loss, float* dload, cudaStream_t st) {
+    balance_loss_kernel<<<1, 32, 0, st>>>(load, E, T, bw, dloss, loss, dload);
+    MOEGAN_CHECK_LAUNCH("balance_loss_kernel");
+    return MOEGAN_OK;
+}
+
+}  // namespace moegan

@@ -1,0 +1,428 @@
+// Grouped GEMM on 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// One persistent CTA per SM, 10 warps:
+//   warps 0-7  epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM, apply bias / GELU /
+//              GELU' and store straight to global (warp w owns TMEM lanes 32*(w%4).. and column half w/4)
+//   warp 8     TMA producer (one elected lane): fills a STAGES-deep ring of {A 128x64, B BNx64} bf16 tiles
+//   warp 9     TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K = 16 each) per stage
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
+// accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1).
+//
+// Work decomposition ("kinds", see umma_gemm.cuh):
+//   ROWS_*  the dispatched token rows are cut into 128-row blocks; the plan array (built on the device
+//           by dispatch_plan) says how many blocks are in use and which expert owns each block, so
+//           ragged expert groups need no host synchronisation.  B tiles come from the owning expert's
+//           weight matrix (K-major for the forward GEMMs, MN-major for dgrad).
+//   WGRAD   one output tile per (expert, 128 x BN block of the weight gradient); the reduction runs
+//           over that expert's rows (both operands MN-major, i.e. read "transposed" straight out of the
+//           row-major activation buffers - no transposed copies are ever materialised).
+// fp32 mode: operands are bf16 (hi | lo) pairs and the main loop runs 3 passes (hi*hi, hi*lo, lo*hi).
+#include "umma_gemm.cuh"
+#include "ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace moegan {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                    // 64 bf16 = 128 B = one SWIZZLE_128B span
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int WARP_TMA = 8;
+constexpr int WARP_MMA = 9;
+constexpr int NUM_THREADS = 320;
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
+
+template <int BN> struct Cfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+};
+
+struct Tile {
+    int mb, nb, e;
+    int nkb_pp;   // k-blocks per pass
+    int row0;     // WGRAD: first reduction row of the expert
+};
+
+template <int BN, int KIND>
+__device__ __forceinline__ int total_tiles(const GemmParams& p) {
+    const int n_blocks = (p.N + BN - 1) / BN;
+    if (KIND == GEMM_WGRAD) return p.E * ((p.dimA + BM - 1) / BM) * n_blocks;
+    const int m_blocks = p.m_blocks_host >= 0 ? p.m_blocks_host : __ldg(p.plan + 0);
+    return m_blocks * n_blocks;
+}
+
+template <int BN, int KIND>
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
+    Tile t;
+    const int n_blocks = (p.N + BN - 1) / BN;
+    if (KIND == GEMM_WGRAD) {
+        const int mA = (p.dimA + BM - 1) / BM;
+        t.e = tile / (mA * n_blocks);
+        const int rem = tile - t.e * (mA * n_blocks);
+        t.mb = rem / n_blocks;
+        t.nb = rem - t.mb * n_blocks;
+        int r0, r1;
+        if (p.k_rows_host >= 0) { r0 = 0; r1 = p.k_rows_host; }
+        else { r0 = __ldg(p.plan + PLAN_OFF + t.e); r1 = __ldg(p.plan + PLAN_OFF + t.e + 1); }
+        t.row0 = r0;
+        t.nkb_pp = (r1 - r0 + BK - 1) / BK;
+    } else {
+        t.mb = tile / n_blocks;
+        t.nb = tile - t.mb * n_blocks;
+        t.e = p.m_blocks_host >= 0 ? 0 : __ldg(p.plan + PLAN_BLK + t.mb);
+        t.row0 = 0;
+        t.nkb_pp = p.K / BK;
+    }
+    return t;
+}
+
+// ---- epilogue store helpers (one thread = one output row, 32 consecutive columns) ------------------
+__device__ __forceinline__ void store32_f32(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(dst)[i] = u;
+    }
+}
+__device__ __forceinline__ void store32_split(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[32]) {
+    float lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        float h;
+        split_bf16(v[i], h, lo[i]);
+    }
+    store32_bf16(dst_hi, v);   // rounding v to bf16 gives exactly hi
+    store32_bf16(dst_lo, lo);
+}
+__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* src, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        v[8 * i + 0] = bf16_lo_to_float(u.x); v[8 * i + 1] = bf16_hi_to_float(u.x);
+        v[8 * i + 2] = bf16_lo_to_float(u.y); v[8 * i + 3] = bf16_hi_to_float(u.y);
+        v[8 * i + 4] = bf16_lo_to_float(u.z); v[8 * i + 5] = bf16_hi_to_float(u.z);
+        v[8 * i + 6] = bf16_lo_to_float(u.w); v[8 * i + 7] = bf16_hi_to_float(u.w);
+    }
+}
+__device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+}
+
+template <int BN, int KIND>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
+    const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == WARP_TMA && lane == 0) {
+        ptx::prefetch_tmap(&mapA);
+        ptx::prefetch_tmap(&mapB);
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == WARP_MMA) {
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int ntiles = total_tiles<BN, KIND>(p);
+    const uint32_t mn_lbo = p.mn_lbo ? p.mn_lbo : 8192u;   // bytes between 64-element MN groups (one TMA box)
+    const uint32_t mn_sbo = p.mn_sbo ? p.mn_sbo : 1024u;   // bytes between 8-row K groups
+    const uint32_t mn_kadv = p.mn_kadv ? p.mn_kadv : 2048u; // bytes per UMMA_K = 16 rows
+
+    if (warp == WARP_TMA) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const Tile t = decode_tile<BN, KIND>(p, tile);
+                const int nkb = t.nkb_pp * p.passes;
+                int pass = 0, kk = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_BYTES;
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const int a_lo = (pass == 2) ? p.a_lo_off : 0;
+                    const int b_lo = (pass == 1) ? p.b_lo_off : 0;
+                    if (KIND == GEMM_WGRAD) {
+                        const int krow = t.row0 + kk * BK;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            ptx::tma_load_2d(a_dst + i * 8192u, &mapA, full_bar(stage), a_lo + t.mb * BM + i * 64, krow);
+                        const int brow = p.b_rel ? kk * BK : krow;
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            ptx::tma_load_2d(b_dst + i * 8192u, &mapB, full_bar(stage), b_lo + t.nb * BN + i * 64, brow);
+                    } else {
+                        const int ablk = p.a_mod > 0 ? (t.mb % p.a_mod) : t.mb;
+                        ptx::tma_load_2d(a_dst, &mapA, full_bar(stage), a_lo + kk * BK, ablk * BM);
+                        if (KIND == GEMM_ROWS_BK) {
+                            ptx::tma_load_2d(b_dst, &mapB, full_bar(stage), b_lo + kk * BK, t.e * p.b_rows_per_expert + t.nb * BN);
+                        } else {
+                            const int brow = t.e * p.b_rows_per_expert + kk * BK;
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                ptx::tma_load_2d(b_dst + i * 8192u, &mapB, full_bar(stage), b_lo + t.nb * BN + i * 64, brow);
+                        }
+                    }
+                    if (++kk == t.nkb_pp) { kk = 0; ++pass; }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, KIND == GEMM_WGRAD ? 1 : 0, KIND == GEMM_ROWS_BK ? 0 : 1);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const Tile t = decode_tile<BN, KIND>(p, tile);
+                const int nkb = t.nkb_pp * p.passes;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                if (nkb == 0) {
+                    ptx::mbar_arrive(tfull_bar(acc));               // empty expert: epilogue writes zeros
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = (KIND == GEMM_WGRAD) ? ptx::umma_smem_desc(a_addr + k * mn_kadv, mn_lbo, mn_sbo)
+                                                                 : ptx::umma_smem_desc(a_addr + k * 32u, 16u, 1024u);
+                        const uint64_t db = (KIND == GEMM_ROWS_BK) ? ptx::umma_smem_desc(b_addr + k * 32u, 16u, 1024u)
+                                                                   : ptx::umma_smem_desc(b_addr + k * mn_kadv, mn_lbo, mn_sbo);
+                        ptx::umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty_bar(stage));             // smem slot reusable once these MMAs retire
+                    if (kb == nkb - 1) ptx::umma_commit(tfull_bar(acc));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        const int q = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = warp >> 2;        // which half of the BN columns
+        const int row_in_tile = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const Tile t = decode_tile<BN, KIND>(p, tile);
+            const int nkb = t.nkb_pp * p.passes;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const int grow = t.mb * BM + row_in_tile;      // row inside the (expert's) output
+            bool row_ok; long long out_row;
+            if (KIND == GEMM_WGRAD) { row_ok = grow < p.dimA; out_row = (long long)t.e * p.dimA + grow; }
+            else                    { row_ok = grow < p.out_rows_valid; out_row = grow; }
+#pragma unroll 1
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+                float v[32];
+                if (nkb > 0) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                }
+                const int col0 = t.nb * BN + c;
+                if (row_ok && col0 < p.N) {
+                const int epi = p.epi;
+                if (epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3) {
+                    const float* b = p.bias + (long long)t.e * p.N + col0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(b) + i);
+                        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                    }
+                }
+                switch (epi) {
+                case EPI_F32:
+                case EPI_BIAS_F32:
+                    store32_f32(reinterpret_cast<float*>(p.out0) + out_row * p.ld_out0 + col0, v);
+                    break;
+                case EPI_BF16:
+                case EPI_BIAS_BF16:
+                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
+                    break;
+                case EPI_GELU_BF16: {
+                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out1) + out_row * p.ld_out1 + col0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
+                    break;
+                }
+                case EPI_GELU_X3: {
+                    store32_f32(reinterpret_cast<float*>(p.out1) + out_row * p.ld_out1 + col0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf<true>(v[i]);
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0;
+                    store32_split(o, o + p.out_split_off, v);
+                    break;
+                }
+                case EPI_DGELU_BF16: {
+                    float a[32];
+                    load32_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ld_aux + col0, a);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad<false>(a[i]);
+                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
+                    break;
+                }
+                case EPI_DGELU_X3: {
+                    float a[32];
+                    load32_f32(reinterpret_cast<const float*>(p.aux) + out_row * p.ld_aux + col0, a);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad<true>(a[i]);
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0;
+                    store32_split(o, o + p.out_split_off, v);
+                    break;
+                }
+                default: break;
+                }
+                }  // row_ok && col0 < N
+                __syncwarp();   // tcgen05.ld is warp-collective: reconverge before the next chunk
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        __syncwarp();
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode_fn();
+    MOEGAN_REQUIRE(enc != nullptr, MOEGAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0, MOEGAN_ERR_MISALIGNED, "GEMM operand not 16-byte aligned");
+    MOEGAN_REQUIRE((o.pitch * 2) % 16 == 0, MOEGAN_ERR_MISALIGNED, "GEMM operand row pitch (%llu elements) not a multiple of 16 bytes",
+                   (unsigned long long)o.pitch);
+    cuuint64_t dims[2] = {o.inner, o.outer};
+    cuuint64_t strides[1] = {o.pitch * 2};
+    cuuint32_t box[2] = {64u, box_outer};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOEGAN_REQUIRE(r == CUDA_SUCCESS, MOEGAN_ERR_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; inner %llu outer %llu pitch %llu box %u)",
+                   (int)r, (unsigned long long)o.inner, (unsigned long long)o.outer, (unsigned long long)o.pitch, box_outer);
+    return MOEGAN_OK;
+}
+
+template <int BN, int KIND>
+int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)Cfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    umma_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, p);
+    MOEGAN_CHECK_LAUNCH("umma_gemm_kernel");
+    return MOEGAN_OK;
+}
+
+}  // namespace
+
+int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& B, GemmParams p, long long max_tiles,
+                     cudaStream_t stream) {
+    if (max_tiles <= 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(BN == 128 || BN == 256, MOEGAN_ERR_UNSUPPORTED, "BN must be 128 or 256");
+    MOEGAN_REQUIRE(p.N % 32 == 0, MOEGAN_ERR_BAD_SHAPE, "GEMM N (%d) must be a multiple of 32", p.N);
+    MOEGAN_REQUIRE(kind == GEMM_WGRAD || p.K % BK == 0, MOEGAN_ERR_BAD_SHAPE, "GEMM K (%d) must be a multiple of 64", p.K);
+    MOEGAN_REQUIRE(p.passes == 1 || p.passes == 3, MOEGAN_ERR_BAD_SHAPE, "passes must be 1 or 3");
+    CUtensorMap ma, mb;
+    int rc;
+    const uint32_t a_box = (kind == GEMM_WGRAD) ? 64u : 128u;
+    const uint32_t b_box = (kind == GEMM_ROWS_BK) ? (uint32_t)BN : 64u;
+    if ((rc = make_tmap(&ma, A, a_box)) != MOEGAN_OK) return rc;
+    if ((rc = make_tmap(&mb, B, b_box)) != MOEGAN_OK) return rc;
+    const int sms = num_sms();
+    const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_>(ma, mb, p, grid, stream)
+    if (BN == 256) {
+        if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(256, GEMM_ROWS_BK);
+        if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(256, GEMM_ROWS_BMN);
+        if (kind == GEMM_WGRAD) MOEGAN_DISPATCH(256, GEMM_WGRAD);
+    } else {
+        if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(128, GEMM_ROWS_BK);
+        if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(128, GEMM_ROWS_BMN);
+        if (kind == GEMM_WGRAD) MOEGAN_DISPATCH(128, GEMM_WGRAD);
+    }
+#undef MOEGAN_DISPATCH
+    set_error("unknown GEMM kind %d", kind);
+    return MOEGAN_ERR_UNSUPPORTED;
+}
+
+}  // namespace moegan
