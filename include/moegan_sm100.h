@@ -190,6 +190,13 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
  * kind 2: A [K,S*M] (M contiguous), B [K,S*N].    precision as above.  Used by tests and bench only. */
 int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K,
                      const void* A, const void* B, float* C, void* stream);
+/* instrumentation for bench.py: number of kernel launches this library has enqueued so far (all threads) */
+int64_t moegan_debug_launch_count(void);
+/* GEMM profiling: when enabled, every tcgen05 GEMM launch is bracketed by cudaEventRecord on its own stream.
+ * moegan_debug_profile_read synchronises those events and returns up to max_n (ms, flops-tag) records in
+ * launch order, then clears the list.  tag = the `kind * 1000 + BN` of the launch. */
+int moegan_debug_profile_enable(int32_t on);
+int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n);
 /* debug: override the MN-major shared-memory descriptor parameters of the GEMM (0 = built-in defaults) */
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes);
 /* fp32 [rows, cols] -> bf16 operand [rows, S*cols] */

@@ -2,7 +2,10 @@
 #include "kernels.cuh"
 #include "umma_gemm.cuh"
 
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 namespace moegan {
 
@@ -27,6 +30,33 @@ int num_sms() {
             sms = 148;
     }
     return sms;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional GEMM profiling (bench.py) ----
+struct ProfRec { cudaEvent_t beg, end; int tag; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+bool profile_begin(cudaStream_t st, int tag, void** handle) {
+    *handle = nullptr;
+    if (!g_prof_on) return false;
+    ProfRec* r = new ProfRec;
+    r->tag = tag;
+    if (cudaEventCreate(&r->beg) != cudaSuccess || cudaEventCreate(&r->end) != cudaSuccess) { delete r; return false; }
+    cudaEventRecord(r->beg, st);
+    *handle = r;
+    return true;
+}
+void profile_end(cudaStream_t st, void* handle) {
+    if (handle == nullptr) return;
+    ProfRec* r = reinterpret_cast<ProfRec*>(handle);
+    cudaEventRecord(r->end, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(*r);
+    delete r;
 }
 
 int validate_shape(const moegan_shape* s) {
@@ -105,6 +135,25 @@ int64_t moegan_plan_ints(int32_t m_cap) { return PLAN_BLK + m_cap / 128 + 8; }
 int64_t moegan_router_bwd_workspace_bytes(const moegan_shape* s) {
     if (s == nullptr) return 0;
     return (int64_t)router_bwd_layout(s).total;
+}
+int64_t moegan_debug_launch_count(void) { return g_launches.load(); }
+int moegan_debug_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return MOEGAN_OK;
+}
+int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.end);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.beg, r.end);
+        if (n < max_n) { if (ms_out) ms_out[n] = ms; if (tag_out) tag_out[n] = r.tag; ++n; }
+        cudaEventDestroy(r.beg); cudaEventDestroy(r.end);
+    }
+    g_prof.clear();
+    return n;
 }
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes) {
     g_mn_lbo = lbo_bytes; g_mn_sbo = sbo_bytes; g_mn_kadv = kadv_bytes;

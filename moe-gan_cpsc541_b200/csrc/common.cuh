@@ -24,6 +24,7 @@ constexpr int PLAN_BLK = 88;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
+void count_launch();
 
 #define MOEGAN_CHECK_CUDA(expr)                                   \
     do {                                                          \
@@ -35,6 +36,7 @@ int num_sms();
     do {                                                              \
         cudaError_t _e = cudaGetLastError();                          \
         if (_e != cudaSuccess) return ::moegan::cuda_fail(_e, name);  \
+        ::moegan::count_launch();                                     \
     } while (0)
 
 #define MOEGAN_REQUIRE(cond, status, ...)      \

@@ -388,7 +388,10 @@ int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
                                                (int)Cfg<BN>::SMEM_BYTES));
         attr_set = true;
     }
+    void* prof = nullptr;
+    profile_begin(stream, KIND * 1000 + BN, &prof);
     umma_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, p);
+    profile_end(stream, prof);
     MOEGAN_CHECK_LAUNCH("umma_gemm_kernel");
     return MOEGAN_OK;
 }

@@ -113,17 +113,24 @@ def _check_routing(r, ora, E, k):
 @pytest.mark.parametrize("shape", [
     dict(B=2, H=8, W=8, d=128, Dt=64, E=8, k=2),
     dict(B=3, H=5, W=5, d=256, Dt=128, E=4, k=2),      # ragged: T=75, tokens_per_sample not a multiple of 32
-    dict(B=8, H=4, W=4, d=512, Dt=512, E=8, k=2),      # block-4 geometry of the generator, microbench expert config
-    dict(B=2, H=16, W=16, d=128, Dt=512, E=8, k=3),
+    dict(B=8, H=4, W=4, d=512, Dt=512, E=8, k=2, mu_scale=8.0),   # block-4 geometry, microbench expert config
+    dict(B=8, H=4, W=4, d=512, Dt=512, E=8, k=2, mu_scale=30.0),  # saturated logits: many exact ties at the -20 clamp
+    dict(B=2, H=16, W=16, d=128, Dt=512, E=8, k=3, mu_scale=15.0),
 ])
 def test_topk_vs_oracle(shape, precision):
     s = shape
-    params, x, w, dout, gp, eps = _random_case(7 + s["d"] + s["k"], s["B"], s["H"], s["W"], s["d"], s["Dt"], s["E"])
+    params, x, w, dout, gp, eps = _random_case(7 + s["d"] + s["k"], s["B"], s["H"], s["W"], s["d"], s["Dt"], s["E"],
+                                               mu_scale=s.get("mu_scale", 30.0))
     m = G.build_module(params, s["d"], s["Dt"], s["E"], top_k=s["k"], precision=precision)
     r = G.run_cuda(m, x, w, eps, 1.0, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
     ora = G.run_oracle(params, x, w, eps, 1.0, top_k=s["k"], dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
-    excluded = _check_routing(r, ora, s["E"], s["k"])
-    assert len(excluded) == 0, f"tokens under the 1e-6 gap in a seeded case: {excluded.tolist()}"
+    excluded = _check_routing(r, ora, s["E"], s["k"])     # bit-exact on every token with a top-k logit gap >= 1e-6
+    T = s["B"] * s["H"] * s["W"]
+    print(f"tokens excluded (top-k logit gap < 1e-6): {len(excluded)}/{T}: {excluded.tolist()}")
+    if s.get("mu_scale", 30.0) < 20.0:
+        assert len(excluded) == 0
+    # ties are broken towards the lowest expert index on both sides, so even the excluded tokens agree here
+    assert np.array_equal(r["aux"]["topk_idx"], ora["cache"].idx)
     tol = TOL[precision]
     assert G.rel_err(r["probs"], ora["probs"]) < 1e-4
     assert np.allclose(r["aux"]["gates"].sum(axis=1), 1.0, atol=1e-5)
@@ -162,7 +169,7 @@ def test_dense_dprobs_generic_path_matches_fused_load():
 def test_kl_unsaturated_and_eps_buffers():
     """KL below the clamp -> non-zero KL gradient (SURVEY 0.6 'unreachable in practice' branch) and the
     eps=None convention: buffers are redrawn in place (t2i_moe_gan.py:349-351) and reused for parity."""
-    params, x, w, dout, gp, eps = _random_case(31, 2, 4, 4, 128, 64, 4, mu_scale=10.0, rho=0.55, temperature=1.5)
+    params, x, w, dout, gp, eps = _random_case(31, 2, 4, 4, 128, 64, 4, mu_scale=3.0, rho=0.55, temperature=1.5)
     m = G.build_module(params, 128, 64, 4, precision="fp32")
     torch.manual_seed(5)
     xt = torch.from_numpy(x).cuda().requires_grad_(True)
@@ -182,7 +189,7 @@ def test_kl_unsaturated_and_eps_buffers():
 
 def test_empty_expert_and_eval_topk():
     """An expert that receives no token: zero weight gradient, no NaN; eval path of a top_k module is hard top-1."""
-    params, x, w, dout, gp, eps = _random_case(41, 2, 8, 8, 128, 64, 4)
+    params, x, w, dout, gp, eps = _random_case(41, 2, 8, 8, 128, 64, 4, mu_scale=5.0)
     # tp[:, 0] = sum_k |w_k| > 0 for every sample; Wc[128, 0] = -50 drives expert 0's logit to the -20 clamp
     w = np.abs(w)
     params["router.text_mu"][:] = 0.0
