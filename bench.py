@@ -237,14 +237,17 @@ def run_b200_arm(args, rank, world, local_rank):
         barrier()
         evs = []
         n0 = lib.moegan_debug_launch_count()
+        host_t0 = time.perf_counter()
         for _ in range(steps):
             flush.zero_()                                          # L2 flush between timed iterations (not timed)
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             evs.append((a, b))
+        host_ms = (time.perf_counter() - host_t0) * 1e3      # CPU time to enqueue the steps (no sync inside)
         barrier()
         n1 = lib.moegan_debug_launch_count()
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        timed.host_ms = host_ms
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,6 +256,7 @@ def run_b200_arm(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clk:
         total_ms, launches = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = clk.summary()
+    host_enqueue_ms = timed.host_ms / args.steps
     e2e_ms, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2))
 
     # ---- live GEMM timing for the roofline (CUDA events recorded by the library on the launching stream) ----
@@ -314,6 +318,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "cpu_baseline": {"value": cpu_T / cpu_sec, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                              "sample": f"full step (T={cpu_T}) x 5 reps, median {cpu_sec * 1e3:.0f} ms; numpy fp32 oracle port"},
             "moe_block_fwd_bwd_us": ms_per_step * 1e3,
+            "host_enqueue_us_per_step": host_enqueue_ms * 1e3,
         }
         print(json.dumps(line), flush=True)
 

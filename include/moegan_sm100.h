@@ -135,7 +135,8 @@ int moegan_prep_weights(const moegan_shape* s, const float* const* w1_host_ptrs,
 /* ---- experts -------------------------------------------------------------------------------- */
 /* replaces: SparseExpertFFN.forward for all experts (t2i_moe_gan.py:262-263, loops :467-468 / :476-482):
  * two grouped GEMMs on tcgen05.  a_op = x_op (sparse) or x_copy (dense: shared by all experts).
- * pre [m_cap,4d] (bf16, or fp32 when precision==1), h_op [m_cap, S*4d], y [m_cap,d] (bf16 / fp32). */
+ * pre [m_cap,4d]: what the backward needs from the first GEMM - precision 0: bf16 gelu'(x W1^T + b1);
+ * precision 1: fp32 pre-activation; NULL for a forward-only call.  h_op [m_cap, S*4d] = gelu(.), y [m_cap,d] (bf16 / fp32). */
 int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const float* b1s,
                    const void* W2_op, const float* b2s, void* pre, void* h_op, void* y, void* stream);
 

@@ -86,6 +86,13 @@ static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 struct RouterBwdWs {
     size_t draw, dfp_op, dtau_part, dtl, dwc_part, dWc, dtp, dtp_op, w_op, dWf, dWt, total;
 };
+static int dwf_splits(const moegan_shape* s) {   // split-K factor of the dWf = x^T dfp GEMM (few output tiles, long K = T)
+    const int nkb = (s->T + 63) / 64;
+    int ks = nkb / 4;
+    if (ks < 1) ks = 1;
+    if (ks > 64) ks = 64;
+    return ks;
+}
 static RouterBwdWs router_bwd_layout(const moegan_shape* s) {
     const size_t S = s->precision == 1 ? 2 : 1;
     const size_t H = MOEGAN_ROUTER_HID;
@@ -100,7 +107,7 @@ static RouterBwdWs router_bwd_layout(const moegan_shape* s) {
     w.dtp = o;       o = align256(o + (size_t)s->B * H * 4);
     w.dtp_op = o;    o = align256(o + (size_t)s->B * S * H * 2);
     w.w_op = o;      o = align256(o + (size_t)s->B * S * s->Dt * 2);
-    w.dWf = o;       o = align256(o + (size_t)s->d * H * 4);
+    w.dWf = o;       o = align256(o + (size_t)dwf_splits(s) * s->d * H * 4);
     w.dWt = o;       o = align256(o + (size_t)s->Dt * H * 4);
     w.total = o;
     return w;
@@ -248,7 +255,8 @@ int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
                    const void* W2_op, const float* b2s, void* pre, void* h_op, void* y, void* stream) {
     CHECK_SHAPE(s);
     if (s->T == 0) return MOEGAN_OK;
-    REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(b1s); REQ_PTR(W2_op); REQ_PTR(b2s); REQ_PTR(pre); REQ_PTR(h_op); REQ_PTR(y);
+    REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(b1s); REQ_PTR(W2_op); REQ_PTR(b2s); REQ_PTR(h_op); REQ_PTR(y);
+    // pre == NULL: forward-only call, nothing is saved for the backward pass
     const uint64_t S = s->precision == 1 ? 2 : 1;
     const int d = s->d, hid = 4 * s->d;
     const int T_pad = ceil_div(s->T, 128) * 128;
@@ -324,7 +332,7 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         GemmParams p = base_params(s, plan);
         p.N = hid; p.K = d; p.a_lo_off = d; p.b_lo_off = hid;
         p.b_rows_per_expert = d;
-        p.epi = s->precision == 1 ? EPI_DGELU_X3 : EPI_DGELU_BF16;
+        p.epi = s->precision == 1 ? EPI_DGELU_X3 : EPI_MUL_BF16;
         p.aux = pre; p.ld_aux = hid;
         p.out0 = dpre_op; p.ld_out0 = (long long)S * hid; p.out_split_off = hid;
         RUN(launch_umma_gemm(GEMM_ROWS_BMN, 256, A, B, p, m_blocks * (hid / 256), st));
@@ -436,8 +444,9 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
         GemmOperand B{dfp_op, S * H, (uint64_t)s->T, S * H};
         GemmParams p = base;
         p.N = (int)H; p.dimA = d; p.a_lo_off = d; p.b_lo_off = (int)H; p.k_rows_host = s->T;
+        p.k_splits = dwf_splits(s);                       // partials summed by reparam_kl_bwd_kernel
         p.out0 = dWf; p.ld_out0 = (long long)H;
-        RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)(d / 128), st));
+        RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)(d / 128) * p.k_splits, st));
     }
     {   // dw [B, Dt] = dtp [B,128] * Wt[Dt,128]^T
         GemmOperand A{dtp_op, S * H, (uint64_t)s->B, S * H};
@@ -456,7 +465,7 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
         p.out0 = dWt; p.ld_out0 = (long long)H;
         RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)ceil_div(Dt, 128), st));
     }
-    RUN(launch_reparam_kl_bwd(s, dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampled, kl_out, dkl,
+    RUN(launch_reparam_kl_bwd(s, dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampled, dwf_splits(s), kl_out, dkl,
                               dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c, st));
     return MOEGAN_OK;
 }

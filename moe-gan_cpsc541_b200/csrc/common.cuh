@@ -85,28 +85,52 @@ __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
 __device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
-// erf, Abramowitz-Stegun 7.1.26: |abs err| <= 1.5e-7.  Used by the bf16-precision epilogues where the
-// GEMM epilogue must stay under the tensor-pipe time; the fp32 (3-pass) mode uses erff().
-__device__ __forceinline__ float erf_fast(float x) {
-    const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(t, p, 1.421413741f);
-    p = fmaf(t, p, -0.284496736f);
-    p = fmaf(t, p, 0.254829592f);
-    const float r = fmaf(-p * t, __expf(-ax * ax), 1.0f);
-    return copysignf(r, x);
+// ---- GELU (exact erf form, nn.GELU(approximate='none'), t2i_moe_gan.py:258) ----------------------------
+// Precise variants (fp32 / 3-pass mode): erff / expf.
+// Fast variants (bf16 mode; the result is rounded to bf16 = 2^-9 relative anyway): ONE MUFU per erf instead of
+// the two (rcp + ex2) of the textbook rational forms, because the SFU pipe (4 lanes/SMSP) is what bounds a
+// GELU epilogue running under a tcgen05 main loop:
+//     erf(x/sqrt2) ~= tanh(x * (b0 + b1 x^2 + b2 x^4 + b3 x^6)),  |x| clamped to 5.5
+// coefficients = weighted least-squares (minimax-refined) fit of atanh(erf(z)); max |erf error| 1.3e-5 before
+// the tanh.approx error (2^-11 relative).
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float erf_sqrt2_fast(float x) {      // erf(x / sqrt(2))
+    const float xc = clampf(x, -5.5f, 5.5f);
+    const float s = xc * xc;
+    float p = fmaf(s, -1.3688055686176932e-05f, -0.00019445275122756945f);
+    p = fmaf(s, p, 0.036546657541717965f);
+    p = fmaf(s, p, 0.797820262700123f);
+    return tanh_approx(xc * p);
 }
 template <bool PRECISE>
-__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU(approximate='none'), t2i_moe_gan.py:258
-    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
-    return 0.5f * x * (1.0f + e);
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_sqrt2_fast(x);
+    const float h = 0.5f * x;
+    return fmaf(h, e, h);
 }
+// gelu'(x) = Phi(x) + x * phi(x)
 template <bool PRECISE>
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
-    const float pdf = (PRECISE ? expf(-0.5f * x * x) : __expf(-0.5f * x * x)) * 0.39894228040143268f;
-    return fmaf(x, pdf, 0.5f * (1.0f + e));
+    const float e = PRECISE ? erff(x * 0.70710678118654752f) : erf_sqrt2_fast(x);
+    const float pdf = (PRECISE ? expf(-0.5f * x * x) : ex2_approx(-0.72134752044448170f * x * x)) * 0.39894228040143268f;
+    return fmaf(x, pdf, fmaf(0.5f, e, 0.5f));
+}
+// both at once (shares the erf): used by the forward epilogue, which stores gelu'(pre) for the backward pass
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& dg) {
+    const float e = erf_sqrt2_fast(x);
+    const float h = 0.5f * x;
+    g = fmaf(h, e, h);
+    const float pdf = ex2_approx(-0.72134752044448170f * x * x) * 0.39894228040143268f;
+    dg = fmaf(x, pdf, fmaf(0.5f, e, 0.5f));
 }
 #endif  // __CUDACC__
 

@@ -17,25 +17,32 @@ constexpr int MAX_SEG = 8;   // d <= 1024: a warp covers 128 columns per segment
 __global__ void __launch_bounds__(1024)
 plan_kernel(const int* __restrict__ chunk_counts, const float* __restrict__ chunk_colsum, int nchunks, int T, int E, int dense,
             int m_cap, int* __restrict__ plan, int* __restrict__ chunk_base, float* __restrict__ load) {
-    __shared__ int warp_tot[32];
-    __shared__ float fred[32];
     __shared__ int tot_e[MOEGAN_MAX_EXPERTS];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int off_e[MOEGAN_MAX_EXPERTS + 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;   // warp w owns expert w (E <= 32 warps)
 
-    // ---- balance load: deterministic column sums of the soft probs over chunks ----
-    for (int e = 0; e < E; ++e) {
+    if (wid < E) {
+        // ---- balance load: column sum of the soft probs over chunks, fixed order -> deterministic ----
+        const int e = wid;
         float acc = 0.0f;
-        for (int c = tid; c < nchunks; c += 1024) acc += chunk_colsum[(size_t)c * E + e];
+        for (int c = lane; c < nchunks; c += 32) acc += chunk_colsum[(size_t)c * E + e];
         acc = warp_sum(acc);
-        if (lane == 0) fred[wid] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            float s = 0.0f;
-            for (int w = 0; w < 32; ++w) s += fred[w];
-            load[e] = s;
+        if (lane == 0) load[e] = acc;
+        if (!dense) {
+            // ---- exclusive scan of this expert's chunk histogram: lane owns a contiguous run of chunks ----
+            const int per = (nchunks + 31) / 32;
+            const int c0 = lane * per, c1 = min(c0 + per, nchunks);
+            int local = 0;
+            for (int c = c0; c < c1; ++c) local += chunk_counts[(size_t)c * E + e];
+            int incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int run = incl - local;
+            for (int c = c0; c < c1; ++c) { chunk_base[(size_t)c * E + e] = run; run += chunk_counts[(size_t)c * E + e]; }
+            if (lane == 31) tot_e[e] = incl;
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     if (dense) {
         const int T_pad = (T + 127) / 128 * 128;
@@ -46,49 +53,25 @@ plan_kernel(const int* __restrict__ chunk_counts, const float* __restrict__ chun
         if (tid == 0) { plan[0] = E * bpe; plan[1] = E * T_pad; plan[2] = T_pad; }
         return;
     }
-
-    // ---- sparse: per-expert exclusive scan of the chunk histograms ----
-    const int ipt = (nchunks + 1023) / 1024;   // consecutive chunks per thread
-    const int c0 = tid * ipt;
-    for (int e = 0; e < E; ++e) {
-        int local = 0;
-        for (int i = 0; i < ipt; ++i) { const int c = c0 + i; if (c < nchunks) local += chunk_counts[(size_t)c * E + e]; }
-        int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int w = warp_tot[lane];
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-            warp_tot[lane] = wi - w;             // exclusive warp offsets
-            if (lane == 31) tot_e[e] = wi;
-        }
-        __syncthreads();
-        int run = warp_tot[wid] + incl - local;
-        for (int i = 0; i < ipt; ++i) {
-            const int c = c0 + i;
-            if (c < nchunks) { chunk_base[(size_t)c * E + e] = run; run += chunk_counts[(size_t)c * E + e]; }
-        }
-        __syncthreads();
-    }
     if (tid == 0) {
         int off = 0;
         for (int e = 0; e < E; ++e) {
+            off_e[e] = off;
             plan[PLAN_OFF + e] = off;
             plan[PLAN_CNT + e] = tot_e[e];
             off += (tot_e[e] + 127) / 128 * 128;
         }
         if (off > m_cap) off = m_cap;            // cannot happen (m_cap is an upper bound); guards the buffers
+        off_e[E] = off;
         plan[PLAN_OFF + E] = off;
         plan[0] = off / 128; plan[1] = off; plan[2] = 0;
     }
     __syncthreads();
-    for (int e = 0; e < E; ++e) {
-        const int b0 = plan[PLAN_OFF + e] / 128, b1 = plan[PLAN_OFF + e + 1] / 128;
-        for (int i = b0 + tid; i < b1; i += 1024) plan[PLAN_BLK + i] = e;
+    const int nblk = off_e[E] / 128;
+    for (int i = tid; i < nblk; i += 1024) {
+        int e = 0;
+        while (e + 1 < E && i * 128 >= off_e[e + 1]) ++e;
+        plan[PLAN_BLK + i] = e;
     }
 }
 
@@ -319,32 +302,37 @@ uncombine_kernel(const void* __restrict__ dx_rows, const int* __restrict__ token
         if (s < nseg) *reinterpret_cast<float4*>(dx + (size_t)t * d + s * 128 + lane * 4) = acc[s];
 }
 
-// bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c]
-__global__ void __launch_bounds__(256)
+// bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c].
+// CTA = (expert, 64 columns), 32 warps stride the rows, two rows in flight per warp.
+__global__ void __launch_bounds__(1024)
 colsum_grouped_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restrict__ src, int cols, int split, int T, int dense,
                       float* __restrict__ out) {
-    __shared__ float red[8][64];
+    __shared__ float red[32][64];
     const int e = blockIdx.y;
-    const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
-    const int wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + lane * 2;
     const int ld = split ? 2 * cols : cols;
     const int r0 = __ldg(plan + PLAN_OFF + e);
     const int r1 = r0 + (dense ? T : __ldg(plan + PLAN_CNT + e));
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int r = r0 + wid; r < r1; r += 8) {
+    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+    auto add_row = [&](int r, float& x0, float& x1) {
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + c));
-        a0 += bf16_lo_to_float(u); a1 += bf16_hi_to_float(u);
+        x0 += bf16_lo_to_float(u); x1 += bf16_hi_to_float(u);
         if (split) {
             const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + cols + c));
-            a0 += bf16_lo_to_float(v); a1 += bf16_hi_to_float(v);
+            x0 += bf16_lo_to_float(v); x1 += bf16_hi_to_float(v);
         }
-    }
-    red[wid][(threadIdx.x & 31) * 2] = a0;
-    red[wid][(threadIdx.x & 31) * 2 + 1] = a1;
+    };
+    int r = r0 + wid;
+    for (; r + 32 < r1; r += 64) { add_row(r, a0, a1); add_row(r + 32, b0, b1); }
+    if (r < r1) add_row(r, a0, a1);
+    red[wid][lane * 2] = a0 + b0;
+    red[wid][lane * 2 + 1] = a1 + b1;
     __syncthreads();
     if (threadIdx.x < 64) {
         float s = 0.0f;
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < 32; ++w) s += red[w][threadIdx.x];
         out[(size_t)e * cols + blockIdx.x * 64 + threadIdx.x] = s;
     }
 }
@@ -436,7 +424,7 @@ int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* 
 
 int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* out, cudaStream_t st) {
     dim3 grid(cols / 64, s->E);
-    colsum_grouped_kernel<<<grid, 256, 0, st>>>(plan, reinterpret_cast<const __nv_bfloat16*>(src_op), cols, s->precision == 1, s->T,
+    colsum_grouped_kernel<<<grid, 1024, 0, st>>>(plan, reinterpret_cast<const __nv_bfloat16*>(src_op), cols, s->precision == 1, s->T,
                                                 s->dense, out);
     MOEGAN_CHECK_LAUNCH("colsum_grouped_kernel");
     return MOEGAN_OK;

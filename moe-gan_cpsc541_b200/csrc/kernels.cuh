@@ -24,7 +24,7 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
 int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* dWt, const float* dWc,
                           const float* mu_f, const float* rho_f, const float* eps_f,
                           const float* mu_t, const float* rho_t, const float* eps_t,
-                          const float* mu_c, const float* rho_c, const float* eps_c, int sampled,
+                          const float* mu_c, const float* rho_c, const float* eps_c, int sampled, int f_splits,
                           const float* kl_out, const float* dkl,
                           float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c, cudaStream_t st);
 int launch_balance_loss(const float* load, int E, int T, float bw, const float* dloss, float* loss, float* dload, cudaStream_t st);

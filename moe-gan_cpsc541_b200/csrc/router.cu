@@ -83,35 +83,53 @@ __global__ void kl_finalize_kernel(const float* __restrict__ kl_part, int nparts
 // =====================================================================================================
 // K2a: text half of the router, once per sample  (t2i_moe_gan.py:365, text rows of :371)
 // =====================================================================================================
-__global__ void __launch_bounds__(HID)
+constexpr int TX_SPLIT = 4;
+__global__ void __launch_bounds__(HID * TX_SPLIT)
 text_fwd_kernel(const float* __restrict__ w, const float* __restrict__ Wt, const float* __restrict__ Wc,
                 int Dt, int E, float* __restrict__ tp, float* __restrict__ tl) {
     extern __shared__ float sm[];
-    float* ws = sm;            // [Dt]
-    float* tps = sm + Dt;      // [128]
-    const int b = blockIdx.x, j = threadIdx.x;
-    for (int k = j; k < Dt; k += HID) ws[k] = nan_to_num_router(w[(size_t)b * Dt + k]);
+    float* ws = sm;                    // [Dt]
+    float* part = sm + Dt;             // [TX_SPLIT][128]
+    float* tps = part + TX_SPLIT * HID;   // [128]
+    const int b = blockIdx.x, tid = threadIdx.x, j = tid & (HID - 1), q = tid >> 7;
+    for (int k = tid; k < Dt; k += HID * TX_SPLIT) ws[k] = nan_to_num_router(w[(size_t)b * Dt + k]);
     __syncthreads();
-    float acc = 0.0f;
-    for (int k = 0; k < Dt; ++k) acc = fmaf(ws[k], Wt[(size_t)k * HID + j], acc);
-    tp[(size_t)b * HID + j] = acc;
-    tps[j] = acc;
+    const int kper = (Dt + TX_SPLIT - 1) / TX_SPLIT;
+    const int k0 = q * kper, k1 = min(k0 + kper, Dt);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {       // 4 independent loads in flight
+        a0 = fmaf(ws[k], Wt[(size_t)k * HID + j], a0);
+        a1 = fmaf(ws[k + 1], Wt[(size_t)(k + 1) * HID + j], a1);
+        a2 = fmaf(ws[k + 2], Wt[(size_t)(k + 2) * HID + j], a2);
+        a3 = fmaf(ws[k + 3], Wt[(size_t)(k + 3) * HID + j], a3);
+    }
+    for (; k < k1; ++k) a0 = fmaf(ws[k], Wt[(size_t)k * HID + j], a0);
+    part[q * HID + j] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (j < E) {
-        float s = 0.0f;
-        for (int i = 0; i < HID; ++i) s = fmaf(tps[i], Wc[(size_t)(HID + i) * E + j], s);
-        tl[(size_t)b * E + j] = s;
+    if (q == 0) {
+        const float acc = (part[j] + part[HID + j]) + (part[2 * HID + j] + part[3 * HID + j]);
+        tp[(size_t)b * HID + j] = acc;
+        tps[j] = acc;
+    }
+    __syncthreads();
+    if (tid < E) {
+        float sacc = 0.0f;
+        for (int i = 0; i < HID; ++i) sacc = fmaf(tps[i], Wc[(size_t)(HID + i) * E + tid], sacc);
+        tl[(size_t)b * E + tid] = sacc;
     }
 }
 
 // =====================================================================================================
-// K2: fused router forward.  CTA = 32 tokens (one permutation chunk), 4 warps x 8 tokens, lane owns 4 of
-// the 128 projection columns.  Wf streams through shared memory in 32-row chunks (cp.async, double
-// buffered); the epilogue is warp-per-token: logits, temperature, clamps, softmax, clamp+renorm, top-k.
+// K2: fused router forward.  CTA = 32 tokens (one permutation chunk), 8 warps: warp (g, q) accumulates
+// tokens 8q..8q+7 over the k rows of parity-half g of every smem chunk (split-K inside the CTA, so every
+// SMSP has two resident warps even though there is only one CTA per SM at T = 4096); lane owns 4 of the 128
+// projection columns.  Wf streams through shared memory in 32-row chunks (cp.async, double buffered).
+// Epilogue is warp-per-token: logits, temperature, clamps, softmax, clamp+renorm, top-k, histogram.
 // =====================================================================================================
 constexpr int RT_TOK = MOEGAN_CHUNK;   // 32 tokens per CTA
 constexpr int RT_KC = 32;              // k rows per smem chunk
-constexpr int RT_THREADS = 128;
+constexpr int RT_THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
@@ -129,13 +147,14 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
                   int* __restrict__ topk_idx, float* __restrict__ gates,
                   int* __restrict__ chunk_counts, float* __restrict__ chunk_colsum) {
     extern __shared__ __align__(16) uint8_t rsm[];
-    float* Ws = reinterpret_cast<float*>(rsm);                    // [2][RT_KC][128]
+    float* Ws = reinterpret_cast<float*>(rsm);                    // [2][RT_KC][128]  (reused for the split-K exchange)
     float* xs = Ws + 2 * RT_KC * HID;                             // [2][RT_TOK][RT_KC]
     float* WcT = xs + 2 * RT_TOK * RT_KC;                         // [E][128]
-    float* colsum_s = WcT + E * HID;                              // [4][32]
-    int* cnt_s = reinterpret_cast<int*>(colsum_s + 4 * 32);       // [32]
+    float* colsum_s = WcT + E * HID;                              // [8][32]
+    int* cnt_s = reinterpret_cast<int*>(colsum_s + 8 * 32);       // [32]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = wid >> 2, q = wid & 3;
     const int chunk = blockIdx.x;
     const int t0 = chunk * RT_TOK;
 
@@ -149,19 +168,15 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         const int k0 = c * RT_KC;
         float* wdst = Ws + buf * RT_KC * HID;
 #pragma unroll
-        for (int i = 0; i < (RT_KC * HID / 4) / RT_THREADS; ++i) {     // 8 x 16 B per thread
+        for (int i = 0; i < (RT_KC * HID / 4) / RT_THREADS; ++i) {     // 4 x 16 B per thread
             const int idx = tid + i * RT_THREADS;
             cp_async16(wdst + idx * 4, Wf + (size_t)k0 * HID + idx * 4, true);
         }
-        float* xdst = xs + buf * RT_TOK * RT_KC;
-#pragma unroll
-        for (int i = 0; i < (RT_TOK * RT_KC / 4) / RT_THREADS; ++i) {  // 2 x 16 B per thread
-            const int idx = tid + i * RT_THREADS;
-            const int tok = idx >> 3, q4 = idx & 7;
-            const bool ok = (t0 + tok) < T;
-            const float* src = x + (size_t)(ok ? (t0 + tok) : 0) * d + k0 + q4 * 4;
-            cp_async16(xdst + tok * RT_KC + q4 * 4, src, ok);
-        }
+        float* xdst = xs + buf * RT_TOK * RT_KC;                       // 1 x 16 B per thread
+        const int tok = tid >> 3, q4 = tid & 7;
+        const bool ok = (t0 + tok) < T;
+        const float* src = x + (size_t)(ok ? (t0 + tok) : 0) * d + k0 + q4 * 4;
+        cp_async16(xdst + tok * RT_KC + q4 * 4, src, ok);
     };
 
     float acc[8][4];
@@ -176,25 +191,21 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         if (c + 1 < nchunks) { load_chunk(c + 1, buf ^ 1); cp_async_commit(); cp_async_wait<1>(); }
         else                 { cp_async_wait<0>(); }
         {   // nan_to_num on the x elements this thread staged (identity on finite input, :338-340)
-            float* xdst = xs + buf * RT_TOK * RT_KC;
-#pragma unroll
-            for (int i = 0; i < (RT_TOK * RT_KC / 4) / RT_THREADS; ++i) {
-                const int idx = tid + i * RT_THREADS;
-                float4* p4 = reinterpret_cast<float4*>(xdst + (idx >> 3) * RT_KC + (idx & 7) * 4);
-                float4 v = *p4;
-                v.x = nan_to_num_router(v.x); v.y = nan_to_num_router(v.y);
-                v.z = nan_to_num_router(v.z); v.w = nan_to_num_router(v.w);
-                *p4 = v;
-            }
+            float4* p4 = reinterpret_cast<float4*>(xs + buf * RT_TOK * RT_KC + (tid >> 3) * RT_KC + (tid & 7) * 4);
+            float4 v = *p4;
+            v.x = nan_to_num_router(v.x); v.y = nan_to_num_router(v.y);
+            v.z = nan_to_num_router(v.z); v.w = nan_to_num_router(v.w);
+            *p4 = v;
         }
         __syncthreads();
         const float* wsrc = Ws + buf * RT_KC * HID;
-        const float* xsrc = xs + buf * RT_TOK * RT_KC + (wid * 8) * RT_KC;
+        const float* xsrc = xs + buf * RT_TOK * RT_KC + (q * 8) * RT_KC;
         float part[8][4];
 #pragma unroll
         for (int a = 0; a < 8; ++a) { part[a][0] = part[a][1] = part[a][2] = part[a][3] = 0.0f; }
 #pragma unroll
-        for (int kq = 0; kq < RT_KC / 4; ++kq) {
+        for (int kq4 = 0; kq4 < RT_KC / 8; ++kq4) {
+            const int kq = g * (RT_KC / 8) + kq4;       // this warp group's half of the chunk
             float4 xv[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) xv[a] = *reinterpret_cast<const float4*>(xsrc + a * RT_KC + kq * 4);
@@ -217,18 +228,24 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         __syncthreads();
     }
 
-    // ------------------------------- warp-per-token epilogue -------------------------------
+    // ---- split-K exchange through shared memory: P[g][q][a][128] (32 KB, aliases the W staging buffers) ----
+    float* P = Ws;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+        *reinterpret_cast<float4*>(P + ((g * 4 + q) * 8 + a) * HID + lane * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    __syncthreads();
+
+    // ------------------------------- warp-per-token epilogue (4 tokens per warp) -------------------------------
     const float tau = clampf(__ldg(temperature) * af, 0.5f, 5.0f);   // (:375)
     float my_colsum = 0.0f;
 #pragma unroll 1
-    for (int a = 0; a < 8; ++a) {
-        const int t = t0 + wid * 8 + a;
+    for (int a4 = 0; a4 < 4; ++a4) {
+        const int a = g * 4 + a4;
+        const int t = t0 + q * 8 + a;
         if (t >= T) break;   // warp-uniform
-        float f0, f1, f2, f3;
-        // select acc[a] without dynamic register indexing
-        f0 = f1 = f2 = f3 = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (q == a) { f0 = acc[q][0]; f1 = acc[q][1]; f2 = acc[q][2]; f3 = acc[q][3]; }
+        const float4 p0 = *reinterpret_cast<const float4*>(P + ((0 * 4 + q) * 8 + a) * HID + lane * 4);
+        const float4 p1 = *reinterpret_cast<const float4*>(P + ((1 * 4 + q) * 8 + a) * HID + lane * 4);
+        const float f0 = p0.x + p1.x, f1 = p0.y + p1.y, f2 = p0.z + p1.z, f3 = p0.w + p1.w;
         if (fp != nullptr) *reinterpret_cast<float4*>(fp + (size_t)t * HID + lane * 4) = make_float4(f0, f1, f2, f3);
         float my_raw = 0.0f;
         for (int e = 0; e < E; ++e) {
@@ -288,7 +305,10 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
     colsum_s[wid * 32 + lane] = my_colsum;
     __syncthreads();
     if (tid < E) {
-        chunk_colsum[(size_t)chunk * E + tid] = (colsum_s[tid] + colsum_s[32 + tid]) + (colsum_s[64 + tid] + colsum_s[96 + tid]);
+        float cs = 0.0f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) cs += colsum_s[w8 * 32 + tid];   // fixed order -> deterministic
+        chunk_colsum[(size_t)chunk * E + tid] = cs;
         chunk_counts[(size_t)chunk * E + tid] = cnt_s[tid];
     }
 }
@@ -297,7 +317,7 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
 // B3: gates/probs -> raw logits gradient, dfp operand, dtau partials (warp per token)
 // =====================================================================================================
 constexpr int RB_THREADS = 256;
-constexpr int RB_TOK = 64;   // tokens per CTA
+constexpr int RB_TOK = 16;   // tokens per CTA (8 warps x 2)
 
 __global__ void __launch_bounds__(RB_THREADS)
 router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict__ Wc, const int* __restrict__ topk_idx,
@@ -395,66 +415,57 @@ router_bwd_dtl_kernel(const float* __restrict__ draw, int tps, int E, float* __r
     }
 }
 
-// dWc[0:128] partials: part[blk][j][e] = sum over 256 tokens of fp[t, j] * draw[t, e]
-constexpr int WC_TOK = 256;
+// dWc[0:128] partials: part[blk][j][e] = sum over the block's 32 tokens of fp[t, j] * draw[t, e]
+constexpr int WC_TOK = 32;
 __global__ void __launch_bounds__(HID)
 router_bwd_dwc_part_kernel(const float* __restrict__ fp, const float* __restrict__ draw, int T, int E, float* __restrict__ part) {
-    __shared__ float ds[64 * 32];
+    __shared__ float ds[WC_TOK * MOEGAN_MAX_EXPERTS];
     const int j = threadIdx.x;
-    const int tbeg = blockIdx.x * WC_TOK;
-    float acc[MOEGAN_MAX_EXPERTS];
+    const int t0 = blockIdx.x * WC_TOK;
+    const int nt = min(WC_TOK, T - t0);
+    for (int i = j; i < nt * E; i += HID) ds[i] = draw[(size_t)t0 * E + i];
+    float f[WC_TOK];
 #pragma unroll
-    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) acc[e] = 0.0f;
-    for (int t0 = tbeg; t0 < min(tbeg + WC_TOK, T); t0 += 64) {
-        const int nt = min(64, T - t0);
-        __syncthreads();
-        for (int i = j; i < nt * E; i += HID) ds[i] = draw[(size_t)t0 * E + i];
-        __syncthreads();
-        for (int tt = 0; tt < nt; ++tt) {
-            const float f = fp[(size_t)(t0 + tt) * HID + j];
+    for (int tt = 0; tt < WC_TOK; ++tt) f[tt] = tt < nt ? fp[(size_t)(t0 + tt) * HID + j] : 0.0f;   // 32 loads in flight
+    __syncthreads();
+    for (int e = 0; e < E; ++e) {
+        float acc = 0.0f;
 #pragma unroll
-            for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e)
-                if (e < E) acc[e] = fmaf(f, ds[tt * E + e], acc[e]);
-        }
+        for (int tt = 0; tt < WC_TOK; ++tt) acc = fmaf(f[tt], tt < nt ? ds[tt * E + e] : 0.0f, acc);
+        part[((size_t)blockIdx.x * HID + j) * E + e] = acc;
     }
-#pragma unroll
-    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e)
-        if (e < E) part[((size_t)blockIdx.x * HID + j) * E + e] = acc[e];
 }
 
-// Finishes the small router reductions: dWc (top from partials, bottom from tp/dtl), dtp (+ operand copy),
-// dtemperature.  grid = 1 + B blocks:  block 0 -> dWc + dtemperature;  block 1+b -> dtp[b].
+// Finishes the small router reductions.  grid = 1 + B + E blocks of 256 threads:
+//   block 0            dtemperature
+//   blocks 1 .. B      dtp[b] (+ bf16 operand copy)
+//   blocks B+1 .. B+E  dWc: 128 outputs each of the top half (sum of the token-block partials) and of the
+//                      bottom half (sum_b tp[b, j] * dtl[b, e])
 __global__ void __launch_bounds__(256)
 router_bwd_small_kernel(const float* __restrict__ dwc_part, int nparts, const float* __restrict__ tp, const float* __restrict__ dtl,
                         const float* __restrict__ Wc, const float* __restrict__ dtau_part, int ntau,
                         const float* __restrict__ temperature, float af, int B, int E, int split,
                         float* __restrict__ dWc, float* __restrict__ dtp, __nv_bfloat16* __restrict__ dtp_op,
                         float* __restrict__ dtemperature) {
+    __shared__ float red[256];
     const int tid = threadIdx.x;
     if (blockIdx.x == 0) {
-        for (int i = tid; i < HID * E; i += 256) {            // top rows
-            float s = 0.0f;
-            for (int pz = 0; pz < nparts; ++pz) s += dwc_part[(size_t)pz * HID * E + i];
-            dWc[i] = s;
-        }
-        for (int i = tid; i < HID * E; i += 256) {            // bottom rows: sum_b tp[b, j] * dtl[b, e]
-            const int j = i / E, e = i - j * E;
-            float s = 0.0f;
-            for (int b = 0; b < B; ++b) s = fmaf(tp[(size_t)b * HID + j], dtl[(size_t)b * E + e], s);
-            dWc[HID * E + i] = s;
-        }
+        float s = 0.0f;
+        for (int i = tid; i < ntau; i += 256) s += dtau_part[i];
+        red[tid] = s;
+        __syncthreads();
         if (tid < 32) {
-            float s = 0.0f;
-            for (int i = tid; i < ntau; i += 32) s += dtau_part[i];
-            s = warp_sum(s);
+            float v = 0.0f;
+            for (int i = tid; i < 256; i += 32) v += red[i];
+            v = warp_sum(v);
             if (tid == 0) {
                 const float ta = __ldg(temperature) * af;
                 const float tau = clampf(ta, 0.5f, 5.0f);
-                const float dtau = -s / tau;
+                const float dtau = -v / tau;
                 dtemperature[0] = (ta >= 0.5f && ta <= 5.0f) ? dtau * af : 0.0f;   // clamp mask (:375)
             }
         }
-    } else {
+    } else if ((int)blockIdx.x <= B) {
         const int b = blockIdx.x - 1;
         if (tid < HID) {
             float s = 0.0f;
@@ -466,6 +477,25 @@ router_bwd_small_kernel(const float* __restrict__ dwc_part, int nparts, const fl
             dtp_op[(size_t)b * ld + tid] = __float2bfloat16_rn(hi);
             if (split) dtp_op[(size_t)b * ld + HID + tid] = __float2bfloat16_rn(lo);
         }
+    } else {
+        const int o = (blockIdx.x - 1 - B) * 128 + (tid & 127);   // flat index into [128][E]
+        const int h = tid >> 7;
+        float a0 = 0.0f, a1 = 0.0f;
+        int pz = h;
+        for (; pz + 2 < nparts; pz += 4) {                          // two independent chains per thread
+            a0 += dwc_part[(size_t)pz * HID * E + o];
+            a1 += dwc_part[(size_t)(pz + 2) * HID * E + o];
+        }
+        for (; pz < nparts; pz += 2) a0 += dwc_part[(size_t)pz * HID * E + o];
+        red[tid] = a0 + a1;
+        __syncthreads();
+        if (h == 0) {
+            dWc[o] = red[tid] + red[tid + 128];
+            const int j = o / E, e = o - j * E;                     // bottom rows
+            float s = 0.0f;
+            for (int b = 0; b < B; ++b) s = fmaf(tp[(size_t)b * HID + j], dtl[(size_t)b * E + e], s);
+            dWc[HID * E + o] = s;
+        }
     }
 }
 
@@ -475,7 +505,7 @@ reparam_kl_bwd_kernel(const float* __restrict__ dWf, const float* __restrict__ d
                       const float* __restrict__ mu_f, const float* __restrict__ rho_f, const float* __restrict__ eps_f,
                       const float* __restrict__ mu_t, const float* __restrict__ rho_t, const float* __restrict__ eps_t,
                       const float* __restrict__ mu_c, const float* __restrict__ rho_c, const float* __restrict__ eps_c,
-                      int n_f, int n_t, int n_c, int sampled, const float* __restrict__ kl_out, const float* __restrict__ dkl,
+                      int n_f, int n_t, int n_c, int f_splits, int sampled, const float* __restrict__ kl_out, const float* __restrict__ dkl,
                       float* __restrict__ dmu_f, float* __restrict__ drho_f, float* __restrict__ dmu_t, float* __restrict__ drho_t,
                       float* __restrict__ dmu_c, float* __restrict__ drho_c) {
     const int n = n_f + n_t + n_c;
@@ -490,7 +520,9 @@ reparam_kl_bwd_kernel(const float* __restrict__ dWf, const float* __restrict__ d
         if (i < n_f)            { j = i;             dW = dWf; mu = mu_f; rho = rho_f; eps = eps_f; dmu = dmu_f; drho = drho_f; }
         else if (i < n_f + n_t) { j = i - n_f;       dW = dWt; mu = mu_t; rho = rho_t; eps = eps_t; dmu = dmu_t; drho = drho_t; }
         else                    { j = i - n_f - n_t; dW = dWc; mu = mu_c; rho = rho_c; eps = eps_c; dmu = dmu_c; drho = drho_c; }
-        const float g = dW[j], m = mu[j], r = rho[j];
+        float g = dW[j];
+        if (i < n_f) for (int sp = 1; sp < f_splits; ++sp) g += dWf[(size_t)sp * n_f + j];   // split-K partials of the dWf GEMM
+        const float m = mu[j], r = rho[j];
         float gm, gr;
         if (sampled) {
             const float rc = clampf(r, -8.0f, 4.0f);
@@ -565,13 +597,13 @@ int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_
 }
 
 int launch_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, cudaStream_t st) {
-    text_fwd_kernel<<<s->B, HID, (s->Dt + HID) * sizeof(float), st>>>(w, Wt, Wc, s->Dt, s->E, tp, tl);
+    text_fwd_kernel<<<s->B, HID * TX_SPLIT, (s->Dt + (TX_SPLIT + 1) * HID) * sizeof(float), st>>>(w, Wt, Wc, s->Dt, s->E, tp, tl);
     MOEGAN_CHECK_LAUNCH("text_fwd_kernel");
     return MOEGAN_OK;
 }
 
 static size_t router_fwd_smem(int E) {
-    return (size_t)(2 * RT_KC * HID + 2 * RT_TOK * RT_KC + E * HID + 4 * 32) * sizeof(float) + 32 * sizeof(int);
+    return (size_t)(2 * RT_KC * HID + 2 * RT_TOK * RT_KC + E * HID + 8 * 32) * sizeof(float) + 32 * sizeof(int);
 }
 
 int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
@@ -613,7 +645,7 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
     const int nparts = router_bwd_dwc_parts(s);
     router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_part);
     MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
-    router_bwd_small_kernel<<<1 + s->B, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
+    router_bwd_small_kernel<<<1 + s->B + s->E, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
                                                      temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
                                                      reinterpret_cast<__nv_bfloat16*>(dtp_op), dtemperature);
     MOEGAN_CHECK_LAUNCH("router_bwd_small_kernel");
@@ -623,13 +655,13 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
 int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* dWt, const float* dWc,
                           const float* mu_f, const float* rho_f, const float* eps_f,
                           const float* mu_t, const float* rho_t, const float* eps_t,
-                          const float* mu_c, const float* rho_c, const float* eps_c, int sampled,
+                          const float* mu_c, const float* rho_c, const float* eps_c, int sampled, int f_splits,
                           const float* kl_out, const float* dkl,
                           float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c, cudaStream_t st) {
     const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
     const int blocks = ceil_div(n_f + n_t + n_c, 256 * 2);
     reparam_kl_bwd_kernel<<<blocks, 256, 0, st>>>(dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c,
-                                                  n_f, n_t, n_c, sampled, kl_out, dkl, dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c);
+                                                  n_f, n_t, n_c, f_splits, sampled, kl_out, dkl, dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c);
     MOEGAN_CHECK_LAUNCH("reparam_kl_bwd_kernel");
     return MOEGAN_OK;
 }

@@ -44,7 +44,7 @@ template <int BN> struct Cfg {
 };
 
 struct Tile {
-    int mb, nb, e;
+    int mb, nb, e, split;
     int nkb_pp;   // k-blocks per pass
     int row0;     // WGRAD: first reduction row of the expert
 };
@@ -52,7 +52,7 @@ struct Tile {
 template <int BN, int KIND>
 __device__ __forceinline__ int total_tiles(const GemmParams& p) {
     const int n_blocks = (p.N + BN - 1) / BN;
-    if (KIND == GEMM_WGRAD) return p.E * ((p.dimA + BM - 1) / BM) * n_blocks;
+    if (KIND == GEMM_WGRAD) return p.E * ((p.dimA + BM - 1) / BM) * n_blocks * (p.k_splits > 1 ? p.k_splits : 1);
     const int m_blocks = p.m_blocks_host >= 0 ? p.m_blocks_host : __ldg(p.plan + 0);
     return m_blocks * n_blocks;
 }
@@ -61,8 +61,12 @@ template <int BN, int KIND>
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
     Tile t;
     const int n_blocks = (p.N + BN - 1) / BN;
+    t.split = 0;
     if (KIND == GEMM_WGRAD) {
         const int mA = (p.dimA + BM - 1) / BM;
+        const int ks = p.k_splits > 1 ? p.k_splits : 1;
+        t.split = tile % ks;
+        tile /= ks;
         t.e = tile / (mA * n_blocks);
         const int rem = tile - t.e * (mA * n_blocks);
         t.mb = rem / n_blocks;
@@ -70,8 +74,11 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
         int r0, r1;
         if (p.k_rows_host >= 0) { r0 = 0; r1 = p.k_rows_host; }
         else { r0 = __ldg(p.plan + PLAN_OFF + t.e); r1 = __ldg(p.plan + PLAN_OFF + t.e + 1); }
-        t.row0 = r0;
-        t.nkb_pp = (r1 - r0 + BK - 1) / BK;
+        const int nkb_all = (r1 - r0 + BK - 1) / BK;
+        const int per = (nkb_all + ks - 1) / ks;                 // k-blocks per split
+        const int kb0 = min(t.split * per, nkb_all);
+        t.row0 = r0 + kb0 * BK;
+        t.nkb_pp = min(per, nkb_all - kb0);
     } else {
         t.mb = tile / n_blocks;
         t.nb = tile - t.mb * n_blocks;
@@ -255,7 +262,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             ptx::tc_fence_after();
             const int grow = t.mb * BM + row_in_tile;      // row inside the (expert's) output
             bool row_ok; long long out_row;
-            if (KIND == GEMM_WGRAD) { row_ok = grow < p.dimA; out_row = (long long)t.e * p.dimA + grow; }
+            if (KIND == GEMM_WGRAD) { row_ok = grow < p.dimA; out_row = ((long long)t.split * p.E + t.e) * p.dimA + grow; }
             else                    { row_ok = grow < p.out_rows_valid; out_row = grow; }
 #pragma unroll 1
             for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
@@ -291,25 +298,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
                     break;
                 case EPI_GELU_BF16: {
-                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out1) + out_row * p.ld_out1 + col0, v);
+                    if (p.out1 != nullptr) {
+                        float dg[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+                        for (int i = 0; i < 32; ++i) gelu_and_grad_fast(v[i], v[i], dg[i]);
+                        store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out1) + out_row * p.ld_out1 + col0, dg);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+                    }
                     store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
                     break;
                 }
                 case EPI_GELU_X3: {
-                    store32_f32(reinterpret_cast<float*>(p.out1) + out_row * p.ld_out1 + col0, v);
+                    if (p.out1 != nullptr) store32_f32(reinterpret_cast<float*>(p.out1) + out_row * p.ld_out1 + col0, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = gelu_erf<true>(v[i]);
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0;
                     store32_split(o, o + p.out_split_off, v);
                     break;
                 }
-                case EPI_DGELU_BF16: {
+                case EPI_MUL_BF16: {
                     float a[32];
                     load32_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ld_aux + col0, a);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad<false>(a[i]);
+                    for (int i = 0; i < 32; ++i) v[i] *= a[i];
                     store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
                     break;
                 }

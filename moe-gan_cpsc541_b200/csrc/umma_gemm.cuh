@@ -15,9 +15,9 @@ enum GemmEpilogue : int {
     EPI_BF16 = 1,       // out0 bf16 = acc
     EPI_BIAS_BF16 = 2,  // out0 bf16 = acc + bias[e, n]
     EPI_BIAS_F32 = 3,   // out0 fp32 = acc + bias[e, n]
-    EPI_GELU_BF16 = 4,  // pre = acc + bias;  out1 bf16 = pre;  out0 bf16 = gelu(pre)
+    EPI_GELU_BF16 = 4,  // pre = acc + bias;  out0 bf16 = gelu(pre);  out1 bf16 = gelu'(pre) (skipped when out1 == NULL)
     EPI_GELU_X3 = 5,    // pre = acc + bias;  out1 fp32 = pre;  out0 (hi | lo) = gelu(pre)
-    EPI_DGELU_BF16 = 6, // out0 bf16 = acc * gelu'(aux bf16)
+    EPI_MUL_BF16 = 6,   // out0 bf16 = acc * aux bf16        (aux = gelu'(pre) saved by EPI_GELU_BF16)
     EPI_DGELU_X3 = 7    // out0 (hi | lo) = acc * gelu'(aux fp32)
 };
 
@@ -38,6 +38,8 @@ struct GemmParams {
     int b_rows_per_expert;  // ROWS_BK: rows of B per expert (= N);  ROWS_BMN: K rows per expert
     int m_blocks_host;      // ROWS: >= 0 -> ungrouped, this many 128-row blocks, expert 0;  < 0 -> read plan
     int k_rows_host;        // WGRAD: >= 0 -> ungrouped, reduction over rows [0, k_rows_host);  < 0 -> read plan
+    int k_splits;           // WGRAD: split the reduction over this many CTAs; split s writes its partial to
+                            //        out0 + s * E * dimA * N (the consumer sums the partials).  0/1 = off
     int dimA;               // WGRAD: output rows per expert
     int E;                  // WGRAD: experts
     const int* plan;        // device plan array (see common.cuh)

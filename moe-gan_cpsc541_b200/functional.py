@@ -161,7 +161,7 @@ class MoEBlockFunction(torch.autograd.Function):
                     "moegan_dispatch_gather")
         # ---- K4: experts ----------------------------------------------------------------------------
         W1_op, b1s, W2_op, b2s = wcache.get(cfg, shape, w1, b1, w2, b2)
-        pre = torch.empty((m_cap, hid), dtype=act_dt, device=dev)
+        pre = torch.empty((m_cap, hid), dtype=act_dt, device=dev) if need_bwd else None   # gelu'(pre) (bf16) / pre (fp32)
         h_op = torch.empty((m_cap, S * hid), dtype=bf16, device=dev)
         y = torch.empty((m_cap, d), dtype=act_dt, device=dev)
         C.check(lib.moegan_ffn_fwd(shape, C.ptr(plan), C.ptr(a_op), C.ptr(W1_op), C.ptr(b1s), C.ptr(W2_op), C.ptr(b2s),
