@@ -253,8 +253,34 @@ def run_b200_arm(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), int(n1 - n0)
 
+    # The device-resident number replays ONE CUDA graph of the whole step (forward, backward, gradient all-reduce):
+    # the step is ~30 launches of 2-80 us each, so eager Python launch latency would otherwise be what is measured.
+    launch_mode = "eager"
+    step_value = step_device
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_device()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n_before = lib.moegan_debug_launch_count()
+            with torch.cuda.graph(graph):
+                step_device()
+            launches_per_graph = int(lib.moegan_debug_launch_count() - n_before)
+            step_value = graph.replay
+            launch_mode = "cuda_graph"
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
     with ClockSampler(local_rank) as clk:
-        total_ms, launches = timed(step_device, args.steps, max(args.warmup, 3))
+        total_ms, launches = timed(step_value, args.steps, max(args.warmup, 3))
+    if launch_mode == "cuda_graph":
+        launches = launches_per_graph * args.steps
     clocks = clk.summary()
     host_enqueue_ms = timed.host_ms / args.steps
     e2e_ms, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2))
@@ -305,7 +331,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(), "tokens_per_gpu": T, "l2": "256 MiB buffer zeroed between timed iterations",
-                       "parallelism": f"dp{world}" if world > 1 else "single", "router": "fp32", "experts": "bf16 in / fp32 acc (tcgen05)"},
+                       "parallelism": f"dp{world}" if world > 1 else "single", "launch": launch_mode, "router": "fp32", "experts": "bf16 in / fp32 acc (tcgen05)"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + w_host.numel() * 4), "d2h_bytes_per_step": 4},
@@ -330,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="moe_block")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

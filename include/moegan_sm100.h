@@ -185,6 +185,54 @@ int moegan_balance_loss_fwd(const float* load, int32_t E, int32_t T, float balan
 int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balance_weight, const float* dloss,
                             float* dload, void* stream);
 
+/* ---- whole block in one call ------------------------------------------------------------------ */
+/* The same pipeline as the calls above (sample+KL -> text -> router -> plan -> gather/convert -> experts ->
+ * combine, and its backward), enqueued by ONE call per direction with every intermediate carved out of ONE
+ * caller-owned workspace: this is what SparseMoE.forward uses, so the host cost per step is two FFI calls.
+ * Byte offsets of the intermediates inside the forward workspace (all 256-byte aligned): */
+typedef struct {
+    int64_t Wf, Wt, Wc, Wf_op, Wt_op, tp, tl, fp, raw, topk_idx, gates, chunk_counts, chunk_colsum, plan, chunk_base,
+            x_copy, a_op, row_token, row_gate, token_rows, pre, h_op, y, total;   /* -1 = not present */
+} moegan_block_layout;
+
+typedef struct {
+    const float* x;             /* [T,d] */
+    const float* w;             /* [B,Dt] */
+    const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;
+    const void* W1_op; const float* b1s; const void* W2_op; const float* b2s;   /* from moegan_prep_weights */
+    float annealing_factor;
+    int32_t sampled;            /* 1: training (weights sampled, KL computed) */
+    int32_t need_backward;      /* 1: keep what moegan_block_bwd needs */
+    float* out;                 /* [T,d] */
+    float* probs;               /* [T,E] */
+    float* load;                /* [E] */
+    float* kl_out;              /* [MOEGAN_KL_OUT_FLOATS] */
+    void* workspace; int64_t workspace_bytes;
+} moegan_block_fwd_args;
+
+typedef struct {
+    const void* fwd_workspace;  /* the forward call's workspace (need_backward = 1), untouched since */
+    const float* w;
+    const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;
+    const void* W1_op; const void* W2_op; const float* kl_out;
+    const float* dout;          /* [T,d] */
+    const float* dkl;           /* [1] or NULL */
+    const float* dprobs;        /* [T,E] or NULL */
+    const float* dload;         /* [E] or NULL */
+    float annealing_factor;
+    int32_t sampled;
+    float* dx;                  /* [T,d] */
+    float* dw;                  /* [B,Dt]  (NULL in hard mode) */
+    float *dmu_f, *drho_f, *dmu_t, *drho_t, *dmu_c, *drho_c, *dtemperature;   /* NULL in hard mode */
+    float *dW1, *db1, *dW2, *db2;   /* [E,4d,d] [E,4d] [E,d,4d] [E,d] */
+    void* workspace; int64_t workspace_bytes;
+} moegan_block_bwd_args;
+
+int64_t moegan_block_fwd_workspace(const moegan_shape* s, int32_t need_backward, moegan_block_layout* layout /* may be NULL */);
+int64_t moegan_block_bwd_workspace(const moegan_shape* s);
+int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void* stream);
+int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void* stream);
+
 /* ---- test / bench hook ---------------------------------------------------------------------- */
 /* Plain (ungrouped) GEMM on the same tcgen05 kernel, fp32 out:  C[M,N] = op(A) * op(B).
  * kind 0: A [M,S*K] K-major, B [N,S*K] K-major.   kind 1: A [M,S*K] K-major, B [K,S*N] (N contiguous).

@@ -26,6 +26,35 @@ class Shape(ctypes.Structure):
                 ("T", "d", "Dt", "E", "k", "B", "tokens_per_sample", "precision", "dense", "hard", "m_cap")]
 
 
+class BlockLayout(ctypes.Structure):
+    """moegan_block_layout: byte offsets inside the forward workspace (-1 = absent)."""
+    _fields_ = [(n, c_int64) for n in
+                ("Wf", "Wt", "Wc", "Wf_op", "Wt_op", "tp", "tl", "fp", "raw", "topk_idx", "gates", "chunk_counts", "chunk_colsum",
+                 "plan", "chunk_base", "x_copy", "a_op", "row_token", "row_gate", "token_rows", "pre", "h_op", "y", "total")]
+
+
+class BlockFwdArgs(ctypes.Structure):
+    """moegan_block_fwd_args."""
+    _fields_ = ([(n, c_void_p) for n in
+                 ("x", "w", "mu_f", "rho_f", "eps_f", "mu_t", "rho_t", "eps_t", "mu_c", "rho_c", "eps_c", "temperature",
+                  "W1_op", "b1s", "W2_op", "b2s")]
+                + [("annealing_factor", c_float), ("sampled", c_int32), ("need_backward", c_int32)]
+                + [(n, c_void_p) for n in ("out", "probs", "load", "kl_out", "workspace")]
+                + [("workspace_bytes", c_int64)])
+
+
+class BlockBwdArgs(ctypes.Structure):
+    """moegan_block_bwd_args."""
+    _fields_ = ([(n, c_void_p) for n in
+                 ("fwd_workspace", "w", "mu_f", "rho_f", "eps_f", "mu_t", "rho_t", "eps_t", "mu_c", "rho_c", "eps_c", "temperature",
+                  "W1_op", "W2_op", "kl_out", "dout", "dkl", "dprobs", "dload")]
+                + [("annealing_factor", c_float), ("sampled", c_int32)]
+                + [(n, c_void_p) for n in
+                   ("dx", "dw", "dmu_f", "drho_f", "dmu_t", "drho_t", "dmu_c", "drho_c", "dtemperature", "dW1", "db1", "dW2", "db2",
+                    "workspace")]
+                + [("workspace_bytes", c_int64)])
+
+
 _P = c_void_p
 _SP = POINTER(Shape)
 
@@ -51,6 +80,10 @@ SIGNATURES = {
     "moegan_router_bwd": (c_int32, [_SP] + [_P] * 16 + [c_float, c_int32] + [_P] * 9 + [_P] * 2 + [_P] * 9 + [_P, c_int64] + [_P]),
     "moegan_balance_loss_fwd": (c_int32, [_P, c_int32, c_int32, c_float, _P, _P]),
     "moegan_balance_loss_bwd": (c_int32, [_P, c_int32, c_int32, c_float, _P, _P, _P]),
+    "moegan_block_fwd_workspace": (c_int64, [_SP, c_int32, POINTER(BlockLayout)]),
+    "moegan_block_bwd_workspace": (c_int64, [_SP]),
+    "moegan_block_fwd": (c_int32, [_SP, POINTER(BlockFwdArgs), _P]),
+    "moegan_block_bwd": (c_int32, [_SP, POINTER(BlockBwdArgs), _P]),
     "moegan_umma_gemm": (c_int32, [c_int32] * 5 + [_P] * 3 + [_P]),
     "moegan_debug_set_mn_desc": (c_int32, [c_int32] * 3),
     "moegan_debug_launch_count": (c_int64, []),

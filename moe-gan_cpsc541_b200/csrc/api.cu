@@ -481,6 +481,137 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
     return launch_balance_loss(load, E, T, balance_weight, dloss, nullptr, dload, (cudaStream_t)stream);
 }
 
+// ---- whole block in one call -------------------------------------------------------------------------
+static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layout* L) {
+    const size_t S = s->precision == 1 ? 2 : 1, H = MOEGAN_ROUTER_HID;
+    const size_t T = s->T, d = s->d, Dt = s->Dt, E = s->E, k = s->k, B = s->B, hid = 4 * d, m_cap = s->m_cap;
+    const size_t nch = (T + MOEGAN_CHUNK - 1) / MOEGAN_CHUNK > 0 ? (T + MOEGAN_CHUNK - 1) / MOEGAN_CHUNK : 1;
+    const size_t act = s->precision == 1 ? 4 : 2;
+    size_t o = 0;
+    auto take = [&](size_t bytes, bool present) -> int64_t {
+        if (!present) return -1;
+        const size_t at = o;
+        o = align256(o + (bytes > 0 ? bytes : 1));
+        return (int64_t)at;
+    };
+    L->Wf = take(d * H * 4, true);
+    L->Wt = take(Dt * H * 4, true);
+    L->Wc = take(2 * H * E * 4, true);
+    L->Wf_op = take(d * S * H * 2, need_bwd);
+    L->Wt_op = take(Dt * S * H * 2, need_bwd);
+    L->tp = take(B * H * 4, true);
+    L->tl = take(B * E * 4, true);
+    L->fp = take(T * H * 4, need_bwd);
+    L->raw = take(T * E * 4, true);
+    L->topk_idx = take(T * k * 4, true);
+    L->gates = take(T * k * 4, true);
+    L->chunk_counts = take(nch * E * 4, true);
+    L->chunk_colsum = take(nch * E * 4, true);
+    L->plan = take((size_t)moegan_plan_ints(s->m_cap) * 4, true);
+    L->chunk_base = take(nch * E * 4, true);
+    L->x_copy = take(T * S * d * 2, need_bwd || s->dense);
+    L->a_op = s->dense ? L->x_copy : take(m_cap * S * d * 2, true);
+    L->row_token = take(m_cap * 4, !s->dense);
+    L->row_gate = take(m_cap * 4, !s->dense);
+    L->token_rows = take(T * k * 4, !s->dense);
+    L->pre = take(m_cap * hid * act, need_bwd);
+    L->h_op = take(m_cap * S * hid * 2, true);
+    L->y = take(m_cap * d * act, true);
+    L->total = (int64_t)o;
+}
+
+struct BlockBwdWs { size_t dy_op, dgate_row, dpre_op, dx_rows, dx_router, router_ws, total; };
+static BlockBwdWs block_bwd_layout(const moegan_shape* s) {
+    const size_t S = s->precision == 1 ? 2 : 1, d = s->d, hid = 4 * (size_t)s->d, m_cap = s->m_cap;
+    const size_t act = s->precision == 1 ? 4 : 2;
+    BlockBwdWs w;
+    size_t o = 0;
+    w.dy_op = o;     o = align256(o + m_cap * S * d * 2);
+    w.dgate_row = o; o = align256(o + m_cap * 4);
+    w.dpre_op = o;   o = align256(o + m_cap * S * hid * 2);
+    w.dx_rows = o;   o = align256(o + m_cap * d * act);
+    w.dx_router = o; o = align256(o + (size_t)s->T * d * 4);
+    w.router_ws = o; o = align256(o + router_bwd_layout(s).total);
+    w.total = o;
+    return w;
+}
+
+int64_t moegan_block_fwd_workspace(const moegan_shape* s, int32_t need_backward, moegan_block_layout* layout) {
+    if (validate_shape(s) != MOEGAN_OK) return -1;
+    moegan_block_layout L;
+    block_layout(s, need_backward, &L);
+    if (layout != nullptr) *layout = L;
+    return L.total;
+}
+int64_t moegan_block_bwd_workspace(const moegan_shape* s) {
+    if (validate_shape(s) != MOEGAN_OK) return -1;
+    return (int64_t)block_bwd_layout(s).total;
+}
+
+int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(a);
+    REQ_PTR(a->x); REQ_PTR(a->w); REQ_PTR(a->out); REQ_PTR(a->probs); REQ_PTR(a->load); REQ_PTR(a->kl_out); REQ_PTR(a->workspace);
+    moegan_block_layout L;
+    block_layout(s, a->need_backward, &L);
+    MOEGAN_REQUIRE(a->workspace_bytes >= L.total, MOEGAN_ERR_BAD_SHAPE, "block_fwd: workspace %lld < required %lld bytes",
+                   (long long)a->workspace_bytes, (long long)L.total);
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, MOEGAN_ERR_MISALIGNED, "block_fwd: workspace must be 256-byte aligned");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+    auto P = [&](int64_t off) -> void* { return off < 0 ? nullptr : ws + off; };
+    auto F = [&](int64_t off) -> float* { return reinterpret_cast<float*>(P(off)); };
+    auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
+    if (s->T == 0) return MOEGAN_OK;
+    RUN(moegan_router_sample_kl_fwd(s, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c, a->sampled,
+                                    F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), a->kl_out, stream));
+    RUN(moegan_router_text_fwd(s, a->w, F(L.Wt), F(L.Wc), F(L.tp), F(L.tl), stream));
+    RUN(moegan_router_fwd(s, a->x, F(L.Wf), F(L.Wc), F(L.tl), a->temperature, a->annealing_factor, F(L.fp), F(L.raw), a->probs,
+                          I(L.topk_idx), F(L.gates), I(L.chunk_counts), F(L.chunk_colsum), stream));
+    RUN(moegan_dispatch_plan(s, I(L.chunk_counts), F(L.chunk_colsum), I(L.plan), I(L.chunk_base), a->load, stream));
+    if (s->dense) {
+        RUN(moegan_convert_tokens(s, a->x, P(L.x_copy), stream));
+    } else {
+        RUN(moegan_dispatch_gather(s, a->x, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), P(L.a_op), P(L.x_copy),
+                                   I(L.row_token), F(L.row_gate), I(L.token_rows), stream));
+    }
+    RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
+    RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->out, stream));
+    return MOEGAN_OK;
+}
+
+int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void* stream) {
+    CHECK_SHAPE(s);
+    REQ_PTR(a);
+    REQ_PTR(a->fwd_workspace); REQ_PTR(a->dout); REQ_PTR(a->dx); REQ_PTR(a->workspace);
+    MOEGAN_REQUIRE(s->T > 0, MOEGAN_ERR_BAD_SHAPE, "block_bwd: T must be positive");
+    moegan_block_layout L;
+    block_layout(s, 1, &L);
+    const BlockBwdWs W = block_bwd_layout(s);
+    MOEGAN_REQUIRE(a->workspace_bytes >= (int64_t)W.total, MOEGAN_ERR_BAD_SHAPE, "block_bwd: workspace %lld < required %lld bytes",
+                   (long long)a->workspace_bytes, (long long)W.total);
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, MOEGAN_ERR_MISALIGNED, "block_bwd: workspace must be 256-byte aligned");
+    uint8_t* fw = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(a->fwd_workspace));
+    uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+    auto P = [&](int64_t off) -> void* { return off < 0 ? nullptr : fw + off; };
+    auto F = [&](int64_t off) -> float* { return reinterpret_cast<float*>(P(off)); };
+    auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
+    float* dgate_row = reinterpret_cast<float*>(ws + W.dgate_row);
+    float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
+    RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, stream));
+    RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, ws + W.dpre_op, ws + W.dx_rows,
+                       a->dW1, a->db1, a->dW2, a->db2, stream));
+    if (!s->hard) {
+        RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
+                              I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
+                              a->sampled, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c,
+                              a->kl_out, a->sampled ? a->dkl : nullptr,
+                              a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
+                              ws + W.router_ws, (int64_t)router_bwd_layout(s).total, stream));
+    }
+    RUN(moegan_uncombine_bwd(s, ws + W.dx_rows, I(L.token_rows), dx_router, a->dx, stream));
+    return MOEGAN_OK;
+}
+
 // ---- test / bench hooks ----------------------------------------------------------------------------
 int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* C, void* stream) {
     REQ_PTR(A); REQ_PTR(B); REQ_PTR(C);

@@ -3,12 +3,14 @@ KL and balance-load reductions) as ONE torch.autograd.Function, and the balance 
 
 Reference path replaced: SparseMoE.forward + BayesianRouter.forward / kl_divergence + SparseExpertFFN.forward
 (moegan/t2i_moe_gan.py:249-491) and AuroraGANLoss.moe_balance_loss (:951-1000).
-PyTorch is used here only for device memory, the current stream and autograd bookkeeping.
+PyTorch is used here only for device memory, the current stream and autograd bookkeeping: each direction is
+ONE FFI call (moegan_block_fwd / moegan_block_bwd) working out of ONE workspace allocation.
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -41,8 +43,33 @@ class MoEConfig:
                             self.precision, self.dense, self.hard)
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+class _Plan:
+    """Per-configuration constants (shape struct, workspace sizes, layout), computed once."""
+    __slots__ = ("shape", "fwd_bytes", "fwd_bytes_nobwd", "bwd_bytes", "layout", "layout_nobwd")
+
+
+_PLANS: Dict[tuple, _Plan] = {}
+
+
+def _plan_for(cfg: MoEConfig) -> _Plan:
+    key = (cfg.B, cfg.tokens_per_sample, cfg.d, cfg.Dt, cfg.E, cfg.k, cfg.dense, cfg.hard, cfg.precision)
+    p = _PLANS.get(key)
+    if p is None:
+        lib = C.lib()
+        p = _Plan()
+        p.shape = cfg.shape()
+        p.layout, p.layout_nobwd = C.BlockLayout(), C.BlockLayout()
+        p.fwd_bytes = int(lib.moegan_block_fwd_workspace(p.shape, 1, ctypes.byref(p.layout)))
+        p.fwd_bytes_nobwd = int(lib.moegan_block_fwd_workspace(p.shape, 0, ctypes.byref(p.layout_nobwd)))
+        p.bwd_bytes = int(lib.moegan_block_bwd_workspace(p.shape))
+        if min(p.fwd_bytes, p.fwd_bytes_nobwd, p.bwd_bytes) < 0:
+            raise RuntimeError("moegan: unsupported shape: " + C.last_error())
+        _PLANS[key] = p
+    return p
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -54,17 +81,20 @@ class WeightCache:
     """bf16 operand copies of the expert weights, rebuilt only when a parameter changed (optimizer step).
 
     The reference re-casts every nn.Linear weight on every autocast forward; here both generator forwards
-    of a train step (D-step under no_grad, G-step with grad) share one conversion.
+    of a train step (D-step under no_grad, G-step with grad) share one conversion.  While a CUDA graph is
+    being captured the conversion is always enqueued (a replay must re-convert the then-current weights).
     """
 
     def __init__(self):
         self.key = None
         self.bufs = None
+        self.capture_bufs = None
 
     def get(self, cfg: MoEConfig, shape: C.Shape, w1: Sequence[torch.Tensor], b1, w2, b2):
+        capturing = torch.cuda.is_current_stream_capturing()
         key = (cfg.precision, cfg.d, cfg.E,
                tuple((p.data_ptr(), p._version) for group in (w1, b1, w2, b2) for p in group))
-        if key == self.key and self.bufs is not None:
+        if not capturing and key == self.key and self.bufs is not None:
             return self.bufs
         dev = w1[0].device
         S = 2 if cfg.precision == 1 else 1
@@ -74,184 +104,144 @@ class WeightCache:
         b1s = torch.empty((cfg.E, hid), dtype=torch.float32, device=dev)
         b2s = torch.empty((cfg.E, cfg.d), dtype=torch.float32, device=dev)
         rc = C.lib().moegan_prep_weights(shape, C.ptr_array(w1), C.ptr_array(b1), C.ptr_array(w2), C.ptr_array(b2),
-                                         C.ptr(W1_op), C.ptr(b1s), C.ptr(W2_op), C.ptr(b2s), _stream())
+                                         C.ptr(W1_op), C.ptr(b1s), C.ptr(W2_op), C.ptr(b2s), C.c_void_p(_stream_ptr()))
         C.check(rc, "moegan_prep_weights")
-        self.key, self.bufs = key, (W1_op, b1s, W2_op, b2s)
-        return self.bufs
+        bufs = (W1_op, b1s, W2_op, b2s)
+        if capturing:
+            self.capture_bufs = bufs
+        else:
+            self.key, self.bufs = key, bufs
+        return bufs
 
 
-class _Saved:
-    """Intermediate device buffers kept for backward (plain attributes, never autograd-tracked)."""
-    pass
+def _dp(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_I32_VIEWS = ("topk_idx", "chunk_counts", "plan", "chunk_base", "row_token", "token_rows")
+
+
+def workspace_views(ws: torch.Tensor, layout: "C.BlockLayout", cfg: MoEConfig) -> dict:
+    """Typed views of the routing state inside a forward workspace (tests / diagnostics only)."""
+    T, E, k, m_cap = cfg.T, cfg.E, cfg.k, C.m_cap(cfg.T, cfg.E, cfg.k, cfg.dense)
+    shapes = {"raw": (T, E), "gates": (T, k), "topk_idx": (T, k), "token_rows": (T, k), "row_token": (m_cap,),
+              "row_gate": (m_cap,), "plan": (int(C.lib().moegan_plan_ints(m_cap)),)}
+    out = {}
+    for name, shp in shapes.items():
+        off = getattr(layout, name)
+        if off < 0:
+            out[name] = None
+            continue
+        n = 1
+        for v in shp:
+            n *= v
+        dt = torch.int32 if name in _I32_VIEWS else torch.float32
+        out[name] = ws[off:off + 4 * n].view(dt).view(shp)
+    return out
 
 
 class MoEBlockFunction(torch.autograd.Function):
     """(x_tok [T,d], w [B,Dt], eps x3, router params x7, expert params x4E) -> (out [T,d], kl [], probs [T,E], load [E])."""
 
+    _last = None   # (workspace, layout, cfg) of the most recent forward, for tests / diagnostics
+
+    @staticmethod
+    def last_aux() -> dict:
+        ws, layout, cfg = MoEBlockFunction._last
+        return workspace_views(ws, layout, cfg)
+
     @staticmethod
     def forward(ctx, cfg: MoEConfig, wcache: WeightCache, x_tok, w, eps_f, eps_t, eps_c,
                 mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature, *expert_params):
         lib = C.lib()
-        E, d, Dt, T, B, k = cfg.E, cfg.d, cfg.Dt, cfg.T, cfg.B, cfg.k
-        for name, t in (("x", x_tok), ("w", w), ("feature_mu", mu_f), ("temperature", temperature)):
-            _require_cuda(t, name)
+        E, d, T = cfg.E, cfg.d, cfg.T
+        _require_cuda(x_tok, "x"); _require_cuda(w, "w"); _require_cuda(mu_f, "router.feature_mu")
         dev = x_tok.device
-        f32, bf16, i32 = torch.float32, torch.bfloat16, torch.int32
+        f32 = torch.float32
         x_tok = x_tok.contiguous().float()
         w = w.contiguous().float()
         router_params = [p.contiguous() for p in (mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature)]
-        mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature = router_params
-        w1 = [expert_params[4 * e + 0] for e in range(E)]
-        b1 = [expert_params[4 * e + 1] for e in range(E)]
-        w2 = [expert_params[4 * e + 2] for e in range(E)]
-        b2 = [expert_params[4 * e + 3] for e in range(E)]
-        shape = cfg.shape()
-        st = _stream()
-        S = 2 if cfg.precision == 1 else 1
-        hid = 4 * d
-        m_cap = shape.m_cap
-        nchunks = (T + C.CHUNK - 1) // C.CHUNK
+        w1 = expert_params[0::4]; b1 = expert_params[1::4]; w2 = expert_params[2::4]; b2 = expert_params[3::4]
+        plan = _plan_for(cfg)
         need_bwd = cfg.need_backward
-        act_dt = f32 if cfg.precision == 1 else bf16
+        W1_op, b1s, W2_op, b2s = wcache.get(cfg, plan.shape, w1, b1, w2, b2)
 
-        sv = _Saved()
-        # ---- K1: sampled router weights + KL --------------------------------------------------------
-        Wf = torch.empty((d, HID), dtype=f32, device=dev)
-        Wt = torch.empty((Dt, HID), dtype=f32, device=dev)
-        Wc = torch.empty((2 * HID, E), dtype=f32, device=dev)
-        Wf_op = torch.empty((d, S * HID), dtype=bf16, device=dev) if need_bwd else None
-        Wt_op = torch.empty((Dt, S * HID), dtype=bf16, device=dev) if need_bwd else None
-        kl_out = torch.empty((C.KL_OUT_FLOATS,), dtype=f32, device=dev)
-        C.check(lib.moegan_router_sample_kl_fwd(shape, C.ptr(mu_f), C.ptr(rho_f), C.ptr(eps_f), C.ptr(mu_t), C.ptr(rho_t),
-                                                C.ptr(eps_t), C.ptr(mu_c), C.ptr(rho_c), C.ptr(eps_c), 1 if cfg.sampled else 0,
-                                                C.ptr(Wf), C.ptr(Wt), C.ptr(Wc), C.ptr(Wf_op), C.ptr(Wt_op), C.ptr(kl_out), st),
-                "moegan_router_sample_kl_fwd")
-        # ---- K2: router -----------------------------------------------------------------------------
-        tp = torch.empty((B, HID), dtype=f32, device=dev)
-        tl = torch.empty((B, E), dtype=f32, device=dev)
-        C.check(lib.moegan_router_text_fwd(shape, C.ptr(w), C.ptr(Wt), C.ptr(Wc), C.ptr(tp), C.ptr(tl), st), "moegan_router_text_fwd")
-        fp = torch.empty((T, HID), dtype=f32, device=dev) if need_bwd else None
-        raw = torch.empty((T, E), dtype=f32, device=dev)
-        probs = torch.empty((T, E), dtype=f32, device=dev)
-        topk_idx = torch.empty((T, k), dtype=i32, device=dev)
-        gates = torch.empty((T, k), dtype=f32, device=dev)
-        chunk_counts = torch.empty((max(nchunks, 1), E), dtype=i32, device=dev)
-        chunk_colsum = torch.empty((max(nchunks, 1), E), dtype=f32, device=dev)
-        C.check(lib.moegan_router_fwd(shape, C.ptr(x_tok), C.ptr(Wf), C.ptr(Wc), C.ptr(tl), C.ptr(temperature),
-                                      float(cfg.annealing_factor), C.ptr(fp), C.ptr(raw), C.ptr(probs), C.ptr(topk_idx), C.ptr(gates),
-                                      C.ptr(chunk_counts), C.ptr(chunk_colsum), st), "moegan_router_fwd")
-        # ---- K3: dispatch ---------------------------------------------------------------------------
-        plan = torch.empty((int(lib.moegan_plan_ints(m_cap)),), dtype=i32, device=dev)
-        chunk_base = torch.empty((max(nchunks, 1), E), dtype=i32, device=dev)
-        load = torch.empty((E,), dtype=f32, device=dev)
-        C.check(lib.moegan_dispatch_plan(shape, C.ptr(chunk_counts), C.ptr(chunk_colsum), C.ptr(plan), C.ptr(chunk_base), C.ptr(load), st),
-                "moegan_dispatch_plan")
-        x_copy = torch.empty((T, S * d), dtype=bf16, device=dev) if (need_bwd or cfg.dense) else None
-        row_token = row_gate = token_rows = None
-        if cfg.dense:
-            C.check(lib.moegan_convert_tokens(shape, C.ptr(x_tok), C.ptr(x_copy), st), "moegan_convert_tokens")
-            a_op = x_copy
-        else:
-            a_op = torch.empty((m_cap, S * d), dtype=bf16, device=dev)
-            row_token = torch.empty((m_cap,), dtype=i32, device=dev)
-            row_gate = torch.empty((m_cap,), dtype=f32, device=dev)
-            token_rows = torch.empty((T, k), dtype=i32, device=dev)
-            C.check(lib.moegan_dispatch_gather(shape, C.ptr(x_tok), C.ptr(topk_idx), C.ptr(gates), C.ptr(plan), C.ptr(chunk_base),
-                                               C.ptr(a_op), C.ptr(x_copy), C.ptr(row_token), C.ptr(row_gate), C.ptr(token_rows), st),
-                    "moegan_dispatch_gather")
-        # ---- K4: experts ----------------------------------------------------------------------------
-        W1_op, b1s, W2_op, b2s = wcache.get(cfg, shape, w1, b1, w2, b2)
-        pre = torch.empty((m_cap, hid), dtype=act_dt, device=dev) if need_bwd else None   # gelu'(pre) (bf16) / pre (fp32)
-        h_op = torch.empty((m_cap, S * hid), dtype=bf16, device=dev)
-        y = torch.empty((m_cap, d), dtype=act_dt, device=dev)
-        C.check(lib.moegan_ffn_fwd(shape, C.ptr(plan), C.ptr(a_op), C.ptr(W1_op), C.ptr(b1s), C.ptr(W2_op), C.ptr(b2s),
-                                   C.ptr(pre), C.ptr(h_op), C.ptr(y), st), "moegan_ffn_fwd")
-        # ---- K5: combine ----------------------------------------------------------------------------
+        ws = torch.empty((plan.fwd_bytes if need_bwd else plan.fwd_bytes_nobwd,), dtype=torch.uint8, device=dev)
         out = torch.empty((T, d), dtype=f32, device=dev)
-        C.check(lib.moegan_combine_fwd(shape, C.ptr(y), C.ptr(gates), C.ptr(token_rows), C.ptr(out), st), "moegan_combine_fwd")
+        probs = torch.empty((T, E), dtype=f32, device=dev)
+        small = torch.empty((E + C.KL_OUT_FLOATS,), dtype=f32, device=dev)     # [load | kl_out]
 
-        kl = kl_out[0].clone() if cfg.sampled else torch.zeros((), dtype=f32, device=dev)   # eval: tensor(0.) (:489)
+        a = C.BlockFwdArgs()
+        a.x, a.w = x_tok.data_ptr(), w.data_ptr()
+        (a.mu_f, a.rho_f, a.mu_t, a.rho_t, a.mu_c, a.rho_c, a.temperature) = [p.data_ptr() for p in router_params]
+        a.eps_f, a.eps_t, a.eps_c = _dp(eps_f), _dp(eps_t), _dp(eps_c)
+        a.W1_op, a.b1s, a.W2_op, a.b2s = W1_op.data_ptr(), b1s.data_ptr(), W2_op.data_ptr(), b2s.data_ptr()
+        a.annealing_factor = float(cfg.annealing_factor)
+        a.sampled = 1 if cfg.sampled else 0
+        a.need_backward = 1 if need_bwd else 0
+        a.out, a.probs = out.data_ptr(), probs.data_ptr()
+        a.load = small.data_ptr()
+        a.kl_out = small.data_ptr() + 4 * E
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        C.check(lib.moegan_block_fwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_fwd")
 
+        load = small[:E]
+        kl = small[E] if cfg.sampled else torch.zeros((), dtype=f32, device=dev)   # eval: tensor(0.) (:489)
         if need_bwd:
-            sv.shape, sv.cfg = shape, cfg
-            sv.x_copy, sv.w, sv.Wf, sv.Wt, sv.Wc, sv.Wf_op, sv.Wt_op = x_copy, w, Wf, Wt, Wc, Wf_op, Wt_op
-            sv.fp, sv.tp, sv.raw, sv.topk_idx, sv.gates = fp, tp, raw, topk_idx, gates
-            sv.plan, sv.a_op, sv.row_token, sv.row_gate, sv.token_rows = plan, a_op, row_token, row_gate, token_rows
-            sv.W1_op, sv.W2_op, sv.pre, sv.h_op, sv.y, sv.kl_out = W1_op, W2_op, pre, h_op, y, kl_out
-            sv.eps = (eps_f, eps_t, eps_c)
-            sv.router_params = router_params
-            ctx.sv = sv
-        # internal routing state for tests / diagnostics (not part of the reference interface)
-        ctx_aux = {"topk_idx": topk_idx, "gates": gates, "plan": plan, "token_rows": token_rows, "row_token": row_token, "raw": raw}
-        MoEBlockFunction.last_aux = ctx_aux
+            ctx.cfg, ctx.plan = cfg, plan
+            ctx.ws, ctx.small = ws, small
+            ctx.w = w
+            ctx.eps = (eps_f, eps_t, eps_c)
+            ctx.router_params = router_params
+            ctx.wops = (W1_op, W2_op)
+        MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
         return out, kl, probs, load
 
     @staticmethod
     def backward(ctx, dout, dkl, dprobs, dload):
         lib = C.lib()
-        sv = ctx.sv
-        cfg, shape = sv.cfg, sv.shape
+        cfg, plan = ctx.cfg, ctx.plan
         E, d, Dt, T, B = cfg.E, cfg.d, cfg.Dt, cfg.T, cfg.B
-        dev = sv.w.device
-        f32, bf16 = torch.float32, torch.bfloat16
-        S = 2 if cfg.precision == 1 else 1
+        dev = ctx.w.device
+        f32 = torch.float32
         hid = 4 * d
-        m_cap = shape.m_cap
-        act_dt = f32 if cfg.precision == 1 else bf16
-        st = _stream()
         dout = torch.zeros((T, d), dtype=f32, device=dev) if dout is None else dout.contiguous().float()
         dprobs = None if dprobs is None else dprobs.contiguous().float()
         dload = None if dload is None else dload.contiguous().float()
         dkl = None if dkl is None else dkl.reshape(1).contiguous().float()
 
-        # B1: combine backward
-        dy_op = torch.empty((m_cap, S * d), dtype=bf16, device=dev)
-        dgate_row = torch.empty((m_cap,), dtype=f32, device=dev)
-        C.check(lib.moegan_combine_bwd(shape, C.ptr(sv.plan), C.ptr(dout), C.ptr(sv.y), C.ptr(sv.row_token), C.ptr(sv.row_gate),
-                                       C.ptr(sv.gates), C.ptr(dy_op), C.ptr(dgate_row), st), "moegan_combine_bwd")
-        # B2: experts backward
-        dpre_op = torch.empty((m_cap, S * hid), dtype=bf16, device=dev)
-        dx_rows = torch.empty((m_cap, d), dtype=act_dt, device=dev)
+        ws_b = torch.empty((plan.bwd_bytes,), dtype=torch.uint8, device=dev)
+        dx = torch.empty((T, d), dtype=f32, device=dev)
         dW1 = torch.empty((E, hid, d), dtype=f32, device=dev)
         db1 = torch.empty((E, hid), dtype=f32, device=dev)
         dW2 = torch.empty((E, d, hid), dtype=f32, device=dev)
         db2 = torch.empty((E, d), dtype=f32, device=dev)
-        C.check(lib.moegan_ffn_bwd(shape, C.ptr(sv.plan), C.ptr(sv.a_op), C.ptr(sv.W1_op), C.ptr(sv.W2_op), C.ptr(sv.pre), C.ptr(sv.h_op),
-                                   C.ptr(dy_op), C.ptr(dpre_op), C.ptr(dx_rows), C.ptr(dW1), C.ptr(db1), C.ptr(dW2), C.ptr(db2), st),
-                "moegan_ffn_bwd")
-        # B3-B6: router backward
+        a = C.BlockBwdArgs()
+        a.fwd_workspace = ctx.ws.data_ptr()
+        a.w = ctx.w.data_ptr()
+        (a.mu_f, a.rho_f, a.mu_t, a.rho_t, a.mu_c, a.rho_c, a.temperature) = [p.data_ptr() for p in ctx.router_params]
+        a.eps_f, a.eps_t, a.eps_c = [_dp(e) for e in ctx.eps]
+        a.W1_op, a.W2_op = ctx.wops[0].data_ptr(), ctx.wops[1].data_ptr()
+        a.kl_out = ctx.small.data_ptr() + 4 * E
+        a.dout, a.dkl, a.dprobs, a.dload = dout.data_ptr(), _dp(dkl), _dp(dprobs), _dp(dload)
+        a.annealing_factor = float(cfg.annealing_factor)
+        a.sampled = 1 if cfg.sampled else 0
+        a.dx = dx.data_ptr()
+        a.dW1, a.db1, a.dW2, a.db2 = dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), db2.data_ptr()
         router_grads = [None] * 7
-        dx_router = None
         dw = None
         if not cfg.hard:
-            mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature = sv.router_params
-            g = [torch.empty_like(p) for p in sv.router_params]
-            dx_router = torch.empty((T, d), dtype=f32, device=dev)
+            sizes = [p.numel() for p in ctx.router_params]
+            flat = torch.empty((sum(sizes),), dtype=f32, device=dev)
+            router_grads = [g.view(p.shape) for g, p in zip(flat.split(sizes), ctx.router_params)]
             dw = torch.empty((B, Dt), dtype=f32, device=dev)
-            ws_bytes = int(lib.moegan_router_bwd_workspace_bytes(shape))
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-            eps_f, eps_t, eps_c = sv.eps
-            C.check(lib.moegan_router_bwd(
-                shape, C.ptr(sv.x_copy), C.ptr(sv.w), C.ptr(sv.Wf), C.ptr(sv.Wt), C.ptr(sv.Wc), C.ptr(sv.Wf_op), C.ptr(sv.Wt_op),
-                C.ptr(sv.fp), C.ptr(sv.tp), C.ptr(sv.raw), C.ptr(sv.topk_idx), C.ptr(sv.token_rows), C.ptr(dgate_row),
-                C.ptr(dprobs), C.ptr(dload), C.ptr(temperature), float(cfg.annealing_factor), 1 if cfg.sampled else 0,
-                C.ptr(mu_f), C.ptr(rho_f), C.ptr(eps_f), C.ptr(mu_t), C.ptr(rho_t), C.ptr(eps_t), C.ptr(mu_c), C.ptr(rho_c), C.ptr(eps_c),
-                C.ptr(sv.kl_out), C.ptr(dkl if cfg.sampled else None),
-                C.ptr(g[0]), C.ptr(g[1]), C.ptr(g[2]), C.ptr(g[3]), C.ptr(g[4]), C.ptr(g[5]), C.ptr(g[6]),
-                C.ptr(dx_router), C.ptr(dw), C.ptr(ws), ws_bytes, st), "moegan_router_bwd")
-            router_grads = g
-        # un-permute + router dx
-        dx = torch.empty((T, d), dtype=f32, device=dev)
-        C.check(lib.moegan_uncombine_bwd(shape, C.ptr(dx_rows), C.ptr(sv.token_rows), C.ptr(dx_router), C.ptr(dx), st),
-                "moegan_uncombine_bwd")
-        expert_grads = []
-        for e in range(E):
-            expert_grads += [dW1[e], db1[e], dW2[e], db2[e]]
-        ctx.sv = None
+            a.dw = dw.data_ptr()
+            (a.dmu_f, a.drho_f, a.dmu_t, a.drho_t, a.dmu_c, a.drho_c, a.dtemperature) = [g.data_ptr() for g in router_grads]
+        a.workspace, a.workspace_bytes = ws_b.data_ptr(), ws_b.numel()
+        C.check(lib.moegan_block_bwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_bwd")
+        expert_grads = [t for quad in zip(dW1.unbind(0), db1.unbind(0), dW2.unbind(0), db2.unbind(0)) for t in quad]
+        ctx.ws = None
         return (None, None, dx, dw, None, None, None, *router_grads, *expert_grads)
-
-
-MoEBlockFunction.last_aux = None
 
 
 class BalanceLossFunction(torch.autograd.Function):
@@ -262,8 +252,8 @@ class BalanceLossFunction(torch.autograd.Function):
         _require_cuda(load, "load")
         load = load.contiguous().float()
         loss = torch.empty((1,), dtype=torch.float32, device=load.device)
-        C.check(C.lib().moegan_balance_loss_fwd(C.ptr(load), load.numel(), int(T), float(balance_weight), C.ptr(loss), _stream()),
-                "moegan_balance_loss_fwd")
+        C.check(C.lib().moegan_balance_loss_fwd(C.ptr(load), load.numel(), int(T), float(balance_weight), C.ptr(loss),
+                                                C.c_void_p(_stream_ptr())), "moegan_balance_loss_fwd")
         ctx.save_for_backward(load)
         ctx.T, ctx.bw = int(T), float(balance_weight)
         return loss.reshape(())
@@ -273,6 +263,6 @@ class BalanceLossFunction(torch.autograd.Function):
         (load,) = ctx.saved_tensors
         dloss = dloss.reshape(1).contiguous().float()
         dload = torch.empty_like(load)
-        C.check(C.lib().moegan_balance_loss_bwd(C.ptr(load), load.numel(), ctx.T, ctx.bw, C.ptr(dloss), C.ptr(dload), _stream()),
-                "moegan_balance_loss_bwd")
+        C.check(C.lib().moegan_balance_loss_bwd(C.ptr(load), load.numel(), ctx.T, ctx.bw, C.ptr(dloss), C.ptr(dload),
+                                                C.c_void_p(_stream_ptr())), "moegan_balance_loss_bwd")
         return dload, None, None

@@ -69,7 +69,7 @@ def run_cuda(m, x, w, eps, af, dout=None, gp=None, kl_coef=0.0, bal_coef=0.0, ba
     res["out_strides"] = tuple(out.stride())
     res["kl"] = float(kl.detach().cpu())
     res["probs"] = probs.detach().cpu().numpy()
-    aux = p.MoEBlockFunction.last_aux
+    aux = p.MoEBlockFunction.last_aux()
     res["aux"] = {k: (v.detach().cpu().numpy() if v is not None else None) for k, v in aux.items()}
     return res
 

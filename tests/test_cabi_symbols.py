@@ -37,3 +37,20 @@ def test_sizes_and_error_reporting(pkg):
     rc = lib.moegan_convert_tokens(s, None, None, None)
     assert rc == -2 and "NULL" in C.last_error()
     assert lib.moegan_router_bwd_workspace_bytes(s) > 0
+
+
+def test_ctypes_struct_layouts_match_the_header(pkg):
+    """sizeof / field order of the argument structs as a C compiler lays them out (values from g++ on the header)."""
+    import ctypes
+    C = pkg._cabi
+    assert ctypes.sizeof(C.Shape) == 44
+    assert ctypes.sizeof(C.BlockLayout) == 192
+    assert ctypes.sizeof(C.BlockFwdArgs) == 192 and C.BlockFwdArgs.out.offset == 144
+    assert ctypes.sizeof(C.BlockBwdArgs) == 280 and C.BlockBwdArgs.dx.offset == 160 and C.BlockBwdArgs.workspace_bytes.offset == 272
+    s = C.make_shape(4096, 512, 512, 8, 2, 8, 512, 0, False, False)
+    lay = C.BlockLayout()
+    n = C.lib().moegan_block_fwd_workspace(s, 1, ctypes.byref(lay))
+    assert n == lay.total > 0 and lay.plan % 256 == 0 and lay.pre > 0
+    n0 = C.lib().moegan_block_fwd_workspace(s, 0, ctypes.byref(lay))
+    assert 0 < n0 < n and lay.pre == -1 and lay.fp == -1
+    assert C.lib().moegan_block_bwd_workspace(s) > 0
