@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py - the driver's measurement contract for the MoE-GAN hot path.
+"""bench.py - the driver's measurement contract for the MoE-GAN hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload moe_block]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload train_step|moe_block] [--no-graph]
 
-One "step" = one forward + backward pass of the Bayesian-routed MoE block over one batch of synthetic tokens
-(BASELINE.json configs[1]: 8 experts, top-2, 4096 tokens x 512 dim, fixed eps).  For N > 1 the driver starts one
-rank per GPU with torch.distributed.run; every rank processes its own batch (weak scaling) and the parameter
-gradients are all-reduced with NCCL inside the step.
+Default workload `train_step` (BASELINE.json configs[2]; at N GPUs it is configs[3]'s data-parallel step):
+one "step" = one full MoE-GAN train iteration - D-step (adv + matching-aware + R1) and G-step (adv + KL + balance),
+both AdamW updates - on a batch of 256 synthetic 64x64 images + synthetic CLIP text embeddings PER GPU, bf16
+autocast, fp32 router, generator MoE blocks on the sm_100a kernels.  Weak scaling: 256 images per GPU, gradients
+all-reduced with NCCL (bucketed, overlapped with backward).  metric = train images/s (whole job).
 
-Prints ONE JSON line (rank 0).  `value` = tokens/s with inputs resident in HBM; `e2e` = the same metric through
-the public module call with HOST (pinned) inputs, H2D copy and a D2H loss read inside the timed region;
-`roofline` = the tcgen05 grouped GEMM (dominant kernel) against the measured bf16 peak; `cpu_baseline` = the CPU
-oracle port of the same step on the box's host cores.  `--impl reference` times that CPU port as the reference arm.
+`moe_block` = BASELINE configs[1] (8 experts, top-2, 4096 tokens x 512, fwd+bwd).  It and configs[4] (inference:
+generate 1024 images, eval-mode hard top-1 routing) are also run briefly inside the default workload and reported
+under "moe_block" / "inference" in the same JSON line.
+
+JSON keys follow the contract: `value` has inputs resident in HBM; `e2e` goes through the public call with pinned
+HOST buffers (H2D inside, D2H loss read inside); `roofline` is the tcgen05 grouped-GEMM family timed live with CUDA
+events on its launch stream; `cpu_baseline` is the CPU port (torch-CPU restatement of the reference MoE block inside the same PyTorch host
+model) on a bounded sample; `--impl reference` prints that CPU arm as its own line.
 """
 from __future__ import annotations
 
@@ -28,26 +34,23 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 PKG = "moe-gan_cpsc541_b200"
 
-# configs[1] of BASELINE.json
+# BASELINE configs[1]
 WL = dict(B=8, H=16, W=32, d=512, Dt=512, E=8, k=2, mu_scale=8.0, af=1.0)
-METRIC = "moe_block_fwd_bwd_tokens_per_s"
-UNIT = "tokens/s"
+TRAIN_BATCH = 256          # per GPU (configs[2]); 8 GPUs -> global 2048 (configs[3])
+CPU_BATCH = 8              # configs[0]: the reference's own CPU-runnable case
+INFER_BATCH = 1024         # configs[4]
 
 
-def workload_name():
-    return (f"MoE block microbench (BASELINE configs[1]): E={WL['E']} top-{WL['k']}, T={WL['B'] * WL['H'] * WL['W']} tokens x "
-            f"d={WL['d']}, fwd+bwd, fixed-shape synthetic tokens, router mu x{WL['mu_scale']:g}")
-
-
-def algorithmic_flops():
-    """experts fwd+bwd = 48 * T * k * d^2 (six equal grouped GEMMs)."""
-    T = WL["B"] * WL["H"] * WL["W"]
-    return 48.0 * T * WL["k"] * WL["d"] ** 2
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 def make_numpy_case(seed):
     import numpy as np
-    from oracle import moe_oracle as O   # parameter *shapes/init* helper only; the oracle is not on the measured path
+    from oracle import moe_oracle as O   # parameter shapes / init helper only; the oracle is never on the measured GPU path
     rng = np.random.RandomState(seed)
     params = O.init_params(rng, WL["d"], WL["Dt"], WL["E"], mu_scale=WL["mu_scale"])
     x = rng.standard_normal((WL["B"], WL["d"], WL["H"], WL["W"])).astype(np.float32)
@@ -58,7 +61,7 @@ def make_numpy_case(seed):
 
 
 # --------------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi fields via NVML), runs during the timed region
+# clocks sampler (the nvidia-smi fields, via NVML), runs during the timed region
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
@@ -106,68 +109,189 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def cpu_threads():
+    try:
+        import torch
+        return int(torch.get_num_threads())
+    except Exception:
+        return os.cpu_count() or 1
+
+
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the same step (reference semantics, numpy fp32, all host threads)
+# CPU arm: the reference's train iteration restated with the numpy oracle as the MoE block
 # --------------------------------------------------------------------------------------------------
-def cpu_step_time(reps, sample_tokens=None):
-    import numpy as np
-    from oracle import moe_oracle as O
-    params, x, w, dout, eps = make_numpy_case(0)
-    xt = O.nchw_to_tokens(x)
-    do = O.nchw_to_tokens(dout)
-    tps = WL["H"] * WL["W"]
+def cpu_train_step_time(reps, batch=CPU_BATCH, warmup=1):
+    """One iteration of t2i_moe_gan.py:1262-1421 (no CLIP terms) on the host cores, fp32, batch 8 (configs[0])."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    hm = pkg.host_model
+    from oracle.torch_bridge import TorchSparseMoE
+    torch.manual_seed(0)
+    G, D = hm.AuroraGenerator(), hm.AuroraDiscriminator()
+    for blk in (G.gen_block_4, G.gen_block_8, G.gen_block_16):
+        o = TorchSparseMoE(blk.attn_block.moe.dim, 512)
+        o.load_state_dict(blk.attn_block.moe.state_dict())
+        blk.attn_block.moe = o
+    opt_g = torch.optim.AdamW(G.parameters(), lr=2e-4, betas=(0.5, 0.999), weight_decay=0.01)
+    opt_d = torch.optim.AdamW(D.parameters(), lr=2e-4, betas=(0.5, 0.999), weight_decay=0.01)
+    real = torch.randn(batch, 3, 64, 64).clamp(-1, 1)
+    text = torch.randn(batch, 512)
+    af, eff_kl = 3.0, 1e-3 * 1e-5
+
+    def balance(probs, bw=0.01):
+        load = probs.sum(0) + 1e-6
+        frac = load / probs.shape[0]
+        cv = frac.std() / (frac.mean() + 1e-6)
+        return bw * torch.nan_to_num(torch.clamp(probs.shape[1] * cv, 0.0, 10.0), nan=0.0)
+
+    def step():
+        z = torch.randn(batch, 512)
+        opt_d.zero_grad()
+        r = real.clone().requires_grad_(True)
+        real_pred = D(r, text)
+        r1 = hm.r1_penalty(real_pred, r, 10.0)
+        with torch.no_grad():
+            fake16, _, _, _ = G(z, text, return_intermediate=True, return_routing=True, annealing_factor=af)
+        d_loss = hm.discriminator_adv_loss(real_pred, D(fake16.detach(), text), D(r.detach(), text[torch.randperm(batch)])) + r1
+        d_loss.backward()
+        torch.nn.utils.clip_grad_norm_(D.parameters(), 0.7)
+        opt_d.step()
+        opt_g.zero_grad()
+        fake16, fake8, kl, routing = G(z, text, return_intermediate=True, return_routing=True, annealing_factor=af)
+        kl = torch.clamp(kl, max=50.0)
+        g_loss = hm.generator_adv_loss(D(fake16, text)) + balance(routing[-1]) + eff_kl * kl
+        g_loss.backward()
+        torch.nn.utils.clip_grad_norm_(G.parameters(), 0.8)
+        opt_g.step()
+
+    for _ in range(warmup):
+        step()
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        out, kl, probs, cache = O.moe_forward(xt, w, params, eps, WL["af"], True, top_k=WL["k"], tokens_per_sample=tps, dtype=np.float32)
+        step()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2], batch
+
+
+def cpu_moe_block_time(reps):
+    import numpy as np
+    from oracle import moe_oracle as O
+    params, x, w, dout, eps = make_numpy_case(0)
+    xt, do = O.nchw_to_tokens(x), O.nchw_to_tokens(dout)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out, kl, probs, cache = O.moe_forward(xt, w, params, eps, WL["af"], True, top_k=WL["k"], tokens_per_sample=WL["H"] * WL["W"], dtype=np.float32)
         O.moe_backward(cache, params, eps, do, dtype=np.float32)
         times.append(time.perf_counter() - t0)
     times.sort()
     return times[len(times) // 2], xt.shape[0]
 
 
-def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-        return int(n)
-    except Exception:
-        return os.cpu_count() or 1
+def moe_block_workload_name():
+    return (f"MoE block microbench (BASELINE configs[1]): E={WL['E']} top-{WL['k']}, T={WL['B'] * WL['H'] * WL['W']} tokens x "
+            f"d={WL['d']}, fwd+bwd, synthetic tokens, router mu x{WL['mu_scale']:g}")
+
+
+def train_workload_name(world):
+    return (f"MoE-GAN full train step (BASELINE configs[2]{'/[3]' if world > 1 else ''}): generator+discriminator, adv + R1 + KL + balance losses, "
+            f"64x64 synthetic images + synthetic CLIP text embeddings, batch {TRAIN_BATCH}/GPU, bf16 autocast, fp32 router, AdamW x2")
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    sec, T = cpu_step_time(max(1, args.steps), None) if args.steps else (None, None)
-    for _ in range(max(0, args.warmup - 1)):
-        pass
-    val = T / sec
-    cores = cpu_threads()
+    if args.workload == "moe_block":
+        sec, units = cpu_moe_block_time(max(1, args.steps))
+        metric, unit, wl = "moe_block_fwd_bwd_tokens_per_s", "tokens/s", moe_block_workload_name()
+        sample = f"full step (T={units}) x {args.steps} reps, median; numpy fp32 oracle port of t2i_moe_gan.py:249-491"
+    else:
+        sec, units = cpu_train_step_time(max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+        metric, unit, wl = "train_imgs_per_s", "imgs/s", train_workload_name(1)
+        sample = (f"batch {units} (BASELINE configs[0]) x {args.steps} reps, median {sec * 1e3:.0f} ms/step; fp32; the reference's train iteration "
+                  "(t2i_moe_gan.py:1262-1421, no CLIP terms) restated on the PyTorch host model with a torch-CPU port of the reference MoE block (oracle/torch_bridge.py) - "
+                  "the reference tree itself is pure Python and does not travel to the GPU box")
+    val = units / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name()},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"full step (T={T}) x {args.steps} reps, median; numpy fp32 oracle port of t2i_moe_gan.py:249-491 "
-                                   "(the reference is pure Python/PyTorch and does not travel to the GPU box)"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": wl},
+        "cpu_baseline": {"value": val, "unit": unit, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
-# B200 arm
+# shared timing helpers (GPU)
 # --------------------------------------------------------------------------------------------------
-def run_b200_arm(args, rank, world, local_rank):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+class Timer:
+    def __init__(self, torch, dist, world, dev, lib):
+        self.torch, self.dist, self.world, self.dev, self.lib = torch, dist, world, dev, lib
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, warmup):
+        """W untimed + K timed steps; per-step CUDA events on the launching stream, L2 flushed between steps; MAX over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        evs = []
+        n0 = self.lib.moegan_debug_launch_count()
+        h0 = time.perf_counter()
+        for _ in range(steps):
+            self.flush.zero_()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        host_ms = (time.perf_counter() - h0) * 1e3
+        self.barrier()
+        n1 = self.lib.moegan_debug_launch_count()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()), int(n1 - n0), host_ms
+
+    def gemm_profile(self, fn, steps):
+        """Durations (ms) of every tcgen05 GEMM launch in `steps` eager steps, measured by CUDA events the library
+        records around the launch on its own stream."""
+        C = importlib.import_module(PKG)._cabi
+        self.lib.moegan_debug_profile_enable(1)
+        self.barrier()
+        for _ in range(steps):
+            self.flush.zero_()
+            fn()
+        self.barrier()
+        cap = 4096 * max(steps, 1)
+        ms_buf = (C.c_float * cap)()
+        tag_buf = (C.c_int32 * cap)()
+        n = self.lib.moegan_debug_profile_read(ms_buf, tag_buf, cap)
+        self.lib.moegan_debug_profile_enable(0)
+        return [ms_buf[i] for i in range(n)], [tag_buf[i] for i in range(n)]
+
+
+def traffic_from_profiles(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------
+# workload: MoE block microbench (configs[1])
+# --------------------------------------------------------------------------------------------------
+def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
+    import torch
     pkg = importlib.import_module(PKG)
-    C = pkg._cabi
-    lib = C.lib()
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    lib = pkg._cabi.lib()
     params, x_np, w_np, dout_np, eps_np = make_numpy_case(1000 + rank)          # rank-offset data ...
     params, _, _, _, _ = make_numpy_case(0)                                      # ... identical weights on every rank
     moe = pkg.SparseMoE(WL["d"], WL["Dt"], WL["E"], top_k=WL["k"], precision="bf16")
@@ -176,33 +300,16 @@ def run_b200_arm(args, rank, world, local_rank):
         sd["router." + k] = moe.state_dict()["router." + k]
     moe.load_state_dict(sd)
     moe.to(dev).train()
-    plist = [p for p in moe.parameters()]
+    plist = list(moe.parameters())
     T = WL["B"] * WL["H"] * WL["W"]
-
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)       # NHWC memory, as norm3 produces (:561)
     x_host = torch.from_numpy(x_np).pin_memory()
     w_host = torch.from_numpy(w_np).pin_memory()
-    x_dev = x_host.to(dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)   # NHWC memory, as norm3 produces (:561)
+    x_dev = nhwc(x_host.to(dev)).requires_grad_(True)
     w_dev = w_host.to(dev).requires_grad_(True)
-    dout = torch.from_numpy(dout_np).to(dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    dout = nhwc(torch.from_numpy(dout_np).to(dev))
     eps = tuple(torch.from_numpy(eps_np[k]).to(dev) for k in ("epsilon_f", "epsilon_t", "epsilon_c"))
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=dev) if world > 1 else None
-
-    def allreduce_grads():
-        if world == 1:
-            return
-        off = 0
-        for p in plist:
-            n = p.numel()
-            flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(flat)
-        flat.mul_(1.0 / world)
-        off = 0
-        for p in plist:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+    red = pkg.GradReducer(plist)
 
     def step_device():
         for p in plist:
@@ -211,53 +318,21 @@ def run_b200_arm(args, rank, world, local_rank):
         w_dev.grad = None
         out, kl, probs = moe(x_dev, w_dev, WL["af"], eps=eps)
         loss = (out * dout).sum() + 1e-3 * kl
-        loss.backward()
-        allreduce_grads()
+        red.begin(); loss.backward(); red.finish()
         return loss
 
     def step_e2e():
         for p in plist:
             p.grad = None
-        xd = x_host.to(dev, non_blocking=True).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+        xd = nhwc(x_host.to(dev, non_blocking=True)).requires_grad_(True)
         wd = w_host.to(dev, non_blocking=True).requires_grad_(True)
         out, kl, probs = moe(xd, wd, WL["af"])                    # public call: eps redrawn on the device (:349-351)
         loss = (out * dout).sum() + 1e-3 * kl
-        loss.backward()
-        allreduce_grads()
+        red.begin(); loss.backward(); red.finish()
         return float(loss.item())                                 # D2H read of the step's result
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        evs = []
-        n0 = lib.moegan_debug_launch_count()
-        host_t0 = time.perf_counter()
-        for _ in range(steps):
-            flush.zero_()                                          # L2 flush between timed iterations (not timed)
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            evs.append((a, b))
-        host_ms = (time.perf_counter() - host_t0) * 1e3      # CPU time to enqueue the steps (no sync inside)
-        barrier()
-        n1 = lib.moegan_debug_launch_count()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        timed.host_ms = host_ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), int(n1 - n0)
-
-    # The device-resident number replays ONE CUDA graph of the whole step (forward, backward, gradient all-reduce):
-    # the step is ~30 launches of 2-80 us each, so eager Python launch latency would otherwise be what is measured.
-    launch_mode = "eager"
-    step_value = step_device
-    if not args.no_graph:
+    launch_mode, step_value, launches_per_graph = "eager", step_device, None
+    if use_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -271,92 +346,212 @@ def run_b200_arm(args, rank, world, local_rank):
             with torch.cuda.graph(graph):
                 step_device()
             launches_per_graph = int(lib.moegan_debug_launch_count() - n_before)
-            step_value = graph.replay
-            launch_mode = "cuda_graph"
+            step_value, launch_mode = graph.replay, "cuda_graph"
         except Exception as e:  # noqa
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
             torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
-        total_ms, launches = timed(step_value, args.steps, max(args.warmup, 3))
-    if launch_mode == "cuda_graph":
-        launches = launches_per_graph * args.steps
-    clocks = clk.summary()
-    host_enqueue_ms = timed.host_ms / args.steps
-    e2e_ms, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2))
-
-    # ---- live GEMM timing for the roofline (CUDA events recorded by the library on the launching stream) ----
-    lib.moegan_debug_profile_enable(1)
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        step_device()
-    barrier()
-    n_rec = 16 * args.steps
-    ms_buf = (C.c_float * n_rec)()
-    tag_buf = (C.c_int32 * n_rec)()
-    n = lib.moegan_debug_profile_read(ms_buf, tag_buf, n_rec)
-    lib.moegan_debug_profile_enable(0)
-    per_step = n // args.steps if args.steps else 0
-    gemm_ms = []
-    for s in range(args.steps):
-        gemm_ms += [ms_buf[s * per_step + i] for i in range(min(6, per_step))]     # the six expert GEMMs lead each step's router GEMMs
-    expert_order = ["ffn1_fwd", "ffn2_fwd", "dgrad2", "dgrad1", "wgrad2", "wgrad1"]
+    with ClockSampler(dev.index) as clk:
+        total_ms, launches, host_ms = T_.run(step_value, steps, warmup)
+    if launches_per_graph is not None:
+        launches = launches_per_graph * steps
+    e2e_ms, _, _ = T_.run(step_e2e, steps, max(2, warmup // 2))
+    ms_list, _ = T_.gemm_profile(step_device, steps)
+    per_step = len(ms_list) // steps if steps else 0
+    names = ["ffn1_fwd", "ffn2_fwd", "dgrad2", "dgrad1", "wgrad2", "wgrad1"]     # the six expert GEMMs lead each step's router GEMMs
     by_kernel = {}
-    for s in range(args.steps):
-        for i, name in enumerate(expert_order[:per_step]):
-            by_kernel.setdefault(name, []).append(ms_buf[s * per_step + i])
-    mean_gemm_ms = sum(gemm_ms) / max(len(gemm_ms), 1)
-    flops_per_launch = algorithmic_flops() / 6.0
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    achieved_tf = flops_per_launch / (mean_gemm_ms * 1e-3) / 1e12 if mean_gemm_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("umma_gemm_dram_bytes_per_launch")
-    except Exception:
-        pass
+    for s in range(steps):
+        for i, nm in enumerate(names[:per_step]):
+            by_kernel.setdefault(nm, []).append(ms_list[s * per_step + i])
+    all6 = [v for vs in by_kernel.values() for v in vs]
+    mean_ms = sum(all6) / max(len(all6), 1)
+    flops_per_launch = 48.0 * T * WL["k"] * WL["d"] ** 2 / 6.0                     # 48*T*k*d^2 over six equal GEMMs
+    pk = peaks()
+    peak_tf = float(pk.get("bf16_tflops", 1590.0))
+    ach = flops_per_launch / (mean_ms * 1e-3) / 1e12 if mean_ms > 0 else 0.0
+    ms_per_step = total_ms / steps
+    return {
+        "ms_per_step": ms_per_step, "tokens_per_s": T * world / (ms_per_step * 1e-3), "launch": launch_mode,
+        "clocks": clk.summary(), "gpu_launches": launches, "host_enqueue_us_per_step": host_ms / steps * 1e3,
+        "e2e": {"value": T * world / (e2e_ms / steps * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms / steps,
+                "h2d_bytes_per_step": int(x_host.numel() * 4 + w_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (six grouped expert GEMMs per step)", "achieved": ach, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernels timed individually)" if pk else "fallback 1590 (B200_PROFILING.md)",
+                     "traffic": traffic_from_profiles("umma_gemm_moe_block"), "flops_per_launch": flops_per_launch,
+                     "mean_launch_us": mean_ms * 1e3, "per_kernel_us": {k: 1e3 * sum(v) / len(v) for k, v in by_kernel.items()}},
+        "tokens": T,
+    }
 
-    if rank == 0:
-        cpu_sec, cpu_T = cpu_step_time(5)
-        ms_per_step = total_ms / args.steps
-        value = T * world / (ms_per_step * 1e-3)
-        e2e_val = T * world / (e2e_ms / args.steps * 1e-3)
+
+# --------------------------------------------------------------------------------------------------
+# workload: full train step (configs[2] / [3]) and inference (configs[4])
+# --------------------------------------------------------------------------------------------------
+def build_models(pkg, dev, seed=0):
+    import torch
+    torch.manual_seed(seed)                       # identical initial weights on every rank
+    G = pkg.host_model.AuroraGenerator().to(dev)
+    D = pkg.host_model.AuroraDiscriminator().to(dev)
+    return G, D
+
+
+def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
+    import torch
+    pkg = importlib.import_module(PKG)
+    lib = pkg._cabi.lib()
+    G, D = build_models(pkg, dev)
+    B = TRAIN_BATCH
+    torch.manual_seed(1234 + rank)                # rank-offset data
+    real_host = torch.randn(B, 3, 64, 64).clamp(-1, 1).pin_memory()
+    text_host = torch.randn(B, 512).pin_memory()
+    real, text = real_host.to(dev), text_host.to(dev)
+
+    def make_trainer(graph):
+        return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph)
+
+    launch_mode = "eager"
+    trainer = make_trainer(False)
+    launches_per_graph = None
+    if use_graph:
+        try:
+            tg = make_trainer(True)
+            n_before = lib.moegan_debug_launch_count()
+            tg._capture(real, text)
+            # launches counted during capture = 3 warm-up steps + the captured one
+            launches_per_graph = int(lib.moegan_debug_launch_count() - n_before) // 4
+            trainer, launch_mode = tg, "cuda_graph"
+        except Exception as e:  # noqa
+            if rank == 0:
+                print(f"[bench] CUDA graph capture of the train step failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
+            trainer = make_trainer(False)
+
+    with ClockSampler(dev.index) as clk:
+        total_ms, launches, host_ms = T_.run(lambda: trainer.step(real, text), steps, warmup)
+    if launches_per_graph is not None:
+        launches = launches_per_graph * steps
+    e2e_ms, _, _ = T_.run(lambda: trainer.step_from_host(real_host, text_host), steps, max(2, warmup // 2))
+
+    # roofline of the tcgen05 grouped GEMM family inside the step (eager pass; events recorded by the library)
+    eager = trainer if launch_mode == "eager" else make_trainer(False)
+    nprof = max(2, min(steps, 4))
+    ms_list, tags = T_.gemm_profile(lambda: eager._step_impl(real, text), nprof)
+    per_step = len(ms_list) // nprof if nprof else 0
+    # every expert GEMM of every block has the same algorithmic flops: 2*M*N*K with M = E*T, {N,K} = {4d, d} -> 8*E*T*d^2,
+    # and T*d^2 = 16*B*512^2 is the same for the three blocks.  Per step: 3 blocks x (2 forwards x 2 GEMMs +
+    # 4 backward GEMMs) = 24 expert launches (+ 12 small router-backward GEMMs, < 2% of the flops, whose time is included).
+    E = 4
+    flops_per_launch = 8.0 * E * (16 * B) * 512 ** 2
+    step_gemm_ms = sum(ms_list) / nprof if nprof else 0.0
+    expert_launches = 24
+    pk = peaks()
+    peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+    ach = expert_launches * flops_per_launch / (step_gemm_ms * 1e-3) / 1e12 if step_gemm_ms > 0 else 0.0
+    ms_per_step = total_ms / steps
+    res = {
+        "ms_per_step": ms_per_step, "imgs_per_s": B * world / (ms_per_step * 1e-3), "launch": launch_mode, "clocks": clk.summary(),
+        "gpu_launches": launches, "host_enqueue_us_per_step": host_ms / steps * 1e3,
+        "e2e": {"value": B * world / (e2e_ms / steps * 1e-3), "unit": "imgs/s", "ms_per_step": e2e_ms / steps,
+                "h2d_bytes_per_step": int(real_host.numel() * 4 + text_host.numel() * 4), "d2h_bytes_per_step": 8},
+        "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (24 grouped expert GEMMs + 12 router-backward GEMMs per train step)",
+                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels inside a long step)" if pk else "fallback 1590 (B200_PROFILING.md)",
+                     "traffic": traffic_from_profiles("umma_gemm_train_step"), "flops_per_launch": flops_per_launch,
+                     "gemm_ms_per_step": step_gemm_ms, "gemm_launches_per_step": per_step,
+                     "gemm_share_of_step": step_gemm_ms / ms_per_step if ms_per_step else None},
+    }
+    # ---- inference (configs[4]): generate_images semantics, eval-mode hard top-1 routing ----
+    try:
+        zi = torch.randn(INFER_BATCH, 512, device=dev)
+        ti = torch.randn(INFER_BATCH, 512, device=dev)
+        nrep = max(3, steps // 2)
+
+        def infer():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return pkg.host_model.sample_images(G, zi, ti, truncation_psi=0.7)
+        inf_ms, _, _ = T_.run(infer, nrep, 3)
+        res["inference"] = {"imgs_per_s": INFER_BATCH * world / (inf_ms / nrep * 1e-3), "batch": INFER_BATCH,
+                            "ms_per_batch": inf_ms / nrep, "routing": "hard top-1 (eval)", "dtype": "bf16"}
+    except Exception as e:  # noqa
+        res["inference"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    lib = pkg._cabi.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    T_ = Timer(torch, dist, world, dev, lib)
+    warmup = max(args.warmup, 3)
+    use_graph = not args.no_graph
+
+    if args.workload == "moe_block":
+        r = bench_moe_block(args, T_, rank, world, dev, args.steps, warmup, use_graph)
+        if rank != 0:
+            return
+        sec, units = cpu_moe_block_time(5)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "moe_block_fwd_bwd_tokens_per_s", "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(), "tokens_per_gpu": T, "l2": "256 MiB buffer zeroed between timed iterations",
-                       "parallelism": f"dp{world}" if world > 1 else "single", "launch": launch_mode, "router": "fp32", "experts": "bf16 in / fp32 acc (tcgen05)"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(x_host.numel() * 4 + w_host.numel() * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (six grouped expert GEMMs per step)",
-                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed individually)" if peaks else "fallback 1590",
-                         "traffic": traffic, "flops_per_launch": flops_per_launch, "mean_launch_us": mean_gemm_ms * 1e3,
-                         "per_kernel_us": {k: 1e3 * sum(v) / len(v) for k, v in by_kernel.items()}},
-            "cpu_baseline": {"value": cpu_T / cpu_sec, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                             "sample": f"full step (T={cpu_T}) x 5 reps, median {cpu_sec * 1e3:.0f} ms; numpy fp32 oracle port"},
-            "moe_block_fwd_bwd_us": ms_per_step * 1e3,
-            "host_enqueue_us_per_step": host_enqueue_ms * 1e3,
+            "config": {"workload": moe_block_workload_name(), "tokens_per_gpu": r["tokens"], "l2": "256 MiB buffer zeroed between timed iterations",
+                       "parallelism": f"dp{world}" if world > 1 else "single", "launch": r["launch"], "router": "fp32",
+                       "experts": "bf16 in / fp32 acc (tcgen05)"},
+            "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"],
+            "cpu_baseline": {"value": units / sec, "unit": "tokens/s", "cores": cpu_threads(), "kind": "port",
+                             "sample": f"full step (T={units}) x 5 reps, median {sec * 1e3:.0f} ms; numpy fp32 oracle port"},
+            "moe_block_fwd_bwd_us": r["ms_per_step"] * 1e3, "host_enqueue_us_per_step": r["host_enqueue_us_per_step"],
         }
         print(json.dumps(line), flush=True)
+        return
+
+    r = bench_train_step(args, T_, rank, world, dev, args.steps, warmup, use_graph)
+    mb = None
+    if not args.skip_extras:
+        try:
+            mb = bench_moe_block(args, T_, rank, world, dev, max(10, args.steps), 5, use_graph)
+        except Exception as e:  # noqa
+            mb = {"error": f"{type(e).__name__}: {e}"}
+    if rank != 0:
+        return
+    cpu = None
+    if not args.skip_cpu:
+        sec, units = cpu_train_step_time(3, warmup=1)
+        cpu = {"value": units / sec, "unit": "imgs/s", "cores": cpu_threads(), "kind": "port",
+               "sample": (f"batch {units} (BASELINE configs[0]) x 3 reps, median {sec * 1e3:.0f} ms/step, fp32: the reference train iteration "
+                          "(t2i_moe_gan.py:1262-1421, no CLIP terms) on the PyTorch host model with a torch-CPU port of the reference MoE block")}
+    line = {
+        "metric": "train_imgs_per_s", "value": r["imgs_per_s"], "unit": "imgs/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": train_workload_name(world), "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * world,
+                   "image": "real 64x64 -> D; G emits 16x16 (+8x8)", "l2": "256 MiB buffer zeroed between timed iterations",
+                   "parallelism": f"dp{world}" if world > 1 else "single", "launch": r["launch"],
+                   "allreduce": "NCCL, 25 MB buckets from grad-ready hooks on a comm stream" if world > 1 else None},
+        "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "cpu_baseline": cpu,
+        "host_enqueue_us_per_step": r["host_enqueue_us_per_step"], "inference": r.get("inference"),
+    }
+    if mb is not None and "error" not in mb:
+        line["moe_block"] = {"fwd_bwd_us": mb["ms_per_step"] * 1e3, "tokens_per_s": mb["tokens_per_s"], "launch": mb["launch"],
+                             "workload": moe_block_workload_name(), "roofline": mb["roofline"], "e2e": mb["e2e"]}
+    elif mb is not None:
+        line["moe_block"] = mb
+    print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="moe_block")
+    ap.add_argument("--workload", default="train_step", choices=["train_step", "moe_block"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the embedded moe_block microbench")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

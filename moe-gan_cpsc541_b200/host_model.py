@@ -1,0 +1,228 @@
+"""Host model for the full-step configurations (BASELINE configs[2..4]): the generator / discriminator that sit
+AROUND the hot path, restated in plain PyTorch so that the train step can run where the reference tree is not
+available (the GPU box).  These layers are out of the hot-path scope ("stays
+PyTorch/cuDNN"); only the `moe` sub-module of each attention block runs the sm_100a kernels.
+
+Module / parameter names follow the reference (moegan/t2i_moe_gan.py) so that a checkpoint written by
+moegan/sagemaker_train.py:297-301 loads here (`load_reference_checkpoint`):
+    AuroraGenerator :668-855, GenerativeBlock :622-666, ConvolutionBlock :579-621, ModulatedTransformationModule
+    :188-247, ModulatedConv :122-186, AttentionBlock :493-576, AuroraDiscriminator :858-907, losses :917-949.
+
+One deliberate re-formulation: ModulatedConv does not materialise per-sample weights [B,out,in,k,k] and a grouped
+convolution (:158-176); it scales the input by the style, runs ONE ordinary convolution with the shared weight
+and scales the output by the demodulation factor  d[b,o] = rsqrt(sum_i s[b,i]^2 * sum_k W[o,i,k]^2 + 1e-8),
+which is the same function (StyleGAN2's "fused_modconv=False" identity) and is what SURVEY 8(f) N3 asks for.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils.parametrizations import weight_norm
+
+from .sparse_moe import SparseMoE, moe_balance_loss
+
+LATENT_DIM = 512          # t2i_moe_gan.py:20
+TEXT_EMBEDDING_DIM = 512  # :21
+
+
+class ModulatedConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, latent_dim=LATENT_DIM, padding=0, demodulate=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.padding, self.demodulate = padding, demodulate
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        nn.init.kaiming_normal_(self.weight, a=0, mode="fan_in", nonlinearity="leaky_relu")
+        self.modulation = nn.Linear(latent_dim, in_channels)
+        nn.init.normal_(self.modulation.weight, mean=0.0, std=0.02)
+        nn.init.zeros_(self.modulation.bias)
+
+    def forward(self, x, w):
+        s = self.modulation(w)                                            # [B, in]
+        y = F.conv2d(x * s.to(x.dtype)[:, :, None, None], self.weight.to(x.dtype), padding=self.padding)
+        if self.demodulate:
+            wsq = self.weight.float().pow(2).sum(dim=(2, 3))              # [out, in]
+            d = torch.rsqrt(s.float().pow(2) @ wsq.t() + 1e-8)            # [B, out]
+            y = y * d.to(y.dtype)[:, :, None, None]
+        return y
+
+
+class ModulatedTransformationModule(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, latent_dim=LATENT_DIM, use_offset=False, resolution=None):
+        super().__init__()
+        self.use_offset = bool(use_offset and resolution is not None and resolution <= 16)
+        self.modulated_conv = ModulatedConv(in_channels, out_channels, kernel_size, latent_dim=latent_dim, padding=kernel_size // 2)
+        if self.use_offset:
+            self.offset_net = nn.Sequential(nn.Conv2d(in_channels, 32, 3, padding=1), nn.LeakyReLU(0.2, inplace=True),
+                                            nn.Conv2d(32, 2, 3, padding=1))
+        self.activation = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x, w):
+        if self.use_offset:
+            B, _, H, W = x.shape
+            off = self.offset_net(x).permute(0, 2, 3, 1) * 0.05
+            gy, gx = torch.meshgrid(torch.linspace(-1, 1, H, device=x.device), torch.linspace(-1, 1, W, device=x.device), indexing="ij")
+            grid = (torch.stack((gx, gy), dim=2).unsqueeze(0) + off.float()).clamp(-1, 1)
+            x = F.grid_sample(x, grid.to(x.dtype), mode="bilinear", align_corners=False)
+        return self.activation(self.modulated_conv(x, w))
+
+
+class ConvolutionBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, latent_dim=LATENT_DIM, resolution=None):
+        super().__init__()
+        self.mtm1 = ModulatedTransformationModule(in_channels, out_channels, 3, latent_dim, True, resolution)
+        self.mtm2 = ModulatedTransformationModule(out_channels, out_channels, 3, latent_dim, True, resolution)
+        self.skip_proj = ModulatedConv(in_channels, out_channels, 1, latent_dim) if in_channels != out_channels else None
+
+    def forward(self, x, w):
+        out = self.mtm2(self.mtm1(x, w), w)
+        return out + (x if self.skip_proj is None else self.skip_proj(x, w))
+
+
+class AttentionBlock(nn.Module):
+    """proj_in -> LN -> self-attn -> LN -> cross-attn(text, length 1) -> LN -> MoE -> residual -> proj_out (:525-576)."""
+
+    def __init__(self, dim, text_dim=512, heads=8, moe_kwargs=None):
+        super().__init__()
+        self.dim, self.heads = dim, heads
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.text_proj = nn.Linear(text_dim, dim)
+        self.self_attn = nn.MultiheadAttention(dim, heads, batch_first=True)
+        self.cross_attn = nn.MultiheadAttention(dim, heads, batch_first=True)
+        self.moe = SparseMoE(dim, text_dim, **(moe_kwargs or {}))          # <- the hot path
+        self.proj_in = ModulatedConv(dim, dim, 1)
+        self.proj_out = ModulatedConv(dim, dim, 1)
+
+    def forward(self, x, w, text_seq, kl_losses=None, annealing_factor=1.0):
+        B, C, H, W = x.shape
+        t = self.proj_in(x, w).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        n = self.norm1(t)
+        t = t + self.self_attn(n, n, n, need_weights=False)[0]
+        tp = self.text_proj(text_seq)
+        t = t + self.cross_attn(self.norm2(t), tp, tp, need_weights=False)[0]
+        x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        x_norm = self.norm3(t).reshape(B, H, W, C).permute(0, 3, 1, 2)     # NCHW view of NHWC memory (:561)
+        moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
+        if kl_losses is not None:
+            kl_losses.append(moe_kl)
+        return self.proj_out(x_spatial + moe_out.to(x_spatial.dtype), w), probs
+
+
+class GenerativeBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, text_dim=768, upsample=False, resolution=None, moe_kwargs=None):
+        super().__init__()
+        self.upsample = upsample
+        self.conv_block = ConvolutionBlock(in_channels, out_channels, resolution=resolution)
+        self.attn_block = AttentionBlock(out_channels, text_dim=text_dim, moe_kwargs=moe_kwargs)
+
+    def forward(self, x, w, text_seq, kl_losses=None, annealing_factor=1.0):
+        if self.upsample:
+            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        return self.attn_block(self.conv_block(x, w), w, text_seq, kl_losses, annealing_factor)
+
+
+class AuroraGenerator(nn.Module):
+    """z [B,512], text [B,512] -> 16x16 image (+ 8x8 intermediate), summed KL of the 3 MoE routers, routing probs."""
+
+    def __init__(self, latent_dim=LATENT_DIM, text_embedding_dim=TEXT_EMBEDDING_DIM, moe_kwargs=None):
+        super().__init__()
+        self.latent_dim, self.text_embedding_dim = latent_dim, text_embedding_dim
+        td = text_embedding_dim
+        self.text_projection = nn.Sequential(nn.Linear(td, td), nn.LayerNorm(td), nn.LeakyReLU(0.2, inplace=True), nn.Linear(td, td))
+        self.mapping = nn.Sequential(nn.Linear(latent_dim + td, 512), nn.LeakyReLU(0.2, inplace=True),
+                                     nn.Linear(512, 512), nn.LeakyReLU(0.2, inplace=True),
+                                     nn.Linear(512, 512), nn.LeakyReLU(0.2, inplace=True), nn.Linear(512, 512))
+        self.constant = nn.Parameter(torch.randn(1, 512, 4, 4))
+        self.gen_block_4 = GenerativeBlock(512, 512, text_dim=td, upsample=False, resolution=4, moe_kwargs=moe_kwargs)
+        self.gen_block_8 = GenerativeBlock(512, 256, text_dim=td, upsample=True, resolution=8, moe_kwargs=moe_kwargs)
+        self.gen_block_16 = GenerativeBlock(256, 128, text_dim=td, upsample=True, resolution=16, moe_kwargs=moe_kwargs)
+        self.to_rgb_8 = ModulatedConv(256, 3, 1)
+        self.to_rgb_16 = ModulatedConv(128, 3, 1)
+
+    def moe_layers(self) -> List[SparseMoE]:
+        return [self.gen_block_4.attn_block.moe, self.gen_block_8.attn_block.moe, self.gen_block_16.attn_block.moe]
+
+    def forward(self, z, text_embeddings, truncation_psi=0.7, return_routing=False, return_intermediate=False, annealing_factor=1.0):
+        B = z.size(0)
+        if text_embeddings.size(0) != B:
+            if text_embeddings.size(0) != 1:
+                raise ValueError(f"Batch size mismatch: z has batch size {B}, but text_embeddings has batch size {text_embeddings.size(0)}")
+            text_embeddings = text_embeddings.repeat(B, 1)
+        text_seq = self.text_projection(text_embeddings).unsqueeze(1)
+        w = self.mapping(torch.cat([z, text_embeddings], dim=1))
+        if truncation_psi < 1.0:                                            # truncation trick (:799-808)
+            with torch.no_grad():
+                mean_latent = self.mapping(torch.zeros(1, self.latent_dim + self.text_embedding_dim, device=z.device, dtype=z.dtype))
+            w = mean_latent + truncation_psi * (w - mean_latent)
+        kl_losses, routing = [], []
+        x = self.constant.repeat(B, 1, 1, 1)
+        x, p = self.gen_block_4(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x, p = self.gen_block_8(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x_8 = self.to_rgb_8(x, w)
+        x, p = self.gen_block_16(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x_16 = self.to_rgb_16(x, w)
+        kl = sum(kl_losses) if kl_losses else torch.zeros((), device=z.device)
+        if return_routing and return_intermediate:
+            return x_16, x_8, kl, routing
+        if return_routing:
+            return x_16, None, kl, routing
+        if return_intermediate:
+            return x_16, x_8, kl
+        return x_16, kl
+
+
+class AuroraDiscriminator(nn.Module):
+    def __init__(self, text_embedding_dim=TEXT_EMBEDDING_DIM):
+        super().__init__()
+        self.text_projection = nn.Sequential(weight_norm(nn.Linear(text_embedding_dim, 128)), nn.LeakyReLU(0.2, inplace=True))
+        self.conv_layers = nn.Sequential(weight_norm(nn.Conv2d(3, 128, 4, 2, 1)), nn.LeakyReLU(0.2, inplace=True),
+                                         weight_norm(nn.Conv2d(128, 256, 4, 2, 1)), nn.LeakyReLU(0.2, inplace=True))
+        self.output_layer = nn.Sequential(weight_norm(nn.Conv2d(256 + 128, 1, 4, 1, 0)))
+
+    def forward(self, img, text_embedding):
+        f = self.conv_layers(img)
+        t = self.text_projection(text_embedding)[:, :, None, None].expand(-1, -1, f.shape[2], f.shape[3])
+        return self.output_layer(torch.cat([f, t.to(f.dtype)], dim=1)).reshape(-1)   # 16x16 fake -> B logits; 64x64 real -> 169*B
+
+
+# ---- losses (t2i_moe_gan.py:917-949) -------------------------------------------------------------------
+def generator_adv_loss(fake_pred):
+    return F.softplus(-fake_pred).mean()
+
+
+def discriminator_adv_loss(real_pred, fake_pred, mismatched_pred):
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean() + F.softplus(mismatched_pred).mean()
+
+
+def r1_penalty(real_pred, real_images, r1_gamma=10.0):
+    """(gamma / 2) * E ||d D(real) / d real||^2  (:1282-1286)."""
+    (grad_real,) = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_images, create_graph=True)
+    return (r1_gamma / 2) * grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1).pow(2).mean()
+
+
+def sample_images(generator, z, text_embeddings, truncation_psi=0.7):
+    """sample_aurora_gan with tensor embeddings (:1672-1708): eval mode -> hard top-1 routing through the kernels."""
+    was_training = generator.training
+    generator.eval()
+    with torch.no_grad():
+        img, _ = generator(z, text_embeddings, truncation_psi=truncation_psi)
+    generator.train(was_training)
+    return img
+
+
+def load_reference_checkpoint(generator: nn.Module, discriminator: Optional[nn.Module], ckpt: dict) -> None:
+    """{'generator': sd, 'discriminator': sd} as saved by moegan/sagemaker_train.py:297-301.  The only key
+    difference is the discriminator's legacy weight_norm naming (weight_g / weight_v)."""
+    generator.load_state_dict(ckpt["generator"])
+    if discriminator is not None and "discriminator" in ckpt:
+        sd = {}
+        for k, v in ckpt["discriminator"].items():
+            if k.endswith("weight_g"):
+                k = k[:-len("weight_g")] + "parametrizations.weight.original0"
+            elif k.endswith("weight_v"):
+                k = k[:-len("weight_v")] + "parametrizations.weight.original1"
+            sd[k] = v
+        discriminator.load_state_dict(sd)

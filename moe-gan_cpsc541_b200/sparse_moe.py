@@ -92,6 +92,7 @@ class SparseMoE(nn.Module):
         self.experts = nn.ModuleList([SparseExpertFFN(dim) for _ in range(num_experts)])
         self.router = BayesianRouter(dim, text_dim, num_experts)
         self._wcache = WeightCache()
+        self.redraw_eps = True    # False = parity mode "use the epsilon_* buffers as they are" 
         self.last_load: Optional[torch.Tensor] = None   # fused per-expert prob column sums of the last forward
 
     @classmethod
@@ -126,7 +127,8 @@ class SparseMoE(nn.Module):
         precision = self._precision_code()
         if training:   # sampling=self.training (:459)
             if eps is None:
-                r.epsilon_f.normal_(); r.epsilon_t.normal_(); r.epsilon_c.normal_()   # (:349-351), same RNG order
+                if self.redraw_eps:
+                    r.epsilon_f.normal_(); r.epsilon_t.normal_(); r.epsilon_c.normal_()   # (:349-351), same RNG order
                 eps = (r.epsilon_f, r.epsilon_t, r.epsilon_c)
             else:
                 eps = tuple(e.to(device=x.device, dtype=torch.float32).contiguous() for e in eps)

@@ -1,0 +1,285 @@
+"""Data-parallel train step for MoE-GAN: one iteration of the reference loop body
+(moegan/t2i_moe_gan.py:1262-1421, minus the CLIP terms :1384-1387 whose weights are not available offline)
+with the B200 MoE blocks inside the generator.
+
+What is new relative to the reference:
+  * one process per GPU; gradients are all-reduced with NCCL in ~25 MB buckets launched from grad-ready hooks on a
+    communication stream, so the transfer over NVLink overlaps the rest of backward (`GradReducer`);
+  * the balance loss is made exact under data parallelism by all-reducing the [E] load vector (`dp_allreduce_load`);
+  * no host synchronisation inside the step (the reference's `.item()` NaN guards and the `kl > 50` branch are
+    expressed on the device), which lets the whole step (D-step + G-step + both AdamW updates) be captured in ONE
+    CUDA graph and replayed (`use_cuda_graph=True`).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import host_model as hm
+from .sparse_moe import moe_balance_loss
+from .functional import BalanceLossFunction
+
+
+# --------------------------------------------------------------------------------------------------
+# bucketed, overlapped gradient all-reduce
+# --------------------------------------------------------------------------------------------------
+class GradReducer:
+    """Averages .grad of `params` across the process group, bucket by bucket, as soon as a bucket's gradients exist.
+
+    Buckets are filled in reverse parameter order (the order backward produces gradients).  Each bucket is one flat
+    fp32 buffer; when its last gradient has been accumulated the bucket is packed and all-reduced on `comm_stream`
+    while the compute stream keeps running backward.  `finish()` joins the streams and scatters the averages back.
+    """
+
+    def __init__(self, params: Sequence[nn.Parameter], group=None, bucket_bytes: int = 25 << 20, overlap: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = overlap
+        self.buckets: List[List[nn.Parameter]] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self.buckets.append(cur); cur, cur_bytes = [], 0
+            cur.append(p); cur_bytes += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self.pending = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.comm_stream = None
+        self.enabled = False
+        self._handles = []
+        if self.world > 1:
+            for p in self.params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _flat(self, bi: int) -> torch.Tensor:
+        if self.flat[bi] is None:
+            n = sum(p.numel() for p in self.buckets[bi])
+            self.flat[bi] = torch.empty(n, dtype=torch.float32, device=self.buckets[bi][0].device)
+        return self.flat[bi]
+
+    def begin(self) -> None:
+        """Call before backward."""
+        if self.world == 1:
+            return
+        self.enabled = True
+        for bi, b in enumerate(self.buckets):
+            self.pending[bi] = len(b)
+            self.launched[bi] = False
+        if self.overlap and self.buckets and self.buckets[0][0].is_cuda and self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+
+    def _on_grad(self, p: nn.Parameter) -> None:
+        if not self.enabled:
+            return
+        bi = self.bucket_of[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi: int) -> None:
+        self.launched[bi] = True
+        flat = self._flat(bi)
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
+        views = flat.split([p.numel() for p in self.buckets[bi]])
+        torch._foreach_copy_(list(views), [g.reshape(-1) for g in grads])
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat, group=self.group)
+        else:
+            dist.all_reduce(flat, group=self.group)
+
+    def finish(self) -> None:
+        """Call after backward: reduces stragglers, joins the comm stream, writes the averaged gradients back."""
+        if self.world == 1 or not self.enabled:
+            return
+        for bi in range(len(self.buckets)):
+            if not self.launched[bi]:
+                self._launch(bi)          # parameters that received no gradient this step
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        inv = 1.0 / self.world
+        for bi, b in enumerate(self.buckets):
+            views = self._flat(bi).split([p.numel() for p in b])
+            outs = []
+            for p in b:
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                outs.append(p.grad.reshape(-1) if p.grad.is_contiguous() else None)
+            if all(o is not None for o in outs):
+                torch._foreach_copy_(outs, list(views))
+                torch._foreach_mul_(outs, inv)
+            else:
+                for p, v in zip(b, views):
+                    p.grad.copy_(v.view_as(p)).mul_(inv)
+        self.enabled = False
+
+
+class _AllReduceLoad(torch.autograd.Function):
+    """Global per-expert load for the balance loss.  forward: sum over ranks.  backward: x world, because the
+    data-parallel gradient average divides by world a loss term that is already global."""
+
+    @staticmethod
+    def forward(ctx, load, group, world):
+        ctx.world = world
+        out = load.clone()
+        dist.all_reduce(out, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.world, None, None
+
+
+def dp_allreduce_load(load: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return load
+    return _AllReduceLoad.apply(load, group, world)
+
+
+# --------------------------------------------------------------------------------------------------
+# schedule helpers (t2i_moe_gan.py:1168-1178)
+# --------------------------------------------------------------------------------------------------
+def effective_kl_weight(kl_weight: float, epoch: int, kl_annealing_epochs: int = 5) -> float:
+    warm = min(1.0, (epoch / kl_annealing_epochs) ** 2)
+    return kl_weight * (1e-5 + (1.0 - 1e-5) * warm)
+
+
+def temperature_factor(epoch: int) -> float:
+    return max(1.0, 3.0 - epoch * 0.1)
+
+
+# --------------------------------------------------------------------------------------------------
+# the train step
+# --------------------------------------------------------------------------------------------------
+class MoEGANTrainer:
+    def __init__(self, generator: nn.Module, discriminator: nn.Module, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999,
+                 weight_decay: float = 0.01, r1_gamma: float = 10.0, kl_weight: float = 1e-3, balance_weight: float = 0.01,
+                 amp_dtype: Optional[torch.dtype] = torch.bfloat16, group=None, bucket_bytes: int = 25 << 20,
+                 use_cuda_graph: bool = False, exact_dp_balance: bool = True):
+        self.G, self.D = generator, discriminator
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.r1_gamma, self.kl_weight, self.balance_weight = r1_gamma, kl_weight, balance_weight
+        self.amp_dtype = amp_dtype
+        self.exact_dp_balance = exact_dp_balance
+        self.use_cuda_graph = use_cuda_graph
+        cap = dict(capturable=True) if use_cuda_graph else {}
+        # AdamW(lr 2e-4, betas (0.5, 0.999), wd 0.01) for both networks (:1100-1102)
+        self.opt_g = torch.optim.AdamW(self.G.parameters(), lr=lr, betas=(beta1, beta2), weight_decay=weight_decay, **cap)
+        self.opt_d = torch.optim.AdamW(self.D.parameters(), lr=lr, betas=(beta1, beta2), weight_decay=weight_decay, **cap)
+        self.red_g = GradReducer(list(self.G.parameters()), group, bucket_bytes)
+        self.red_d = GradReducer(list(self.D.parameters()), group, bucket_bytes)
+        self.set_epoch(0)
+        self._graph = None
+        self._static: Dict[str, torch.Tensor] = {}
+        self._out: Dict[str, torch.Tensor] = {}
+
+    def set_epoch(self, epoch: int, kl_annealing_epochs: int = 5) -> None:
+        self.annealing_factor = temperature_factor(epoch)
+        self.eff_kl_weight = effective_kl_weight(self.kl_weight, epoch, kl_annealing_epochs)
+        self._graph = None    # schedule constants are baked into a captured graph
+
+    def _autocast(self):
+        dev = next(self.G.parameters()).device.type
+        return torch.autocast(device_type=dev, dtype=self.amp_dtype, enabled=self.amp_dtype is not None)
+
+    # ---- D-step (:1268-1348) ----
+    def d_step(self, real: torch.Tensor, text: torch.Tensor, z: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.opt_d.zero_grad(set_to_none=True)
+        real = real.detach().requires_grad_(True)
+        with self._autocast():
+            real_pred = self.D(real, text)
+            r1 = hm.r1_penalty(real_pred, real, self.r1_gamma)
+            with torch.no_grad():      # module stays in train mode: dense-soft routing, eps redrawn (:1289-1298)
+                fake16, _, _, _ = self.G(z, text, return_intermediate=True, return_routing=True, annealing_factor=self.annealing_factor)
+            fake_pred = self.D(fake16.detach(), text)
+            perm = torch.rand(text.shape[0], device=text.device).argsort()          # device-side randperm (:1303)
+            mismatched_pred = self.D(real.detach(), text[perm])
+            d_gan = hm.discriminator_adv_loss(real_pred, fake_pred, mismatched_pred)
+            d_loss = d_gan + r1
+        self.red_d.begin()
+        d_loss.backward()
+        self.red_d.finish()
+        torch.nn.utils.clip_grad_norm_(self.D.parameters(), max_norm=0.7)           # (:1336), after the all-reduce
+        self.opt_d.step()
+        return {"d_loss": d_gan.detach(), "r1": r1.detach()}
+
+    # ---- G-step (:1350-1421) ----
+    def g_step(self, text: torch.Tensor, z: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.opt_g.zero_grad(set_to_none=True)
+        with self._autocast():
+            fake16, fake8, kl, routing = self.G(z, text, return_intermediate=True, return_routing=True,
+                                                annealing_factor=self.annealing_factor)
+            kl = torch.clamp(kl, max=50.0)                                          # `if kl > 50: clamp(max=50)` without the sync (:1369)
+            kl = torch.nan_to_num(kl, nan=0.0, posinf=50.0, neginf=0.0)
+            fake_pred = self.D(fake16, text)
+            g_gan = hm.generator_adv_loss(fake_pred)
+            last = routing[-1]
+            load = getattr(last, "_moegan_load", None)
+            if load is None:
+                load = last.float().sum(dim=0)
+            T_glob = last.shape[0] * (self.world if self.exact_dp_balance else 1)
+            if self.exact_dp_balance:
+                load = dp_allreduce_load(load, self.group)
+            balance = BalanceLossFunction.apply(load, T_glob, self.balance_weight)
+            g_loss = g_gan + balance + self.eff_kl_weight * kl                       # (:1393, :1402-1404)
+        self.red_g.begin()
+        g_loss.backward()
+        self.red_g.finish()
+        torch.nn.utils.clip_grad_norm_(self.G.parameters(), max_norm=0.8)           # (:1420)
+        self.opt_g.step()
+        return {"g_loss": g_gan.detach(), "kl": kl.detach(), "balance": balance.detach()}
+
+    def _step_impl(self, real: torch.Tensor, text: torch.Tensor) -> Dict[str, torch.Tensor]:
+        z = torch.randn(real.shape[0], hm.LATENT_DIM, device=real.device)           # (:1266)
+        out = self.d_step(real, text, z)
+        out.update(self.g_step(text, z))
+        return out
+
+    def step(self, real: torch.Tensor, text: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One train iteration on device-resident `real` [B,3,64,64] and `text` [B,512]."""
+        if not self.use_cuda_graph:
+            return self._step_impl(real, text)
+        if self._graph is None or self._static["real"].shape != real.shape:
+            self._capture(real, text)
+        self._static["real"].copy_(real, non_blocking=True)
+        self._static["text"].copy_(text, non_blocking=True)
+        self._graph.replay()
+        return self._out
+
+    def step_from_host(self, real_host: torch.Tensor, text_host: torch.Tensor) -> Dict[str, float]:
+        """The end-to-end call: pinned host batch in, host floats out (H2D copy + step + D2H loss read)."""
+        dev = next(self.G.parameters()).device
+        if self.use_cuda_graph and self._graph is not None and self._static["real"].shape == real_host.shape:
+            self._static["real"].copy_(real_host, non_blocking=True)
+            self._static["text"].copy_(text_host, non_blocking=True)
+            self._graph.replay()
+            out = self._out
+        else:
+            out = self.step(real_host.to(dev, non_blocking=True), text_host.to(dev, non_blocking=True))
+        packed = torch.stack([out["d_loss"].float(), out["g_loss"].float()]).cpu()
+        return {"d_loss": float(packed[0]), "g_loss": float(packed[1])}
+
+    def _capture(self, real: torch.Tensor, text: torch.Tensor) -> None:
+        self._static = {"real": real.clone(), "text": text.clone()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up outside capture: lazy inits, optimizer state, NCCL
+                self._step_impl(self._static["real"], self._static["text"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._out = self._step_impl(self._static["real"], self._static["text"])
+        self._graph = g

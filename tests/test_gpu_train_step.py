@@ -1,0 +1,107 @@
+"""GPU tests of the rows around the hot path: the B200 MoE blocks inside the whole generator (drop-in check against the
+CPU oracle module inside the same host model), the full train step (eager and CUDA-graph), and eval-mode inference."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_utils as G_
+
+pytestmark = pytest.mark.gpu
+
+
+def _fixed_eps(gen_cpu, gen_gpu, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    for mc, mg in zip(gen_cpu.moe_layers(), gen_gpu.moe_layers()):
+        for name in ("epsilon_f", "epsilon_t", "epsilon_c"):
+            e = torch.randn(getattr(mc.router, name).shape, generator=g)
+            getattr(mc.router, name).copy_(e)
+            getattr(mg.router, name).copy_(e.cuda())
+        mc.redraw_eps = False
+        mg.redraw_eps = False
+
+
+def test_generator_with_b200_moe_matches_cpu_oracle_generator():
+    """Whole generator forward + backward: MoE blocks on the sm_100a kernels (fp32 mode) vs the numpy-oracle MoE inside
+    the identical PyTorch host model on CPU, same weights, inputs and eps."""
+    from oracle.torch_bridge import OracleSparseMoE
+    pkg = G_.pkg()
+    hm = pkg.host_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    gen_gpu = hm.AuroraGenerator(moe_kwargs=dict(precision="fp32"))
+    gen_cpu = copy.deepcopy(gen_gpu)
+    for blk in (gen_cpu.gen_block_4, gen_cpu.gen_block_8, gen_cpu.gen_block_16):
+        o = OracleSparseMoE(blk.attn_block.moe.dim, 512)
+        o.load_state_dict(blk.attn_block.moe.state_dict())
+        blk.attn_block.moe = o
+    gen_cpu.moe_layers = lambda: [gen_cpu.gen_block_4.attn_block.moe, gen_cpu.gen_block_8.attn_block.moe, gen_cpu.gen_block_16.attn_block.moe]
+    gen_gpu.cuda()
+    _fixed_eps(gen_cpu, gen_gpu)
+    B = 8
+    z, text = torch.randn(B, 512), torch.randn(B, 512)
+    wimg = torch.randn(B, 3, 16, 16)
+    outs = {}
+    for name, gen, dev in (("cpu", gen_cpu, "cpu"), ("gpu", gen_gpu, "cuda")):
+        gen.train()
+        img, img8, kl, probs = gen(z.to(dev), text.to(dev), return_intermediate=True, return_routing=True, annealing_factor=3.0)
+        loss = (img * wimg.to(dev)).sum() + 1e-3 * kl + (probs[-1] * probs[-1]).sum()
+        loss.backward()
+        outs[name] = dict(img=img.detach().cpu(), img8=img8.detach().cpu(), kl=float(kl.detach()), probs=[p.detach().cpu() for p in probs],
+                          grads={n: p.grad.detach().cpu() for n, p in gen.named_parameters() if p.grad is not None})
+    a, b = outs["gpu"], outs["cpu"]
+    assert a["kl"] == b["kl"] == 360.0                                   # 3 routers x 120
+    rel = lambda x, y: float((x - y).abs().max() / y.abs().max().clamp_min(1e-12))
+    assert rel(a["img"], b["img"]) < 1e-3 and rel(a["img8"], b["img8"]) < 1e-3
+    for pa, pb in zip(a["probs"], b["probs"]):
+        assert rel(pa, pb) < 1e-4
+    checked = 0
+    for n, gb in b["grads"].items():
+        if gb.abs().max() < 1e-9:
+            continue
+        assert rel(a["grads"][n], gb) < 5e-3, n
+        checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_runs(use_graph):
+    pkg = G_.pkg()
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    Gm, Dm = hm.AuroraGenerator().cuda(), hm.AuroraDiscriminator().cuda()
+    tr = pkg.MoEGANTrainer(Gm, Dm, amp_dtype=torch.bfloat16, use_cuda_graph=use_graph)
+    B = 16
+    real = torch.randn(B, 3, 64, 64, device="cuda").clamp(-1, 1)
+    text = torch.randn(B, 512, device="cuda")
+    before = {n: p.detach().clone() for n, p in Gm.named_parameters()}
+    for _ in range(3):
+        out = tr.step(real, text)
+    torch.cuda.synchronize()
+    vals = {k: float(v) for k, v in out.items()}
+    assert all(np.isfinite(v) for v in vals.values()), vals
+    assert vals["kl"] == 50.0                                            # 360 clamped to 50 in the loop (:1369-1370)
+    assert 0.0 <= vals["balance"] <= 0.1
+    changed = [n for n, p in Gm.named_parameters() if not torch.equal(p.detach(), before[n])]
+    assert any("moe.experts" in n for n in changed) and any("router.feature_mu" in n for n in changed)
+    h = tr.step_from_host(real.cpu().pin_memory(), text.cpu().pin_memory())
+    assert np.isfinite(h["d_loss"]) and np.isfinite(h["g_loss"])
+
+
+def test_inference_eval_mode_hard_routing():
+    pkg = G_.pkg()
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    Gm = hm.AuroraGenerator().cuda()
+    z, text = torch.randn(32, 512, device="cuda"), torch.randn(32, 512, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        img = hm.sample_images(Gm, z, text)
+    assert img.shape == (32, 3, 16, 16) and torch.isfinite(img).all()
+    Gm.eval()
+    with torch.no_grad():
+        _, _, kl, probs = Gm(z, text, return_intermediate=True, return_routing=True)
+    assert float(kl) == 0.0
+    for p in probs:                                                      # one-hot routing in eval (:392-400)
+        assert set(torch.unique(p).tolist()) <= {0.0, 1.0} and torch.all(p.sum(dim=1) == 1.0)

@@ -1,0 +1,63 @@
+"""The host model (generator/discriminator around the hot path) against the UNMODIFIED reference, CPU, with the
+reference's own SparseMoE plugged into both so that only the surrounding layers are compared.  Needs
+/root/reference, so it runs in the build container only (skipped on the GPU box)."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+REF = "/root/reference/moegan"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not available")
+
+
+def _ref():
+    sys.modules.setdefault("clip", types.ModuleType("clip"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import t2i_moe_gan as ref
+    return ref
+
+
+def test_generator_and_discriminator_match_reference(pkg):
+    ref = _ref()
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    g_ref = ref.AuroraGenerator()
+    d_ref = ref.AuroraDiscriminator()
+    g = hm.AuroraGenerator()
+    d = hm.AuroraDiscriminator()
+    # same parameter names / shapes, so a reference checkpoint loads
+    assert sorted(g.state_dict().keys()) == sorted(g_ref.state_dict().keys())
+    hm.load_reference_checkpoint(g, d, {"generator": g_ref.state_dict(), "discriminator": d_ref.state_dict()})
+    assert sum(p.numel() for p in g.parameters()) == 27769167 and sum(p.numel() for p in d.parameters()) == 603138
+    for blk in (g.gen_block_4, g.gen_block_8, g.gen_block_16):        # compare the surrounding layers only
+        ref_moe = ref.SparseMoE(blk.attn_block.moe.dim, 512)
+        ref_moe.load_state_dict(blk.attn_block.moe.state_dict())
+        blk.attn_block.moe = ref_moe
+    B = 3
+    z, text = torch.randn(B, 512), torch.randn(B, 512)
+    real = torch.randn(B, 3, 64, 64).clamp(-1, 1)
+    for mode in ("train", "eval"):
+        g.train(mode == "train"); g_ref.train(mode == "train")
+        torch.manual_seed(1); a16, a8, akl, aprobs = g(z, text, return_intermediate=True, return_routing=True, annealing_factor=3.0)
+        torch.manual_seed(1); b16, b8, bkl, bprobs = g_ref(z, text, return_intermediate=True, return_routing=True, annealing_factor=3.0)
+        assert a16.shape == (B, 3, 16, 16) and a8.shape == (B, 3, 8, 8)
+        assert torch.allclose(a16, b16, rtol=1e-4, atol=2e-5), (a16 - b16).abs().max()
+        assert torch.allclose(a8, b8, rtol=1e-4, atol=2e-5)
+        assert torch.allclose(akl, bkl) and torch.allclose(aprobs[-1], bprobs[-1], atol=1e-6)
+    assert torch.allclose(d(real, text), d_ref(real, text), rtol=1e-4, atol=1e-5)
+    assert d(real, text).numel() == 169 * B and d(a16.detach(), text).numel() == B
+    # gradients through the re-formulated ModulatedConv
+    g.train(); g_ref.train()
+    torch.manual_seed(2); (g(z, text)[0].square().mean()).backward()
+    torch.manual_seed(2); (g_ref(z, text)[0].square().mean()).backward()
+    for (n1, p1), (n2, p2) in zip(g.named_parameters(), g_ref.named_parameters()):
+        assert n1 == n2
+        if p2.grad is None:
+            continue
+        if p2.grad.abs().max() < 1e-9:      # e.g. norm2 / the cross-attention query path: key length 1 -> exactly 0 in the reference
+            assert p1.grad.abs().max() < 1e-8, n1
+            continue
+        assert (p1.grad - p2.grad).abs().max() / p2.grad.abs().max() < 2e-3, n1

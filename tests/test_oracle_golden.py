@@ -146,3 +146,30 @@ def test_topk_backward_finite_difference():
         fd = (Lp - Lm) / (2 * h)
         an = float((grads[key] * d).sum())
         assert abs(fd - an) < 1e-4 * max(1.0, abs(an)), (key, fd, an)
+
+
+def test_torch_cpu_port_matches_numpy_oracle_and_golden():
+    """oracle/torch_bridge.py (the CPU arm bench.py times) against the golden fixture and the numpy oracle."""
+    import torch
+    from oracle.torch_bridge import TorchSparseMoE, OracleSparseMoE
+    name = "train_d128_E4"
+    c, params, x, w, dout, gp = make_inputs(name)
+    g = load_golden(name)
+    for cls in (TorchSparseMoE, OracleSparseMoE):
+        m = cls(c["d"], c["Dt"], c["E"])
+        sd = {k: torch.from_numpy(v.copy()) for k, v in params.items()}
+        for k in O.EPS_KEYS:
+            sd["router." + k] = torch.from_numpy(g[k].copy())
+        m.load_state_dict(sd)
+        m.redraw_eps = False
+        m.train()
+        xt = torch.from_numpy(x).requires_grad_(True)
+        wt = torch.from_numpy(w).requires_grad_(True)
+        out, kl, probs = m(xt, wt, c["af"])
+        ((out * torch.from_numpy(dout)).sum() + KL_COEF * kl + (probs * torch.from_numpy(gp)).sum()).backward()
+        assert rel_err(out.detach().numpy(), g["out"]) < 2e-5
+        assert rel_err(probs.detach().numpy(), g["probs"]) < 2e-5
+        dprobs_bal = O.balance_loss_bwd(g["probs"].astype(np.float64), BALANCE_WEIGHT, dloss=BAL_COEF)   # golden loss also had the balance term
+        assert float(kl) == float(g["kl"])
+        for k in ("experts.1.net.0.weight", "experts.2.net.2.bias"):
+            assert rel_err(dict(m.named_parameters())[k].grad.numpy(), g["grad." + k]) < 1e-4, k
