@@ -337,8 +337,9 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         p.out0 = dpre_op; p.ld_out0 = (long long)S * hid; p.out_split_off = hid;
         RUN(launch_umma_gemm(GEMM_ROWS_BMN, 256, A, B, p, m_blocks * (hid / 256), st));
     }
-    RUN(launch_colsum_grouped(s, plan, dy_op, d, db2, st));
-    RUN(launch_colsum_grouped(s, plan, dpre_op, hid, db1, st));
+    // bias gradients; the row-split partials live in dW2 / dW1, which the wgrad GEMMs only write further down
+    RUN(launch_colsum_grouped(s, plan, dy_op, d, dW2, db2, st));
+    RUN(launch_colsum_grouped(s, plan, dpre_op, hid, dW1, db1, st));
     {   // dgrad1: dx_rows = dpre W1
         GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
         GemmOperand B{W1_op, S * d, (uint64_t)s->E * hid, S * d};

@@ -303,17 +303,20 @@ uncombine_kernel(const void* __restrict__ dx_rows, const int* __restrict__ token
 }
 
 // bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c].
-// CTA = (expert, 64 columns), 32 warps stride the rows, two rows in flight per warp.
+// Stage 1: CTA = (64 columns, expert, row split): 32 warps stride the split's rows, two rows in flight per warp;
+//          writes part[split][e][c].  Stage 2 sums the splits in a fixed order (deterministic).
 __global__ void __launch_bounds__(1024)
-colsum_grouped_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restrict__ src, int cols, int split, int T, int dense,
-                      float* __restrict__ out) {
+colsum_part_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restrict__ src, int cols, int split, int T, int dense,
+                   int E, int nsplit, float* __restrict__ part) {
     __shared__ float red[32][64];
-    const int e = blockIdx.y;
+    const int e = blockIdx.y, sp = blockIdx.z;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 64 + lane * 2;
     const int ld = split ? 2 * cols : cols;
-    const int r0 = __ldg(plan + PLAN_OFF + e);
-    const int r1 = r0 + (dense ? T : __ldg(plan + PLAN_CNT + e));
+    const int e0 = __ldg(plan + PLAN_OFF + e);
+    const int n = dense ? T : __ldg(plan + PLAN_CNT + e);
+    const int per = (n + nsplit - 1) / nsplit;
+    const int r0 = e0 + min(sp * per, n), r1 = e0 + min((sp + 1) * per, n);
     float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
     auto add_row = [&](int r, float& x0, float& x1) {
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + c));
@@ -333,8 +336,16 @@ colsum_grouped_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restr
         float s = 0.0f;
 #pragma unroll
         for (int w = 0; w < 32; ++w) s += red[w][threadIdx.x];
-        out[(size_t)e * cols + blockIdx.x * 64 + threadIdx.x] = s;
+        part[((size_t)sp * E + e) * cols + blockIdx.x * 64 + threadIdx.x] = s;
     }
+}
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ part, int n, int nsplit, float* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.0f;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * n + i];
+    out[i] = s;
 }
 
 }  // namespace
@@ -422,11 +433,22 @@ int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* 
     return MOEGAN_OK;
 }
 
-int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* out, cudaStream_t st) {
-    dim3 grid(cols / 64, s->E);
-    colsum_grouped_kernel<<<grid, 1024, 0, st>>>(plan, reinterpret_cast<const __nv_bfloat16*>(src_op), cols, s->precision == 1, s->T,
-                                                s->dense, out);
-    MOEGAN_CHECK_LAUNCH("colsum_grouped_kernel");
+int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* scratch, float* out,
+                          cudaStream_t st) {
+    // rows per expert are only known on the device; size the split from the mean (dense: exact)
+    const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;
+    int nsplit = (int)(rows / 1024);
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 32) nsplit = 32;
+    dim3 grid(cols / 64, s->E, nsplit);
+    colsum_part_kernel<<<grid, 1024, 0, st>>>(plan, reinterpret_cast<const __nv_bfloat16*>(src_op), cols, s->precision == 1, s->T,
+                                              s->dense, s->E, nsplit, nsplit == 1 ? out : scratch);
+    MOEGAN_CHECK_LAUNCH("colsum_part_kernel");
+    if (nsplit > 1) {
+        const int n = s->E * cols;
+        colsum_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scratch, n, nsplit, out);
+        MOEGAN_CHECK_LAUNCH("colsum_finish_kernel");
+    }
     return MOEGAN_OK;
 }
 

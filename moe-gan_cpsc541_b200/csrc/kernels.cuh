@@ -43,7 +43,9 @@ int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
                        const float* row_gate, const float* gates, void* dy_op, float* dgate_row, cudaStream_t st);
 int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
                      cudaStream_t st);
-// out[e, c] = sum over the real rows of expert e of (hi + lo)[row, c];  src is a bf16 operand [m_cap, S*cols]
-int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* out, cudaStream_t st);
+// out[e, c] = sum over the real rows of expert e of (hi + lo)[row, c];  src is a bf16 operand [m_cap, S*cols];
+// scratch: >= 32 * E * cols floats (row-split partials)
+int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* scratch, float* out,
+                          cudaStream_t st);
 
 }  // namespace moegan

@@ -120,7 +120,9 @@ class GenerativeBlock(nn.Module):
 
     def forward(self, x, w, text_seq, kl_losses=None, annealing_factor=1.0):
         if self.upsample:
-            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+            # channels-last: ATen's NCHW bilinear kernel parallelises over the (tiny) output H*W only and loops over
+            # N*C serially - 21 ms per call at batch 256 on B200; the NHWC kernel is vectorised over channels
+            x = F.interpolate(x.contiguous(memory_format=torch.channels_last), scale_factor=2, mode="bilinear", align_corners=False)
         return self.attn_block(self.conv_block(x, w), w, text_seq, kl_losses, annealing_factor)
 
 

@@ -143,6 +143,7 @@ def test_topk_vs_oracle(shape, precision):
     dict(B=3, H=5, W=5, d=128, Dt=64, E=4),            # ragged dense: T=75 (TMA zero-fill + row masks)
     dict(B=4, H=8, W=8, d=256, Dt=512, E=4),           # block-8 geometry
     dict(B=2, H=16, W=16, d=128, Dt=512, E=4),         # block-16 geometry
+    dict(B=16, H=16, W=16, d=128, Dt=512, E=4),        # T=4096: multi-split bias-gradient reduction, many M blocks
 ])
 def test_dense_vs_oracle(shape, precision):
     s = shape

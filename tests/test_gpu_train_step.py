@@ -59,7 +59,7 @@ def test_generator_with_b200_moe_matches_cpu_oracle_generator():
         assert rel(pa, pb) < 1e-4
     checked = 0
     for n, gb in b["grads"].items():
-        if gb.abs().max() < 1e-9:
+        if gb.abs().max() < 1e-6:      # numerically-zero gradients (e.g. the cross-attention query path, key length 1)
             continue
         assert rel(a["grads"][n], gb) < 5e-3, n
         checked += 1
