@@ -39,8 +39,9 @@ template <int BN> struct Cfg {
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 4096;   // 4 KB per epilogue warp (TMA-store staging)
     static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
 struct Tile {
@@ -89,32 +90,26 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
     return t;
 }
 
-// ---- epilogue store helpers (one thread = one output row, 32 consecutive columns) ------------------
-__device__ __forceinline__ void store32_f32(float* dst, const float (&v)[32]) {
+// ---- epilogue staging helpers --------------------------------------------------------------------------
+// One thread = one output row, 32 consecutive columns.  The warp's 32 x 32 tile is written to shared memory in the
+// TMA swizzle layout (conflict-free 16-byte stores) and leaves the SM as ONE coalesced bulk tensor store.
+//   bf16: rows of 64 B, SWIZZLE_64B  : 16-byte chunk i of row r sits at chunk i ^ ((r >> 1) & 3)
+//   fp32: rows of 128 B, SWIZZLE_128B: 16-byte chunk i of row r sits at chunk i ^ (r & 7)
+__device__ __forceinline__ void stage32_bf16(uint32_t base, int r, const float (&v)[32]) {
+    const uint32_t row = base + r * 64;
+    const int sw = (r >> 1) & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        ptx::st_shared_v4(row + ((i ^ sw) << 4), pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                          pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+}
+__device__ __forceinline__ void stage32_f32(uint32_t base, int r, const float (&v)[32]) {
+    const uint32_t row = base + r * 128;
+    const int sw = r & 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        reinterpret_cast<uint4*>(dst)[i] = u;
-    }
-}
-__device__ __forceinline__ void store32_split(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[32]) {
-    float lo[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        float h;
-        split_bf16(v[i], h, lo[i]);
-    }
-    store32_bf16(dst_hi, v);   // rounding v to bf16 gives exactly hi
-    store32_bf16(dst_lo, lo);
+        ptx::st_shared_v4(row + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                          __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
 }
 __device__ __forceinline__ void load32_bf16(const __nv_bfloat16* src, float (&v)[32]) {
 #pragma unroll
@@ -136,12 +131,14 @@ __device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
 
 template <int BN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1, const GemmParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
-    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;        // 1024-aligned
+    const uint32_t bar_base = staging_base + C::STAGING_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
@@ -155,6 +152,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == WARP_TMA && lane == 0) {
         ptx::prefetch_tmap(&mapA);
         ptx::prefetch_tmap(&mapB);
+        ptx::prefetch_tmap(&mapO0);
+        ptx::prefetch_tmap(&mapO1);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
         ptx::fence_mbar_init();
@@ -251,19 +250,34 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else {
         // =============================== epilogue warps ===============================
+        // TMEM -> registers -> (bias / GELU / GELU') -> swizzled smem staging -> ONE bulk tensor store per 32x32 tile.
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int half = warp >> 2;        // which half of the BN columns
         const int row_in_tile = q * 32 + lane;
+        const uint32_t stage0 = staging_base + warp * 4096u;   // 4 KB per warp, 1024-aligned
+        const int epi = p.epi;
         int acc = 0; uint32_t acc_phase = 0;
+        bool pending = false;              // this warp has a bulk store in flight that still reads its staging buffer
+        // free the staging buffer of the previous store, write the new tile(s), hand them to the TMA unit
+        auto flush_begin = [&]() {
+            if (pending) { if (lane == 0) ptx::bulk_wait_read0(); __syncwarp(); }
+        };
+        auto flush_end = [&]() {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const Tile t = decode_tile<BN, KIND>(p, tile);
             const int nkb = t.nkb_pp * p.passes;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int grow = t.mb * BM + row_in_tile;      // row inside the (expert's) output
-            bool row_ok; long long out_row;
-            if (KIND == GEMM_WGRAD) { row_ok = grow < p.dimA; out_row = ((long long)t.split * p.E + t.e) * p.dimA + grow; }
-            else                    { row_ok = grow < p.out_rows_valid; out_row = grow; }
+            const int grow = t.mb * BM + row_in_tile;      // this thread's row inside the (expert's) output
+            // first row of this warp's 32-row slab in the output tensor
+            int out_row0; bool slab_ok;
+            if (KIND == GEMM_WGRAD) { out_row0 = (t.split * p.E + t.e) * p.dimA + t.mb * BM + q * 32; slab_ok = (t.mb * BM + q * 32) < p.dimA; }
+            else                    { out_row0 = t.mb * BM + q * 32; slab_ok = out_row0 < p.out_rows_valid; }
+            const long long out_row = (long long)out_row0 + lane;
+            const bool row_ok = (KIND == GEMM_WGRAD) ? (grow < p.dimA) : (out_row < p.out_rows_valid);
 #pragma unroll 1
             for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                 float v[32];
@@ -278,66 +292,118 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int i = 0; i < 32; ++i) v[i] = 0.0f;
                 }
                 const int col0 = t.nb * BN + c;
-                if (row_ok && col0 < p.N) {
-                const int epi = p.epi;
-                if (epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3) {
-                    const float* b = p.bias + (long long)t.e * p.N + col0;
+                if (slab_ok && col0 < p.N) {   // warp-uniform
+                    if (epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3) {
+                        const float* b = p.bias + (long long)t.e * p.N + col0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 f = __ldg(reinterpret_cast<const float4*>(b) + i);
-                        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 f = __ldg(reinterpret_cast<const float4*>(b) + i);
+                            v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                        }
+                    }
+                    switch (epi) {
+                    case EPI_F32:
+                    case EPI_BIAS_F32:
+                        flush_begin();
+                        stage32_f32(stage0, lane, v);
+                        flush_end();
+                        if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
+                        pending = true;
+                        break;
+                    case EPI_BF16:
+                    case EPI_BIAS_BF16:
+                        flush_begin();
+                        stage32_bf16(stage0, lane, v);
+                        flush_end();
+                        if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
+                        pending = true;
+                        break;
+                    case EPI_GELU_BF16: {
+                        if (p.out1 != nullptr) {
+                            float dg[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) gelu_and_grad_fast(v[i], v[i], dg[i]);
+                            flush_begin();
+                            stage32_bf16(stage0 + 2048u, lane, dg);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+                            flush_begin();
+                        }
+                        stage32_bf16(stage0, lane, v);
+                        flush_end();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapO0, stage0, col0, out_row0);
+                            if (p.out1 != nullptr) ptx::tma_store_2d(&mapO1, stage0 + 2048u, col0, out_row0);
+                            ptx::bulk_commit();
+                        }
+                        pending = true;
+                        break;
+                    }
+                    case EPI_GELU_X3: {
+                        if (p.out1 != nullptr) {   // fp32 pre-activation
+                            flush_begin();
+                            stage32_f32(stage0, lane, v);
+                            flush_end();
+                            if (lane == 0) { ptx::tma_store_2d(&mapO1, stage0, col0, out_row0); ptx::bulk_commit(); }
+                            pending = true;
+                        }
+                        float lo[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { v[i] = gelu_erf<true>(v[i]); float h; split_bf16(v[i], h, lo[i]); }
+                        flush_begin();
+                        stage32_bf16(stage0, lane, v);            // rounding v to bf16 gives exactly hi
+                        stage32_bf16(stage0 + 2048u, lane, lo);
+                        flush_end();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapO0, stage0, col0, out_row0);
+                            ptx::tma_store_2d(&mapO0, stage0 + 2048u, col0 + p.out_split_off, out_row0);
+                            ptx::bulk_commit();
+                        }
+                        pending = true;
+                        break;
+                    }
+                    case EPI_MUL_BF16: {
+                        float a[32];
+                        if (row_ok) load32_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ld_aux + col0, a);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) a[i] = 0.0f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= a[i];
+                        flush_begin();
+                        stage32_bf16(stage0, lane, v);
+                        flush_end();
+                        if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
+                        pending = true;
+                        break;
+                    }
+                    case EPI_DGELU_X3: {
+                        float a[32];
+                        if (row_ok) load32_f32(reinterpret_cast<const float*>(p.aux) + out_row * p.ld_aux + col0, a);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) a[i] = 0.0f;
+                        }
+                        float lo[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { v[i] *= gelu_erf_grad<true>(a[i]); float h; split_bf16(v[i], h, lo[i]); }
+                        flush_begin();
+                        stage32_bf16(stage0, lane, v);
+                        stage32_bf16(stage0 + 2048u, lane, lo);
+                        flush_end();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapO0, stage0, col0, out_row0);
+                            ptx::tma_store_2d(&mapO0, stage0 + 2048u, col0 + p.out_split_off, out_row0);
+                            ptx::bulk_commit();
+                        }
+                        pending = true;
+                        break;
+                    }
+                    default: break;
                     }
                 }
-                switch (epi) {
-                case EPI_F32:
-                case EPI_BIAS_F32:
-                    store32_f32(reinterpret_cast<float*>(p.out0) + out_row * p.ld_out0 + col0, v);
-                    break;
-                case EPI_BF16:
-                case EPI_BIAS_BF16:
-                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
-                    break;
-                case EPI_GELU_BF16: {
-                    if (p.out1 != nullptr) {
-                        float dg[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) gelu_and_grad_fast(v[i], v[i], dg[i]);
-                        store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out1) + out_row * p.ld_out1 + col0, dg);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
-                    }
-                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
-                    break;
-                }
-                case EPI_GELU_X3: {
-                    if (p.out1 != nullptr) store32_f32(reinterpret_cast<float*>(p.out1) + out_row * p.ld_out1 + col0, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf<true>(v[i]);
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0;
-                    store32_split(o, o + p.out_split_off, v);
-                    break;
-                }
-                case EPI_MUL_BF16: {
-                    float a[32];
-                    load32_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ld_aux + col0, a);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= a[i];
-                    store32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0, v);
-                    break;
-                }
-                case EPI_DGELU_X3: {
-                    float a[32];
-                    load32_f32(reinterpret_cast<const float*>(p.aux) + out_row * p.ld_aux + col0, a);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad<true>(a[i]);
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + out_row * p.ld_out0 + col0;
-                    store32_split(o, o + p.out_split_off, v);
-                    break;
-                }
-                default: break;
-                }
-                }  // row_ok && col0 < N
                 __syncwarp();   // tcgen05.ld is warp-collective: reconverge before the next chunk
             }
             ptx::tc_fence_before();
@@ -345,6 +411,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
             acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
+        if (pending && lane == 0) ptx::bulk_wait0();   // all bulk stores of this warp have been written
+        __syncwarp();
     }
 
     ptx::tc_fence_before();
@@ -375,6 +443,25 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// 32 x 32 output tile: bf16 -> 64-byte rows (SWIZZLE_64B), fp32 -> 128-byte rows (SWIZZLE_128B)
+int make_out_tmap(CUtensorMap* m, const void* ptr, bool f32, uint64_t cols, uint64_t rows, uint64_t pitch_elems) {
+    EncodeTiledFn enc = get_encode_fn();
+    MOEGAN_REQUIRE(enc != nullptr, MOEGAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    const uint64_t es = f32 ? 4 : 2;
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (pitch_elems * es) % 16 == 0, MOEGAN_ERR_MISALIGNED,
+                   "GEMM output not 16-byte aligned (pitch %llu elements)", (unsigned long long)pitch_elems);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * es};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOEGAN_REQUIRE(r == CUDA_SUCCESS, MOEGAN_ERR_DRIVER, "cuTensorMapEncodeTiled (output) failed (CUresult %d; cols %llu rows %llu pitch %llu)",
+                   (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems);
+    return MOEGAN_OK;
+}
+
 int make_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) {
     EncodeTiledFn enc = get_encode_fn();
     MOEGAN_REQUIRE(enc != nullptr, MOEGAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
@@ -394,7 +481,8 @@ int make_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) {
 }
 
 template <int BN, int KIND>
-int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t stream) {
+int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo0, const CUtensorMap& mo1, const GemmParams& p, int grid,
+                cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -403,7 +491,7 @@ int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     }
     void* prof = nullptr;
     profile_begin(stream, KIND * 1000 + BN, &prof);
-    umma_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, p);
+    umma_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, mo0, mo1, p);
     profile_end(stream, prof);
     MOEGAN_CHECK_LAUNCH("umma_gemm_kernel");
     return MOEGAN_OK;
@@ -424,9 +512,22 @@ int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& 
     const uint32_t b_box = (kind == GEMM_ROWS_BK) ? (uint32_t)BN : 64u;
     if ((rc = make_tmap(&ma, A, a_box)) != MOEGAN_OK) return rc;
     if ((rc = make_tmap(&mb, B, b_box)) != MOEGAN_OK) return rc;
+    // output tensor maps (TMA-store epilogue)
+    CUtensorMap mo0, mo1;
+    MOEGAN_REQUIRE(p.out0 != nullptr, MOEGAN_ERR_NULL_POINTER, "GEMM output is NULL");
+    const bool o0_f32 = (p.epi == EPI_F32 || p.epi == EPI_BIAS_F32);
+    const uint64_t o_rows = (kind == GEMM_WGRAD) ? (uint64_t)(p.k_splits > 1 ? p.k_splits : 1) * p.E * p.dimA : (uint64_t)p.out_rows_valid;
+    const bool o0_split = (p.epi == EPI_GELU_X3 || p.epi == EPI_DGELU_X3);
+    const uint64_t o0_cols = o0_split ? (uint64_t)p.out_split_off + p.N : (uint64_t)p.N;
+    if ((rc = make_out_tmap(&mo0, p.out0, o0_f32, o0_cols, o_rows, (uint64_t)p.ld_out0)) != MOEGAN_OK) return rc;
+    if (p.out1 != nullptr) {
+        if ((rc = make_out_tmap(&mo1, p.out1, p.epi == EPI_GELU_X3, (uint64_t)p.N, o_rows, (uint64_t)p.ld_out1)) != MOEGAN_OK) return rc;
+    } else {
+        mo1 = mo0;
+    }
     const int sms = num_sms();
     const int grid = (int)(max_tiles < sms ? max_tiles : sms);
-#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_>(ma, mb, p, grid, stream)
+#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_>(ma, mb, mo0, mo1, p, grid, stream)
     if (BN == 256) {
         if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(256, GEMM_ROWS_BK);
         if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(256, GEMM_ROWS_BMN);

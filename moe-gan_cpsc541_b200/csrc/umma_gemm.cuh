@@ -49,7 +49,7 @@ struct GemmParams {
     const void* aux;
     const float* bias;      // [E, N]
     long long ld_out0, ld_out1, ld_aux;  // leading dimensions (elements)
-    int out_rows_valid;     // ROWS: rows >= this are not stored
+    int out_rows_valid;     // rows of the output tensor(s): rows >= this are clipped by the TMA store
     int out_split_off;      // column offset of the lo half in out0 for the *_X3 epilogues
     int mn_lbo, mn_sbo, mn_kadv;  // MN-major smem descriptor parameters (bytes); 0 -> defaults
 };
