@@ -21,7 +21,8 @@
  *    accurate to ~2^-16 relative - this is the mode that meets the 1e-4 fp32 parity bar.
  *    "bf16 operand" buffers are [rows, S*cols] bf16 with S = 1 (precision 0) or 2 (hi | lo halves).
  *  - Row-permuted ("dispatched") buffers have m_cap rows (moegan_m_cap()).  Each expert's rows are
- *    contiguous, in ascending token order, and start at a multiple of 128 rows; padding rows are zero.
+ *    contiguous, in ascending token order, and start at a multiple of MOEGAN_ROW_ALIGN (256) rows (one cta_group::2
+ *    MMA tile); padding rows are zero.
  */
 #ifndef MOEGAN_SM100_H
 #define MOEGAN_SM100_H
@@ -41,6 +42,7 @@ extern "C" {
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
 #define MOEGAN_CHUNK 32       /* tokens per router CTA / permutation chunk */
+#define MOEGAN_ROW_ALIGN 256  /* every expert segment of a dispatched buffer starts at a multiple of this many rows */
 #define MOEGAN_KL_PARTS 256   /* scratch partial sums behind kl_out */
 #define MOEGAN_KL_OUT_FLOATS (2 + MOEGAN_KL_PARTS)
 
@@ -71,7 +73,7 @@ typedef struct {
 /* ---- library ------------------------------------------------------------------------------- */
 int moegan_version(void);
 const char* moegan_last_error_string(void); /* host string, valid until the next failing call on this thread */
-/* rows to allocate for dispatched buffers: dense E*ceil128(T); sparse ceil128(T*k) + 128*E */
+/* rows to allocate for dispatched buffers: dense E*ceil256(T); sparse ceil256(T*k) + 256*E */
 int64_t moegan_m_cap(int32_t T, int32_t E, int32_t k, int32_t dense);
 /* int32 elements of the dispatch plan array */
 int64_t moegan_plan_ints(int32_t m_cap);

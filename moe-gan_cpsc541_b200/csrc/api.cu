@@ -135,8 +135,9 @@ int moegan_version(void) { return MOEGAN_ABI_VERSION; }
 const char* moegan_last_error_string(void) { return g_err; }
 
 int64_t moegan_m_cap(int32_t T, int32_t E, int32_t k, int32_t dense) {
-    if (dense) return (int64_t)E * (((int64_t)T + 127) / 128 * 128);
-    return (((int64_t)T * k + 127) / 128 * 128) + 128LL * E;
+    const int64_t A = MOEGAN_ROW_ALIGN;
+    if (dense) return (int64_t)E * (((int64_t)T + A - 1) / A * A);
+    return (((int64_t)T * k + A - 1) / A * A) + A * E;
 }
 int64_t moegan_plan_ints(int32_t m_cap) { return PLAN_BLK + m_cap / 128 + 8; }
 int64_t moegan_router_bwd_workspace_bytes(const moegan_shape* s) {
@@ -259,7 +260,7 @@ int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
     // pre == NULL: forward-only call, nothing is saved for the backward pass
     const uint64_t S = s->precision == 1 ? 2 : 1;
     const int d = s->d, hid = 4 * s->d;
-    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int T_pad = row_pad(s->T);
     const long long m_blocks = s->m_cap / 128;
     cudaStream_t st = (cudaStream_t)stream;
     {   // GEMM1: pre = x W1^T + b1, h = gelu(pre)   (t2i_moe_gan.py:257-258)

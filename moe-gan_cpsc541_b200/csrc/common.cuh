@@ -50,6 +50,7 @@ void count_launch();
 int validate_shape(const moegan_shape* s);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int row_pad(int rows) { return (rows + MOEGAN_ROW_ALIGN - 1) / MOEGAN_ROW_ALIGN * MOEGAN_ROW_ALIGN; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ------------------------------------------------------------------------------

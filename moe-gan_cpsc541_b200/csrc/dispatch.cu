@@ -45,7 +45,7 @@ plan_kernel(const int* __restrict__ chunk_counts, const float* __restrict__ chun
     __syncthreads();
 
     if (dense) {
-        const int T_pad = (T + 127) / 128 * 128;
+        const int T_pad = (T + MOEGAN_ROW_ALIGN - 1) / MOEGAN_ROW_ALIGN * MOEGAN_ROW_ALIGN;
         const int bpe = T_pad / 128;
         if (tid <= E) plan[PLAN_OFF + tid] = tid * T_pad;
         if (tid < E) plan[PLAN_CNT + tid] = T;
@@ -59,7 +59,7 @@ plan_kernel(const int* __restrict__ chunk_counts, const float* __restrict__ chun
             off_e[e] = off;
             plan[PLAN_OFF + e] = off;
             plan[PLAN_CNT + e] = tot_e[e];
-            off += (tot_e[e] + 127) / 128 * 128;
+            off += (tot_e[e] + MOEGAN_ROW_ALIGN - 1) / MOEGAN_ROW_ALIGN * MOEGAN_ROW_ALIGN;
         }
         if (off > m_cap) off = m_cap;            // cannot happen (m_cap is an upper bound); guards the buffers
         off_e[E] = off;
@@ -402,7 +402,7 @@ int launch_prep_weights(const moegan_shape* s, const float* const* w1, const flo
 }
 
 int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, cudaStream_t st) {
-    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int T_pad = row_pad(s->T);
     const int blocks = ceil_div(s->T, 8);
     if (s->precision == 1) combine_fwd_kernel<true><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
     else                   combine_fwd_kernel<false><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
@@ -412,7 +412,7 @@ int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates,
 
 int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
                        const float* row_gate, const float* gates, void* dy_op, float* dgate_row, cudaStream_t st) {
-    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int T_pad = row_pad(s->T);
     const int blocks = ceil_div(s->m_cap, 8);
     __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
     if (s->precision == 1)
@@ -425,7 +425,7 @@ int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
 
 int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
                      cudaStream_t st) {
-    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int T_pad = row_pad(s->T);
     const int blocks = ceil_div(s->T, 8);
     if (s->precision == 1) uncombine_kernel<true><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);
     else                   uncombine_kernel<false><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);

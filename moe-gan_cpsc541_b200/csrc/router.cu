@@ -627,7 +627,7 @@ int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const floa
                              const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
                              const float* temperature, float af, float* draw, void* dfp_op, float* dtau_part, cudaStream_t st) {
     const int blocks = ceil_div(s->T, RB_TOK);
-    const int T_pad = ceil_div(s->T, 128) * 128;
+    const int T_pad = row_pad(s->T);
     router_bwd_logits_kernel<<<blocks, RB_THREADS, (s->E * HID + 8) * sizeof(float), st>>>(
         raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, af, s->T, T_pad, s->E, s->k, s->dense,
         s->precision == 1, draw, reinterpret_cast<__nv_bfloat16*>(dfp_op), dtau_part);

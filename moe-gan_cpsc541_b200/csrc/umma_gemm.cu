@@ -21,6 +21,8 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace moegan {
 
@@ -34,9 +36,12 @@ constexpr int WARP_MMA = 9;
 constexpr int NUM_THREADS = 320;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
 
-template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr uint32_t B_BYTES = BN * BK * 2;
+// CTA2 = cta_group::2: a CTA pair (cluster of 2) computes a 256 x BN tile; each CTA stages its own 128 rows of A and its
+// own HALF of B (BN/2 columns), so the operand bytes entering one SM per k-block drop from 48 KB to 32 KB - at 128x256x64
+// MACs per 512 tensor-pipe cycles that is 64 instead of 96 B/clk/SM, which is what the L2->SM path can actually deliver.
+template <int BN, bool CTA2> struct Cfg {
+    static constexpr int STAGES = CTA2 ? 6 : ((BN == 256) ? 4 : 6);
+    static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
     static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 4096;   // 4 KB per epilogue warp (TMA-store staging)
@@ -50,21 +55,24 @@ struct Tile {
     int row0;     // WGRAD: first reduction row of the expert
 };
 
-template <int BN, int KIND>
+// MB = rows of one scheduled tile: 128, or 256 for a CTA pair (which then splits it 128 + 128 by cluster rank)
+template <int BN, int KIND, bool CTA2>
 __device__ __forceinline__ int total_tiles(const GemmParams& p) {
+    constexpr int MB = CTA2 ? 2 * BM : BM;
     const int n_blocks = (p.N + BN - 1) / BN;
-    if (KIND == GEMM_WGRAD) return p.E * ((p.dimA + BM - 1) / BM) * n_blocks * (p.k_splits > 1 ? p.k_splits : 1);
+    if (KIND == GEMM_WGRAD) return p.E * ((p.dimA + MB - 1) / MB) * n_blocks * (p.k_splits > 1 ? p.k_splits : 1);
     const int m_blocks = p.m_blocks_host >= 0 ? p.m_blocks_host : __ldg(p.plan + 0);
-    return m_blocks * n_blocks;
+    return (CTA2 ? m_blocks / 2 : m_blocks) * n_blocks;
 }
 
-template <int BN, int KIND>
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
+template <int BN, int KIND, bool CTA2>
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int rank) {
+    constexpr int MB = CTA2 ? 2 * BM : BM;
     Tile t;
     const int n_blocks = (p.N + BN - 1) / BN;
     t.split = 0;
     if (KIND == GEMM_WGRAD) {
-        const int mA = (p.dimA + BM - 1) / BM;
+        const int mA = (p.dimA + MB - 1) / MB;
         const int ks = p.k_splits > 1 ? p.k_splits : 1;
         t.split = tile % ks;
         tile /= ks;
@@ -83,10 +91,12 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
     } else {
         t.mb = tile / n_blocks;
         t.nb = tile - t.mb * n_blocks;
+        if (CTA2) t.mb *= 2;     // expert segments are 256-row aligned: both 128-row halves belong to the same expert
         t.e = p.m_blocks_host >= 0 ? 0 : __ldg(p.plan + PLAN_BLK + t.mb);
         t.row0 = 0;
         t.nkb_pp = p.K / BK;
     }
+    if (CTA2) { if (KIND == GEMM_WGRAD) t.mb *= 2; t.mb += rank; }   // this CTA's 128-row half of the pair tile
     return t;
 }
 
@@ -121,6 +131,20 @@ __device__ __forceinline__ void load32_bf16(const __nv_bfloat16* src, float (&v)
         v[8 * i + 6] = bf16_lo_to_float(u.w); v[8 * i + 7] = bf16_hi_to_float(u.w);
     }
 }
+// issue the 64-byte row segment load now, unpack later (software prefetch of the gelu' tile)
+__device__ __forceinline__ void load32_bf16_packed(const __nv_bfloat16* src, uint4 (&u)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+}
+__device__ __forceinline__ void unpack32_bf16(const uint4 (&u)[4], float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[8 * i + 0] = bf16_lo_to_float(u[i].x); v[8 * i + 1] = bf16_hi_to_float(u[i].x);
+        v[8 * i + 2] = bf16_lo_to_float(u[i].y); v[8 * i + 3] = bf16_hi_to_float(u[i].y);
+        v[8 * i + 4] = bf16_lo_to_float(u[i].z); v[8 * i + 5] = bf16_hi_to_float(u[i].z);
+        v[8 * i + 6] = bf16_lo_to_float(u[i].w); v[8 * i + 7] = bf16_hi_to_float(u[i].w);
+    }
+}
 __device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -129,11 +153,11 @@ __device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
     }
 }
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1, const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CTA2>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
@@ -148,26 +172,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;     // 0 = leader CTA of the pair (issues the MMAs)
+    const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == WARP_TMA && lane == 0) {
         ptx::prefetch_tmap(&mapA);
         ptx::prefetch_tmap(&mapB);
         ptx::prefetch_tmap(&mapO0);
         ptx::prefetch_tmap(&mapO1);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+        // CTA2: the leader's full barrier collects both producers' arrive.expect_tx (and both CTAs' TMA bytes); the leader's
+        // TMEM-empty barrier collects the epilogue warps of both CTAs
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), CTA2 ? 2 : 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), CTA2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
         ptx::fence_mbar_init();
     }
     if (warp == WARP_MMA) {
-        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (CTA2) { ptx::tmem_alloc_cta2(tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish_cta2(); }
+        else      { ptx::tmem_alloc(tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CTA2) ptx::cluster_sync_all();     // peer barriers are initialised before anybody signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int ntiles = total_tiles<BN, KIND>(p);
+    const int ntiles = total_tiles<BN, KIND, CTA2>(p);
     const uint32_t mn_lbo = p.mn_lbo ? p.mn_lbo : 8192u;   // bytes between 64-element MN groups (one TMA box)
     const uint32_t mn_sbo = p.mn_sbo ? p.mn_sbo : 1024u;   // bytes between 8-row K groups
     const uint32_t mn_kadv = p.mn_kadv ? p.mn_kadv : 2048u; // bytes per UMMA_K = 16 rows
@@ -176,36 +206,45 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // =============================== TMA producer ===============================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const Tile t = decode_tile<BN, KIND>(p, tile);
+            constexpr int BNL = CTA2 ? BN / 2 : BN;          // B columns staged by THIS CTA
+            const int bn_off = CTA2 ? rank * BNL : 0;
+            for (int tile = tile0; tile < ntiles; tile += tile_stride) {
+                const Tile t = decode_tile<BN, KIND, CTA2>(p, tile, rank);
                 const int nkb = t.nkb_pp * p.passes;
                 int pass = 0, kk = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + A_BYTES;
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    // completion barrier: local, or (CTA2) the LEADER's barrier addressed through the cluster window
+                    const uint32_t fbar = CTA2 ? ptx::mapa_cluster(full_bar(stage), 0) : full_bar(stage);
+                    if (CTA2) ptx::mbar_arrive_expect_tx_cluster(fbar, C::STAGE_BYTES);
+                    else      ptx::mbar_arrive_expect_tx(fbar, C::STAGE_BYTES);
+                    auto ld = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+                        if (CTA2) ptx::tma_load_2d_cta2(dst, m, fbar, c0, c1);
+                        else      ptx::tma_load_2d(dst, m, fbar, c0, c1);
+                    };
                     const int a_lo = (pass == 2) ? p.a_lo_off : 0;
                     const int b_lo = (pass == 1) ? p.b_lo_off : 0;
                     if (KIND == GEMM_WGRAD) {
                         const int krow = t.row0 + kk * BK;
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
-                            ptx::tma_load_2d(a_dst + i * 8192u, &mapA, full_bar(stage), a_lo + t.mb * BM + i * 64, krow);
+                            ld(a_dst + i * 8192u, &mapA, a_lo + t.mb * BM + i * 64, krow);
                         const int brow = p.b_rel ? kk * BK : krow;
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            ptx::tma_load_2d(b_dst + i * 8192u, &mapB, full_bar(stage), b_lo + t.nb * BN + i * 64, brow);
+                        for (int i = 0; i < BNL / 64; ++i)
+                            ld(b_dst + i * 8192u, &mapB, b_lo + t.nb * BN + bn_off + i * 64, brow);
                     } else {
                         const int ablk = p.a_mod > 0 ? (t.mb % p.a_mod) : t.mb;
-                        ptx::tma_load_2d(a_dst, &mapA, full_bar(stage), a_lo + kk * BK, ablk * BM);
+                        ld(a_dst, &mapA, a_lo + kk * BK, ablk * BM);
                         if (KIND == GEMM_ROWS_BK) {
-                            ptx::tma_load_2d(b_dst, &mapB, full_bar(stage), b_lo + kk * BK, t.e * p.b_rows_per_expert + t.nb * BN);
+                            ld(b_dst, &mapB, b_lo + kk * BK, t.e * p.b_rows_per_expert + t.nb * BN + bn_off);
                         } else {
                             const int brow = t.e * p.b_rows_per_expert + kk * BK;
 #pragma unroll
-                            for (int i = 0; i < BN / 64; ++i)
-                                ptx::tma_load_2d(b_dst + i * 8192u, &mapB, full_bar(stage), b_lo + t.nb * BN + i * 64, brow);
+                            for (int i = 0; i < BNL / 64; ++i)
+                                ld(b_dst + i * 8192u, &mapB, b_lo + t.nb * BN + bn_off + i * 64, brow);
                         }
                     }
                     if (++kk == t.nkb_pp) { kk = 0; ++pass; }
@@ -215,18 +254,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp == WARP_MMA) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, KIND == GEMM_WGRAD ? 1 : 0, KIND == GEMM_ROWS_BK ? 0 : 1);
+        if (lane == 0 && rank == 0) {                       // CTA2: only the leader issues; it drives both SMs' tensor cores
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, KIND == GEMM_WGRAD ? 1 : 0, KIND == GEMM_ROWS_BK ? 0 : 1);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const Tile t = decode_tile<BN, KIND>(p, tile);
+            for (int tile = tile0; tile < ntiles; tile += tile_stride) {
+                const Tile t = decode_tile<BN, KIND, CTA2>(p, tile, rank);
                 const int nkb = t.nkb_pp * p.passes;
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue (of both CTAs) has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                if (nkb == 0) {
-                    ptx::mbar_arrive(tfull_bar(acc));               // empty expert: epilogue writes zeros
+                if (nkb == 0) {                                     // empty expert: epilogue writes zeros
+                    ptx::mbar_arrive(tfull_bar(acc));
+                    if (CTA2) ptx::mbar_arrive_cluster(ptx::mapa_cluster(tfull_bar(acc), 1));
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
@@ -239,10 +279,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                                                  : ptx::umma_smem_desc(a_addr + k * 32u, 16u, 1024u);
                         const uint64_t db = (KIND == GEMM_ROWS_BK) ? ptx::umma_smem_desc(b_addr + k * 32u, 16u, 1024u)
                                                                    : ptx::umma_smem_desc(b_addr + k * mn_kadv, mn_lbo, mn_sbo);
-                        ptx::umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CTA2) ptx::umma_bf16_cta2(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else      ptx::umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(empty_bar(stage));             // smem slot reusable once these MMAs retire
-                    if (kb == nkb - 1) ptx::umma_commit(tfull_bar(acc));
+                    // smem slot reusable once these MMAs retire (CTA2: signalled in BOTH CTAs - each producer waits locally)
+                    if (CTA2) { ptx::umma_commit_cta2(empty_bar(stage), 3); if (kb == nkb - 1) ptx::umma_commit_cta2(tfull_bar(acc), 3); }
+                    else      { ptx::umma_commit(empty_bar(stage));         if (kb == nkb - 1) ptx::umma_commit(tfull_bar(acc)); }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 acc ^= 1; if (acc == 0) acc_phase ^= 1u;
@@ -266,9 +308,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             ptx::fence_proxy_async_smem();
             __syncwarp();
         };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const Tile t = decode_tile<BN, KIND>(p, tile);
+        for (int tile = tile0; tile < ntiles; tile += tile_stride) {
+            const Tile t = decode_tile<BN, KIND, CTA2>(p, tile, rank);
             const int nkb = t.nkb_pp * p.passes;
+            // EPI_MUL_BF16: the gelu' tile does not depend on the accumulator - fetch the first 32 columns BEFORE waiting
+            // for the MMAs, and every later chunk one chunk ahead, so its DRAM latency is off the critical path
+            uint4 aux_pf[4] = {};
+            const bool mul_epi = (KIND != GEMM_WGRAD) && (epi == EPI_MUL_BF16);
+            const long long aux_row = (long long)t.mb * BM + row_in_tile;
+            const bool aux_ok = mul_epi && aux_row < p.out_rows_valid;
+            const __nv_bfloat16* aux_base = reinterpret_cast<const __nv_bfloat16*>(p.aux) + aux_row * p.ld_aux + t.nb * BN;
+            if (aux_ok && (t.nb * BN + half * (BN / 2)) < p.N) load32_bf16_packed(aux_base + half * (BN / 2), aux_pf);
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int grow = t.mb * BM + row_in_tile;      // this thread's row inside the (expert's) output
@@ -365,11 +415,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                     case EPI_MUL_BF16: {
                         float a[32];
-                        if (row_ok) load32_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ld_aux + col0, a);
-                        else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) a[i] = 0.0f;
-                        }
+                        unpack32_bf16(aux_pf, a);                 // prefetched one chunk ago (zeros for clipped rows)
+                        const int cn = c + 32;
+                        if (aux_ok && cn < (half + 1) * (BN / 2) && (t.nb * BN + cn) < p.N) load32_bf16_packed(aux_base + cn, aux_pf);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] *= a[i];
                         flush_begin();
@@ -408,7 +456,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CTA2 && rank != 0) ptx::mbar_arrive_cluster(ptx::mapa_cluster(tempty_bar(acc), 0));   // leader's barrier
+                else                   ptx::mbar_arrive(tempty_bar(acc));
+            }
             acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
         if (pending && lane == 0) ptx::bulk_wait0();   // all bulk stores of this warp have been written
@@ -417,10 +468,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CTA2) ptx::cluster_sync_all();     // nobody leaves (or frees TMEM) while the peer may still signal / read
     if (warp == WARP_MMA) {
         __syncwarp();
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if (CTA2) ptx::tmem_dealloc_cta2(tmem_base, C::TMEM_COLS);
+        else      ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -480,21 +533,41 @@ int make_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) {
     return MOEGAN_OK;
 }
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool CTA2>
 int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo0, const CUtensorMap& mo1, const GemmParams& p, int grid,
                 cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)Cfg<BN>::SMEM_BYTES));
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)Cfg<BN, CTA2>::SMEM_BYTES));
         attr_set = true;
     }
     void* prof = nullptr;
-    profile_begin(stream, KIND * 1000 + BN, &prof);
-    umma_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, mo0, mo1, p);
+    profile_begin(stream, KIND * 1000 + BN + (CTA2 ? 100000 : 0), &prof);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, CTA2>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, KIND, CTA2>, ma, mb, mo0, mo1, p);
     profile_end(stream, prof);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(umma_gemm_kernel)");
     MOEGAN_CHECK_LAUNCH("umma_gemm_kernel");
     return MOEGAN_OK;
+}
+
+bool cta2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MOEGAN_DISABLE_CTA2"); v = (e != nullptr && e[0] == '1') ? 0 : 1; }
+    return v == 1;
 }
 
 }  // namespace
@@ -508,8 +581,12 @@ int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& 
     MOEGAN_REQUIRE(p.passes == 1 || p.passes == 3, MOEGAN_ERR_BAD_SHAPE, "passes must be 1 or 3");
     CUtensorMap ma, mb;
     int rc;
+    // CTA pairs (cta_group::2, 256-row tiles) whenever the shape allows: full 256-column blocks, and either the grouped
+    // row plan (expert segments are 256-row aligned, see MOEGAN_ROW_ALIGN) or a weight-gradient with 256 | dimA
+    const bool cta2 = cta2_enabled() && BN == 256 && p.N % 256 == 0 &&
+                      (kind == GEMM_WGRAD ? (p.dimA % 256 == 0) : (p.m_blocks_host < 0));
     const uint32_t a_box = (kind == GEMM_WGRAD) ? 64u : 128u;
-    const uint32_t b_box = (kind == GEMM_ROWS_BK) ? (uint32_t)BN : 64u;
+    const uint32_t b_box = (kind == GEMM_ROWS_BK) ? (uint32_t)(cta2 ? BN / 2 : BN) : 64u;
     if ((rc = make_tmap(&ma, A, a_box)) != MOEGAN_OK) return rc;
     if ((rc = make_tmap(&mb, B, b_box)) != MOEGAN_OK) return rc;
     // output tensor maps (TMA-store epilogue)
@@ -526,8 +603,16 @@ int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& 
         mo1 = mo0;
     }
     const int sms = num_sms();
+    if (cta2) {
+        long long pairs = (max_tiles + 1) / 2;               // max_tiles counts 128-row tiles
+        if (pairs > sms / 2) pairs = sms / 2;
+        const int grid2 = (int)(2 * pairs);
+        if (kind == GEMM_ROWS_BK) return launch_impl<256, GEMM_ROWS_BK, true>(ma, mb, mo0, mo1, p, grid2, stream);
+        if (kind == GEMM_ROWS_BMN) return launch_impl<256, GEMM_ROWS_BMN, true>(ma, mb, mo0, mo1, p, grid2, stream);
+        return launch_impl<256, GEMM_WGRAD, true>(ma, mb, mo0, mo1, p, grid2, stream);
+    }
     const int grid = (int)(max_tiles < sms ? max_tiles : sms);
-#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_>(ma, mb, mo0, mo1, p, grid, stream)
+#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_, false>(ma, mb, mo0, mo1, p, grid, stream)
     if (BN == 256) {
         if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(256, GEMM_ROWS_BK);
         if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(256, GEMM_ROWS_BMN);

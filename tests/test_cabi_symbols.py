@@ -26,11 +26,11 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_sizes_and_error_reporting(pkg):
     C = pkg._cabi
     lib = C.lib()
-    assert C.m_cap(4096, 8, 2, False) == 4096 * 2 + 128 * 8
-    assert C.m_cap(75, 4, 4, True) == 4 * 128
+    assert C.m_cap(4096, 8, 2, False) == 4096 * 2 + 256 * 8
+    assert C.m_cap(75, 4, 4, True) == 4 * 256
     assert lib.moegan_plan_ints(1024) == 88 + 8 + 8
     # bad shapes are rejected on the host with a message, nothing is launched (no GPU needed)
-    bad = C.Shape(100, 100, 64, 4, 4, 4, 25, 0, 1, 0, 512)
+    bad = C.Shape(100, 100, 64, 4, 4, 4, 25, 0, 1, 0, 1024)
     rc = lib.moegan_convert_tokens(bad, None, None, None)
     assert rc == -1 and "multiple of 128" in C.last_error()
     s = C.make_shape(128, 128, 64, 4, 4, 2, 64, 0, True, False)

@@ -95,8 +95,8 @@ def _check_routing(r, ora, E, k):
     keep = gap >= 1e-6
     idx = r["aux"]["topk_idx"]
     assert np.array_equal(idx[keep], cache.idx[keep]), f"routing mismatch; excluded tokens: {excluded.tolist()}"
-    # the permutation is a pure function of the assignment: stable, expert-contiguous, 128-row aligned
-    counts, offs, row_token, token_rows = O.stable_permutation(idx, E)
+    # the permutation is a pure function of the assignment: stable, expert-contiguous, 256-row aligned
+    counts, offs, row_token, token_rows = O.stable_permutation(idx, E, block=256)   # MOEGAN_ROW_ALIGN
     plan = r["aux"]["plan"]
     assert plan[0] * 128 == offs[-1] and plan[1] == offs[-1]
     assert np.array_equal(plan[8:8 + E + 1], offs)
@@ -223,7 +223,7 @@ def test_microbench_size_properties():
     r1 = G.run_cuda(m, x, w, eps, 1.0, dout=dout)
     T = B * H * W
     idx, plan = r1["aux"]["topk_idx"], r1["aux"]["plan"]
-    counts, offs, row_token, token_rows = O.stable_permutation(idx, E)
+    counts, offs, row_token, token_rows = O.stable_permutation(idx, E, block=256)
     assert counts.sum() == T * k and np.array_equal(plan[48:48 + E], counts)            # checksum of the histogram
     assert np.array_equal(r1["aux"]["token_rows"], token_rows)
     assert np.array_equal(r1["aux"]["row_token"][:offs[-1]], row_token)                 # stable + sorted inside experts
