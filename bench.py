@@ -399,6 +399,7 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     import torch
     pkg = importlib.import_module(PKG)
     lib = pkg._cabi.lib()
+    torch.backends.cudnn.benchmark = True          # autotune the (fixed-shape) convolutions of the host model, incl. R1's double backward
     G, D = build_models(pkg, dev)
     B = TRAIN_BATCH
     torch.manual_seed(1234 + rank)                # rank-offset data

@@ -584,7 +584,7 @@ int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& 
     // CTA pairs (cta_group::2, 256-row tiles) whenever the shape allows: full 256-column blocks, and either the grouped
     // row plan (expert segments are 256-row aligned, see MOEGAN_ROW_ALIGN) or a weight-gradient with 256 | dimA
     const bool cta2 = cta2_enabled() && BN == 256 && p.N % 256 == 0 &&
-                      (kind == GEMM_WGRAD ? (p.dimA % 256 == 0) : (p.m_blocks_host < 0));
+                      (kind == GEMM_WGRAD ? (p.dimA % 256 == 0) : (p.m_blocks_host < 0 || p.m_blocks_host % 2 == 0));
     const uint32_t a_box = (kind == GEMM_WGRAD) ? 64u : 128u;
     const uint32_t b_box = (kind == GEMM_ROWS_BK) ? (uint32_t)(cta2 ? BN / 2 : BN) : 64u;
     if ((rc = make_tmap(&ma, A, a_box)) != MOEGAN_OK) return rc;

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
 pkg = importlib.import_module("moe-gan_cpsc541_b200")
+torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 G = pkg.host_model.AuroraGenerator().cuda(); D = pkg.host_model.AuroraDiscriminator().cuda()
 tr = pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=False)
