@@ -155,10 +155,13 @@ int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
                        void* dy_op, float* dgate_row, void* stream);
 
 /* autograd of the experts (B2): dgrad + wgrad grouped GEMMs and bias column sums.
- * dpre_op [m_cap, S*4d], dx_rows [m_cap,d] (bf16 / fp32), dW1 [E,4d,d], db1 [E,4d], dW2 [E,d,4d], db2 [E,d] fp32. */
+ * dpre_op [m_cap, S*4d], dx_rows [m_cap,d] (bf16 / fp32), dW1 [E,4d,d], db1 [E,4d], dW2 [E,d,4d], db2 [E,d] fp32;
+ * scratch: moegan_ffn_bwd_scratch_bytes(). */
 int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
                    const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
-                   float* dW1, float* db1, float* dW2, float* db2, void* stream);
+                   float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream);
+/* bytes of scratch moegan_ffn_bwd needs (split-K partials of the weight gradients when E*d*4d gives too few tiles) */
+int64_t moegan_ffn_bwd_scratch_bytes(const moegan_shape* s);
 
 /* un-permute + sum of the k expert contributions per token, plus the router's dx:  dx [T,d] fp32. */
 int moegan_uncombine_bwd(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows,

@@ -75,7 +75,8 @@ SIGNATURES = {
     "moegan_ffn_fwd": (c_int32, [_SP] + [_P] * 9 + [_P]),
     "moegan_combine_fwd": (c_int32, [_SP] + [_P] * 4 + [_P]),
     "moegan_combine_bwd": (c_int32, [_SP] + [_P] * 8 + [_P]),
-    "moegan_ffn_bwd": (c_int32, [_SP] + [_P] * 13 + [_P]),
+    "moegan_ffn_bwd": (c_int32, [_SP] + [_P] * 13 + [_P, c_int64] + [_P]),
+    "moegan_ffn_bwd_scratch_bytes": (c_int64, [_SP]),
     "moegan_uncombine_bwd": (c_int32, [_SP] + [_P] * 4 + [_P]),
     "moegan_router_bwd": (c_int32, [_SP] + [_P] * 16 + [c_float, c_int32] + [_P] * 9 + [_P] * 2 + [_P] * 9 + [_P, c_int64] + [_P]),
     "moegan_balance_loss_fwd": (c_int32, [_P, c_int32, c_int32, c_float, _P, _P]),

@@ -83,6 +83,25 @@ static int g_mn_lbo = 0, g_mn_sbo = 0, g_mn_kadv = 0;   // debug overrides (0 = 
 
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// split-K factor for a grouped weight-gradient GEMM whose output has too few tiles to fill the chip (small d, huge T)
+static int wgrad_splits(const moegan_shape* s, int dimA, int N) {
+    const int BN = N % 256 == 0 ? 256 : 128;
+    const long long tiles = (long long)s->E * ceil_div(dimA, 128) * ceil_div(N, BN);
+    if (tiles >= 148) return 1;
+    const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;   // mean rows per expert
+    long long ks = (2 * 148 + tiles - 1) / tiles;
+    const long long max_ks = rows / 256 > 1 ? rows / 256 : 1;     // keep >= 4 k-blocks per split
+    if (ks > max_ks) ks = max_ks;
+    if (ks > 64) ks = 64;
+    return (int)ks;
+}
+static size_t ffn_bwd_scratch_bytes_impl(const moegan_shape* s) {
+    const size_t d = s->d, hid = 4 * (size_t)s->d;
+    const size_t k2 = wgrad_splits(s, s->d, 4 * s->d), k1 = wgrad_splits(s, 4 * s->d, s->d);
+    const size_t a = k2 > 1 ? k2 * s->E * d * hid * 4 : 0, b = k1 > 1 ? k1 * s->E * d * hid * 4 : 0;
+    return (a > b ? a : b) + 256;
+}
+
 struct RouterBwdWs {
     size_t draw, dfp_op, dtau_part, dtl, dwc_part, dWc, dtp, dtp_op, w_op, dWf, dWt, total;
 };
@@ -143,6 +162,10 @@ int64_t moegan_plan_ints(int32_t m_cap) { return PLAN_BLK + m_cap / 128 + 8; }
 int64_t moegan_router_bwd_workspace_bytes(const moegan_shape* s) {
     if (s == nullptr) return 0;
     return (int64_t)router_bwd_layout(s).total;
+}
+int64_t moegan_ffn_bwd_scratch_bytes(const moegan_shape* s) {
+    if (s == nullptr) return 0;
+    return (int64_t)ffn_bwd_scratch_bytes_impl(s);
 }
 int64_t moegan_debug_launch_count(void) { return g_launches.load(); }
 int moegan_debug_profile_enable(int32_t on) {
@@ -311,8 +334,11 @@ int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
 
 int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
                    const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
-                   float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+                   float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream) {
     CHECK_SHAPE(s);
+    MOEGAN_REQUIRE(scratch_bytes >= (int64_t)ffn_bwd_scratch_bytes_impl(s) && (scratch != nullptr || ffn_bwd_scratch_bytes_impl(s) <= 256),
+                   MOEGAN_ERR_BAD_SHAPE, "ffn_bwd: scratch %lld < required %lld bytes", (long long)scratch_bytes,
+                   (long long)ffn_bwd_scratch_bytes_impl(s));
     REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(W2_op); REQ_PTR(pre); REQ_PTR(h_op); REQ_PTR(dy_op); REQ_PTR(dpre_op);
     REQ_PTR(dx_rows); REQ_PTR(dW1); REQ_PTR(db1); REQ_PTR(dW2); REQ_PTR(db2);
     const uint64_t S = s->precision == 1 ? 2 : 1;
@@ -356,8 +382,11 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         GemmOperand B{h_op, S * hid, (uint64_t)s->m_cap, S * hid};
         GemmParams p = base_params(s, plan);
         p.N = hid; p.dimA = d; p.a_lo_off = d; p.b_lo_off = hid;
-        p.epi = EPI_F32; p.out0 = dW2; p.ld_out0 = hid;
-        RUN(launch_umma_gemm(GEMM_WGRAD, 256, A, B, p, (long long)s->E * (d / 128) * (hid / 256), st));
+        const int ks = wgrad_splits(s, d, hid);
+        p.k_splits = ks;
+        p.epi = EPI_F32; p.out0 = ks > 1 ? scratch : (void*)dW2; p.ld_out0 = hid;
+        RUN(launch_umma_gemm(GEMM_WGRAD, 256, A, B, p, (long long)s->E * (d / 128) * (hid / 256) * ks, st));
+        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(scratch), (long long)s->E * d * hid, ks, dW2, st));
     }
     {   // wgrad1: dW1[e] = dpre_e^T x_e   [4d, d]
         GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
@@ -365,8 +394,11 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         GemmParams p = base_params(s, plan);
         p.N = d; p.dimA = hid; p.a_lo_off = hid; p.b_lo_off = d;
         p.b_rel = s->dense ? 1 : 0;
-        p.epi = EPI_F32; p.out0 = dW1; p.ld_out0 = d;
-        RUN(launch_umma_gemm(GEMM_WGRAD, BNd, A, B, p, (long long)s->E * (hid / 128) * (d / BNd), st));
+        const int ks = wgrad_splits(s, hid, d);
+        p.k_splits = ks;
+        p.epi = EPI_F32; p.out0 = ks > 1 ? scratch : (void*)dW1; p.ld_out0 = d;
+        RUN(launch_umma_gemm(GEMM_WGRAD, BNd, A, B, p, (long long)s->E * (hid / 128) * (d / BNd) * ks, st));
+        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(scratch), (long long)s->E * d * hid, ks, dW1, st));
     }
     return MOEGAN_OK;
 }
@@ -522,7 +554,7 @@ static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layou
     L->total = (int64_t)o;
 }
 
-struct BlockBwdWs { size_t dy_op, dgate_row, dpre_op, dx_rows, dx_router, router_ws, total; };
+struct BlockBwdWs { size_t dy_op, dgate_row, dpre_op, dx_rows, dx_router, router_ws, ffn_scratch, total; };
 static BlockBwdWs block_bwd_layout(const moegan_shape* s) {
     const size_t S = s->precision == 1 ? 2 : 1, d = s->d, hid = 4 * (size_t)s->d, m_cap = s->m_cap;
     const size_t act = s->precision == 1 ? 4 : 2;
@@ -534,6 +566,7 @@ static BlockBwdWs block_bwd_layout(const moegan_shape* s) {
     w.dx_rows = o;   o = align256(o + m_cap * d * act);
     w.dx_router = o; o = align256(o + (size_t)s->T * d * 4);
     w.router_ws = o; o = align256(o + router_bwd_layout(s).total);
+    w.ffn_scratch = o; o = align256(o + ffn_bwd_scratch_bytes_impl(s));
     w.total = o;
     return w;
 }
@@ -601,7 +634,7 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
     RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, stream));
     RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, ws + W.dpre_op, ws + W.dx_rows,
-                       a->dW1, a->db1, a->dW2, a->db2, stream));
+                       a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream));
     if (!s->hard) {
         RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
                               I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,

@@ -452,4 +452,12 @@ int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void
     return MOEGAN_OK;
 }
 
+// out[i] = sum_s part[s * n + i], fixed order (deterministic split-K / split-row finish)
+int launch_sum_partials(const float* part, long long n, int nsplit, float* out, cudaStream_t st) {
+    if (n <= 0) return MOEGAN_OK;
+    colsum_finish_kernel<<<(int)ceil_div64(n, 256), 256, 0, st>>>(part, (int)n, nsplit, out);
+    MOEGAN_CHECK_LAUNCH("sum_partials");
+    return MOEGAN_OK;
+}
+
 }  // namespace moegan

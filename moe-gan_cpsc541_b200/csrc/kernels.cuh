@@ -48,4 +48,6 @@ int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* 
 int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* scratch, float* out,
                           cudaStream_t st);
 
+int launch_sum_partials(const float* part, long long n, int nsplit, float* out, cudaStream_t st);
+
 }  // namespace moegan

@@ -415,25 +415,41 @@ router_bwd_dtl_kernel(const float* __restrict__ draw, int tps, int E, float* __r
     }
 }
 
-// dWc[0:128] partials: part[blk][j][e] = sum over the block's 32 tokens of fp[t, j] * draw[t, e]
-constexpr int WC_TOK = 32;
+// dWc[0:128] partials: part[blk][j][e] = sum over the block's token range of fp[t, j] * draw[t, e].
+// At most WC_MAX_PARTS blocks, so the finishing sum stays short however large T is.
+constexpr int WC_TOK = 32;          // tokens per inner chunk (fp values held in registers)
+constexpr int WC_MAX_PARTS = 128;
 __global__ void __launch_bounds__(HID)
-router_bwd_dwc_part_kernel(const float* __restrict__ fp, const float* __restrict__ draw, int T, int E, float* __restrict__ part) {
+router_bwd_dwc_part_kernel(const float* __restrict__ fp, const float* __restrict__ draw, int T, int E, int tok_per_block,
+                           float* __restrict__ part) {
     __shared__ float ds[WC_TOK * MOEGAN_MAX_EXPERTS];
     const int j = threadIdx.x;
-    const int t0 = blockIdx.x * WC_TOK;
-    const int nt = min(WC_TOK, T - t0);
-    for (int i = j; i < nt * E; i += HID) ds[i] = draw[(size_t)t0 * E + i];
-    float f[WC_TOK];
+    const int tb0 = blockIdx.x * tok_per_block;
+    const int tb1 = min(tb0 + tok_per_block, T);
+    float acc[MOEGAN_MAX_EXPERTS];
 #pragma unroll
-    for (int tt = 0; tt < WC_TOK; ++tt) f[tt] = tt < nt ? fp[(size_t)(t0 + tt) * HID + j] : 0.0f;   // 32 loads in flight
-    __syncthreads();
-    for (int e = 0; e < E; ++e) {
-        float acc = 0.0f;
+    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) acc[e] = 0.0f;
+    for (int t0 = tb0; t0 < tb1; t0 += WC_TOK) {
+        const int nt = min(WC_TOK, tb1 - t0);
+        __syncthreads();
+        for (int i = j; i < nt * E; i += HID) ds[i] = draw[(size_t)t0 * E + i];
+        float f[WC_TOK];
 #pragma unroll
-        for (int tt = 0; tt < WC_TOK; ++tt) acc = fmaf(f[tt], tt < nt ? ds[tt * E + e] : 0.0f, acc);
-        part[((size_t)blockIdx.x * HID + j) * E + e] = acc;
+        for (int tt = 0; tt < WC_TOK; ++tt) f[tt] = tt < nt ? fp[(size_t)(t0 + tt) * HID + j] : 0.0f;   // 32 loads in flight
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) {
+            if (e < E) {
+                float a = acc[e];
+#pragma unroll
+                for (int tt = 0; tt < WC_TOK; ++tt) a = fmaf(f[tt], tt < nt ? ds[tt * E + e] : 0.0f, a);
+                acc[e] = a;
+            }
+        }
     }
+#pragma unroll
+    for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e)
+        if (e < E) part[((size_t)blockIdx.x * HID + j) * E + e] = acc[e];
 }
 
 // Finishes the small router reductions.  grid = 1 + B + E blocks of 256 threads:
@@ -635,7 +651,11 @@ int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const floa
     return MOEGAN_OK;
 }
 int router_bwd_logits_blocks(const moegan_shape* s) { return ceil_div(s->T, RB_TOK); }
-int router_bwd_dwc_parts(const moegan_shape* s) { return ceil_div(s->T, WC_TOK); }
+static int dwc_tok_per_block(const moegan_shape* s) {
+    const int chunks = ceil_div(s->T, WC_TOK);
+    return ceil_div(chunks, WC_MAX_PARTS) * WC_TOK;
+}
+int router_bwd_dwc_parts(const moegan_shape* s) { return ceil_div(s->T, dwc_tok_per_block(s)); }
 
 int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,
                             const float* dtau_part, const float* temperature, float af,
@@ -643,7 +663,7 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
     router_bwd_dtl_kernel<<<s->B, 256, 0, st>>>(draw, s->tokens_per_sample, s->E, dtl);
     MOEGAN_CHECK_LAUNCH("router_bwd_dtl_kernel");
     const int nparts = router_bwd_dwc_parts(s);
-    router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_part);
+    router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_tok_per_block(s), dwc_part);
     MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
     router_bwd_small_kernel<<<1 + s->B + s->E, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
                                                      temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
