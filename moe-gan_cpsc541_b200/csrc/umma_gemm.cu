@@ -52,7 +52,8 @@ template <int BN, bool CTA2> struct Cfg {
 struct Tile {
     int mb, nb, e, split;
     int nkb_pp;   // k-blocks per pass
-    int row0;     // WGRAD: first reduction row of the expert
+    int row0;     // WGRAD: first reduction row of this tile (expert start + split offset)
+    int rel0;     // WGRAD: the same, relative to the expert's first row (dense mode: B rows are shared by all experts)
 };
 
 // MB = rows of one scheduled tile: 128, or 256 for a CTA pair (which then splits it 128 + 128 by cluster rank)
@@ -87,6 +88,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int r
         const int per = (nkb_all + ks - 1) / ks;                 // k-blocks per split
         const int kb0 = min(t.split * per, nkb_all);
         t.row0 = r0 + kb0 * BK;
+        t.rel0 = kb0 * BK;
         t.nkb_pp = min(per, nkb_all - kb0);
     } else {
         t.mb = tile / n_blocks;
@@ -94,6 +96,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int r
         if (CTA2) t.mb *= 2;     // expert segments are 256-row aligned: both 128-row halves belong to the same expert
         t.e = p.m_blocks_host >= 0 ? 0 : __ldg(p.plan + PLAN_BLK + t.mb);
         t.row0 = 0;
+        t.rel0 = 0;
         t.nkb_pp = p.K / BK;
     }
     if (CTA2) { if (KIND == GEMM_WGRAD) t.mb *= 2; t.mb += rank; }   // this CTA's 128-row half of the pair tile
@@ -231,7 +234,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
                             ld(a_dst + i * 8192u, &mapA, a_lo + t.mb * BM + i * 64, krow);
-                        const int brow = p.b_rel ? kk * BK : krow;
+                        const int brow = p.b_rel ? t.rel0 + kk * BK : krow;
 #pragma unroll
                         for (int i = 0; i < BNL / 64; ++i)
                             ld(b_dst + i * 8192u, &mapB, b_lo + t.nb * BN + bn_off + i * 64, brow);
