@@ -197,7 +197,7 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
  * Byte offsets of the intermediates inside the forward workspace (all 256-byte aligned): */
 typedef struct {
     int64_t Wf, Wt, Wc, Wf_op, Wt_op, tp, tl, fp, raw, topk_idx, gates, chunk_counts, chunk_colsum, plan, chunk_base,
-            x_copy, a_op, row_token, row_gate, token_rows, pre, h_op, y, total;   /* -1 = not present */
+            x_copy, a_op, row_token, row_gate, token_rows, pre, h_op, y, eps_f, eps_t, eps_c, total;   /* -1 = not present */
 } moegan_block_layout;
 
 typedef struct {
@@ -218,7 +218,8 @@ typedef struct {
 typedef struct {
     const void* fwd_workspace;  /* the forward call's workspace (need_backward = 1), untouched since */
     const float* w;
-    const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;
+    const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;   /* eps_* may be NULL: the forward
+                                   call keeps its own copy of the eps it consumed inside fwd_workspace */
     const void* W1_op; const void* W2_op; const float* kl_out;
     const float* dout;          /* [T,d] */
     const float* dkl;           /* [1] or NULL */

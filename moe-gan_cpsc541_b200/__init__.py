@@ -3,7 +3,7 @@
 `importlib.import_module("moe-gan_cpsc541_b200")`."""
 from . import _cabi
 from .functional import MoEBlockFunction, BalanceLossFunction, MoEConfig, WeightCache
-from . import host_model, trainer
+from . import host_model, trainer, data
 from .trainer import MoEGANTrainer, GradReducer, dp_allreduce_load
 from .sparse_moe import SparseMoE, BayesianRouter, SparseExpertFFN, moe_balance_loss, install, NUM_EXPERTS
 

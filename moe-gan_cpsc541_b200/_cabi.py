@@ -30,7 +30,8 @@ class BlockLayout(ctypes.Structure):
     """moegan_block_layout: byte offsets inside the forward workspace (-1 = absent)."""
     _fields_ = [(n, c_int64) for n in
                 ("Wf", "Wt", "Wc", "Wf_op", "Wt_op", "tp", "tl", "fp", "raw", "topk_idx", "gates", "chunk_counts", "chunk_colsum",
-                 "plan", "chunk_base", "x_copy", "a_op", "row_token", "row_gate", "token_rows", "pre", "h_op", "y", "total")]
+                 "plan", "chunk_base", "x_copy", "a_op", "row_token", "row_gate", "token_rows", "pre", "h_op", "y", "eps_f", "eps_t", "eps_c",
+                 "total")]
 
 
 class BlockFwdArgs(ctypes.Structure):

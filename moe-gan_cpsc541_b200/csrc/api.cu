@@ -551,6 +551,10 @@ static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layou
     L->pre = take(m_cap * hid * act, need_bwd);
     L->h_op = take(m_cap * S * hid * 2, true);
     L->y = take(m_cap * d * act, true);
+    // the eps the forward consumed (the caller's buffers are redrawn by the next training forward)
+    L->eps_f = take(d * H * 4, need_bwd);
+    L->eps_t = take(Dt * H * 4, need_bwd);
+    L->eps_c = take(2 * H * E * 4, need_bwd);
     L->total = (int64_t)o;
 }
 
@@ -611,6 +615,12 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     }
     RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
     RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->out, stream));
+    if (a->need_backward && a->sampled) {
+        cudaStream_t st = (cudaStream_t)stream;
+        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_f), a->eps_f, (size_t)s->d * MOEGAN_ROUTER_HID * 4, cudaMemcpyDeviceToDevice, st));
+        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_t), a->eps_t, (size_t)s->Dt * MOEGAN_ROUTER_HID * 4, cudaMemcpyDeviceToDevice, st));
+        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_c), a->eps_c, (size_t)2 * MOEGAN_ROUTER_HID * s->E * 4, cudaMemcpyDeviceToDevice, st));
+    }
     return MOEGAN_OK;
 }
 
@@ -638,7 +648,7 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     if (!s->hard) {
         RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
                               I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
-                              a->sampled, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c,
+                              a->sampled, a->mu_f, a->rho_f, F(L.eps_f), a->mu_t, a->rho_t, F(L.eps_t), a->mu_c, a->rho_c, F(L.eps_c),
                               a->kl_out, a->sampled ? a->dkl : nullptr,
                               a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
                               ws + W.router_ws, (int64_t)router_bwd_layout(s).total, stream));

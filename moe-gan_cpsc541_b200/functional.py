@@ -191,7 +191,6 @@ class MoEBlockFunction(torch.autograd.Function):
             ctx.cfg, ctx.plan = cfg, plan
             ctx.ws, ctx.small = ws, small
             ctx.w = w
-            ctx.eps = (eps_f, eps_t, eps_c)
             ctx.router_params = router_params
             ctx.wops = (W1_op, W2_op)
         MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
@@ -220,7 +219,6 @@ class MoEBlockFunction(torch.autograd.Function):
         a.fwd_workspace = ctx.ws.data_ptr()
         a.w = ctx.w.data_ptr()
         (a.mu_f, a.rho_f, a.mu_t, a.rho_t, a.mu_c, a.rho_c, a.temperature) = [p.data_ptr() for p in ctx.router_params]
-        a.eps_f, a.eps_t, a.eps_c = [_dp(e) for e in ctx.eps]
         a.W1_op, a.W2_op = ctx.wops[0].data_ptr(), ctx.wops[1].data_ptr()
         a.kl_out = ctx.small.data_ptr() + 4 * E
         a.dout, a.dkl, a.dprobs, a.dload = dout.data_ptr(), _dp(dkl), _dp(dprobs), _dp(dload)

@@ -144,6 +144,29 @@ class AuroraGenerator(nn.Module):
         self.to_rgb_8 = ModulatedConv(256, 3, 1)
         self.to_rgb_16 = ModulatedConv(128, 3, 1)
 
+        self._use_checkpointing = False
+
+    def enable_checkpointing(self):
+        """Non-reentrant activation checkpointing of the three generative blocks (t2i_moe_gan.py:712-760).  The RNG
+        state is preserved, so the recomputation redraws the same router eps."""
+        self._use_checkpointing = True
+        return self
+
+    def disable_checkpointing(self):
+        self._use_checkpointing = False
+        return self
+
+    def _run_block(self, block, x, w, text_seq, kl_losses, annealing_factor):
+        if self._use_checkpointing and self.training and torch.is_grad_enabled():
+            def fn(x_, w_, t_):
+                kl = []
+                out, probs = block(x_, w_, t_, kl, annealing_factor)
+                return out, probs, kl[0]
+            out, probs, kl0 = torch.utils.checkpoint.checkpoint(fn, x, w, text_seq, use_reentrant=False)
+            kl_losses.append(kl0)
+            return out, probs
+        return block(x, w, text_seq, kl_losses, annealing_factor)
+
     def moe_layers(self) -> List[SparseMoE]:
         return [self.gen_block_4.attn_block.moe, self.gen_block_8.attn_block.moe, self.gen_block_16.attn_block.moe]
 
@@ -161,10 +184,10 @@ class AuroraGenerator(nn.Module):
             w = mean_latent + truncation_psi * (w - mean_latent)
         kl_losses, routing = [], []
         x = self.constant.repeat(B, 1, 1, 1)
-        x, p = self.gen_block_4(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
-        x, p = self.gen_block_8(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x, p = self._run_block(self.gen_block_4, x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x, p = self._run_block(self.gen_block_8, x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
         x_8 = self.to_rgb_8(x, w)
-        x, p = self.gen_block_16(x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
+        x, p = self._run_block(self.gen_block_16, x, w, text_seq, kl_losses, annealing_factor); routing.append(p)
         x_16 = self.to_rgb_16(x, w)
         kl = sum(kl_losses) if kl_losses else torch.zeros((), device=z.device)
         if return_routing and return_intermediate:

@@ -64,8 +64,44 @@ class BayesianRouter(nn.Module):
         kl = torch.nan_to_num(kl, nan=0.0, posinf=200.0, neginf=0.0)
         return torch.clamp(kl, min=0.0, max=120.0)
 
-    def forward(self, *a, **kw):
-        raise RuntimeError("BayesianRouter runs fused inside SparseMoE.forward on the B200 path; call the SparseMoE module")
+    @torch.no_grad()
+    def forward(self, feature, text_embedding, sampling=True, annealing_factor=1.0):
+        """Same contract as the reference (:335-402): feature [T,dim], text_embedding [T,text_dim] (the per-token expansion
+        the reference builds at :456) -> (probs [T,E], logits [T,E]).  Runs the router kernels (sample+KL, text
+        projection, fused router); inference-only here - gradients flow through SparseMoE.forward, which is what
+        the model calls."""
+        from . import _cabi as C
+        if not feature.is_cuda:
+            raise RuntimeError("BayesianRouter (B200 path) needs CUDA tensors: there is no CPU fallback")
+        lib = C.lib()
+        T, d = feature.shape
+        Dt, E = text_embedding.shape[1], self.num_experts
+        dev, f32 = feature.device, torch.float32
+        training = bool(sampling and self.training)
+        if training:
+            self.epsilon_f.normal_(); self.epsilon_t.normal_(); self.epsilon_c.normal_()
+        hard = not self.training
+        k = 1 if hard else E
+        shp = C.make_shape(T, d, Dt, E, k, T, 1, 1, not hard, hard)       # one "sample" per token: text rows are per token here
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        Wf = torch.empty((d, 128), dtype=f32, device=dev); Wt = torch.empty((Dt, 128), dtype=f32, device=dev)
+        Wc = torch.empty((256, E), dtype=f32, device=dev); kl = torch.empty((C.KL_OUT_FLOATS,), dtype=f32, device=dev)
+        C.check(lib.moegan_router_sample_kl_fwd(shp, C.ptr(self.feature_mu), C.ptr(self.feature_rho), C.ptr(self.epsilon_f),
+                                                C.ptr(self.text_mu), C.ptr(self.text_rho), C.ptr(self.epsilon_t),
+                                                C.ptr(self.combined_mu), C.ptr(self.combined_rho), C.ptr(self.epsilon_c),
+                                                1 if training else 0, C.ptr(Wf), C.ptr(Wt), C.ptr(Wc), None, None, C.ptr(kl), st),
+                "moegan_router_sample_kl_fwd")
+        tp = torch.empty((T, 128), dtype=f32, device=dev); tl = torch.empty((T, E), dtype=f32, device=dev)
+        x = feature.contiguous().float(); w = text_embedding.contiguous().float()
+        C.check(lib.moegan_router_text_fwd(shp, C.ptr(w), C.ptr(Wt), C.ptr(Wc), C.ptr(tp), C.ptr(tl), st), "moegan_router_text_fwd")
+        nch = max((T + C.CHUNK - 1) // C.CHUNK, 1)
+        raw = torch.empty((T, E), dtype=f32, device=dev); probs = torch.empty((T, E), dtype=f32, device=dev)
+        idx = torch.empty((T, k), dtype=torch.int32, device=dev); gates = torch.empty((T, k), dtype=f32, device=dev)
+        cc = torch.empty((nch, E), dtype=torch.int32, device=dev); cs = torch.empty((nch, E), dtype=f32, device=dev)
+        C.check(lib.moegan_router_fwd(shp, C.ptr(x), C.ptr(Wf), C.ptr(Wc), C.ptr(tl), C.ptr(self.temperature), float(annealing_factor),
+                                      None, C.ptr(raw), C.ptr(probs), C.ptr(idx), C.ptr(gates), C.ptr(cc), C.ptr(cs), st), "moegan_router_fwd")
+        tau = torch.clamp(self.temperature * annealing_factor, min=0.5, max=5.0)
+        return probs, torch.clamp(raw / tau, min=-20.0, max=20.0)
 
 
 class SparseMoE(nn.Module):

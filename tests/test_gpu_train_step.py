@@ -105,3 +105,59 @@ def test_inference_eval_mode_hard_routing():
     assert float(kl) == 0.0
     for p in probs:                                                      # one-hot routing in eval (:392-400)
         assert set(torch.unique(p).tolist()) <= {0.0, 1.0} and torch.all(p.sum(dim=1) == 1.0)
+
+
+def test_activation_checkpointing_matches_plain_backward():
+    """enable_checkpointing() (t2i_moe_gan.py:712-760, non-reentrant): the recomputation redraws the same eps, the MoE
+    autograd node is re-entrant, and the block keeps the eps it consumed - gradients equal the plain run bit for bit."""
+    pkg = G_.pkg()
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    Gm = hm.AuroraGenerator(moe_kwargs=dict(precision="fp32")).cuda()
+    z, text = torch.randn(4, 512, device="cuda"), torch.randn(4, 512, device="cuda")
+    grads = []
+    for ckpt in (False, True):
+        Gm.zero_grad(set_to_none=True)
+        Gm.enable_checkpointing() if ckpt else Gm.disable_checkpointing()
+        torch.manual_seed(11)
+        img, kl = Gm(z, text, annealing_factor=2.0)
+        (img.square().mean() + 1e-3 * kl).backward()
+        grads.append({n: p.grad.detach().clone() for n, p in Gm.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys()
+    for n in grads[0]:
+        den = grads[0][n].abs().max().clamp_min(1e-12)
+        assert float((grads[0][n] - grads[1][n]).abs().max() / den) < 1e-5, n
+
+
+def test_two_forwards_then_backward_of_the_first_uses_its_own_eps():
+    """The block saves the eps it consumed: a later training forward (which redraws router.epsilon_*) must not change
+    the gradients of an earlier one."""
+    pkg = G_.pkg()
+    torch.manual_seed(0)
+    moe = pkg.SparseMoE(128, 64, 4, precision="fp32").cuda()
+    x = torch.randn(2, 128, 8, 8, device="cuda", requires_grad=True)
+    w = torch.randn(2, 64, device="cuda", requires_grad=True)
+    torch.manual_seed(5)
+    out1, kl1, p1 = moe(x, w, 1.0)
+    eps_used = [getattr(moe.router, n).clone() for n in ("epsilon_f", "epsilon_t", "epsilon_c")]
+    out2, _, _ = moe(x.detach(), w.detach(), 1.0)          # redraws the buffers
+    out1.square().sum().backward()
+    g_late = moe.router.feature_rho.grad.clone()
+    moe.zero_grad(set_to_none=True); x.grad = None; w.grad = None
+    o, _, _ = moe(x, w, 1.0, eps=tuple(eps_used))
+    o.square().sum().backward()
+    assert torch.equal(o, out1)
+    assert float((moe.router.feature_rho.grad - g_late).abs().max()) == 0.0
+
+
+def test_bayesian_router_forward_matches_block_probs():
+    pkg = G_.pkg()
+    torch.manual_seed(0)
+    moe = pkg.SparseMoE(128, 64, 4, precision="fp32").cuda().eval()
+    x = torch.randn(2, 128, 4, 4, device="cuda"); w = torch.randn(2, 64, device="cuda")
+    with torch.no_grad():
+        _, _, probs_blk = moe(x, w, 1.5)
+    feat = x.permute(0, 2, 3, 1).reshape(-1, 128)
+    text = w.repeat_interleave(16, dim=0)                 # the reference's per-token expansion (:456)
+    probs, logits = moe.router(feat, text, sampling=False, annealing_factor=1.5)
+    assert torch.equal(probs, probs_blk) and logits.shape == (32, 4) and float(logits.abs().max()) <= 20.0
