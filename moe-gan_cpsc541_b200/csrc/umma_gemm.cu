@@ -124,16 +124,6 @@ __device__ __forceinline__ void stage32_f32(uint32_t base, int r, const float (&
         ptx::st_shared_v4(row + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
                           __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
 }
-__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* src, float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
-        v[8 * i + 0] = bf16_lo_to_float(u.x); v[8 * i + 1] = bf16_hi_to_float(u.x);
-        v[8 * i + 2] = bf16_lo_to_float(u.y); v[8 * i + 3] = bf16_hi_to_float(u.y);
-        v[8 * i + 4] = bf16_lo_to_float(u.z); v[8 * i + 5] = bf16_hi_to_float(u.z);
-        v[8 * i + 6] = bf16_lo_to_float(u.w); v[8 * i + 7] = bf16_hi_to_float(u.w);
-    }
-}
 // issue the 64-byte row segment load now, unpack later (software prefetch of the gelu' tile)
 __device__ __forceinline__ void load32_bf16_packed(const __nv_bfloat16* src, uint4 (&u)[4]) {
 #pragma unroll
@@ -375,12 +365,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         if (p.out1 != nullptr) {
                             float dg[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) gelu_and_grad_fast(v[i], v[i], dg[i]);
+                            for (int i = 0; i < 32; i += 2) gelu_pair_h2<true>(v[i], v[i + 1], v[i], v[i + 1], dg[i], dg[i + 1]);
                             flush_begin();
                             stage32_bf16(stage0 + 2048u, lane, dg);
                         } else {
+                            float u0, u1;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+                            for (int i = 0; i < 32; i += 2) gelu_pair_h2<false>(v[i], v[i + 1], v[i], v[i + 1], u0, u1);
                             flush_begin();
                         }
                         stage32_bf16(stage0, lane, v);
