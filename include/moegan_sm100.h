@@ -194,6 +194,8 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
 /* The same pipeline as the calls above (sample+KL -> text -> router -> plan -> gather/convert -> experts ->
  * combine, and its backward), enqueued by ONE call per direction with every intermediate carved out of ONE
  * caller-owned workspace: this is what SparseMoE.forward uses, so the host cost per step is two FFI calls.
+ * Independent sub-chains (weight conversion in the forward, the router's backward in the backward) are forked onto a
+ * library-owned side stream and joined before their results are needed (MOEGAN_DISABLE_SIDE_STREAM=1 turns this off).
  * Byte offsets of the intermediates inside the forward workspace (all 256-byte aligned): */
 typedef struct {
     int64_t Wf, Wt, Wc, Wf_op, Wt_op, tp, tl, fp, raw, topk_idx, gates, chunk_counts, chunk_colsum, plan, chunk_base,
@@ -204,7 +206,10 @@ typedef struct {
     const float* x;             /* [T,d] */
     const float* w;             /* [B,Dt] */
     const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;
-    const void* W1_op; const float* b1s; const void* W2_op; const float* b2s;   /* from moegan_prep_weights */
+    const void* W1_op; const float* b1s; const void* W2_op; const float* b2s;   /* stacked expert operands (moegan_prep_weights) */
+    /* host arrays of E device pointers, or all NULL: when set, the call (re)builds W1_op/b1s/W2_op/b2s from the per-expert
+     * fp32 parameters first - on an internal side stream, overlapped with the router and dispatch kernels */
+    const float* const* prep_w1; const float* const* prep_b1; const float* const* prep_w2; const float* const* prep_b2;
     float annealing_factor;
     int32_t sampled;            /* 1: training (weights sampled, KL computed) */
     int32_t need_backward;      /* 1: keep what moegan_block_bwd needs */

@@ -38,7 +38,7 @@ class BlockFwdArgs(ctypes.Structure):
     """moegan_block_fwd_args."""
     _fields_ = ([(n, c_void_p) for n in
                  ("x", "w", "mu_f", "rho_f", "eps_f", "mu_t", "rho_t", "eps_t", "mu_c", "rho_c", "eps_c", "temperature",
-                  "W1_op", "b1s", "W2_op", "b2s")]
+                  "W1_op", "b1s", "W2_op", "b2s", "prep_w1", "prep_b1", "prep_w2", "prep_b2")]
                 + [("annealing_factor", c_float), ("sampled", c_int32), ("need_backward", c_int32)]
                 + [(n, c_void_p) for n in ("out", "probs", "load", "kl_out", "workspace")]
                 + [("workspace_bytes", c_int64)])

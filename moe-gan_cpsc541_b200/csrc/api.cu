@@ -3,6 +3,7 @@
 #include "umma_gemm.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -515,6 +516,40 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
     return launch_balance_loss(load, E, T, balance_weight, dloss, nullptr, dload, (cudaStream_t)stream);
 }
 
+// ---- side stream: independent sub-chains of a block call run concurrently with the expert GEMMs ----------
+// (the router's backward chain / the weight conversion are many small launches that leave most SMs idle).  Fork and join
+// are cudaEventRecord / cudaStreamWaitEvent pairs, so the pattern is legal inside CUDA-graph capture too.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false, tried = false; };
+static SideStream g_side;
+static std::mutex g_side_mu;
+static bool side_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MOEGAN_DISABLE_SIDE_STREAM"); v = (e != nullptr && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+static SideStream* side_stream() {
+    if (!side_enabled()) return nullptr;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (!g_side.tried) {
+        g_side.tried = true;
+        g_side.ok = cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!g_side.ok) cudaGetLastError();
+    }
+    return g_side.ok ? &g_side : nullptr;
+}
+static int side_fork(SideStream* ss, cudaStream_t main_st) {
+    MOEGAN_CHECK_CUDA(cudaEventRecord(ss->fork, main_st));
+    MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    return MOEGAN_OK;
+}
+static int side_join(SideStream* ss, cudaStream_t main_st) {
+    MOEGAN_CHECK_CUDA(cudaEventRecord(ss->join, ss->s));
+    MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(main_st, ss->join, 0));
+    return MOEGAN_OK;
+}
+
 // ---- whole block in one call -------------------------------------------------------------------------
 static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layout* L) {
     const size_t S = s->precision == 1 ? 2 : 1, H = MOEGAN_ROUTER_HID;
@@ -601,6 +636,13 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     auto F = [&](int64_t off) -> float* { return reinterpret_cast<float*>(P(off)); };
     auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
     if (s->T == 0) return MOEGAN_OK;
+    // weight conversion (only when the caller's cache is stale) overlaps the router / dispatch kernels
+    SideStream* ss = (a->prep_w1 != nullptr) ? side_stream() : nullptr;
+    if (a->prep_w1 != nullptr) {
+        if (ss != nullptr) RUN(side_fork(ss, (cudaStream_t)stream));
+        RUN(moegan_prep_weights(s, a->prep_w1, a->prep_b1, a->prep_w2, a->prep_b2, const_cast<void*>(a->W1_op), const_cast<float*>(a->b1s),
+                                const_cast<void*>(a->W2_op), const_cast<float*>(a->b2s), ss != nullptr ? (void*)ss->s : stream));
+    }
     RUN(moegan_router_sample_kl_fwd(s, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c, a->sampled,
                                     F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), a->kl_out, stream));
     RUN(moegan_router_text_fwd(s, a->w, F(L.Wt), F(L.Wc), F(L.tp), F(L.tl), stream));
@@ -613,6 +655,7 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
         RUN(moegan_dispatch_gather(s, a->x, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), P(L.a_op), P(L.x_copy),
                                    I(L.row_token), F(L.row_gate), I(L.token_rows), stream));
     }
+    if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
     RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
     RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->out, stream));
     if (a->need_backward && a->sampled) {
@@ -643,6 +686,10 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dgate_row = reinterpret_cast<float*>(ws + W.dgate_row);
     float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
     RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, stream));
+    // the router's backward only needs dgate_row: run it on the side stream while the expert GEMMs own the main stream
+    SideStream* ss = s->hard ? nullptr : side_stream();
+    void* rstream = stream;
+    if (ss != nullptr) { RUN(side_fork(ss, (cudaStream_t)stream)); rstream = ss->s; }
     RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, ws + W.dpre_op, ws + W.dx_rows,
                        a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream));
     if (!s->hard) {
@@ -651,7 +698,8 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
                               a->sampled, a->mu_f, a->rho_f, F(L.eps_f), a->mu_t, a->rho_t, F(L.eps_t), a->mu_c, a->rho_c, F(L.eps_c),
                               a->kl_out, a->sampled ? a->dkl : nullptr,
                               a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
-                              ws + W.router_ws, (int64_t)router_bwd_layout(s).total, stream));
+                              ws + W.router_ws, (int64_t)router_bwd_layout(s).total, rstream));
+        if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
     }
     RUN(moegan_uncombine_bwd(s, ws + W.dx_rows, I(L.token_rows), dx_router, a->dx, stream));
     return MOEGAN_OK;

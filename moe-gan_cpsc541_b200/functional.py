@@ -90,28 +90,26 @@ class WeightCache:
         self.bufs = None
         self.capture_bufs = None
 
-    def get(self, cfg: MoEConfig, shape: C.Shape, w1: Sequence[torch.Tensor], b1, w2, b2):
+    def get(self, cfg: MoEConfig, w1: Sequence[torch.Tensor], b1, w2, b2):
+        """Returns (buffers, stale).  When `stale`, the caller passes the parameter pointer tables to moegan_block_fwd,
+        which converts on a side stream overlapped with the router kernels."""
         capturing = torch.cuda.is_current_stream_capturing()
         key = (cfg.precision, cfg.d, cfg.E,
                tuple((p.data_ptr(), p._version) for group in (w1, b1, w2, b2) for p in group))
         if not capturing and key == self.key and self.bufs is not None:
-            return self.bufs
+            return self.bufs, False
         dev = w1[0].device
         S = 2 if cfg.precision == 1 else 1
         hid = 4 * cfg.d
-        W1_op = torch.empty((cfg.E * hid, S * cfg.d), dtype=torch.bfloat16, device=dev)
-        W2_op = torch.empty((cfg.E * cfg.d, S * hid), dtype=torch.bfloat16, device=dev)
-        b1s = torch.empty((cfg.E, hid), dtype=torch.float32, device=dev)
-        b2s = torch.empty((cfg.E, cfg.d), dtype=torch.float32, device=dev)
-        rc = C.lib().moegan_prep_weights(shape, C.ptr_array(w1), C.ptr_array(b1), C.ptr_array(w2), C.ptr_array(b2),
-                                         C.ptr(W1_op), C.ptr(b1s), C.ptr(W2_op), C.ptr(b2s), C.c_void_p(_stream_ptr()))
-        C.check(rc, "moegan_prep_weights")
-        bufs = (W1_op, b1s, W2_op, b2s)
+        bufs = (torch.empty((cfg.E * hid, S * cfg.d), dtype=torch.bfloat16, device=dev),
+                torch.empty((cfg.E, hid), dtype=torch.float32, device=dev),
+                torch.empty((cfg.E * cfg.d, S * hid), dtype=torch.bfloat16, device=dev),
+                torch.empty((cfg.E, cfg.d), dtype=torch.float32, device=dev))
         if capturing:
             self.capture_bufs = bufs
         else:
             self.key, self.bufs = key, bufs
-        return bufs
+        return bufs, True
 
 
 def _dp(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -164,7 +162,7 @@ class MoEBlockFunction(torch.autograd.Function):
         w1 = expert_params[0::4]; b1 = expert_params[1::4]; w2 = expert_params[2::4]; b2 = expert_params[3::4]
         plan = _plan_for(cfg)
         need_bwd = cfg.need_backward
-        W1_op, b1s, W2_op, b2s = wcache.get(cfg, plan.shape, w1, b1, w2, b2)
+        (W1_op, b1s, W2_op, b2s), stale = wcache.get(cfg, w1, b1, w2, b2)
 
         ws = torch.empty((plan.fwd_bytes if need_bwd else plan.fwd_bytes_nobwd,), dtype=torch.uint8, device=dev)
         out = torch.empty((T, d), dtype=f32, device=dev)
@@ -176,6 +174,9 @@ class MoEBlockFunction(torch.autograd.Function):
         (a.mu_f, a.rho_f, a.mu_t, a.rho_t, a.mu_c, a.rho_c, a.temperature) = [p.data_ptr() for p in router_params]
         a.eps_f, a.eps_t, a.eps_c = _dp(eps_f), _dp(eps_t), _dp(eps_c)
         a.W1_op, a.b1s, a.W2_op, a.b2s = W1_op.data_ptr(), b1s.data_ptr(), W2_op.data_ptr(), b2s.data_ptr()
+        if stale:
+            tabs = [C.ptr_array(g) for g in (w1, b1, w2, b2)]       # kept alive until the call returns
+            a.prep_w1, a.prep_b1, a.prep_w2, a.prep_b2 = [ctypes.cast(t, C.c_void_p) for t in tabs]
         a.annealing_factor = float(cfg.annealing_factor)
         a.sampled = 1 if cfg.sampled else 0
         a.need_backward = 1 if need_bwd else 0

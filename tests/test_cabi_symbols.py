@@ -45,7 +45,7 @@ def test_ctypes_struct_layouts_match_the_header(pkg):
     C = pkg._cabi
     assert ctypes.sizeof(C.Shape) == 44
     assert ctypes.sizeof(C.BlockLayout) == 216
-    assert ctypes.sizeof(C.BlockFwdArgs) == 192 and C.BlockFwdArgs.out.offset == 144
+    assert ctypes.sizeof(C.BlockFwdArgs) == 224 and C.BlockFwdArgs.out.offset == 176
     assert ctypes.sizeof(C.BlockBwdArgs) == 280 and C.BlockBwdArgs.dx.offset == 160 and C.BlockBwdArgs.workspace_bytes.offset == 272
     s = C.make_shape(4096, 512, 512, 8, 2, 8, 512, 0, False, False)
     lay = C.BlockLayout()
