@@ -457,7 +457,8 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
                                  draw, dfp_op, dtau_part, st));
     RUN(launch_router_bwd_small(s, fp, draw, tp, Wc, dtau_part, temperature, annealing_factor, dtl, dwc_part, dWc, dtp, dtp_op,
                                 dtemperature, st));
-    RUN(launch_to_operand(w, s->B, Dt, s->precision == 1, 1, w_op, st));
+    const bool text_simt = router_bwd_text_simt_ok(s);     // tiny batches: one SIMT kernel instead of two tensor-core GEMMs
+    if (!text_simt) RUN(launch_to_operand(w, s->B, Dt, s->precision == 1, 1, w_op, st));
 
     GemmParams base;
     memset(&base, 0, sizeof(base));
@@ -483,6 +484,9 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
         p.out0 = dWf; p.ld_out0 = (long long)H;
         RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)(d / 128) * p.k_splits, st));
     }
+    if (text_simt) {
+        RUN(launch_router_bwd_text(s, w, dtp, Wt, dw, dWt, st));
+    } else {
     {   // dw [B, Dt] = dtp [B,128] * Wt[Dt,128]^T
         GemmOperand A{dtp_op, S * H, (uint64_t)s->B, S * H};
         GemmOperand B{Wt_op, S * H, (uint64_t)Dt, S * H};
@@ -499,6 +503,7 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
         p.N = (int)H; p.dimA = Dt; p.a_lo_off = Dt; p.b_lo_off = (int)H; p.k_rows_host = s->B;
         p.out0 = dWt; p.ld_out0 = (long long)H;
         RUN(launch_umma_gemm(GEMM_WGRAD, 128, A, B, p, (long long)ceil_div(Dt, 128), st));
+    }
     }
     RUN(launch_reparam_kl_bwd(s, dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampled, dwf_splits(s), kl_out, dkl,
                               dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c, st));

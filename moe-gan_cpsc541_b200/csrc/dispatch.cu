@@ -111,14 +111,16 @@ gather_kernel(const float* __restrict__ x, const int* __restrict__ topk_idx, con
         int idx[MOEGAN_MAX_TOPK], rows[MOEGAN_MAX_TOPK];
 #pragma unroll
         for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) { idx[j] = (valid && j < k) ? topk_idx[(size_t)t * k + j] : -1; rows[j] = -1; }
+        // lane e holds expert e's first row for this chunk: ONE coalesced load instead of E dependent ones
+        const int my_base = lane < E ? plan[PLAN_OFF + lane] + chunk_base[(size_t)chunk * E + lane] : 0;
         for (int e = 0; e < E; ++e) {
             bool has = false;
 #pragma unroll
             for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) has |= (idx[j] == e);
             const unsigned b = __ballot_sync(0xffffffffu, has);
+            const int base_e = __shfl_sync(0xffffffffu, my_base, e);
             if (has) {
-                const int rank = __popc(b & ((1u << lane) - 1u));       // tokens before me in this chunk (stable)
-                const int row = plan[PLAN_OFF + e] + chunk_base[(size_t)chunk * E + e] + rank;
+                const int row = base_e + __popc(b & ((1u << lane) - 1u));   // tokens before me in this chunk (stable)
 #pragma unroll
                 for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) if (idx[j] == e) rows[j] = row;
             }

@@ -21,6 +21,8 @@ int router_bwd_dwc_parts(const moegan_shape* s);
 int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,
                             const float* dtau_part, const float* temperature, float af,
                             float* dtl, float* dwc_part, float* dWc, float* dtp, void* dtp_op, float* dtemperature, cudaStream_t st);
+bool router_bwd_text_simt_ok(const moegan_shape* s);
+int launch_router_bwd_text(const moegan_shape* s, const float* w, const float* dtp, const float* Wt, float* dw, float* dWt, cudaStream_t st);
 int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* dWt, const float* dWc,
                           const float* mu_f, const float* rho_f, const float* eps_f,
                           const float* mu_t, const float* rho_t, const float* eps_t,

@@ -515,6 +515,28 @@ router_bwd_small_kernel(const float* __restrict__ dwc_part, int nparts, const fl
     }
 }
 
+// Text side of B4 for small batches: dw[b, k] = sum_j dtp[b, j] Wt[k, j]  and  dWt[k, j] = sum_b nan_to_num(w)[b, k] dtp[b, j].
+// grid = Dt blocks of 128 threads (thread j): block k owns row k of Wt.  B <= 64 only (registers); larger batches use
+// the tcgen05 GEMMs.
+constexpr int TXB_MAX_B = 64;
+__global__ void __launch_bounds__(HID)
+router_bwd_text_kernel(const float* __restrict__ w, const float* __restrict__ dtp, const float* __restrict__ Wt, int B, int Dt,
+                       float* __restrict__ dw, float* __restrict__ dWt) {
+    __shared__ float red[4][TXB_MAX_B];
+    const int k = blockIdx.x, j = threadIdx.x, lane = j & 31, wid = j >> 5;
+    const float wt = Wt[(size_t)k * HID + j];
+    float acc = 0.0f;
+    for (int b = 0; b < B; ++b) {
+        const float g = dtp[(size_t)b * HID + j];
+        acc = fmaf(nan_to_num_router(__ldg(w + (size_t)b * Dt + k)), g, acc);
+        const float p = warp_sum(g * wt);
+        if (lane == 0) red[wid][b] = p;
+    }
+    dWt[(size_t)k * HID + j] = acc;
+    __syncthreads();
+    if (j < B) dw[(size_t)j * Dt + k] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+}
+
 // B5 + B6: dW -> (dmu, drho) through the reparameterisation clamps, plus the KL gradient.
 __global__ void __launch_bounds__(256)
 reparam_kl_bwd_kernel(const float* __restrict__ dWf, const float* __restrict__ dWt, const float* __restrict__ dWc,
@@ -669,6 +691,13 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
                                                      temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
                                                      reinterpret_cast<__nv_bfloat16*>(dtp_op), dtemperature);
     MOEGAN_CHECK_LAUNCH("router_bwd_small_kernel");
+    return MOEGAN_OK;
+}
+
+bool router_bwd_text_simt_ok(const moegan_shape* s) { return s->B <= TXB_MAX_B; }
+int launch_router_bwd_text(const moegan_shape* s, const float* w, const float* dtp, const float* Wt, float* dw, float* dWt, cudaStream_t st) {
+    router_bwd_text_kernel<<<s->Dt, HID, 0, st>>>(w, dtp, Wt, s->B, s->Dt, dw, dWt);
+    MOEGAN_CHECK_LAUNCH("router_bwd_text_kernel");
     return MOEGAN_OK;
 }
 
