@@ -40,11 +40,11 @@ constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
 // own HALF of B (BN/2 columns), so the operand bytes entering one SM per k-block drop from 48 KB to 32 KB - at 128x256x64
 // MACs per 512 tensor-pipe cycles that is 64 instead of 96 B/clk/SM, which is what the L2->SM path can actually deliver.
 template <int BN, bool CTA2> struct Cfg {
-    static constexpr int STAGES = CTA2 ? 4 : ((BN == 256) ? 3 : 4);
+    static constexpr int STAGES = CTA2 ? 6 : ((BN == 256) ? 4 : 6);
     static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
-    static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 8192;   // 2 x 4 KB per epilogue warp (double-buffered TMA-store staging)
+    static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 4096;   // 4 KB per epilogue warp (TMA-store staging)
     static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
@@ -289,22 +289,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int half = warp >> 2;        // which half of the BN columns
         const int row_in_tile = q * 32 + lane;
-        // two 4 KB staging buffers per warp, used alternately: a chunk only has to wait for the bulk store issued TWO
-        // chunks ago to have finished reading shared memory, so the TMA store latency is off the critical path
-        const uint32_t stage_base_w = staging_base + warp * 8192u;
-        uint32_t stage0 = stage_base_w;
-        uint32_t chunk_no = 0;
+        const uint32_t stage0 = staging_base + warp * 4096u;   // 4 KB per warp, 1024-aligned
         const int epi = p.epi;
         int acc = 0; uint32_t acc_phase = 0;
-        bool pending = false;              // this warp has bulk stores in flight
-        auto flush_begin = [&]() {         // pick the buffer for this chunk and make sure its previous store has been read
-            stage0 = stage_base_w + (chunk_no & 1u) * 4096u;
-            ++chunk_no;
-            if (pending) { if (lane == 0) ptx::bulk_wait_read1(); __syncwarp(); }
-        };
-        auto flush_begin_same = [&]() {    // a second store from the SAME buffer inside one chunk (fp32-mode epilogues)
-            if (lane == 0) ptx::bulk_wait_read0();
-            __syncwarp();
+        bool pending = false;              // this warp has a bulk store in flight that still reads its staging buffer
+        // free the staging buffer of the previous store, write the new tile(s), hand them to the TMA unit
+        auto flush_begin = [&]() {
+            if (pending) { if (lane == 0) ptx::bulk_wait_read0(); __syncwarp(); }
         };
         auto flush_end = [&]() {
             ptx::fence_proxy_async_smem();
@@ -404,7 +395,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         float lo[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) { v[i] = gelu_erf<true>(v[i]); float h; split_bf16(v[i], h, lo[i]); }
-                        if (p.out1 != nullptr) flush_begin_same(); else flush_begin();
+                        flush_begin();
                         stage32_bf16(stage0, lane, v);            // rounding v to bf16 gives exactly hi
                         stage32_bf16(stage0 + 2048u, lane, lo);
                         flush_end();
