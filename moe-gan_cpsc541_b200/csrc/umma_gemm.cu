@@ -45,8 +45,7 @@ template <int BN, bool CTA2> struct Cfg {
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
     static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 4096;   // 4 KB per epilogue warp (TMA-store staging)
-    static constexpr uint32_t BIAS_BYTES = NUM_EPI_WARPS * 512;       // per epilogue warp: the bias of its 128 columns
-    static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16 + BIAS_BYTES;
+    static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
@@ -162,7 +161,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-    const uint32_t bias_smem = tmem_slot + 16u;                                  // 16-byte aligned
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
     const int warp = threadIdx.x >> 5;
@@ -314,17 +312,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const bool aux_ok = mul_epi && aux_row < p.out_rows_valid;
             const __nv_bfloat16* aux_base = reinterpret_cast<const __nv_bfloat16*>(p.aux) + aux_row * p.ld_aux + t.nb * BN;
             if (aux_ok && (t.nb * BN + half * (BN / 2)) < p.N) load32_bf16_packed(aux_base + half * (BN / 2), aux_pf);
-            // bias of this warp's BN/2 columns -> its shared-memory slice, also before the wait (the per-chunk global
-            // loads used to sit on the critical path of every chunk)
+            // bias of this warp's BN/2 (<= 128) columns: ONE float4 per lane, fetched before the wait and broadcast with
+            // shuffles per chunk (the per-chunk global loads used to sit on the critical path of every chunk)
             const bool has_bias = (epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3);
-            const uint32_t my_bias = bias_smem + warp * 512u;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_bias) {
-                __syncwarp();
                 const int bc = t.nb * BN + half * (BN / 2) + lane * 4;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane * 4 < BN / 2 && bc < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)t.e * p.N + bc));
-                ptx::st_shared_v4(my_bias + lane * 16u, __float_as_uint(bv.x), __float_as_uint(bv.y), __float_as_uint(bv.z), __float_as_uint(bv.w));
-                __syncwarp();
+                if (lane * 4 < BN / 2 && bc < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)t.e * p.N + bc));
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -351,12 +345,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int col0 = t.nb * BN + c;
                 if (slab_ok && col0 < p.N) {   // warp-uniform
                     if (has_bias) {
-                        const uint32_t bsrc = my_bias + static_cast<uint32_t>(c - half * (BN / 2)) * 4u;
+                        const int l0 = (c - half * (BN / 2)) >> 2;      // lane holding the bias of this chunk's first column
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float4 f;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(bsrc + i * 16u));
-                            v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                            v[4 * i + 0] += __shfl_sync(0xffffffffu, bias4.x, l0 + i);
+                            v[4 * i + 1] += __shfl_sync(0xffffffffu, bias4.y, l0 + i);
+                            v[4 * i + 2] += __shfl_sync(0xffffffffu, bias4.z, l0 + i);
+                            v[4 * i + 3] += __shfl_sync(0xffffffffu, bias4.w, l0 + i);
                         }
                     }
                     switch (epi) {
