@@ -251,3 +251,41 @@ def test_microbench_size_properties():
                 out_ref[sel] += gates[sel, j:j + 1] * (h @ W2.T + b2)
     got = torch.from_numpy(O.nchw_to_tokens(r1["out"])).cuda()
     assert float((got - out_ref).abs().max() / out_ref.abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=2, H=8, W=8, d=128, Dt=64, E=16, k=4, mu_scale=10.0),
+    dict(B=2, H=8, W=8, d=128, Dt=64, E=32, k=8, mu_scale=10.0),     # MOEGAN_MAX_EXPERTS / MOEGAN_MAX_TOPK
+    dict(B=1, H=8, W=8, d=128, Dt=64, E=32, k=None, mu_scale=10.0),  # dense with 32 experts
+    dict(B=2, H=4, W=4, d=1024, Dt=64, E=2, k=1, mu_scale=3.0),      # largest supported dim, top-1 soft training gate
+])
+def test_expert_count_and_topk_limits(shape):
+    s = shape
+    params, x, w, dout, gp, eps = _random_case(77 + s["E"], s["B"], s["H"], s["W"], s["d"], s["Dt"], s["E"], mu_scale=s["mu_scale"])
+    m = G.build_module(params, s["d"], s["Dt"], s["E"], top_k=s["k"], precision="fp32")
+    r = G.run_cuda(m, x, w, eps, 1.0, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    ora = G.run_oracle(params, x, w, eps, 1.0, top_k=s["k"], dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    if s["k"] is not None:
+        _check_routing(r, ora, s["E"], s["k"])
+    assert G.rel_err(r["probs"], ora["probs"]) < 1e-4
+    assert G.rel_err(r["out"], ora["out"]) < 1e-4
+    G.compare_grads(r, ora, params, 1e-4)
+
+
+def test_fp16_autocast_and_bf16_input_follow_the_reference_contract():
+    """Under autocast (the reference uses fp16 autocast, t2i_moe_gan.py:1278) precision='auto' runs the bf16 tensor-core
+    path with an fp32 router; the output has x's dtype and the reference's NCHW-view strides."""
+    params, x, w, dout, gp, eps = _random_case(91, 2, 8, 8, 128, 64, 4)
+    m = G.build_module(params, 128, 64, 4, precision="auto")
+    ora = G.run_oracle(params, x, w, eps, 1.0)
+    xt, wt = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    e = tuple(torch.from_numpy(eps[k]).cuda() for k in O.EPS_KEYS)
+    for dt in (torch.float16, torch.bfloat16):
+        with torch.autocast("cuda", dtype=dt):
+            out, kl, probs = m(xt, wt, 1.0, eps=e)
+        assert out.dtype == torch.float32 and probs.dtype == torch.float32 and float(kl) == 120.0
+        assert G.rel_err(out.cpu().numpy(), ora["out"]) < 2e-2 and G.rel_err(probs.cpu().numpy(), ora["probs"]) < 1e-4
+    out32, _, _ = m(xt, wt, 1.0, eps=e)                       # no autocast -> fp32-accurate 3-pass mode
+    assert G.rel_err(out32.detach().cpu().numpy(), ora["out"]) < 1e-4
+    outb, _, _ = m(xt.bfloat16(), wt, 1.0, eps=e)             # low-precision input: output follows x.dtype
+    assert outb.dtype == torch.bfloat16 and outb.shape == xt.shape and outb.stride() == out32.stride()
