@@ -284,7 +284,7 @@ def test_fp16_autocast_and_bf16_input_follow_the_reference_contract():
         with torch.autocast("cuda", dtype=dt):
             out, kl, probs = m(xt, wt, 1.0, eps=e)
         assert out.dtype == torch.float32 and probs.dtype == torch.float32 and float(kl) == 120.0
-        assert G.rel_err(out.cpu().numpy(), ora["out"]) < 2e-2 and G.rel_err(probs.cpu().numpy(), ora["probs"]) < 1e-4
+        assert G.rel_err(out.detach().cpu().numpy(), ora["out"]) < 2e-2 and G.rel_err(probs.detach().cpu().numpy(), ora["probs"]) < 1e-4
     out32, _, _ = m(xt, wt, 1.0, eps=e)                       # no autocast -> fp32-accurate 3-pass mode
     assert G.rel_err(out32.detach().cpu().numpy(), ora["out"]) < 1e-4
     outb, _, _ = m(xt.bfloat16(), wt, 1.0, eps=e)             # low-precision input: output follows x.dtype
