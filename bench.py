@@ -392,6 +392,11 @@ def build_models(pkg, dev, seed=0):
     torch.manual_seed(seed)                       # identical initial weights on every rank
     G = pkg.host_model.AuroraGenerator().to(dev)
     D = pkg.host_model.AuroraDiscriminator().to(dev)
+    if os.environ.get("MOEGAN_BENCH_CHANNELS_LAST", "1") == "1":
+        # NHWC conv stacks: cuDNN's tensor-core kernels are NHWC-native (no nchw<->nhwc transposes around every conv) and
+        # the MoE blocks consume NHWC tokens anyway
+        G = G.to(memory_format=torch.channels_last)
+        D = D.to(memory_format=torch.channels_last)
     return G, D
 
 
@@ -406,6 +411,8 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     real_host = torch.randn(B, 3, 64, 64).clamp(-1, 1).pin_memory()
     text_host = torch.randn(B, 512).pin_memory()
     real, text = real_host.to(dev), text_host.to(dev)
+    if os.environ.get("MOEGAN_BENCH_CHANNELS_LAST", "1") == "1":
+        real = real.contiguous(memory_format=torch.channels_last)
 
     def make_trainer(graph):
         return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph)

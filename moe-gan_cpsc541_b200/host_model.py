@@ -42,7 +42,9 @@ class ModulatedConv(nn.Module):
 
     def forward(self, x, w):
         s = self.modulation(w)                                            # [B, in]
-        y = F.conv2d(x * s.to(x.dtype)[:, :, None, None], self.weight.to(x.dtype), padding=self.padding)
+        # under autocast F.conv2d casts (and caches) the weight itself; an explicit .to() would re-cast on every call
+        wgt = self.weight if (torch.is_autocast_enabled() or self.weight.dtype == x.dtype) else self.weight.to(x.dtype)
+        y = F.conv2d(x * s.to(x.dtype)[:, :, None, None], wgt, padding=self.padding)
         if self.demodulate:
             wsq = self.weight.float().pow(2).sum(dim=(2, 3))              # [out, in]
             d = torch.rsqrt(s.float().pow(2) @ wsq.t() + 1e-8)            # [B, out]
