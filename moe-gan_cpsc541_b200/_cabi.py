@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmoegan_sm100.so")
+LIB_PATH = os.environ.get("MOEGAN_LIB_PATH") or os.path.join(HERE, "libmoegan_sm100.so")   # override: A/B builds in tools/
 
 ROUTER_HID = 128
 MAX_EXPERTS = 32

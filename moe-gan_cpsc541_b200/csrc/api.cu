@@ -88,7 +88,7 @@ static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 static int wgrad_splits(const moegan_shape* s, int dimA, int N) {
     const int BN = N % 256 == 0 ? 256 : 128;
     const long long tiles = (long long)s->E * ceil_div(dimA, 128) * ceil_div(N, BN);
-    if (tiles >= 148) return 1;
+    if (tiles >= 96) return 1;       // >= 0.65 of a wave: the split's partial-sum traffic (ks x E x 8 d^2 x 4 B) costs more than the idle SMs
     const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;   // mean rows per expert
     long long ks = (2 * 148 + tiles - 1) / tiles;
     const long long max_ks = rows / 256 > 1 ? rows / 256 : 1;     // keep >= 4 k-blocks per split

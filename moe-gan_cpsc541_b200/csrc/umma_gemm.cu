@@ -30,23 +30,48 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = 128 B = one SWIZZLE_128B span
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int WARP_TMA = 8;
-constexpr int WARP_MMA = 9;
-constexpr int NUM_THREADS = 320;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t SMEM_LIMIT = 232448;    // 227 KB opt-in maximum per CTA
+
+// Epilogue warps: the K = d GEMMs (FFN1, dgrad2) have a 2-8 k-block main loop under a GELU / GELU' epilogue, i.e. they
+// are bound by how fast the epilogue warps drain TMEM.  With 2 warps per SM sub-partition the tcgen05.ld -> math ->
+// st.shared -> fence -> TMA-store chain of each warp is latency bound (IPC 0.3), so the row GEMMs run 16 epilogue warps
+// (4 per sub-partition; TMEM lane quarter = warp % 4, column group = warp / 4).  The weight-gradient GEMMs have a long
+// reduction and a trivial epilogue: they keep 8 warps and spend the shared memory on pipeline stages instead.
+template <int KIND> struct Warps {
+    static constexpr int EPI = (KIND == GEMM_WGRAD) ? 8 : 16;
+    static constexpr int TMA = EPI;
+    static constexpr int MMA = EPI + 1;
+    static constexpr int THREADS = (EPI + 2) * 32;
+};
+
+// bytes of TMA-store staging per epilogue warp: one 32x32 bf16 tile = 2 KB; two of them (gelu + gelu', hi + lo) or one
+// 32x32 fp32 tile = 4 KB
+// EPI_MUL_BF16: 2 KB output tile + a two-deep ring of 2 KB gelu' tiles that the warp TMA-loads one tile ahead
+__host__ __device__ constexpr uint32_t staging_per_warp(int epi) {
+    return epi == EPI_MUL_BF16 ? 6144u : (epi == EPI_BF16 || epi == EPI_BIAS_BF16) ? 2048u : 4096u;
+}
+__host__ __device__ constexpr bool epi_has_bias(int epi) { return epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3; }
 
 // CTA2 = cta_group::2: a CTA pair (cluster of 2) computes a 256 x BN tile; each CTA stages its own 128 rows of A and its
 // own HALF of B (BN/2 columns), so the operand bytes entering one SM per k-block drop from 48 KB to 32 KB - at 128x256x64
 // MACs per 512 tensor-pipe cycles that is 64 instead of 96 B/clk/SM, which is what the L2->SM path can actually deliver.
-template <int BN, bool CTA2> struct Cfg {
-    static constexpr int STAGES = CTA2 ? 6 : ((BN == 256) ? 4 : 6);
+template <int BN, int KIND, bool CTA2, int EPI> struct Cfg {
+    static constexpr int NEW = Warps<KIND>::EPI;
     static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
-    static constexpr uint32_t STAGING_BYTES = NUM_EPI_WARPS * 4096;   // 4 KB per epilogue warp (TMA-store staging)
-    static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+    static constexpr uint32_t STAGING_PER_WARP = staging_per_warp(EPI);
+    static constexpr uint32_t STAGING_BYTES = NEW * STAGING_PER_WARP;
+    static constexpr uint32_t BIAS_BYTES = NEW * 256;                 // <= 64 fp32 bias values per epilogue warp
+    // barriers: 2*STAGES smem full/empty, 4 TMEM full/empty, the TMEM base slot, 2 aux-ring barriers per epilogue warp
+    static constexpr uint32_t BAR_BYTES = 512;
+    static constexpr uint32_t FIXED = STAGING_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /* manual alignment */;
+    static constexpr int FIT = (int)((SMEM_LIMIT - FIXED) / STAGE_BYTES);
+    static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+    static_assert(STAGES >= 2, "pipeline too shallow");
+    static_assert(8 * (2 * STAGES + 5 + 2 * NEW) <= BAR_BYTES, "barrier region");
 };
 
 struct Tile {
@@ -124,10 +149,12 @@ __device__ __forceinline__ void stage32_f32(uint32_t base, int r, const float (&
         ptx::st_shared_v4(row + ((i ^ sw) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
                           __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
 }
-// issue the 64-byte row segment load now, unpack later (software prefetch of the gelu' tile)
-__device__ __forceinline__ void load32_bf16_packed(const __nv_bfloat16* src, uint4 (&u)[4]) {
+// inverse of stage32_bf16: row r of a 32x32 bf16 tile that a SWIZZLE_64B TMA load wrote to shared memory
+__device__ __forceinline__ void unstage32_bf16(uint32_t base, int r, uint4 (&u)[4]) {
+    const uint32_t row = base + r * 64;
+    const int sw = (r >> 1) & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    for (int i = 0; i < 4; ++i) u[i] = ptx::ld_shared_u4(row + ((i ^ sw) << 4));
 }
 __device__ __forceinline__ void unpack32_bf16(const uint4 (&u)[4], float (&v)[32]) {
 #pragma unroll
@@ -146,22 +173,27 @@ __device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
     }
 }
 
-template <int BN, int KIND, bool CTA2>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int KIND, bool CTA2, int EPI>
+__global__ void __launch_bounds__(Warps<KIND>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1, const GemmParams p) {
-    using C = Cfg<BN, CTA2>;
+    using C = Cfg<BN, KIND, CTA2, EPI>;
+    constexpr int NUM_EPI_WARPS = Warps<KIND>::EPI;
+    constexpr int WARP_TMA = Warps<KIND>::TMA;
+    constexpr int WARP_MMA = Warps<KIND>::MMA;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
     const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;        // 1024-aligned
-    const uint32_t bar_base = staging_base + C::STAGING_BYTES;
+    const uint32_t bias_base = staging_base + C::STAGING_BYTES;
+    const uint32_t bar_base = bias_base + C::BIAS_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+    auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 5 + 2 * w + b); };   // EPI_MUL_BF16 only
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -178,6 +210,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // TMEM-empty barrier collects the epilogue warps of both CTAs
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), CTA2 ? 2 : 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), CTA2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
+        if (EPI == EPI_MUL_BF16)
+            for (int w = 0; w < NUM_EPI_WARPS; ++w) { ptx::mbar_init(aux_bar(w, 0), 1); ptx::mbar_init(aux_bar(w, 1), 1); }
         ptx::fence_mbar_init();
     }
     if (warp == WARP_MMA) {
@@ -286,11 +320,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else {
         // =============================== epilogue warps ===============================
         // TMEM -> registers -> (bias / GELU / GELU') -> swizzled smem staging -> ONE bulk tensor store per 32x32 tile.
+        constexpr int CGROUPS = NUM_EPI_WARPS / 4;      // column groups (4 for the row GEMMs, 2 for WGRAD)
+        constexpr int CW = BN / CGROUPS;                // columns per warp: 32 .. 128
+        constexpr int NCH = CW / 32;                    // 32-column chunks per warp and tile
+        constexpr bool HAS_BIAS = epi_has_bias(EPI);
+        static_assert(!HAS_BIAS || CW <= 64, "bias slot holds 64 values");
         const int q = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = warp >> 2;        // which half of the BN columns
+        const int cg = warp >> 2;          // column group
         const int row_in_tile = q * 32 + lane;
-        const uint32_t stage0 = staging_base + warp * 4096u;   // 4 KB per warp, 1024-aligned
-        const int epi = p.epi;
+        const uint32_t stage0 = staging_base + warp * C::STAGING_PER_WARP;
+        const uint32_t bias_slot = bias_base + warp * 256u;
         int acc = 0; uint32_t acc_phase = 0;
         bool pending = false;              // this warp has a bulk store in flight that still reads its staging buffer
         // free the staging buffer of the previous store, write the new tile(s), hand them to the TMA unit
@@ -301,24 +340,42 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             ptx::fence_proxy_async_smem();
             __syncwarp();
         };
+        const int cbase = cg * CW;                                  // first column of this warp inside the tile
+        // EPI_MUL_BF16: the gelu' tile (aux) does not depend on the accumulator.  Each warp TMA-loads its own 32x32 aux
+        // tiles into a two-deep ring, two chunks (= one 256-column tile) ahead of their use: exact bytes, DRAM latency off
+        // the critical path.  (Plain row-strided loads thrash the ~30 KB of L1 left next to 225 KB of shared memory: ncu
+        // showed every 32-byte sector fetched twice.)  chunk sequence number cc -> (tile0 + cc / NCH * stride, cc % NCH).
+        uint32_t aux_cc = 0, aux_phase = 0;
+        auto aux_issue = [&](uint32_t cc) {                          // lane 0 only
+            const int tl = tile0 + (int)(cc / NCH) * tile_stride;
+            if (tl >= ntiles) return;
+            const Tile tn = decode_tile<BN, KIND, CTA2>(p, tl, rank);
+            const int col = tn.nb * BN + cbase + (int)(cc % NCH) * 32;
+            const int row = tn.mb * BM + q * 32;
+            if (row < p.out_rows_valid && col < p.N) {               // same predicate as the consumer's (slab_ok && col0 < N)
+                const uint32_t bar = aux_bar(warp, cc & 1);
+                ptx::mbar_arrive_expect_tx(bar, 2048u);
+                ptx::tma_load_2d(stage0 + 2048u + (cc & 1u) * 2048u, &mapO1, bar, col, row);
+            }
+        };
+        if (EPI == EPI_MUL_BF16 && lane == 0) { aux_issue(0); aux_issue(1); }
         for (int tile = tile0; tile < ntiles; tile += tile_stride) {
             const Tile t = decode_tile<BN, KIND, CTA2>(p, tile, rank);
             const int nkb = t.nkb_pp * p.passes;
-            // EPI_MUL_BF16: the gelu' tile does not depend on the accumulator - fetch the first 32 columns BEFORE waiting
-            // for the MMAs, and every later chunk one chunk ahead, so its DRAM latency is off the critical path
-            uint4 aux_pf[4] = {};
-            const bool mul_epi = (KIND != GEMM_WGRAD) && (epi == EPI_MUL_BF16);
-            const long long aux_row = (long long)t.mb * BM + row_in_tile;
-            const bool aux_ok = mul_epi && aux_row < p.out_rows_valid;
-            const __nv_bfloat16* aux_base = reinterpret_cast<const __nv_bfloat16*>(p.aux) + aux_row * p.ld_aux + t.nb * BN;
-            if (aux_ok && (t.nb * BN + half * (BN / 2)) < p.N) load32_bf16_packed(aux_base + half * (BN / 2), aux_pf);
-            // bias of this warp's BN/2 (<= 128) columns: ONE float4 per lane, fetched before the wait and broadcast with
-            // shuffles per chunk (the per-chunk global loads used to sit on the critical path of every chunk)
-            const bool has_bias = (epi >= EPI_BIAS_BF16 && epi <= EPI_GELU_X3);
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_bias) {
-                const int bc = t.nb * BN + half * (BN / 2) + lane * 4;
-                if (lane * 4 < BN / 2 && bc < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)t.e * p.N + bc));
+            // bias of this warp's CW (<= 64) columns -> private smem slot, fetched before the accumulator wait and read
+            // back as broadcast 16-byte loads (all lanes hold different ROWS of the same columns)
+            if (HAS_BIAS) {
+                constexpr int PER = CW / 32;                        // 1 or 2 values per lane
+                const int bc = t.nb * BN + cbase + lane * PER;
+                const float* bsrc = p.bias + (long long)t.e * p.N + bc;
+                if (PER == 2) {
+                    float2 b2 = make_float2(0.f, 0.f);
+                    if (bc < p.N) b2 = __ldg(reinterpret_cast<const float2*>(bsrc));
+                    ptx::st_shared_v2(bias_slot + lane * 8u, __float_as_uint(b2.x), __float_as_uint(b2.y));
+                } else {
+                    ptx::st_shared_b32(bias_slot + lane * 4u, __float_as_uint(bc < p.N ? __ldg(bsrc) : 0.f));
+                }
+                __syncwarp();
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -329,8 +386,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             else                    { out_row0 = t.mb * BM + q * 32; slab_ok = out_row0 < p.out_rows_valid; }
             const long long out_row = (long long)out_row0 + lane;
             const bool row_ok = (KIND == GEMM_WGRAD) ? (grow < p.dimA) : (out_row < p.out_rows_valid);
-#pragma unroll 1
-            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = cbase + ch * 32;
                 float v[32];
                 if (nkb > 0) {
                     uint32_t r[32];
@@ -342,36 +400,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.0f;
                 }
+                if (ch == NCH - 1) {
+                    // the accumulator is in registers: hand the TMEM stage back to the MMA warp before the math / stores
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CTA2 && rank != 0) ptx::mbar_arrive_cluster(ptx::mapa_cluster(tempty_bar(acc), 0));   // leader's barrier
+                        else                   ptx::mbar_arrive(tempty_bar(acc));
+                    }
+                }
                 const int col0 = t.nb * BN + c;
                 if (slab_ok && col0 < p.N) {   // warp-uniform
-                    if (has_bias) {
-                        const int l0 = (c - half * (BN / 2)) >> 2;      // lane holding the bias of this chunk's first column
+                    if (HAS_BIAS) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            v[4 * i + 0] += __shfl_sync(0xffffffffu, bias4.x, l0 + i);
-                            v[4 * i + 1] += __shfl_sync(0xffffffffu, bias4.y, l0 + i);
-                            v[4 * i + 2] += __shfl_sync(0xffffffffu, bias4.z, l0 + i);
-                            v[4 * i + 3] += __shfl_sync(0xffffffffu, bias4.w, l0 + i);
+                            const float4 b4 = ptx::ld_shared_f4(bias_slot + (uint32_t)(ch * 32 + 4 * i) * 4u);
+                            v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
                         }
                     }
-                    switch (epi) {
-                    case EPI_F32:
-                    case EPI_BIAS_F32:
+                    if (EPI == EPI_F32 || EPI == EPI_BIAS_F32) {
                         flush_begin();
                         stage32_f32(stage0, lane, v);
                         flush_end();
                         if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
                         pending = true;
-                        break;
-                    case EPI_BF16:
-                    case EPI_BIAS_BF16:
+                    } else if (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16) {
                         flush_begin();
                         stage32_bf16(stage0, lane, v);
                         flush_end();
                         if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
                         pending = true;
-                        break;
-                    case EPI_GELU_BF16: {
+                    } else if (EPI == EPI_GELU_BF16) {
                         if (p.out1 != nullptr) {
                             float dg[32];
 #pragma unroll
@@ -392,9 +451,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             ptx::bulk_commit();
                         }
                         pending = true;
-                        break;
-                    }
-                    case EPI_GELU_X3: {
+                    } else if (EPI == EPI_GELU_X3) {
                         if (p.out1 != nullptr) {   // fp32 pre-activation
                             flush_begin();
                             stage32_f32(stage0, lane, v);
@@ -415,13 +472,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             ptx::bulk_commit();
                         }
                         pending = true;
-                        break;
-                    }
-                    case EPI_MUL_BF16: {
+                    } else if (EPI == EPI_MUL_BF16) {
+                        const uint32_t b = aux_cc & 1u;
+                        ptx::mbar_wait(aux_bar(warp, b), (aux_phase >> b) & 1u);
+                        aux_phase ^= 1u << b;
+                        uint4 u[4];
+                        unstage32_bf16(stage0 + 2048u + b * 2048u, lane, u);   // rows the TMA clipped arrive as zeros
+                        __syncwarp();                                          // every lane has read the ring slot
+                        if (lane == 0) aux_issue(aux_cc + 2);
                         float a[32];
-                        unpack32_bf16(aux_pf, a);                 // prefetched one chunk ago (zeros for clipped rows)
-                        const int cn = c + 32;
-                        if (aux_ok && cn < (half + 1) * (BN / 2) && (t.nb * BN + cn) < p.N) load32_bf16_packed(aux_base + cn, aux_pf);
+                        unpack32_bf16(u, a);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] *= a[i];
                         flush_begin();
@@ -429,9 +489,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         flush_end();
                         if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
                         pending = true;
-                        break;
-                    }
-                    case EPI_DGELU_X3: {
+                    } else if (EPI == EPI_DGELU_X3) {
                         float a[32];
                         if (row_ok) load32_f32(reinterpret_cast<const float*>(p.aux) + out_row * p.ld_aux + col0, a);
                         else {
@@ -451,18 +509,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             ptx::bulk_commit();
                         }
                         pending = true;
-                        break;
-                    }
-                    default: break;
                     }
                 }
+                ++aux_cc;
                 __syncwarp();   // tcgen05.ld is warp-collective: reconverge before the next chunk
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CTA2 && rank != 0) ptx::mbar_arrive_cluster(ptx::mapa_cluster(tempty_bar(acc), 0));   // leader's barrier
-                else                   ptx::mbar_arrive(tempty_bar(acc));
             }
             acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
@@ -537,13 +587,14 @@ int make_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) {
     return MOEGAN_OK;
 }
 
-template <int BN, int KIND, bool CTA2>
+template <int BN, int KIND, bool CTA2, int EPI>
 int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo0, const CUtensorMap& mo1, const GemmParams& p, int grid,
                 cudaStream_t stream) {
+    using C = Cfg<BN, KIND, CTA2, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
-        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)Cfg<BN, CTA2>::SMEM_BYTES));
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, KIND, CTA2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)C::SMEM_BYTES));
         attr_set = true;
     }
     void* prof = nullptr;
@@ -551,8 +602,8 @@ int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<BN, CTA2>::SMEM_BYTES;
+    cfg.blockDim = dim3(Warps<KIND>::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -561,11 +612,20 @@ int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, KIND, CTA2>, ma, mb, mo0, mo1, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, KIND, CTA2, EPI>, ma, mb, mo0, mo1, p);
     profile_end(stream, prof);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(umma_gemm_kernel)");
     MOEGAN_CHECK_LAUNCH("umma_gemm_kernel");
     return MOEGAN_OK;
+}
+
+// tile width / CTA-pair variants of one (kind, epilogue) combination
+template <int KIND, int EPI>
+int launch_variant(int BN, bool cta2, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo0, const CUtensorMap& mo1,
+                   const GemmParams& p, int grid, cudaStream_t stream) {
+    if (cta2) return launch_impl<256, KIND, true, EPI>(ma, mb, mo0, mo1, p, grid, stream);
+    if (BN == 256) return launch_impl<256, KIND, false, EPI>(ma, mb, mo0, mo1, p, grid, stream);
+    return launch_impl<128, KIND, false, EPI>(ma, mb, mo0, mo1, p, grid, stream);
 }
 
 bool cta2_enabled() {
@@ -601,33 +661,40 @@ int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& 
     const bool o0_split = (p.epi == EPI_GELU_X3 || p.epi == EPI_DGELU_X3);
     const uint64_t o0_cols = o0_split ? (uint64_t)p.out_split_off + p.N : (uint64_t)p.N;
     if ((rc = make_out_tmap(&mo0, p.out0, o0_f32, o0_cols, o_rows, (uint64_t)p.ld_out0)) != MOEGAN_OK) return rc;
-    if (p.out1 != nullptr) {
+    if (p.epi == EPI_MUL_BF16) {
+        // no second output: the slot carries the map of the aux tensor (same 32x32 SWIZZLE_64B boxes as a bf16 output)
+        MOEGAN_REQUIRE(p.aux != nullptr, MOEGAN_ERR_NULL_POINTER, "GEMM aux tensor is NULL");
+        if ((rc = make_out_tmap(&mo1, p.aux, false, (uint64_t)p.N, o_rows, (uint64_t)p.ld_aux)) != MOEGAN_OK) return rc;
+    } else if (p.out1 != nullptr) {
         if ((rc = make_out_tmap(&mo1, p.out1, p.epi == EPI_GELU_X3, (uint64_t)p.N, o_rows, (uint64_t)p.ld_out1)) != MOEGAN_OK) return rc;
     } else {
         mo1 = mo0;
     }
     const int sms = num_sms();
+    int grid;
     if (cta2) {
         long long pairs = (max_tiles + 1) / 2;               // max_tiles counts 128-row tiles
         if (pairs > sms / 2) pairs = sms / 2;
-        const int grid2 = (int)(2 * pairs);
-        if (kind == GEMM_ROWS_BK) return launch_impl<256, GEMM_ROWS_BK, true>(ma, mb, mo0, mo1, p, grid2, stream);
-        if (kind == GEMM_ROWS_BMN) return launch_impl<256, GEMM_ROWS_BMN, true>(ma, mb, mo0, mo1, p, grid2, stream);
-        return launch_impl<256, GEMM_WGRAD, true>(ma, mb, mo0, mo1, p, grid2, stream);
-    }
-    const int grid = (int)(max_tiles < sms ? max_tiles : sms);
-#define MOEGAN_DISPATCH(BN_, KIND_) return launch_impl<BN_, KIND_, false>(ma, mb, mo0, mo1, p, grid, stream)
-    if (BN == 256) {
-        if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(256, GEMM_ROWS_BK);
-        if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(256, GEMM_ROWS_BMN);
-        if (kind == GEMM_WGRAD) MOEGAN_DISPATCH(256, GEMM_WGRAD);
+        grid = (int)(2 * pairs);
     } else {
-        if (kind == GEMM_ROWS_BK) MOEGAN_DISPATCH(128, GEMM_ROWS_BK);
-        if (kind == GEMM_ROWS_BMN) MOEGAN_DISPATCH(128, GEMM_ROWS_BMN);
-        if (kind == GEMM_WGRAD) MOEGAN_DISPATCH(128, GEMM_WGRAD);
+        grid = (int)(max_tiles < sms ? max_tiles : sms);
     }
-#undef MOEGAN_DISPATCH
-    set_error("unknown GEMM kind %d", kind);
+    // the (kind, epilogue) combinations the library uses; the epilogue is a template parameter so that every instance
+    // carries only its own code path (register budget of the 18-warp row GEMMs: 112 per thread)
+#define MOEGAN_CASE(KIND_, EPI_) \
+    if (kind == KIND_ && p.epi == EPI_) return launch_variant<KIND_, EPI_>(BN, cta2, ma, mb, mo0, mo1, p, grid, stream)
+    MOEGAN_CASE(GEMM_ROWS_BK, EPI_GELU_BF16);
+    MOEGAN_CASE(GEMM_ROWS_BK, EPI_BIAS_BF16);
+    MOEGAN_CASE(GEMM_ROWS_BK, EPI_F32);
+    MOEGAN_CASE(GEMM_ROWS_BK, EPI_GELU_X3);
+    MOEGAN_CASE(GEMM_ROWS_BK, EPI_BIAS_F32);
+    MOEGAN_CASE(GEMM_ROWS_BMN, EPI_MUL_BF16);
+    MOEGAN_CASE(GEMM_ROWS_BMN, EPI_BF16);
+    MOEGAN_CASE(GEMM_ROWS_BMN, EPI_F32);
+    MOEGAN_CASE(GEMM_ROWS_BMN, EPI_DGELU_X3);
+    MOEGAN_CASE(GEMM_WGRAD, EPI_F32);
+#undef MOEGAN_CASE
+    set_error("unsupported GEMM kind %d / epilogue %d combination", kind, p.epi);
     return MOEGAN_ERR_UNSUPPORTED;
 }
 
