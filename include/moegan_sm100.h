@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define MOEGAN_ABI_VERSION 1
+#define MOEGAN_ABI_VERSION 2
 #define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
@@ -149,18 +149,21 @@ int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates,
 
 /* ---- backward ------------------------------------------------------------------------------- */
 /* autograd of the combine: dy_op[r] = gate * dout[token(r)] (zero on padding rows),
- * dgate_row[r] = <dout[token(r)], y[r]>.  gates: [T,k] (dense: the probs, k == E). */
+ * dgate_row[r] = <dout[token(r)], y[r]>.  gates: [T,k] (dense: the probs, k == E).
+ * dy_slab_sums (may be NULL): [m_cap/32, d] fp32 column sums of every 32 consecutive dy rows - moegan_ffn_bwd turns them
+ * into the second Linear's bias gradient without reading dy again. */
 int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y,
                        const int32_t* row_token, const float* row_gate, const float* gates,
-                       void* dy_op, float* dgate_row, void* stream);
+                       void* dy_op, float* dgate_row, float* dy_slab_sums, void* stream);
 
-/* autograd of the experts (B2): dgrad + wgrad grouped GEMMs and bias column sums.
+/* autograd of the experts (B2): dgrad + wgrad grouped GEMMs and bias gradients (db1 from slab sums emitted by the
+ * dgrad epilogue; db2 from dy_slab_sums as written by moegan_combine_bwd, or from a pass over dy_op when it is NULL).
  * dpre_op [m_cap, S*4d], dx_rows [m_cap,d] (bf16 / fp32), dW1 [E,4d,d], db1 [E,4d], dW2 [E,d,4d], db2 [E,d] fp32;
- * scratch: moegan_ffn_bwd_scratch_bytes(). */
+ * scratch: moegan_ffn_bwd_scratch_bytes(), 256-byte aligned. */
 int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
-                   const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
+                   const void* pre, const void* h_op, const void* dy_op, const float* dy_slab_sums, void* dpre_op, void* dx_rows,
                    float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream);
-/* bytes of scratch moegan_ffn_bwd needs (split-K partials of the weight gradients when E*d*4d gives too few tiles) */
+/* bytes of scratch moegan_ffn_bwd needs (split-K partials of under-filled weight gradients, slab sums of dpre) */
 int64_t moegan_ffn_bwd_scratch_bytes(const moegan_shape* s);
 
 /* un-permute + sum of the k expert contributions per token, plus the router's dx:  dx [T,d] fp32. */

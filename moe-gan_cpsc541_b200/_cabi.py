@@ -17,7 +17,7 @@ MAX_EXPERTS = 32
 MAX_TOPK = 8
 CHUNK = 32
 KL_OUT_FLOATS = 2 + 256
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Shape(ctypes.Structure):
@@ -75,8 +75,8 @@ SIGNATURES = {
     "moegan_prep_weights": (c_int32, [_SP] + [POINTER(c_void_p)] * 4 + [_P] * 4 + [_P]),
     "moegan_ffn_fwd": (c_int32, [_SP] + [_P] * 9 + [_P]),
     "moegan_combine_fwd": (c_int32, [_SP] + [_P] * 4 + [_P]),
-    "moegan_combine_bwd": (c_int32, [_SP] + [_P] * 8 + [_P]),
-    "moegan_ffn_bwd": (c_int32, [_SP] + [_P] * 13 + [_P, c_int64] + [_P]),
+    "moegan_combine_bwd": (c_int32, [_SP] + [_P] * 9 + [_P]),
+    "moegan_ffn_bwd": (c_int32, [_SP] + [_P] * 14 + [_P, c_int64] + [_P]),
     "moegan_ffn_bwd_scratch_bytes": (c_int64, [_SP]),
     "moegan_uncombine_bwd": (c_int32, [_SP] + [_P] * 4 + [_P]),
     "moegan_router_bwd": (c_int32, [_SP] + [_P] * 16 + [c_float, c_int32] + [_P] * 9 + [_P] * 2 + [_P] * 9 + [_P, c_int64] + [_P]),

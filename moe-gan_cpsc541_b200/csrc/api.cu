@@ -96,12 +96,21 @@ static int wgrad_splits(const moegan_shape* s, int dimA, int N) {
     if (ks > 64) ks = 64;
     return (int)ks;
 }
-static size_t ffn_bwd_scratch_bytes_impl(const moegan_shape* s) {
+// scratch of moegan_ffn_bwd: [split-K partials of one weight gradient | 32-row slab sums of dpre | slab-sum split stage]
+struct FfnBwdScratch { size_t splitk, dpre_slabs, slab_stage, total; };
+static FfnBwdScratch ffn_bwd_scratch_layout(const moegan_shape* s) {
     const size_t d = s->d, hid = 4 * (size_t)s->d;
     const size_t k2 = wgrad_splits(s, s->d, 4 * s->d), k1 = wgrad_splits(s, 4 * s->d, s->d);
     const size_t a = k2 > 1 ? k2 * s->E * d * hid * 4 : 0, b = k1 > 1 ? k1 * s->E * d * hid * 4 : 0;
-    return (a > b ? a : b) + 256;
+    FfnBwdScratch L;
+    size_t o = 0;
+    L.splitk = o;     o = align256(o + (a > b ? a : b));
+    L.dpre_slabs = o; o = align256(o + (size_t)(s->m_cap / 32) * hid * 4);
+    L.slab_stage = o; o = align256(o + (size_t)slab_sum_splits(s) * s->E * hid * 4);
+    L.total = o + 256;
+    return L;
 }
+static size_t ffn_bwd_scratch_bytes_impl(const moegan_shape* s) { return ffn_bwd_scratch_layout(s).total; }
 
 struct RouterBwdWs {
     size_t draw, dfp_op, dtau_part, dtl, dwc_part, dWc, dtp, dtp_op, w_op, dWf, dWt, total;
@@ -325,21 +334,25 @@ int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates,
 
 // ---- backward --------------------------------------------------------------------------------------
 int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
-                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, void* stream) {
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_slab_sums, void* stream) {
     CHECK_SHAPE(s);
     if (s->T == 0) return MOEGAN_OK;
     REQ_PTR(plan); REQ_PTR(dout); REQ_PTR(y); REQ_PTR(dy_op); REQ_PTR(dgate_row);
     if (s->dense) { REQ_PTR(gates); } else { REQ_PTR(row_token); REQ_PTR(row_gate); }
-    return launch_combine_bwd(s, plan, dout, y, row_token, row_gate, gates, dy_op, dgate_row, (cudaStream_t)stream);
+    return launch_combine_bwd(s, plan, dout, y, row_token, row_gate, gates, dy_op, dgate_row, dy_slab_sums, (cudaStream_t)stream);
 }
 
 int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
-                   const void* pre, const void* h_op, const void* dy_op, void* dpre_op, void* dx_rows,
+                   const void* pre, const void* h_op, const void* dy_op, const float* dy_slab_sums, void* dpre_op, void* dx_rows,
                    float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream) {
     CHECK_SHAPE(s);
-    MOEGAN_REQUIRE(scratch_bytes >= (int64_t)ffn_bwd_scratch_bytes_impl(s) && (scratch != nullptr || ffn_bwd_scratch_bytes_impl(s) <= 256),
-                   MOEGAN_ERR_BAD_SHAPE, "ffn_bwd: scratch %lld < required %lld bytes", (long long)scratch_bytes,
-                   (long long)ffn_bwd_scratch_bytes_impl(s));
+    const FfnBwdScratch SL = ffn_bwd_scratch_layout(s);
+    MOEGAN_REQUIRE(scratch_bytes >= (int64_t)SL.total && scratch != nullptr,
+                   MOEGAN_ERR_BAD_SHAPE, "ffn_bwd: scratch %lld < required %lld bytes", (long long)scratch_bytes, (long long)SL.total);
+    MOEGAN_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, MOEGAN_ERR_MISALIGNED, "ffn_bwd: scratch must be 256-byte aligned");
+    void* splitk = reinterpret_cast<uint8_t*>(scratch) + SL.splitk;
+    float* dpre_slabs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SL.dpre_slabs);
+    float* slab_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SL.slab_stage);
     REQ_PTR(plan); REQ_PTR(a_op); REQ_PTR(W1_op); REQ_PTR(W2_op); REQ_PTR(pre); REQ_PTR(h_op); REQ_PTR(dy_op); REQ_PTR(dpre_op);
     REQ_PTR(dx_rows); REQ_PTR(dW1); REQ_PTR(db1); REQ_PTR(dW2); REQ_PTR(db2);
     const uint64_t S = s->precision == 1 ? 2 : 1;
@@ -363,11 +376,13 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         p.epi = s->precision == 1 ? EPI_DGELU_X3 : EPI_MUL_BF16;
         p.aux = pre; p.ld_aux = hid;
         p.out0 = dpre_op; p.ld_out0 = (long long)S * hid; p.out_split_off = hid;
+        p.colsum_part = dpre_slabs;                       // db1 falls out of this epilogue
         RUN(launch_umma_gemm(GEMM_ROWS_BMN, 256, A, B, p, m_blocks * (hid / 256), st));
     }
-    // bias gradients; the row-split partials live in dW2 / dW1, which the wgrad GEMMs only write further down
-    RUN(launch_colsum_grouped(s, plan, dy_op, d, dW2, db2, st));
-    RUN(launch_colsum_grouped(s, plan, dpre_op, hid, dW1, db1, st));
+    // bias gradients = per-expert sums of the 32-row slab sums (dy: from combine_bwd; dpre: from the epilogue above)
+    RUN(launch_slab_sum(s, plan, dpre_slabs, hid, slab_stage, db1, st));
+    if (dy_slab_sums != nullptr) RUN(launch_slab_sum(s, plan, dy_slab_sums, d, slab_stage, db2, st));
+    else                         RUN(launch_colsum_grouped(s, plan, dy_op, d, dW2, db2, st));   // partials in dW2 (written further down)
     {   // dgrad1: dx_rows = dpre W1
         GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
         GemmOperand B{W1_op, S * d, (uint64_t)s->E * hid, S * d};
@@ -385,9 +400,9 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         p.N = hid; p.dimA = d; p.a_lo_off = d; p.b_lo_off = hid;
         const int ks = wgrad_splits(s, d, hid);
         p.k_splits = ks;
-        p.epi = EPI_F32; p.out0 = ks > 1 ? scratch : (void*)dW2; p.ld_out0 = hid;
+        p.epi = EPI_F32; p.out0 = ks > 1 ? splitk : (void*)dW2; p.ld_out0 = hid;
         RUN(launch_umma_gemm(GEMM_WGRAD, 256, A, B, p, (long long)s->E * (d / 128) * (hid / 256) * ks, st));
-        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(scratch), (long long)s->E * d * hid, ks, dW2, st));
+        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(splitk), (long long)s->E * d * hid, ks, dW2, st));
     }
     {   // wgrad1: dW1[e] = dpre_e^T x_e   [4d, d]
         GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
@@ -397,9 +412,9 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         p.b_rel = s->dense ? 1 : 0;
         const int ks = wgrad_splits(s, hid, d);
         p.k_splits = ks;
-        p.epi = EPI_F32; p.out0 = ks > 1 ? scratch : (void*)dW1; p.ld_out0 = d;
+        p.epi = EPI_F32; p.out0 = ks > 1 ? splitk : (void*)dW1; p.ld_out0 = d;
         RUN(launch_umma_gemm(GEMM_WGRAD, BNd, A, B, p, (long long)s->E * (hid / 128) * (d / BNd) * ks, st));
-        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(scratch), (long long)s->E * d * hid, ks, dW1, st));
+        if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(splitk), (long long)s->E * d * hid, ks, dW1, st));
     }
     return MOEGAN_OK;
 }
@@ -598,7 +613,7 @@ static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layou
     L->total = (int64_t)o;
 }
 
-struct BlockBwdWs { size_t dy_op, dgate_row, dpre_op, dx_rows, dx_router, router_ws, ffn_scratch, total; };
+struct BlockBwdWs { size_t dy_op, dgate_row, dy_slabs, dpre_op, dx_rows, dx_router, router_ws, ffn_scratch, total; };
 static BlockBwdWs block_bwd_layout(const moegan_shape* s) {
     const size_t S = s->precision == 1 ? 2 : 1, d = s->d, hid = 4 * (size_t)s->d, m_cap = s->m_cap;
     const size_t act = s->precision == 1 ? 4 : 2;
@@ -606,6 +621,7 @@ static BlockBwdWs block_bwd_layout(const moegan_shape* s) {
     size_t o = 0;
     w.dy_op = o;     o = align256(o + m_cap * S * d * 2);
     w.dgate_row = o; o = align256(o + m_cap * 4);
+    w.dy_slabs = o;  o = align256(o + (m_cap / 32) * d * 4);
     w.dpre_op = o;   o = align256(o + m_cap * S * hid * 2);
     w.dx_rows = o;   o = align256(o + m_cap * d * act);
     w.dx_router = o; o = align256(o + (size_t)s->T * d * 4);
@@ -690,12 +706,13 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
     float* dgate_row = reinterpret_cast<float*>(ws + W.dgate_row);
     float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
-    RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, stream));
+    float* dy_slabs = reinterpret_cast<float*>(ws + W.dy_slabs);
+    RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, dy_slabs, stream));
     // the router's backward only needs dgate_row: run it on the side stream while the expert GEMMs own the main stream
     SideStream* ss = s->hard ? nullptr : side_stream();
     void* rstream = stream;
     if (ss != nullptr) { RUN(side_fork(ss, (cudaStream_t)stream)); rstream = ss->s; }
-    RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, ws + W.dpre_op, ws + W.dx_rows,
+    RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
                        a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream));
     if (!s->hard) {
         RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),

@@ -236,42 +236,67 @@ combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, 
         if (s < nseg) *reinterpret_cast<float4*>(out + (size_t)t * d + s * 128 + lane * 4) = acc[s];
 }
 
-// combine backward: one warp per dispatched row
+// combine backward: CTA = 32 consecutive dispatched rows (never straddles experts: segments are 256-row aligned), 4 rows per
+// warp.  Also emits the column sums of the CTA's 32 dy rows (colpart [m_cap / 32, d]) - the second Linear's bias gradient
+// is their per-expert sum, so dy is never re-read for it.
 template <bool Y_F32>
 __global__ void __launch_bounds__(256)
 combine_bwd_kernel(const int* __restrict__ plan, const float* __restrict__ dout, const void* __restrict__ y,
                    const int* __restrict__ row_token, const float* __restrict__ row_gate, const float* __restrict__ gates,
                    int T, int T_pad, int d, int E, int dense, int split,
-                   __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row) {
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (r >= __ldg(plan + 1)) return;                  // rows in use
+                   __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row, float* __restrict__ colpart) {
+    __shared__ float4 red[8][MAX_SEG * 32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x * 32 >= __ldg(plan + 1)) return;    // rows in use (a multiple of 128)
     const int ld = split ? 2 * d : d;
-    int t; float g;
-    if (dense) {
-        const int e = r / T_pad; t = r - e * T_pad;
-        if (t >= T) t = -1;
-        g = t >= 0 ? __ldg(gates + (size_t)t * E + e) : 0.0f;
-    } else {
-        t = __ldg(row_token + r);
-        g = t >= 0 ? __ldg(row_gate + r) : 0.0f;
+    const int nseg = d / 128;
+    float4 cs[MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) cs[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+        const int r = blockIdx.x * 32 + i * 8 + wid;
+        int t; float g;
+        if (dense) {
+            const int e = r / T_pad; t = r - e * T_pad;
+            if (t >= T) t = -1;
+            g = t >= 0 ? __ldg(gates + (size_t)t * E + e) : 0.0f;
+        } else {
+            t = __ldg(row_token + r);
+            g = t >= 0 ? __ldg(row_gate + r) : 0.0f;
+        }
+        __nv_bfloat16* dst = dy_op + (size_t)r * ld;
+        if (t < 0) {                                   // padding row: zero (the wgrad GEMMs sum over it)
+            for (int j = lane; j < ld / 4; j += 32) reinterpret_cast<uint2*>(dst)[j] = make_uint2(0u, 0u);
+            if (lane == 0) dgate_row[r] = 0.0f;
+            continue;
+        }
+        float dot = 0.0f;
+#pragma unroll
+        for (int s = 0; s < MAX_SEG; ++s) {
+            if (s < nseg) {
+                const int col = s * 128 + lane * 4;
+                const float4 go = __ldg(reinterpret_cast<const float4*>(dout + (size_t)t * d + col));
+                const float4 yv = load_row4<Y_F32>(y, (size_t)r * d + col);
+                dot = fmaf(go.x, yv.x, fmaf(go.y, yv.y, fmaf(go.z, yv.z, fmaf(go.w, yv.w, dot))));
+                const float4 dv = make_float4(g * go.x, g * go.y, g * go.z, g * go.w);
+                store_operand4(dst + col, d, split != 0, dv);
+                cs[s].x += dv.x; cs[s].y += dv.y; cs[s].z += dv.z; cs[s].w += dv.w;
+            }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) dgate_row[r] = dot;
     }
-    __nv_bfloat16* dst = dy_op + (size_t)r * ld;
-    if (t < 0) {                                       // padding row: zero (the wgrad GEMMs sum over it)
-        for (int i = lane; i < ld / 4; i += 32) reinterpret_cast<uint2*>(dst)[i] = make_uint2(0u, 0u);
-        if (lane == 0) dgate_row[r] = 0.0f;
-        return;
+    if (colpart == nullptr) return;
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s)
+        if (s < nseg) red[wid][s * 32 + lane] = cs[s];
+    __syncthreads();
+    for (int j = threadIdx.x; j < nseg * 32; j += 256) {           // float4 index: columns 4j .. 4j+3 (j = seg * 32 + lane)
+        float4 a = red[0][j];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { const float4 b = red[w][j]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * d)[j] = a;
     }
-    float dot = 0.0f;
-    for (int s = 0; s < d / 128; ++s) {
-        const int col = s * 128 + lane * 4;
-        const float4 go = __ldg(reinterpret_cast<const float4*>(dout + (size_t)t * d + col));
-        const float4 yv = load_row4<Y_F32>(y, (size_t)r * d + col);
-        dot = fmaf(go.x, yv.x, fmaf(go.y, yv.y, fmaf(go.z, yv.z, fmaf(go.w, yv.w, dot))));
-        store_operand4(dst + col, d, split != 0, make_float4(g * go.x, g * go.y, g * go.z, g * go.w));
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) dgate_row[r] = dot;
 }
 
 // dx[t] = sum_j dx_rows[row(t, j)] (+ dx_router[t])
@@ -340,6 +365,29 @@ colsum_part_kernel(const int* __restrict__ plan, const __nv_bfloat16* __restrict
         for (int w = 0; w < 32; ++w) s += red[w][threadIdx.x];
         part[((size_t)sp * E + e) * cols + blockIdx.x * 64 + threadIdx.x] = s;
     }
+}
+// Bias gradients from 32-row slab sums: out[sp][e][c] = sum of part[j][c] over split sp of expert e's slabs j (part =
+// [m_cap / 32, cols], written by combine_bwd_kernel or the dgrad epilogue; slabs past the expert's real rows hold zeros
+// and are skipped).  Thread = column (coalesced rows), 4 slabs in flight; fixed order -> deterministic.
+__global__ void __launch_bounds__(128)
+slab_sum_kernel(const int* __restrict__ plan, const float* __restrict__ part, int cols, int T, int dense, int E, int nsplit,
+                float* __restrict__ out) {
+    const int e = blockIdx.y, sp = blockIdx.z;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= cols) return;
+    const int e0 = __ldg(plan + PLAN_OFF + e);
+    const int n = dense ? T : __ldg(plan + PLAN_CNT + e);
+    const int j0 = e0 / 32, nj = (n + 31) / 32;
+    const int per = (nj + nsplit - 1) / nsplit;
+    const int a = j0 + min(sp * per, nj), b = j0 + min((sp + 1) * per, nj);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int j = a;
+    for (; j + 3 < b; j += 4) {
+        s0 += __ldg(part + (size_t)j * cols + c);       s1 += __ldg(part + (size_t)(j + 1) * cols + c);
+        s2 += __ldg(part + (size_t)(j + 2) * cols + c); s3 += __ldg(part + (size_t)(j + 3) * cols + c);
+    }
+    for (; j < b; ++j) s0 += __ldg(part + (size_t)j * cols + c);
+    out[((size_t)sp * E + e) * cols + c] = (s0 + s1) + (s2 + s3);
 }
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ part, int n, int nsplit, float* __restrict__ out) {
@@ -413,15 +461,39 @@ int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates,
 }
 
 int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
-                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, cudaStream_t st) {
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st) {
     const int T_pad = row_pad(s->T);
-    const int blocks = ceil_div(s->m_cap, 8);
+    const int blocks = s->m_cap / 32;
     __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
     if (s->precision == 1)
-        combine_bwd_kernel<true><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 1, dy, dgate_row);
+        combine_bwd_kernel<true><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 1, dy,
+                                                         dgate_row, dy_colpart);
     else
-        combine_bwd_kernel<false><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 0, dy, dgate_row);
+        combine_bwd_kernel<false><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 0, dy,
+                                                          dgate_row, dy_colpart);
     MOEGAN_CHECK_LAUNCH("combine_bwd_kernel");
+    return MOEGAN_OK;
+}
+
+int slab_sum_splits(const moegan_shape* s) {
+    const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;   // mean rows per expert
+    long long ns = rows / 32 / 16;                     // >= 16 slabs per split
+    if (ns < 1) ns = 1;
+    if (ns > 32) ns = 32;
+    return (int)ns;
+}
+
+// out[e, c] = sum of expert e's slab sums part[m_cap / 32, cols];  scratch: slab_sum_splits() * E * cols floats
+int launch_slab_sum(const moegan_shape* s, const int32_t* plan, const float* part, int cols, float* scratch, float* out, cudaStream_t st) {
+    const int nsplit = slab_sum_splits(s);
+    dim3 grid(ceil_div(cols, 128), s->E, nsplit);
+    slab_sum_kernel<<<grid, 128, 0, st>>>(plan, part, cols, s->T, s->dense, s->E, nsplit, nsplit == 1 ? out : scratch);
+    MOEGAN_CHECK_LAUNCH("slab_sum_kernel");
+    if (nsplit > 1) {
+        const int n = s->E * cols;
+        colsum_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scratch, n, nsplit, out);
+        MOEGAN_CHECK_LAUNCH("colsum_finish_kernel");
+    }
     return MOEGAN_OK;
 }
 

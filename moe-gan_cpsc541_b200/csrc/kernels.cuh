@@ -42,7 +42,9 @@ int launch_prep_weights(const moegan_shape* s, const float* const* w1, const flo
                         const float* const* b2, void* W1_op, float* b1s, void* W2_op, float* b2s, cudaStream_t st);
 int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, cudaStream_t st);
 int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
-                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, cudaStream_t st);
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st);
+int slab_sum_splits(const moegan_shape* s);
+int launch_slab_sum(const moegan_shape* s, const int32_t* plan, const float* part, int cols, float* scratch, float* out, cudaStream_t st);
 int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
                      cudaStream_t st);
 // out[e, c] = sum over the real rows of expert e of (hi + lo)[row, c];  src is a bf16 operand [m_cap, S*cols];

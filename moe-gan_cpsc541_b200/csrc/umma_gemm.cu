@@ -165,6 +165,21 @@ __device__ __forceinline__ void unpack32_bf16(const uint4 (&u)[4], float (&v)[32
         v[8 * i + 6] = bf16_lo_to_float(u[i].w); v[8 * i + 7] = bf16_hi_to_float(u[i].w);
     }
 }
+// v[i] of lane r = element (row r, column i) of a 32x32 tile.  Returns, in lane c, the sum of column c over the 32 rows:
+// a butterfly that halves the number of live columns per step (31 shuffles).  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
 __device__ __forceinline__ void load32_f32(const float* src, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -489,6 +504,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         flush_end();
                         if (lane == 0) { ptx::tma_store_2d(&mapO0, stage0, col0, out_row0); ptx::bulk_commit(); }
                         pending = true;
+                        if (p.colsum_part != nullptr) {
+                            const float cs = warp_colsum32(v, lane);
+                            p.colsum_part[(size_t)(t.mb * 4 + q) * p.N + col0 + lane] = cs;
+                        }
                     } else if (EPI == EPI_DGELU_X3) {
                         float a[32];
                         if (row_ok) load32_f32(reinterpret_cast<const float*>(p.aux) + out_row * p.ld_aux + col0, a);
@@ -509,6 +528,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             ptx::bulk_commit();
                         }
                         pending = true;
+                        if (p.colsum_part != nullptr) {
+                            const float cs = warp_colsum32(v, lane);
+                            p.colsum_part[(size_t)(t.mb * 4 + q) * p.N + col0 + lane] = cs;
+                        }
                     }
                 }
                 ++aux_cc;

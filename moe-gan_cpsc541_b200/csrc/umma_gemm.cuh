@@ -48,6 +48,8 @@ struct GemmParams {
     void* out1;
     const void* aux;
     const float* bias;      // [E, N]
+    float* colsum_part;     // EPI_MUL_BF16 / EPI_DGELU_X3: if set, [rows / 32, N] fp32 column sums of every 32-row slab of the
+                            // (unrounded) output - the bias gradient falls out of the dgrad epilogue instead of a second pass
     long long ld_out0, ld_out1, ld_aux;  // leading dimensions (elements)
     int out_rows_valid;     // rows of the output tensor(s): rows >= this are clipped by the TMA store
     int out_split_off;      // column offset of the lo half in out0 for the *_X3 epilogues

@@ -58,7 +58,7 @@ def probe(name):
                                    C.ptr(h), C.ptr(y), st), "ffn_fwd")
 
     def bwd():
-        C.check(lib.moegan_ffn_bwd(shp, C.ptr(plan), C.ptr(a_op), C.ptr(W1), C.ptr(W2), C.ptr(pre), C.ptr(h), C.ptr(dy), C.ptr(dpre), C.ptr(dxr),
+        C.check(lib.moegan_ffn_bwd(shp, C.ptr(plan), C.ptr(a_op), C.ptr(W1), C.ptr(W2), C.ptr(pre), C.ptr(h), C.ptr(dy), None, C.ptr(dpre), C.ptr(dxr),
                                    C.ptr(dW1), C.ptr(db1), C.ptr(dW2), C.ptr(db2), C.ptr(scratch), sb, st), "ffn_bwd")
 
     def run(fn, per):
