@@ -247,6 +247,37 @@ int64_t moegan_block_bwd_workspace(const moegan_shape* s);
 int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void* stream);
 int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void* stream);
 
+/* ---- layers around the block ------------------------------------------ */
+/* replaces: nn.LayerNorm(dim) of AttentionBlock.norm1-3 (t2i_moe_gan.py:513-515, applied :541,:553,:561).
+ * x [rows,d] fp32 or bf16 (x_is_bf16), y fp32 [rows,d]; mean / rstd [rows] are what the backward needs.
+ * d: multiple of 128, <= 1024. */
+int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d,
+                         float eps, float* y, float* mean, float* rstd, void* stream);
+int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d);
+/* dx fp32 [rows,d]; dgamma_dbeta fp32 [2,d] (row 0 = weight gradient, row 1 = bias gradient), deterministic. */
+int moegan_layernorm_bwd(const float* dy, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
+                         const float* rstd, int64_t rows, int32_t d, float* dx, float* dgamma_dbeta,
+                         void* scratch, int64_t scratch_bytes, void* stream);
+
+/* replaces: the modulate / demodulate / LeakyReLU element-wise steps of ModulatedConv + the activation of
+ * ModulatedTransformationModule (t2i_moe_gan.py:158-186, :243-245) in "scale the activations" form:
+ * out[b,p,c] = leaky_relu(x[b,p,c] * s[b,c], slope)  (slope = 1: no activation).  x / out: NHWC [B,P,C], fp32 or bf16;
+ * s: fp32 [B,C]; C: multiple of 128.  Backward: dx and ds[b,c] = sum_p in ONE pass (deterministic). */
+int moegan_channel_scale_fwd(const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C, float slope,
+                             void* out, void* stream);
+int64_t moegan_channel_scale_bwd_scratch_bytes(int32_t B, int32_t P, int32_t C);
+int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C,
+                             float slope, void* dx, float* ds, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* replaces: the learned-offset resampling of ModulatedTransformationModule (t2i_moe_gan.py:219-240):
+ * grid = clamp(meshgrid(linspace(-1,1)) + 0.05 * off, -1, 1);  out = F.grid_sample(x, grid, bilinear, zeros,
+ * align_corners=False).  x / out / g / dx: NHWC [B,H,W,C] fp32 or bf16; off / doff: fp32 [B,H,W,2] = (x, y) offsets
+ * as produced by offset_net (before the 0.05 scale).  C: multiple of 128; H*W <= 512 for the backward. */
+int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H, int32_t W, int32_t C,
+                             void* out, void* stream);
+int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H,
+                             int32_t W, int32_t C, void* dx, float* doff, void* stream);
+
 /* ---- test / bench hook ---------------------------------------------------------------------- */
 /* Plain (ungrouped) GEMM on the same tcgen05 kernel, fp32 out:  C[M,N] = op(A) * op(B).
  * kind 0: A [M,S*K] K-major, B [N,S*K] K-major.   kind 1: A [M,S*K] K-major, B [K,S*N] (N contiguous).

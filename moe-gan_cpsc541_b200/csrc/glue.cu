@@ -1,0 +1,441 @@
+// Bandwidth-bound kernels for the layers directly around the MoE block:
+//   * LayerNorm forward / backward (AttentionBlock.norm1-3, t2i_moe_gan.py:513-515,561) - warp per token row, the
+//     weight / bias gradients as deterministic two-stage column sums (ATen's gamma/beta kernel needs 0.5 ms for the
+//     [65536, 128] case of the 16x16 block);
+//   * channel_scale: out = leaky_relu(x * s[b, c]) on NHWC activations, one pass forward, one pass backward that also
+//     reduces ds[b, c] - the modulate / demodulate / activation steps of ModulatedConv (:158-186) written as
+//     "scale the activations" instead of materialising per-sample weights;
+//   * offset_sample: the learned-offset bilinear resampling of ModulatedTransformationModule (:219-240) on NHWC
+//     activations: grid = clamp(base + 0.05 * off, -1, 1), F.grid_sample(bilinear, zeros, align_corners=False).
+// All of them are HBM-bound: every tensor is read or written exactly once per pass, with 8- or 16-byte accesses along the
+// contiguous channel dimension.
+#include "kernels.cuh"
+
+namespace moegan {
+
+namespace {
+
+// ---- 4 consecutive channels as fp32, from / to fp32 or bf16 storage ---------------------------------------
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ float4 load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+};
+template <typename T> __device__ __forceinline__ float load1(const T* p);
+template <> __device__ __forceinline__ float load1<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void store1(T* p, float v);
+template <> __device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// =====================================================================================================
+// LayerNorm over the last dimension (d = 128 * nseg <= 1024), eps inside the sqrt (nn.LayerNorm)
+// =====================================================================================================
+constexpr int LN_MAX_SEG = 8;
+
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int d,
+                     float eps, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int nseg = d / 128;
+    float4 v[LN_MAX_SEG];
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < LN_MAX_SEG; ++s)
+        if (s < nseg) { v[s] = Vec4<TIN>::load(x + r * d + s * 128 + lane * 4); sum += (v[s].x + v[s].y) + (v[s].z + v[s].w); }
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int s = 0; s < LN_MAX_SEG; ++s)
+        if (s < nseg) {
+            const float a = v[s].x - mean, b = v[s].y - mean, c = v[s].z - mean, e = v[s].w - mean;
+            sq += (a * a + b * b) + (c * c + e * e);
+        }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+    for (int s = 0; s < LN_MAX_SEG; ++s)
+        if (s < nseg) {
+            const int c = s * 128 + lane * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = (v[s].x - mean) * rstd * g.x + b.x; o.y = (v[s].y - mean) * rstd * g.y + b.y;
+            o.z = (v[s].z - mean) * rstd * g.z + b.z; o.w = (v[s].w - mean) * rstd * g.w + b.w;
+            *reinterpret_cast<float4*>(y + r * d + c) = o;
+        }
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+}
+
+// dx = rstd * (gamma*g - mean_d(gamma*g) - xhat * mean_d(gamma*g*xhat)); per-CTA partial column sums of g*xhat and g.
+// Each warp walks rows r = warp_global, += total_warps; the CTA's 8 warps are combined through shared memory.
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows, int d,
+                     float* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
+    __shared__ float4 red[8][LN_MAX_SEG * 32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nseg = d / 128;
+    float4 gam[LN_MAX_SEG], dg[LN_MAX_SEG], db[LN_MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < LN_MAX_SEG; ++s) {
+        dg[s] = make_float4(0.f, 0.f, 0.f, 0.f); db[s] = dg[s]; gam[s] = dg[s];
+        if (s < nseg) gam[s] = __ldg(reinterpret_cast<const float4*>(gamma + s * 128 + lane * 4));
+    }
+    const float inv_d = 1.0f / (float)d;
+    for (long long r = (long long)blockIdx.x * 8 + wid; r < rows; r += (long long)gridDim.x * 8) {
+        const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+        float4 xh[LN_MAX_SEG], gg[LN_MAX_SEG];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int s = 0; s < LN_MAX_SEG; ++s)
+            if (s < nseg) {
+                const long long o = r * d + s * 128 + lane * 4;
+                const float4 xv = Vec4<TIN>::load(x + o);
+                const float4 gv = __ldg(reinterpret_cast<const float4*>(g + o));
+                xh[s] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+                dg[s].x += gv.x * xh[s].x; dg[s].y += gv.y * xh[s].y; dg[s].z += gv.z * xh[s].z; dg[s].w += gv.w * xh[s].w;
+                db[s].x += gv.x; db[s].y += gv.y; db[s].z += gv.z; db[s].w += gv.w;
+                gg[s] = make_float4(gv.x * gam[s].x, gv.y * gam[s].y, gv.z * gam[s].z, gv.w * gam[s].w);
+                s1 += (gg[s].x + gg[s].y) + (gg[s].z + gg[s].w);
+                s2 += (gg[s].x * xh[s].x + gg[s].y * xh[s].y) + (gg[s].z * xh[s].z + gg[s].w * xh[s].w);
+            }
+        s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+        for (int s = 0; s < LN_MAX_SEG; ++s)
+            if (s < nseg) {
+                float4 o;
+                o.x = rstd * (gg[s].x - s1 - xh[s].x * s2); o.y = rstd * (gg[s].y - s1 - xh[s].y * s2);
+                o.z = rstd * (gg[s].z - s1 - xh[s].z * s2); o.w = rstd * (gg[s].w - s1 - xh[s].w * s2);
+                *reinterpret_cast<float4*>(dx + r * d + s * 128 + lane * 4) = o;
+            }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int s = 0; s < LN_MAX_SEG; ++s)
+            if (s < nseg) red[wid][s * 32 + lane] = pass == 0 ? dg[s] : db[s];
+        __syncthreads();
+        for (int j = threadIdx.x; j < nseg * 32; j += 256) {
+            float4 a = red[0][j];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { const float4 b = red[w][j]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+            reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * 2 + pass) * d)[j] = a;
+        }
+        __syncthreads();
+    }
+}
+// out[i] = sum_b part[b * n + i]  (fixed order)
+__global__ void __launch_bounds__(256)
+partial_sum_kernel(const float* __restrict__ part, int n, int nparts, float* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float s0 = 0.f, s1 = 0.f;
+    int b = 0;
+    for (; b + 1 < nparts; b += 2) { s0 += part[(size_t)b * n + i]; s1 += part[(size_t)(b + 1) * n + i]; }
+    if (b < nparts) s0 += part[(size_t)b * n + i];
+    out[i] = s0 + s1;
+}
+
+// =====================================================================================================
+// channel_scale: out[b, p, c] = lrelu(x[b, p, c] * s[b, c], slope)      x: [B, P, C] (NHWC), s: [B, C] fp32
+// =====================================================================================================
+// forward: grid-stride over groups of 4 channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_scale_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s, long long n4, int P, int C, float slope, T* __restrict__ out) {
+    const int c4 = C / 4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const long long bp = i / c4;
+        const int c = (int)(i - bp * c4) * 4;
+        const long long b = bp / P;
+        const float4 v = Vec4<T>::load(x + i * 4);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(s + b * C + c));
+        float4 o = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
+        o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+        o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+        Vec4<T>::store(out + i * 4, o);
+    }
+}
+// backward: CTA = (sample b, 128-channel group, pixel split); warp w takes pixels w, w+8, ...; lane = 4 channels.
+//   m = g * (x*s > 0 ? 1 : slope);  dx = m * s;  ds[b, c] = sum_p m * x   (partials over the pixel splits, summed in order)
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_scale_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ s, int P, int C, float slope,
+                         int psplit, T* __restrict__ dx, float* __restrict__ ds_part /* [psplit][B][C] */, int Bn) {
+    __shared__ float4 red[8][32];
+    const int b = blockIdx.y, cgp = blockIdx.x, sp = blockIdx.z;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cgp * 128 + lane * 4;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(s + (size_t)b * C + c));
+    const int per = (P + psplit - 1) / psplit;
+    const int p0 = sp * per, p1 = min(P, p0 + per);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0 + wid; p < p1; p += 8) {
+        const size_t o = ((size_t)b * P + p) * C + c;
+        const float4 gv = Vec4<T>::load(g + o), xv = Vec4<T>::load(x + o);
+        float4 m;
+        m.x = xv.x * sc.x > 0.f ? gv.x : gv.x * slope; m.y = xv.y * sc.y > 0.f ? gv.y : gv.y * slope;
+        m.z = xv.z * sc.z > 0.f ? gv.z : gv.z * slope; m.w = xv.w * sc.w > 0.f ? gv.w : gv.w * slope;
+        Vec4<T>::store(dx + o, make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w));
+        acc.x += m.x * xv.x; acc.y += m.y * xv.y; acc.z += m.z * xv.z; acc.w += m.w * xv.w;
+    }
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        float4 a = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { const float4 t = red[w][lane]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        *reinterpret_cast<float4*>(ds_part + ((size_t)sp * Bn + b) * C + c) = a;
+    }
+}
+
+// =====================================================================================================
+// offset_sample (NHWC): out[b, i, j, :] = bilinear(x[b], grid(b, i, j)),  grid = clamp(base + 0.05 * off, -1, 1)
+// =====================================================================================================
+struct Tap {            // the 4 bilinear taps of one output pixel
+    int idx[4];         // pixel index y * W + x inside the sample, -1 = outside (zero padding)
+    float w[4];
+    float wx, wy;       // fractional parts
+    float sx, sy;       // d(off) -> d(ix) chain: 0.05 * W / 2 where the clamp passes gradient, else 0
+};
+__device__ __forceinline__ Tap make_tap(float offx, float offy, int i, int j, int H, int W) {
+    Tap t;
+    const float bx = W > 1 ? -1.0f + 2.0f * (float)j / (float)(W - 1) : -1.0f;      // torch.linspace(-1, 1, W)
+    const float by = H > 1 ? -1.0f + 2.0f * (float)i / (float)(H - 1) : -1.0f;
+    float gx = bx + 0.05f * offx, gy = by + 0.05f * offy;
+    t.sx = (gx >= -1.0f && gx <= 1.0f) ? 0.05f * 0.5f * (float)W : 0.0f;
+    t.sy = (gy >= -1.0f && gy <= 1.0f) ? 0.05f * 0.5f * (float)H : 0.0f;
+    gx = fminf(fmaxf(gx, -1.0f), 1.0f); gy = fminf(fmaxf(gy, -1.0f), 1.0f);
+    const float ix = ((gx + 1.0f) * (float)W - 1.0f) * 0.5f;                         // align_corners = False
+    const float iy = ((gy + 1.0f) * (float)H - 1.0f) * 0.5f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    t.wx = ix - fx; t.wy = iy - fy;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+    t.idx[0] = (vy0 && vx0) ? y0 * W + x0 : -1;           t.w[0] = (1.0f - t.wx) * (1.0f - t.wy);
+    t.idx[1] = (vy0 && vx1) ? y0 * W + x0 + 1 : -1;       t.w[1] = t.wx * (1.0f - t.wy);
+    t.idx[2] = (vy1 && vx0) ? (y0 + 1) * W + x0 : -1;     t.w[2] = (1.0f - t.wx) * t.wy;
+    t.idx[3] = (vy1 && vx1) ? (y0 + 1) * W + x0 + 1 : -1; t.w[3] = t.wx * t.wy;
+    return t;
+}
+
+// forward: warp per output pixel, lanes over channels (4 per lane and 128-channel segment)
+template <typename T>
+__global__ void __launch_bounds__(256)
+offset_sample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ off, long long npix, int H, int W, int C, T* __restrict__ out) {
+    const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= npix) return;
+    const int HW = H * W;
+    const long long b = p / HW;
+    const int ij = (int)(p - b * HW);
+    const Tap t = make_tap(__ldg(off + p * 2), __ldg(off + p * 2 + 1), ij / W, ij % W, H, W);
+    const T* xb = x + (size_t)b * HW * C;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t.idx[k] >= 0) {
+                const float4 v = Vec4<T>::load(xb + (size_t)t.idx[k] * C + c);
+                a.x = fmaf(t.w[k], v.x, a.x); a.y = fmaf(t.w[k], v.y, a.y); a.z = fmaf(t.w[k], v.z, a.z); a.w = fmaf(t.w[k], v.w, a.w);
+            }
+        Vec4<T>::store(out + (size_t)p * C + c, a);
+    }
+}
+// backward w.r.t. the offsets: warp per output pixel, reduction over channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+offset_sample_bwd_off_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ off, long long npix, int H, int W, int C,
+                             float* __restrict__ doff) {
+    const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= npix) return;
+    const int HW = H * W;
+    const long long b = p / HW;
+    const int ij = (int)(p - b * HW);
+    const Tap t = make_tap(__ldg(off + p * 2), __ldg(off + p * 2 + 1), ij / W, ij % W, H, W);
+    const T* xb = x + (size_t)b * HW * C;
+    float gix = 0.f, giy = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 gv = Vec4<T>::load(g + (size_t)p * C + c);
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = t.idx[k] >= 0 ? Vec4<T>::load(xb + (size_t)t.idx[k] * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float omy = 1.0f - t.wy, omx = 1.0f - t.wx;
+#define MOEGAN_TAPGRAD(f)                                                                                   \
+        gix += gv.f * ((v[1].f - v[0].f) * omy + (v[3].f - v[2].f) * t.wy);                               \
+        giy += gv.f * ((v[2].f - v[0].f) * omx + (v[3].f - v[1].f) * t.wx);
+        MOEGAN_TAPGRAD(x) MOEGAN_TAPGRAD(y) MOEGAN_TAPGRAD(z) MOEGAN_TAPGRAD(w)
+#undef MOEGAN_TAPGRAD
+    }
+    gix = warp_sum(gix); giy = warp_sum(giy);
+    if (lane == 0) { doff[p * 2] = gix * t.sx; doff[p * 2 + 1] = giy * t.sy; }
+}
+// backward w.r.t. the input: CTA = (sample, group of CC channels); THREAD = one channel, which it owns exclusively, so the
+// scatter into the sample's [HW, CC] accumulator tile in shared memory needs no atomics and runs in a fixed order.
+template <typename T, int CC>
+__global__ void __launch_bounds__(CC)
+offset_sample_bwd_in_kernel(const T* __restrict__ g, const float* __restrict__ off, int H, int W, int C, T* __restrict__ dx) {
+    extern __shared__ float smem[];
+    const int HW = H * W;
+    float* acc = smem;                                   // [HW][CC]
+    int* tidx = reinterpret_cast<int*>(smem + HW * CC);  // [HW][4]
+    float* tw = reinterpret_cast<float*>(tidx + HW * 4); // [HW][4]
+    const int b = blockIdx.y, c = blockIdx.x * CC + threadIdx.x;
+    for (int p = threadIdx.x; p < HW; p += CC) {
+        const Tap t = make_tap(__ldg(off + ((size_t)b * HW + p) * 2), __ldg(off + ((size_t)b * HW + p) * 2 + 1), p / W, p % W, H, W);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tidx[p * 4 + k] = t.idx[k]; tw[p * 4 + k] = t.w[k]; }
+    }
+    for (int p = 0; p < HW; ++p) acc[p * CC + threadIdx.x] = 0.0f;
+    __syncthreads();
+    const T* gb = g + (size_t)b * HW * C + c;
+    constexpr int U = 8;
+    for (int p0 = 0; p0 < HW; p0 += U) {
+        float gv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) gv[u] = (p0 + u < HW) ? load1<T>(gb + (size_t)(p0 + u) * C) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u < HW) {
+                const int4 id = *reinterpret_cast<const int4*>(tidx + (p0 + u) * 4);
+                const float4 w = *reinterpret_cast<const float4*>(tw + (p0 + u) * 4);
+                if (id.x >= 0) acc[id.x * CC + threadIdx.x] += w.x * gv[u];
+                if (id.y >= 0) acc[id.y * CC + threadIdx.x] += w.y * gv[u];
+                if (id.z >= 0) acc[id.z * CC + threadIdx.x] += w.z * gv[u];
+                if (id.w >= 0) acc[id.w * CC + threadIdx.x] += w.w * gv[u];
+            }
+        }
+    }
+    T* db = dx + (size_t)b * HW * C + c;
+    for (int p = 0; p < HW; ++p) store1<T>(db + (size_t)p * C, acc[p * CC + threadIdx.x]);
+}
+
+inline int grid_cap(long long blocks) {
+    const long long cap = (long long)num_sms() * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+// ---- launchers ------------------------------------------------------------------------------------------------
+int ln_bwd_blocks(long long rows) {
+    long long b = (rows + 7) / 8;
+    const long long cap = (long long)num_sms() * 4;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, float* y,
+                         float* mean, float* rstd, cudaStream_t st) {
+    if (rows == 0) return MOEGAN_OK;
+    const int blocks = (int)((rows + 7) / 8);
+    if (x_bf16) layernorm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, rows, d, eps, y, mean, rstd);
+    else        layernorm_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), gamma, beta, rows, d, eps, y, mean, rstd);
+    MOEGAN_CHECK_LAUNCH("layernorm_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_layernorm_bwd(const float* g, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd, long long rows,
+                         int d, float* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st) {
+    if (rows == 0) {
+        MOEGAN_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, (size_t)2 * d * 4, st));
+        return MOEGAN_OK;
+    }
+    const int blocks = ln_bwd_blocks(rows);
+    if (x_bf16) layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(g, reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, rows, d, dx, scratch);
+    else        layernorm_bwd_kernel<float><<<blocks, 256, 0, st>>>(g, reinterpret_cast<const float*>(x), gamma, mean, rstd, rows, d, dx, scratch);
+    MOEGAN_CHECK_LAUNCH("layernorm_bwd_kernel");
+    // scratch = [blocks][2][d] = [blocks][2d]  ->  [dgamma | dbeta]
+    partial_sum_kernel<<<ceil_div(2 * d, 256), 256, 0, st>>>(scratch, 2 * d, blocks, dgamma_dbeta);
+    MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_channel_scale_fwd(const void* x, int bf16, const float* s, int B, int P, int C, float slope, void* out, cudaStream_t st) {
+    const long long n4 = (long long)B * P * C / 4;
+    if (n4 == 0) return MOEGAN_OK;
+    const int blocks = grid_cap((n4 + 255) / 256);
+    if (bf16) channel_scale_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), s, n4, P, C, slope, reinterpret_cast<__nv_bfloat16*>(out));
+    else      channel_scale_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), s, n4, P, C, slope, reinterpret_cast<float*>(out));
+    MOEGAN_CHECK_LAUNCH("channel_scale_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+int channel_scale_psplit(int B, int P, int C) {
+    // enough CTAs to fill the chip: B * C/128 * psplit >= ~4 per SM, at least 8 pixels (one per warp) per split
+    long long ctas = (long long)B * (C / 128);
+    int ps = 1;
+    while (ctas * ps < (long long)num_sms() * 4 && ps * 2 * 8 <= P && ps < 64) ps *= 2;
+    return ps;
+}
+
+int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const float* s, int B, int P, int C, float slope, void* dx, float* ds,
+                             float* scratch, cudaStream_t st) {
+    if ((long long)B * P * C == 0) return MOEGAN_OK;
+    const int ps = channel_scale_psplit(B, P, C);
+    dim3 grid(C / 128, B, ps);
+    float* part = ps == 1 ? ds : scratch;
+    if (bf16) channel_scale_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), s, P, C, slope, ps,
+                                                                             reinterpret_cast<__nv_bfloat16*>(dx), part, B);
+    else      channel_scale_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), s, P, C, slope, ps,
+                                                                     reinterpret_cast<float*>(dx), part, B);
+    MOEGAN_CHECK_LAUNCH("channel_scale_bwd_kernel");
+    if (ps > 1) {
+        partial_sum_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, ds);
+        MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
+    }
+    return MOEGAN_OK;
+}
+
+int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, int H, int W, int C, void* out, cudaStream_t st) {
+    const long long npix = (long long)B * H * W;
+    if (npix == 0) return MOEGAN_OK;
+    const int blocks = (int)((npix + 7) / 8);
+    if (bf16) offset_sample_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), off, npix, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+    else      offset_sample_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), off, npix, H, W, C, reinterpret_cast<float*>(out));
+    MOEGAN_CHECK_LAUNCH("offset_sample_fwd_kernel");
+    return MOEGAN_OK;
+}
+
+template <typename T>
+static int launch_bwd_in(const T* g, const float* off, int B, int H, int W, int C, T* dx, cudaStream_t st) {
+    constexpr int CC = 64;
+    const size_t smem = (size_t)H * W * (CC * 4 + 32);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(offset_sample_bwd_in_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(C / CC, B);
+    offset_sample_bwd_in_kernel<T, CC><<<grid, CC, smem, st>>>(g, off, H, W, C, dx);
+    MOEGAN_CHECK_LAUNCH("offset_sample_bwd_in_kernel");
+    return MOEGAN_OK;
+}
+
+int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float* off, int B, int H, int W, int C, void* dx, float* doff,
+                             cudaStream_t st) {
+    const long long npix = (long long)B * H * W;
+    if (npix == 0) return MOEGAN_OK;
+    const int blocks = (int)((npix + 7) / 8);
+    if (bf16) {
+        offset_sample_bwd_off_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), off, npix, H, W, C, doff);
+        MOEGAN_CHECK_LAUNCH("offset_sample_bwd_off_kernel");
+        return launch_bwd_in<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(g), off, B, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx), st);
+    }
+    offset_sample_bwd_off_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), off, npix, H, W, C, doff);
+    MOEGAN_CHECK_LAUNCH("offset_sample_bwd_off_kernel");
+    return launch_bwd_in<float>(reinterpret_cast<const float*>(g), off, B, H, W, C, reinterpret_cast<float*>(dx), st);
+}
+
+}  // namespace moegan

@@ -1,0 +1,156 @@
+"""Host side of the bandwidth-bound layers directly around the MoE block: autograd wrappers over
+the C ABI entry points `moegan_layernorm_*`, `moegan_channel_scale_*`, `moegan_offset_sample_*` (csrc/glue.cu).
+
+Each public function states the reference computation it replaces.  CUDA tensors always go through the library (a missing
+`.so` raises); for CPU tensors the function evaluates that reference formula with plain torch ops - this is only the
+definition the CPU arm / the pinning tests of the host model use, never a substitute for the kernels on a GPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi as C
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _is_bf16(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise TypeError(f"moegan glue kernels take fp32 or bf16 activations, got {t.dtype}")
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm (t2i_moe_gan.py:513-515 -> :541, :553, :561)
+# --------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        d = x.shape[-1]
+        x2 = x.reshape(-1, d)
+        if x2.dtype not in (torch.float32, torch.bfloat16):
+            x2 = x2.float()
+        x2 = x2.contiguous()
+        rows = x2.shape[0]
+        wf, bf = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty(rows, d, device=x.device, dtype=torch.float32)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        C.check(C.lib().moegan_layernorm_fwd(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), C.ptr(mean),
+                                             C.ptr(rstd), _stream()), "moegan_layernorm_fwd")
+        ctx.save_for_backward(x2, wf, mean, rstd)
+        ctx.x_shape, ctx.x_dtype, ctx.w_dtype = x.shape, x.dtype, weight.dtype
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, wf, mean, rstd = ctx.saved_tensors
+        rows, d = x2.shape
+        g = gy.reshape(rows, d).float().contiguous()
+        lib = C.lib()
+        dx = torch.empty(rows, d, device=g.device, dtype=torch.float32)
+        dgb = torch.empty(2, d, device=g.device, dtype=torch.float32)
+        nbytes = int(lib.moegan_layernorm_bwd_scratch_bytes(rows, d))
+        scratch = torch.empty(nbytes, device=g.device, dtype=torch.uint8)
+        C.check(lib.moegan_layernorm_bwd(C.ptr(g), C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d, C.ptr(dx),
+                                         C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd")
+        return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """`nn.LayerNorm(d)(x)` over the last dimension; fp32 result (what autocast's LayerNorm returns as well)."""
+    if not x.is_cuda:
+        return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps)
+    return _LayerNormFn.apply(x, weight, bias, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# per-(sample, channel) scale + LeakyReLU  (ModulatedConv modulate / demodulate, t2i_moe_gan.py:158-186; MTM activation :243)
+# --------------------------------------------------------------------------------------------------
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+class _ChannelScaleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, slope):
+        B, Cn, H, W = x.shape
+        xc = _nhwc(x if x.dtype in (torch.float32, torch.bfloat16) else x.float())
+        sf = s.detach().float().contiguous()
+        out = torch.empty_like(xc)                      # keeps the channels-last strides
+        C.check(C.lib().moegan_channel_scale_fwd(C.ptr(xc), _is_bf16(xc), C.ptr(sf), B, H * W, Cn, float(slope), C.ptr(out), _stream()),
+                "moegan_channel_scale_fwd")
+        ctx.save_for_backward(xc, sf)
+        ctx.slope, ctx.x_dtype, ctx.s_dtype = float(slope), x.dtype, s.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, sf = ctx.saved_tensors
+        B, Cn, H, W = xc.shape
+        gc = _nhwc(g.to(xc.dtype))
+        lib = C.lib()
+        dx = torch.empty_like(xc)
+        ds = torch.empty(B, Cn, device=xc.device, dtype=torch.float32)
+        nbytes = int(lib.moegan_channel_scale_bwd_scratch_bytes(B, H * W, Cn))
+        scratch = torch.empty(nbytes, device=xc.device, dtype=torch.uint8)
+        C.check(lib.moegan_channel_scale_bwd(C.ptr(gc), C.ptr(xc), _is_bf16(xc), C.ptr(sf), B, H * W, Cn, ctx.slope, C.ptr(dx), C.ptr(ds),
+                                             C.ptr(scratch), nbytes, _stream()), "moegan_channel_scale_bwd")
+        return dx.to(ctx.x_dtype), ds.to(ctx.s_dtype), None
+
+
+def channel_scale(x: torch.Tensor, s: torch.Tensor, slope: float = 1.0) -> torch.Tensor:
+    """`F.leaky_relu(x * s[:, :, None, None], slope)` for x [B,C,H,W], s [B,C]; slope = 1.0 means no activation."""
+    if x.is_cuda and x.shape[1] % 128 == 0 and x.dim() == 4:
+        return _ChannelScaleFn.apply(x, s, slope)
+    y = x * s.to(x.dtype)[:, :, None, None]            # CPU definition; also tiny channel counts (to_rgb: 3 channels)
+    return y if slope == 1.0 else F.leaky_relu(y, slope)
+
+
+# --------------------------------------------------------------------------------------------------
+# learned-offset bilinear resampling (ModulatedTransformationModule, t2i_moe_gan.py:219-240)
+# --------------------------------------------------------------------------------------------------
+class _OffsetSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, off_raw):
+        B, Cn, H, W = x.shape
+        xc = _nhwc(x if x.dtype in (torch.float32, torch.bfloat16) else x.float())
+        off = off_raw.detach().permute(0, 2, 3, 1).float().contiguous()          # [B,H,W,2]: (x offset, y offset)
+        out = torch.empty_like(xc)
+        C.check(C.lib().moegan_offset_sample_fwd(C.ptr(xc), _is_bf16(xc), C.ptr(off), B, H, W, Cn, C.ptr(out), _stream()),
+                "moegan_offset_sample_fwd")
+        ctx.save_for_backward(xc, off)
+        ctx.x_dtype, ctx.off_dtype = x.dtype, off_raw.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, off = ctx.saved_tensors
+        B, Cn, H, W = xc.shape
+        gc = _nhwc(g.to(xc.dtype))
+        dx = torch.empty_like(xc)
+        doff = torch.empty_like(off)
+        C.check(C.lib().moegan_offset_sample_bwd(C.ptr(gc), C.ptr(xc), _is_bf16(xc), C.ptr(off), B, H, W, Cn, C.ptr(dx), C.ptr(doff), _stream()),
+                "moegan_offset_sample_bwd")
+        return dx.to(ctx.x_dtype), doff.permute(0, 3, 1, 2).to(ctx.off_dtype)
+
+
+def offset_sample_reference(x: torch.Tensor, off_raw: torch.Tensor) -> torch.Tensor:
+    """The reference computation in torch ops (t2i_moe_gan.py:222-240)."""
+    B, _, H, W = x.shape
+    off = off_raw.permute(0, 2, 3, 1) * 0.05
+    gy, gx = torch.meshgrid(torch.linspace(-1, 1, H, device=x.device), torch.linspace(-1, 1, W, device=x.device), indexing="ij")
+    grid = (torch.stack((gx, gy), dim=2).unsqueeze(0) + off.float()).clamp(-1, 1)
+    return F.grid_sample(x, grid.to(x.dtype), mode="bilinear", align_corners=False)
+
+
+def offset_sample(x: torch.Tensor, off_raw: torch.Tensor) -> torch.Tensor:
+    """x [B,C,H,W] resampled at meshgrid + 0.05 * off_raw (off_raw [B,2,H,W] = offset_net(x): channel 0 = x, 1 = y)."""
+    if x.is_cuda and x.shape[1] % 128 == 0 and x.shape[2] * x.shape[3] <= 512:
+        return _OffsetSampleFn.apply(x, off_raw)
+    return offset_sample_reference(x, off_raw)

@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.utils.parametrizations import weight_norm
 
+from . import glue
 from .sparse_moe import SparseMoE, moe_balance_loss
 
 LATENT_DIM = 512          # t2i_moe_gan.py:20
@@ -40,16 +41,19 @@ class ModulatedConv(nn.Module):
         nn.init.normal_(self.modulation.weight, mean=0.0, std=0.02)
         nn.init.zeros_(self.modulation.bias)
 
-    def forward(self, x, w):
+    def forward(self, x, w, act_slope=None):
+        """act_slope: fuse the LeakyReLU that ModulatedTransformationModule applies to the result (:243-245)."""
         s = self.modulation(w)                                            # [B, in]
         # under autocast F.conv2d casts (and caches) the weight itself; an explicit .to() would re-cast on every call
         wgt = self.weight if (torch.is_autocast_enabled() or self.weight.dtype == x.dtype) else self.weight.to(x.dtype)
-        y = F.conv2d(x * s.to(x.dtype)[:, :, None, None], wgt, padding=self.padding)
+        # modulate: x * s  /  demodulate (+ activation): lrelu(y * d) - one fused pass each on the GPU (glue.channel_scale)
+        y = F.conv2d(glue.channel_scale(x, s), wgt, padding=self.padding)
+        slope = 1.0 if act_slope is None else float(act_slope)
         if self.demodulate:
             wsq = self.weight.float().pow(2).sum(dim=(2, 3))              # [out, in]
             d = torch.rsqrt(s.float().pow(2) @ wsq.t() + 1e-8)            # [B, out]
-            y = y * d.to(y.dtype)[:, :, None, None]
-        return y
+            return glue.channel_scale(y, d, slope)
+        return y if act_slope is None else F.leaky_relu(y, slope)
 
 
 class ModulatedTransformationModule(nn.Module):
@@ -60,16 +64,13 @@ class ModulatedTransformationModule(nn.Module):
         if self.use_offset:
             self.offset_net = nn.Sequential(nn.Conv2d(in_channels, 32, 3, padding=1), nn.LeakyReLU(0.2, inplace=True),
                                             nn.Conv2d(32, 2, 3, padding=1))
-        self.activation = nn.LeakyReLU(0.2, inplace=True)
+        self.activation = nn.LeakyReLU(0.2, inplace=True)             # kept for the module tree; applied inside modulated_conv
 
     def forward(self, x, w):
         if self.use_offset:
-            B, _, H, W = x.shape
-            off = self.offset_net(x).permute(0, 2, 3, 1) * 0.05
-            gy, gx = torch.meshgrid(torch.linspace(-1, 1, H, device=x.device), torch.linspace(-1, 1, W, device=x.device), indexing="ij")
-            grid = (torch.stack((gx, gy), dim=2).unsqueeze(0) + off.float()).clamp(-1, 1)
-            x = F.grid_sample(x, grid.to(x.dtype), mode="bilinear", align_corners=False)
-        return self.activation(self.modulated_conv(x, w))
+            # grid = clamp(meshgrid + 0.05 * offset_net(x), -1, 1); bilinear resampling (glue.offset_sample: NHWC kernels)
+            x = glue.offset_sample(x, self.offset_net(x))
+        return self.modulated_conv(x, w, act_slope=self.activation.negative_slope)
 
 
 class ConvolutionBlock(nn.Module):
@@ -100,13 +101,14 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x, w, text_seq, kl_losses=None, annealing_factor=1.0):
         B, C, H, W = x.shape
+        ln = lambda m, v: glue.layer_norm(v, m.weight, m.bias, m.eps)     # nn.LayerNorm through the library's kernels
         t = self.proj_in(x, w).permute(0, 2, 3, 1).reshape(B, H * W, C)
-        n = self.norm1(t)
+        n = ln(self.norm1, t)
         t = t + self.self_attn(n, n, n, need_weights=False)[0]
         tp = self.text_proj(text_seq)
-        t = t + self.cross_attn(self.norm2(t), tp, tp, need_weights=False)[0]
+        t = t + self.cross_attn(ln(self.norm2, t), tp, tp, need_weights=False)[0]
         x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
-        x_norm = self.norm3(t).reshape(B, H, W, C).permute(0, 3, 1, 2)     # NCHW view of NHWC memory (:561)
+        x_norm = ln(self.norm3, t).reshape(B, H, W, C).permute(0, 3, 1, 2)  # NCHW view of NHWC memory (:561)
         moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
         if kl_losses is not None:
             kl_losses.append(moe_kl)

@@ -1,0 +1,144 @@
+"""GPU parity of the kernels around the MoE block against the torch ops they replace in the
+reference model: nn.LayerNorm (t2i_moe_gan.py:513-515), the modulate / demodulate / LeakyReLU element-wise steps of
+ModulatedConv (:158-186, :243) and the learned-offset grid_sample of ModulatedTransformationModule (:219-240).
+The comparison runs on the CPU in fp64 / fp32 torch ops on identical inputs; bars: 1e-5 (fp32 storage), 2e-2 (bf16)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gpu_utils as G_
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return G_.rel_err(a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy())
+
+
+@pytest.mark.parametrize("rows,d", [(4099, 128), (1024, 256), (333, 512), (5, 1024), (70001, 128)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_matches_torch(rows, d, dtype):
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 2 + 0.5).to(dtype)
+    w = torch.randn(d, generator=g) * 0.5 + 1.0
+    b = torch.randn(d, generator=g) * 0.1
+    gy = torch.randn(rows, d, generator=g)
+    xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (d,), wr, br, 1e-5)
+    yr.backward(gy.double())
+    xc = x.cuda().requires_grad_(True); wc = w.cuda().requires_grad_(True); bc = b.cuda().requires_grad_(True)
+    yc = glue.layer_norm(xc, wc, bc, 1e-5)
+    assert yc.dtype == torch.float32 and yc.shape == x.shape
+    yc.backward(gy.cuda())
+    tol = 2e-5 if dtype == torch.float32 else 2e-2      # dx is returned in the input's dtype
+    assert _rel(yc, yr) < 2e-5
+    assert _rel(xc.grad, xr.grad) < tol
+    assert _rel(wc.grad, wr.grad) < 2e-5
+    assert _rel(bc.grad, br.grad) < 2e-5
+    # deterministic: bit-identical on a second run
+    xc2 = x.cuda().requires_grad_(True); wc2 = w.cuda().requires_grad_(True); bc2 = b.cuda().requires_grad_(True)
+    glue.layer_norm(xc2, wc2, bc2, 1e-5).backward(gy.cuda())
+    assert torch.equal(wc2.grad, wc.grad) and torch.equal(bc2.grad, bc.grad) and torch.equal(xc2.grad, xc.grad)
+
+
+def test_layernorm_3d_input_and_autocast():
+    glue = G_.pkg().glue
+    x = torch.randn(4, 64, 256, device="cuda")
+    ln = torch.nn.LayerNorm(256).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = glue.layer_norm(x.bfloat16(), ln.weight, ln.bias, ln.eps)
+        ref = ln(x.bfloat16())
+    assert y.dtype == ref.dtype == torch.float32
+    assert _rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 128, 16, 16), (2, 256, 8, 8), (5, 512, 4, 4), (300, 128, 4, 4), (2, 128, 64, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("slope", [1.0, 0.2])
+def test_channel_scale_matches_torch(B, C, H, W, dtype, slope):
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(B * C + H)
+    x = torch.randn(B, C, H, W, generator=g).to(dtype)
+    s = torch.randn(B, C, generator=g)
+    go = torch.randn(B, C, H, W, generator=g).to(dtype)
+    xr = x.double().requires_grad_(True); sr = s.double().requires_grad_(True)
+    yr = xr * sr[:, :, None, None]
+    yr = yr if slope == 1.0 else F.leaky_relu(yr, slope)
+    yr.backward(go.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True); sc = s.cuda().requires_grad_(True)
+    yc = glue.channel_scale(xc, sc, slope)
+    assert yc.dtype == dtype and yc.is_contiguous(memory_format=torch.channels_last)
+    yc.backward(go.cuda())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert _rel(yc, yr) < tol
+    assert _rel(xc.grad, xr.grad) < tol
+    assert _rel(sc.grad, sr.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_channel_scale_nchw_input_and_small_channels():
+    """NCHW-contiguous input is converted; channel counts the kernel does not take (to_rgb: 3) use the torch formula."""
+    glue = G_.pkg().glue
+    x = torch.randn(2, 128, 8, 8, device="cuda"); s = torch.randn(2, 128, device="cuda")
+    assert _rel(glue.channel_scale(x, s, 0.2), F.leaky_relu(x * s[:, :, None, None], 0.2)) < 1e-6
+    x3 = torch.randn(2, 3, 8, 8, device="cuda"); s3 = torch.randn(2, 3, device="cuda")
+    assert _rel(glue.channel_scale(x3, s3), x3 * s3[:, :, None, None]) < 1e-6
+
+
+@pytest.mark.parametrize("B,C,H,W,scale", [(2, 128, 16, 16, 1.0), (3, 256, 8, 8, 10.0), (2, 512, 4, 4, 30.0), (4, 128, 16, 16, 60.0),
+                                           (2, 128, 4, 4, 0.0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_offset_sample_matches_grid_sample(B, C, H, W, scale, dtype):
+    """scale stretches the raw offsets so that taps cross pixel borders (10), leave the image (zero padding) and hit the
+    [-1, 1] clamp of the grid (30, 60: 0.05 * 60 = 3 grid units)."""
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(C + H + int(scale))
+    x = torch.randn(B, C, H, W, generator=g).to(dtype)
+    off = torch.randn(B, 2, H, W, generator=g) * scale
+    go = torch.randn(B, C, H, W, generator=g).to(dtype)
+    xr = x.double().requires_grad_(True); offr = off.double().requires_grad_(True)
+    # reference formula in fp64 (glue.offset_sample_reference builds its base grid in fp32: restated here for fp64)
+    gy, gx = torch.meshgrid(torch.linspace(-1, 1, H, dtype=torch.float64), torch.linspace(-1, 1, W, dtype=torch.float64), indexing="ij")
+    grid = (torch.stack((gx, gy), dim=2).unsqueeze(0) + offr.permute(0, 2, 3, 1) * 0.05).clamp(-1, 1)
+    yr = F.grid_sample(xr, grid, mode="bilinear", align_corners=False)
+    yr.backward(go.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True); offc = off.cuda().requires_grad_(True)
+    yc = glue.offset_sample(xc, offc)
+    assert yc.dtype == dtype and yc.shape == x.shape
+    yc.backward(go.cuda())
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert _rel(yc, yr) < tol
+    assert _rel(xc.grad, xr.grad) < tol
+    assert _rel(offc.grad, offr.grad) < (1e-4 if dtype == torch.float32 else 3e-2)
+    # and against the fp32 torch-op restatement of the reference lines
+    with torch.no_grad():
+        assert _rel(yc, glue.offset_sample_reference(x.cuda().float(), off.cuda())) < tol
+    # deterministic scatter
+    xc2 = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True); offc2 = off.cuda().requires_grad_(True)
+    glue.offset_sample(xc2, offc2).backward(go.cuda())
+    assert torch.equal(xc2.grad, xc.grad) and torch.equal(offc2.grad, offc.grad)
+
+
+def test_modulated_transformation_module_matches_torch_ops(monkeypatch):
+    """The host model's MTM / ModulatedConv on the GPU kernels vs the same module evaluated with the torch-op definitions
+    (CPU, fp32): forward and all gradients."""
+    hm = G_.pkg().host_model
+    torch.manual_seed(0)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # the cuDNN convolutions in between, in full fp32
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    mtm = hm.ModulatedTransformationModule(128, 256, 3, use_offset=True, resolution=8)
+    with torch.no_grad():                               # non-trivial offsets
+        for p in mtm.offset_net.parameters():
+            p.mul_(8.0)
+    x = torch.randn(3, 128, 8, 8); w = torch.randn(3, 512)
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    yr = mtm(xr, wr); go = torch.randn_like(yr); yr.backward(go)
+    ref = {n: p.grad.clone() for n, p in mtm.named_parameters()}
+    mtm.zero_grad(); mtm.cuda()
+    xc = x.cuda().requires_grad_(True); wc = w.cuda().requires_grad_(True)
+    yc = mtm(xc, wc); yc.backward(go.cuda())
+    assert _rel(yc, yr) < 1e-4
+    assert _rel(xc.grad, xr.grad) < 1e-4 and _rel(wc.grad, wr.grad) < 1e-4
+    for n, p in mtm.named_parameters():
+        assert _rel(p.grad, ref[n]) < 2e-4, n

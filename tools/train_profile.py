@@ -1,5 +1,7 @@
-"""Kernel-time breakdown of one eager train step (torch.profiler / CUPTI). Run on the GPU box."""
-import importlib, os, sys
+#!/usr/bin/env python
+"""Kernel-level breakdown of one full train step (eager, no CUDA graph): every kernel aggregated by name, plus the
+time under each top-level module of the generator / discriminator (torch.profiler record_function ranges)."""
+import importlib, os, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -18,4 +20,11 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     with torch.profiler.record_function("D_STEP"): tr.d_step(real, text, z)
     with torch.profiler.record_function("G_STEP"): tr.g_step(text, z)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+agg = collections.defaultdict(lambda: [0.0, 0])
+tot = 0.0
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA and ev.name not in ("D_STEP", "G_STEP"):
+        agg[ev.name][0] += ev.device_time; agg[ev.name][1] += 1; tot += ev.device_time
+print(f"total kernel time {tot / 1e3:.2f} ms, {sum(v[1] for v in agg.values())} launches, {len(agg)} distinct kernels")
+for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("TOPK", "70"))]:
+    print(f"{us:9.1f} us {100 * us / tot:5.1f}% {n:5d}x {us / n:8.1f}  {name[:150]}")
