@@ -249,25 +249,28 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
 
 /* ---- layers around the block ------------------------------------------ */
 /* replaces: nn.LayerNorm(dim) of AttentionBlock.norm1-3 (t2i_moe_gan.py:513-515, applied :541,:553,:561).
- * x [rows,d] fp32 or bf16 (x_is_bf16), y fp32 [rows,d]; mean / rstd [rows] are what the backward needs.
- * d: multiple of 128, <= 1024. */
+ * x [rows,d] fp32 or bf16 (x_is_bf16), y [rows,d] fp32 or bf16 (y_is_bf16: the rounding autocast's consumer would apply
+ * anyway); mean / rstd [rows] fp32 are what the backward needs.  d: multiple of 128, <= 1024. */
 int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d,
-                         float eps, float* y, float* mean, float* rstd, void* stream);
+                         float eps, void* y, int32_t y_is_bf16, float* mean, float* rstd, void* stream);
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d);
-/* dx fp32 [rows,d]; dgamma_dbeta fp32 [2,d] (row 0 = weight gradient, row 1 = bias gradient), deterministic. */
-int moegan_layernorm_bwd(const float* dy, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
-                         const float* rstd, int64_t rows, int32_t d, float* dx, float* dgamma_dbeta,
+/* dy fp32 or bf16; dx [rows,d] in x's dtype; dgamma_dbeta fp32 [2,d] (row 0 = weight gradient, row 1 = bias gradient),
+ * deterministic. */
+int moegan_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma,
+                         const float* mean, const float* rstd, int64_t rows, int32_t d, void* dx, float* dgamma_dbeta,
                          void* scratch, int64_t scratch_bytes, void* stream);
 
 /* replaces: the modulate / demodulate / LeakyReLU element-wise steps of ModulatedConv + the activation of
  * ModulatedTransformationModule (t2i_moe_gan.py:158-186, :243-245) in "scale the activations" form:
  * out[b,p,c] = leaky_relu(x[b,p,c] * s[b,c], slope)  (slope = 1: no activation).  x / out: NHWC [B,P,C], fp32 or bf16;
- * s: fp32 [B,C]; C: multiple of 128.  Backward: dx and ds[b,c] = sum_p in ONE pass (deterministic). */
-int moegan_channel_scale_fwd(const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C, float slope,
-                             void* out, void* stream);
+ * s [B,C] fp32 or bf16 (s_is_bf16); C: multiple of 128.  Backward: dx and ds[b,c] = sum_p (in s's dtype) in ONE pass over
+ * g and x (deterministic). */
+int moegan_channel_scale_fwd(const void* x, int32_t is_bf16, const void* s, int32_t s_is_bf16, int32_t B, int32_t P, int32_t C,
+                             float slope, void* out, void* stream);
 int64_t moegan_channel_scale_bwd_scratch_bytes(int32_t B, int32_t P, int32_t C);
-int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C,
-                             float slope, void* dx, float* ds, void* scratch, int64_t scratch_bytes, void* stream);
+int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, const void* s, int32_t s_is_bf16, int32_t B,
+                             int32_t P, int32_t C, float slope, void* dx, void* ds, void* scratch, int64_t scratch_bytes,
+                             void* stream);
 
 /* replaces: the learned-offset resampling of ModulatedTransformationModule (t2i_moe_gan.py:219-240):
  * grid = clamp(meshgrid(linspace(-1,1)) + 0.05 * off, -1, 1);  out = F.grid_sample(x, grid, bilinear, zeros,

@@ -86,12 +86,12 @@ SIGNATURES = {
     "moegan_block_bwd_workspace": (c_int64, [_SP]),
     "moegan_block_fwd": (c_int32, [_SP, POINTER(BlockFwdArgs), _P]),
     "moegan_block_bwd": (c_int32, [_SP, POINTER(BlockBwdArgs), _P]),
-    "moegan_layernorm_fwd": (c_int32, [_P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, _P, _P, _P]),
+    "moegan_layernorm_fwd": (c_int32, [_P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, c_int32, _P, _P, _P]),
     "moegan_layernorm_bwd_scratch_bytes": (c_int64, [c_int64, c_int32]),
-    "moegan_layernorm_bwd": (c_int32, [_P, _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
-    "moegan_channel_scale_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
+    "moegan_layernorm_bwd": (c_int32, [_P, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
+    "moegan_channel_scale_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "moegan_channel_scale_bwd_scratch_bytes": (c_int64, [c_int32, c_int32, c_int32]),
-    "moegan_channel_scale_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),
+    "moegan_channel_scale_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),
     "moegan_offset_sample_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "moegan_offset_sample_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "moegan_umma_gemm": (c_int32, [c_int32] * 5 + [_P] * 3 + [_P]),

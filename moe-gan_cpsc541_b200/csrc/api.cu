@@ -734,23 +734,24 @@ static int check_ln(int64_t rows, int32_t d) {
     return MOEGAN_OK;
 }
 int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
-                         float* y, float* mean, float* rstd, void* stream) {
+                         void* y, int32_t y_is_bf16, float* mean, float* rstd, void* stream) {
     RUN(check_ln(rows, d));
     REQ_PTR(x); REQ_PTR(gamma); REQ_PTR(beta); REQ_PTR(y); REQ_PTR(mean); REQ_PTR(rstd);
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0, MOEGAN_ERR_MISALIGNED, "layernorm_fwd: pointers must be 16-byte aligned");
-    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, mean, rstd, (cudaStream_t)stream);
+    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, y_is_bf16, mean, rstd, (cudaStream_t)stream);
 }
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d) { return (int64_t)ln_bwd_blocks(rows) * 2 * d * 4 + 256; }
-int moegan_layernorm_bwd(const float* dy, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean, const float* rstd,
-                         int64_t rows, int32_t d, float* dx, float* dgamma_dbeta, void* scratch, int64_t scratch_bytes, void* stream) {
+int moegan_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
+                         const float* rstd, int64_t rows, int32_t d, void* dx, float* dgamma_dbeta, void* scratch, int64_t scratch_bytes,
+                         void* stream) {
     RUN(check_ln(rows, d));
     REQ_PTR(dy); REQ_PTR(x); REQ_PTR(gamma); REQ_PTR(mean); REQ_PTR(rstd); REQ_PTR(dx); REQ_PTR(dgamma_dbeta); REQ_PTR(scratch);
     MOEGAN_REQUIRE(scratch_bytes >= moegan_layernorm_bwd_scratch_bytes(rows, d), MOEGAN_ERR_BAD_SHAPE, "layernorm_bwd: scratch too small");
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
                      reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0, MOEGAN_ERR_MISALIGNED,
                    "layernorm_bwd: pointers must be 16-byte aligned");
-    return launch_layernorm_bwd(dy, x, x_is_bf16, gamma, mean, rstd, rows, d, dx, dgamma_dbeta, reinterpret_cast<float*>(scratch),
+    return launch_layernorm_bwd(dy, dy_is_bf16, x, x_is_bf16, gamma, mean, rstd, rows, d, dx, dgamma_dbeta, reinterpret_cast<float*>(scratch),
                                 (cudaStream_t)stream);
 }
 
@@ -759,27 +760,27 @@ static int check_nhwc(const char* what, int32_t B, int32_t P, int32_t C) {
                    "%s: channels (%d) must be a positive multiple of 128 (B %d, pixels %d)", what, C, B, P);
     return MOEGAN_OK;
 }
-int moegan_channel_scale_fwd(const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C, float slope, void* out,
-                             void* stream) {
+int moegan_channel_scale_fwd(const void* x, int32_t is_bf16, const void* s, int32_t s_is_bf16, int32_t B, int32_t P, int32_t C, float slope,
+                             void* out, void* stream) {
     RUN(check_nhwc("channel_scale_fwd", B, P, C));
     REQ_PTR(x); REQ_PTR(s); REQ_PTR(out);
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(s)) & 15) == 0,
                    MOEGAN_ERR_MISALIGNED, "channel_scale_fwd: pointers must be 16-byte aligned");
-    return launch_channel_scale_fwd(x, is_bf16, s, B, P, C, slope, out, (cudaStream_t)stream);
+    return launch_channel_scale_fwd(x, is_bf16, s, s_is_bf16, B, P, C, slope, out, (cudaStream_t)stream);
 }
 int64_t moegan_channel_scale_bwd_scratch_bytes(int32_t B, int32_t P, int32_t C) {
     if (C < 128 || C % 128 != 0) return 256;
     return (int64_t)channel_scale_psplit(B, P, C) * B * C * 4 + 256;
 }
-int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, const float* s, int32_t B, int32_t P, int32_t C, float slope,
-                             void* dx, float* ds, void* scratch, int64_t scratch_bytes, void* stream) {
+int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, const void* s, int32_t s_is_bf16, int32_t B, int32_t P, int32_t C,
+                             float slope, void* dx, void* ds, void* scratch, int64_t scratch_bytes, void* stream) {
     RUN(check_nhwc("channel_scale_bwd", B, P, C));
     REQ_PTR(g); REQ_PTR(x); REQ_PTR(s); REQ_PTR(dx); REQ_PTR(ds); REQ_PTR(scratch);
     MOEGAN_REQUIRE(scratch_bytes >= moegan_channel_scale_bwd_scratch_bytes(B, P, C), MOEGAN_ERR_BAD_SHAPE, "channel_scale_bwd: scratch too small");
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx) |
                      reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(ds) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0,
                    MOEGAN_ERR_MISALIGNED, "channel_scale_bwd: pointers must be 16-byte aligned");
-    return launch_channel_scale_bwd(g, x, is_bf16, s, B, P, C, slope, dx, ds, reinterpret_cast<float*>(scratch), (cudaStream_t)stream);
+    return launch_channel_scale_bwd(g, x, is_bf16, s, s_is_bf16, B, P, C, slope, dx, ds, reinterpret_cast<float*>(scratch), (cudaStream_t)stream);
 }
 int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H, int32_t W, int32_t C, void* out,
                              void* stream) {

@@ -42,10 +42,10 @@ template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16*
 // =====================================================================================================
 constexpr int LN_MAX_SEG = 8;
 
-template <typename TIN>
+template <typename TIN, typename TOUT>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int d,
-                     float eps, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                     float eps, TOUT* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -72,18 +72,18 @@ layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma,
             float4 o;
             o.x = (v[s].x - mean) * rstd * g.x + b.x; o.y = (v[s].y - mean) * rstd * g.y + b.y;
             o.z = (v[s].z - mean) * rstd * g.z + b.z; o.w = (v[s].w - mean) * rstd * g.w + b.w;
-            *reinterpret_cast<float4*>(y + r * d + c) = o;
+            Vec4<TOUT>::store(y + r * d + c, o);
         }
     if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
 }
 
 // dx = rstd * (gamma*g - mean_d(gamma*g) - xhat * mean_d(gamma*g*xhat)); per-CTA partial column sums of g*xhat and g.
 // Each warp walks rows r = warp_global, += total_warps; the CTA's 8 warps are combined through shared memory.
-template <typename TIN>
+template <typename TG, typename TIN>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const float* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
+layernorm_bwd_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows, int d,
-                     float* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
+                     TIN* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
     __shared__ float4 red[8][LN_MAX_SEG * 32];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nseg = d / 128;
@@ -103,7 +103,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const TIN* __restrict__ x, con
             if (s < nseg) {
                 const long long o = r * d + s * 128 + lane * 4;
                 const float4 xv = Vec4<TIN>::load(x + o);
-                const float4 gv = __ldg(reinterpret_cast<const float4*>(g + o));
+                const float4 gv = Vec4<TG>::load(g + o);
                 xh[s] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
                 dg[s].x += gv.x * xh[s].x; dg[s].y += gv.y * xh[s].y; dg[s].z += gv.z * xh[s].z; dg[s].w += gv.w * xh[s].w;
                 db[s].x += gv.x; db[s].y += gv.y; db[s].z += gv.z; db[s].w += gv.w;
@@ -118,7 +118,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const TIN* __restrict__ x, con
                 float4 o;
                 o.x = rstd * (gg[s].x - s1 - xh[s].x * s2); o.y = rstd * (gg[s].y - s1 - xh[s].y * s2);
                 o.z = rstd * (gg[s].z - s1 - xh[s].z * s2); o.w = rstd * (gg[s].w - s1 - xh[s].w * s2);
-                *reinterpret_cast<float4*>(dx + r * d + s * 128 + lane * 4) = o;
+                Vec4<TIN>::store(dx + r * d + s * 128 + lane * 4, o);
             }
     }
     for (int pass = 0; pass < 2; ++pass) {
@@ -135,32 +135,33 @@ layernorm_bwd_kernel(const float* __restrict__ g, const TIN* __restrict__ x, con
         __syncthreads();
     }
 }
-// out[i] = sum_b part[b * n + i]  (fixed order)
+// out[i] = sum_b part[b * n + i]  (fixed order); out fp32 or bf16
+template <typename TOUT>
 __global__ void __launch_bounds__(256)
-partial_sum_kernel(const float* __restrict__ part, int n, int nparts, float* __restrict__ out) {
+partial_sum_kernel(const float* __restrict__ part, int n, int nparts, TOUT* __restrict__ out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float s0 = 0.f, s1 = 0.f;
     int b = 0;
     for (; b + 1 < nparts; b += 2) { s0 += part[(size_t)b * n + i]; s1 += part[(size_t)(b + 1) * n + i]; }
     if (b < nparts) s0 += part[(size_t)b * n + i];
-    out[i] = s0 + s1;
+    store1<TOUT>(out + i, s0 + s1);
 }
 
 // =====================================================================================================
 // channel_scale: out[b, p, c] = lrelu(x[b, p, c] * s[b, c], slope)      x: [B, P, C] (NHWC), s: [B, C] fp32
 // =====================================================================================================
 // forward: grid-stride over groups of 4 channels
-template <typename T>
+template <typename T, typename TS>
 __global__ void __launch_bounds__(256)
-channel_scale_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s, long long n4, int P, int C, float slope, T* __restrict__ out) {
+channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, long long n4, int P, int C, float slope, T* __restrict__ out) {
     const int c4 = C / 4;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         const long long bp = i / c4;
         const int c = (int)(i - bp * c4) * 4;
         const long long b = bp / P;
         const float4 v = Vec4<T>::load(x + i * 4);
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(s + b * C + c));
+        const float4 sc = Vec4<TS>::load(s + b * C + c);
         float4 o = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
         o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
         o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
@@ -169,15 +170,15 @@ channel_scale_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s, l
 }
 // backward: CTA = (sample b, 128-channel group, pixel split); warp w takes pixels w, w+8, ...; lane = 4 channels.
 //   m = g * (x*s > 0 ? 1 : slope);  dx = m * s;  ds[b, c] = sum_p m * x   (partials over the pixel splits, summed in order)
-template <typename T>
+template <typename T, typename TS>
 __global__ void __launch_bounds__(256)
-channel_scale_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ s, int P, int C, float slope,
+channel_scale_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const TS* __restrict__ s, int P, int C, float slope,
                          int psplit, T* __restrict__ dx, float* __restrict__ ds_part /* [psplit][B][C] */, int Bn) {
     __shared__ float4 red[8][32];
     const int b = blockIdx.y, cgp = blockIdx.x, sp = blockIdx.z;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = cgp * 128 + lane * 4;
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(s + (size_t)b * C + c));
+    const float4 sc = Vec4<TS>::load(s + (size_t)b * C + c);
     const int per = (P + psplit - 1) / psplit;
     const int p0 = sp * per, p1 = min(P, p0 + per);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -336,38 +337,47 @@ int ln_bwd_blocks(long long rows) {
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, float* y,
-                         float* mean, float* rstd, cudaStream_t st) {
+int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
+                         int y_bf16, float* mean, float* rstd, cudaStream_t st) {
     if (rows == 0) return MOEGAN_OK;
     const int blocks = (int)((rows + 7) / 8);
-    if (x_bf16) layernorm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, rows, d, eps, y, mean, rstd);
-    else        layernorm_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), gamma, beta, rows, d, eps, y, mean, rstd);
+    typedef __nv_bfloat16 bf;
+#define MOEGAN_LN_FWD(TI, TO) layernorm_fwd_kernel<TI, TO><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), mean, rstd)
+    if (x_bf16) { if (y_bf16) MOEGAN_LN_FWD(bf, bf); else MOEGAN_LN_FWD(bf, float); }
+    else        { if (y_bf16) MOEGAN_LN_FWD(float, bf); else MOEGAN_LN_FWD(float, float); }
+#undef MOEGAN_LN_FWD
     MOEGAN_CHECK_LAUNCH("layernorm_fwd_kernel");
     return MOEGAN_OK;
 }
 
-int launch_layernorm_bwd(const float* g, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd, long long rows,
-                         int d, float* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st) {
+int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd,
+                         long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st) {
     if (rows == 0) {
         MOEGAN_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, (size_t)2 * d * 4, st));
         return MOEGAN_OK;
     }
     const int blocks = ln_bwd_blocks(rows);
-    if (x_bf16) layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(g, reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, rows, d, dx, scratch);
-    else        layernorm_bwd_kernel<float><<<blocks, 256, 0, st>>>(g, reinterpret_cast<const float*>(x), gamma, mean, rstd, rows, d, dx, scratch);
+    typedef __nv_bfloat16 bf;
+#define MOEGAN_LN_BWD(TG, TI) layernorm_bwd_kernel<TG, TI><<<blocks, 256, 0, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, mean, rstd, rows, d, reinterpret_cast<TI*>(dx), scratch)
+    if (g_bf16) { if (x_bf16) MOEGAN_LN_BWD(bf, bf); else MOEGAN_LN_BWD(bf, float); }
+    else        { if (x_bf16) MOEGAN_LN_BWD(float, bf); else MOEGAN_LN_BWD(float, float); }
+#undef MOEGAN_LN_BWD
     MOEGAN_CHECK_LAUNCH("layernorm_bwd_kernel");
     // scratch = [blocks][2][d] = [blocks][2d]  ->  [dgamma | dbeta]
-    partial_sum_kernel<<<ceil_div(2 * d, 256), 256, 0, st>>>(scratch, 2 * d, blocks, dgamma_dbeta);
+    partial_sum_kernel<float><<<ceil_div(2 * d, 256), 256, 0, st>>>(scratch, 2 * d, blocks, dgamma_dbeta);
     MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
     return MOEGAN_OK;
 }
 
-int launch_channel_scale_fwd(const void* x, int bf16, const float* s, int B, int P, int C, float slope, void* out, cudaStream_t st) {
+int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st) {
     const long long n4 = (long long)B * P * C / 4;
     if (n4 == 0) return MOEGAN_OK;
     const int blocks = grid_cap((n4 + 255) / 256);
-    if (bf16) channel_scale_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), s, n4, P, C, slope, reinterpret_cast<__nv_bfloat16*>(out));
-    else      channel_scale_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), s, n4, P, C, slope, reinterpret_cast<float*>(out));
+    typedef __nv_bfloat16 bf;
+#define MOEGAN_CS_FWD(T, TS) channel_scale_fwd_kernel<T, TS><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), n4, P, C, slope, reinterpret_cast<T*>(out))
+    if (bf16) { if (s_bf16) MOEGAN_CS_FWD(bf, bf); else MOEGAN_CS_FWD(bf, float); }
+    else      { if (s_bf16) MOEGAN_CS_FWD(float, bf); else MOEGAN_CS_FWD(float, float); }
+#undef MOEGAN_CS_FWD
     MOEGAN_CHECK_LAUNCH("channel_scale_fwd_kernel");
     return MOEGAN_OK;
 }
@@ -380,21 +390,21 @@ int channel_scale_psplit(int B, int P, int C) {
     return ps;
 }
 
-int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const float* s, int B, int P, int C, float slope, void* dx, float* ds,
-                             float* scratch, cudaStream_t st) {
+int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* dx,
+                             void* ds, float* scratch, cudaStream_t st) {
     if ((long long)B * P * C == 0) return MOEGAN_OK;
     const int ps = channel_scale_psplit(B, P, C);
     dim3 grid(C / 128, B, ps);
-    float* part = ps == 1 ? ds : scratch;
-    if (bf16) channel_scale_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), s, P, C, slope, ps,
-                                                                             reinterpret_cast<__nv_bfloat16*>(dx), part, B);
-    else      channel_scale_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), s, P, C, slope, ps,
-                                                                     reinterpret_cast<float*>(dx), part, B);
+    typedef __nv_bfloat16 bf;
+#define MOEGAN_CS_BWD(T, TS) channel_scale_bwd_kernel<T, TS><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), P, C, slope, ps, reinterpret_cast<T*>(dx), scratch, B)
+    if (bf16) { if (s_bf16) MOEGAN_CS_BWD(bf, bf); else MOEGAN_CS_BWD(bf, float); }
+    else      { if (s_bf16) MOEGAN_CS_BWD(float, bf); else MOEGAN_CS_BWD(float, float); }
+#undef MOEGAN_CS_BWD
     MOEGAN_CHECK_LAUNCH("channel_scale_bwd_kernel");
-    if (ps > 1) {
-        partial_sum_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, ds);
-        MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
-    }
+    // ds (in s's dtype) = fixed-order sum of the pixel-split partials
+    if (s_bf16) partial_sum_kernel<bf><<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, reinterpret_cast<bf*>(ds));
+    else        partial_sum_kernel<float><<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, reinterpret_cast<float*>(ds));
+    MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
     return MOEGAN_OK;
 }
 

@@ -30,7 +30,7 @@ def _is_bf16(t: torch.Tensor) -> int:
 # --------------------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, out_dtype):
         d = x.shape[-1]
         x2 = x.reshape(-1, d)
         if x2.dtype not in (torch.float32, torch.bfloat16):
@@ -38,11 +38,11 @@ class _LayerNormFn(torch.autograd.Function):
         x2 = x2.contiguous()
         rows = x2.shape[0]
         wf, bf = weight.detach().float().contiguous(), bias.detach().float().contiguous()
-        y = torch.empty(rows, d, device=x.device, dtype=torch.float32)
+        y = torch.empty(rows, d, device=x.device, dtype=out_dtype)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
-        C.check(C.lib().moegan_layernorm_fwd(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), C.ptr(mean),
-                                             C.ptr(rstd), _stream()), "moegan_layernorm_fwd")
+        C.check(C.lib().moegan_layernorm_fwd(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), _is_bf16(y),
+                                             C.ptr(mean), C.ptr(rstd), _stream()), "moegan_layernorm_fwd")
         ctx.save_for_backward(x2, wf, mean, rstd)
         ctx.x_shape, ctx.x_dtype, ctx.w_dtype = x.shape, x.dtype, weight.dtype
         return y.view(x.shape)
@@ -51,22 +51,26 @@ class _LayerNormFn(torch.autograd.Function):
     def backward(ctx, gy):
         x2, wf, mean, rstd = ctx.saved_tensors
         rows, d = x2.shape
-        g = gy.reshape(rows, d).float().contiguous()
+        g = gy.reshape(rows, d)
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        g = g.contiguous()
         lib = C.lib()
-        dx = torch.empty(rows, d, device=g.device, dtype=torch.float32)
+        dx = torch.empty_like(x2)                       # in x's storage dtype, straight from the kernel
         dgb = torch.empty(2, d, device=g.device, dtype=torch.float32)
         nbytes = int(lib.moegan_layernorm_bwd_scratch_bytes(rows, d))
         scratch = torch.empty(nbytes, device=g.device, dtype=torch.uint8)
-        C.check(lib.moegan_layernorm_bwd(C.ptr(g), C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d, C.ptr(dx),
-                                         C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd")
-        return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None
+        C.check(lib.moegan_layernorm_bwd(C.ptr(g), _is_bf16(g), C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d,
+                                         C.ptr(dx), C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd")
+        return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None, None
 
 
-def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    """`nn.LayerNorm(d)(x)` over the last dimension; fp32 result (what autocast's LayerNorm returns as well)."""
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=torch.float32) -> torch.Tensor:
+    """`nn.LayerNorm(d)(x)` over the last dimension.  Result fp32 (what autocast's LayerNorm returns), or bf16 when the
+    only consumer is an autocast matmul that would round it to bf16 first thing anyway (same values, one pass less)."""
     if not x.is_cuda:
-        return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps)
-    return _LayerNormFn.apply(x, weight, bias, eps)
+        return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps).to(out_dtype)
+    return _LayerNormFn.apply(x, weight, bias, eps, out_dtype)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -81,26 +85,27 @@ class _ChannelScaleFn(torch.autograd.Function):
     def forward(ctx, x, s, slope):
         B, Cn, H, W = x.shape
         xc = _nhwc(x if x.dtype in (torch.float32, torch.bfloat16) else x.float())
-        sf = s.detach().float().contiguous()
+        sc = s.detach()
+        sc = (sc if sc.dtype in (torch.float32, torch.bfloat16) else sc.float()).contiguous()
         out = torch.empty_like(xc)                      # keeps the channels-last strides
-        C.check(C.lib().moegan_channel_scale_fwd(C.ptr(xc), _is_bf16(xc), C.ptr(sf), B, H * W, Cn, float(slope), C.ptr(out), _stream()),
-                "moegan_channel_scale_fwd")
-        ctx.save_for_backward(xc, sf)
+        C.check(C.lib().moegan_channel_scale_fwd(C.ptr(xc), _is_bf16(xc), C.ptr(sc), _is_bf16(sc), B, H * W, Cn, float(slope), C.ptr(out),
+                                                 _stream()), "moegan_channel_scale_fwd")
+        ctx.save_for_backward(xc, sc)
         ctx.slope, ctx.x_dtype, ctx.s_dtype = float(slope), x.dtype, s.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xc, sf = ctx.saved_tensors
+        xc, sc = ctx.saved_tensors
         B, Cn, H, W = xc.shape
         gc = _nhwc(g.to(xc.dtype))
         lib = C.lib()
         dx = torch.empty_like(xc)
-        ds = torch.empty(B, Cn, device=xc.device, dtype=torch.float32)
+        ds = torch.empty_like(sc)                       # in s's dtype, straight from the kernel
         nbytes = int(lib.moegan_channel_scale_bwd_scratch_bytes(B, H * W, Cn))
         scratch = torch.empty(nbytes, device=xc.device, dtype=torch.uint8)
-        C.check(lib.moegan_channel_scale_bwd(C.ptr(gc), C.ptr(xc), _is_bf16(xc), C.ptr(sf), B, H * W, Cn, ctx.slope, C.ptr(dx), C.ptr(ds),
-                                             C.ptr(scratch), nbytes, _stream()), "moegan_channel_scale_bwd")
+        C.check(lib.moegan_channel_scale_bwd(C.ptr(gc), C.ptr(xc), _is_bf16(xc), C.ptr(sc), _is_bf16(sc), B, H * W, Cn, ctx.slope, C.ptr(dx),
+                                             C.ptr(ds), C.ptr(scratch), nbytes, _stream()), "moegan_channel_scale_bwd")
         return dx.to(ctx.x_dtype), ds.to(ctx.s_dtype), None
 
 

@@ -101,12 +101,15 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x, w, text_seq, kl_losses=None, annealing_factor=1.0):
         B, C, H, W = x.shape
-        ln = lambda m, v: glue.layer_norm(v, m.weight, m.bias, m.eps)     # nn.LayerNorm through the library's kernels
+        # nn.LayerNorm through the library's kernels; norm1 / norm2 feed autocast matmuls only, which round their input to the
+        # autocast dtype first thing - emit that dtype directly.  norm3 feeds the fp32 router: stays fp32.
+        mm = torch.get_autocast_dtype("cuda") if (x.is_cuda and torch.is_autocast_enabled()) else torch.float32
+        ln = lambda m, v, dt=torch.float32: glue.layer_norm(v, m.weight, m.bias, m.eps, dt)
         t = self.proj_in(x, w).permute(0, 2, 3, 1).reshape(B, H * W, C)
-        n = ln(self.norm1, t)
+        n = ln(self.norm1, t, mm)
         t = t + self.self_attn(n, n, n, need_weights=False)[0]
         tp = self.text_proj(text_seq)
-        t = t + self.cross_attn(ln(self.norm2, t), tp, tp, need_weights=False)[0]
+        t = t + self.cross_attn(ln(self.norm2, t, mm), tp, tp, need_weights=False)[0]
         x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
         x_norm = ln(self.norm3, t).reshape(B, H, W, C).permute(0, 3, 1, 2)  # NCHW view of NHWC memory (:561)
         moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
@@ -211,10 +214,15 @@ class AuroraDiscriminator(nn.Module):
                                          weight_norm(nn.Conv2d(128, 256, 4, 2, 1)), nn.LeakyReLU(0.2, inplace=True))
         self.output_layer = nn.Sequential(weight_norm(nn.Conv2d(256 + 128, 1, 4, 1, 0)))
 
-    def forward(self, img, text_embedding):
-        f = self.conv_layers(img)
+    def features(self, img):
+        return self.conv_layers(img)
+
+    def head(self, f, text_embedding):
         t = self.text_projection(text_embedding)[:, :, None, None].expand(-1, -1, f.shape[2], f.shape[3])
         return self.output_layer(torch.cat([f, t.to(f.dtype)], dim=1)).reshape(-1)   # 16x16 fake -> B logits; 64x64 real -> 169*B
+
+    def forward(self, img, text_embedding):
+        return self.head(self.features(img), text_embedding)
 
 
 # ---- losses (t2i_moe_gan.py:917-949) -------------------------------------------------------------------
@@ -230,6 +238,43 @@ def r1_penalty(real_pred, real_images, r1_gamma=10.0):
     """(gamma / 2) * E ||d D(real) / d real||^2  (:1282-1286)."""
     (grad_real,) = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_images, create_graph=True)
     return (r1_gamma / 2) * grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1).pow(2).mean()
+
+
+def discriminator_real_pass(D: "AuroraDiscriminator", real, text, text_mismatched, r1_gamma=10.0):
+    """The three quantities the D-step needs from the REAL batch (t2i_moe_gan.py:1278-1306): D(real, text),
+    D(real, mismatched text) and the R1 penalty - same values and gradients as
+        real_pred = D(real, text); r1 = r1_penalty(real_pred, real); mis = D(real, text_mismatched)
+    with two re-formulations:
+      * the convolutional features of `real` are computed once and shared by both heads (the reference recomputes them);
+      * d real_pred.sum() / d real is written as an explicit adjoint pass of forward ops (transposed convolutions and
+        LeakyReLU masks) instead of autograd.grad(create_graph=True): the gradient of the penalty w.r.t. the weights
+        then runs through cuDNN's ordinary dgrad / wgrad kernels, not through the generic double-backward convolutions
+        (whose [3,B,64,64] x [128,B,32,32] case alone took 1.4 ms at batch 256).  LeakyReLU is piecewise linear, so the
+        masks are constants of the differentiation, exactly as in autograd's double backward."""
+    c1, c2, c3 = D.conv_layers[0], D.conv_layers[2], D.output_layer[0]
+    slope = D.conv_layers[1].negative_slope
+    W1, W2, W3 = c1.weight, c2.weight, c3.weight        # weight_norm parametrisations: evaluate once
+    a1 = F.conv2d(real, W1, c1.bias, stride=2, padding=1)
+    h1 = F.leaky_relu(a1, slope)
+    a2 = F.conv2d(h1, W2, c2.bias, stride=2, padding=1)
+    f = F.leaky_relu(a2, slope)
+
+    def head(txt):
+        t = D.text_projection(txt)[:, :, None, None].expand(-1, -1, f.shape[2], f.shape[3])
+        return F.conv2d(torch.cat([f, t.to(f.dtype)], dim=1), W3, c3.bias)
+
+    out_real = head(text)
+    real_pred, mismatched_pred = out_real.reshape(-1), head(text_mismatched).reshape(-1)
+    # adjoint of real_pred.sum(): the seed is all-ones and identical for every sample
+    seed = torch.ones(1, 1, out_real.shape[2], out_real.shape[3], device=real.device, dtype=out_real.dtype)
+    d_f = F.conv_transpose2d(seed, W3)[:, : f.shape[1]]                          # [1,256,16,16]
+    one, sl = torch.ones((), device=real.device, dtype=d_f.dtype), torch.full((), slope, device=real.device, dtype=d_f.dtype)
+    d_a2 = d_f * torch.where(a2 > 0, one, sl)                                    # [B,256,16,16]
+    d_h1 = F.conv_transpose2d(d_a2, W2, stride=2, padding=1)
+    d_a1 = d_h1 * torch.where(a1 > 0, one, sl)
+    grad_real = F.conv_transpose2d(d_a1, W1, stride=2, padding=1)                # = d real_pred.sum() / d real
+    r1 = (r1_gamma / 2) * grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1).pow(2).mean()
+    return real_pred, mismatched_pred, r1
 
 
 def sample_images(generator, z, text_embeddings, truncation_psi=0.7):

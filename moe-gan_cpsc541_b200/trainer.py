@@ -165,7 +165,7 @@ class MoEGANTrainer:
     def __init__(self, generator: nn.Module, discriminator: nn.Module, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999,
                  weight_decay: float = 0.01, r1_gamma: float = 10.0, kl_weight: float = 1e-3, balance_weight: float = 0.01,
                  amp_dtype: Optional[torch.dtype] = torch.bfloat16, group=None, bucket_bytes: int = 25 << 20,
-                 use_cuda_graph: bool = False, exact_dp_balance: bool = True):
+                 use_cuda_graph: bool = False, exact_dp_balance: bool = True, fused_real_pass: bool = True):
         self.G, self.D = generator, discriminator
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -173,6 +173,9 @@ class MoEGANTrainer:
         self.amp_dtype = amp_dtype
         self.exact_dp_balance = exact_dp_balance
         self.use_cuda_graph = use_cuda_graph
+        # D(real), D(real, mismatched text) and R1 from one shared feature pass with an explicit adjoint (host_model.
+        # discriminator_real_pass); False = the reference's three separate evaluations + autograd.grad(create_graph=True)
+        self.fused_real_pass = fused_real_pass and isinstance(discriminator, hm.AuroraDiscriminator)
         on_cuda = next(self.G.parameters()).is_cuda
         cap = dict(capturable=True) if use_cuda_graph else {}
         if on_cuda:
@@ -199,15 +202,19 @@ class MoEGANTrainer:
     # ---- D-step (:1268-1348) ----
     def d_step(self, real: torch.Tensor, text: torch.Tensor, z: torch.Tensor) -> Dict[str, torch.Tensor]:
         self.opt_d.zero_grad(set_to_none=True)
-        real = real.detach().requires_grad_(True)
+        real = real.detach()
         with self._autocast():
-            real_pred = self.D(real, text)
-            r1 = hm.r1_penalty(real_pred, real, self.r1_gamma)
+            perm = torch.rand(text.shape[0], device=text.device).argsort()          # device-side randperm (:1303)
+            if self.fused_real_pass:
+                real_pred, mismatched_pred, r1 = hm.discriminator_real_pass(self.D, real, text, text[perm], self.r1_gamma)
+            else:
+                real = real.requires_grad_(True)
+                real_pred = self.D(real, text)
+                r1 = hm.r1_penalty(real_pred, real, self.r1_gamma)
+                mismatched_pred = self.D(real.detach(), text[perm])
             with torch.no_grad():      # module stays in train mode: dense-soft routing, eps redrawn (:1289-1298)
                 fake16, _, _, _ = self.G(z, text, return_intermediate=True, return_routing=True, annealing_factor=self.annealing_factor)
             fake_pred = self.D(fake16.detach(), text)
-            perm = torch.rand(text.shape[0], device=text.device).argsort()          # device-side randperm (:1303)
-            mismatched_pred = self.D(real.detach(), text[perm])
             d_gan = hm.discriminator_adv_loss(real_pred, fake_pred, mismatched_pred)
             d_loss = d_gan + r1
         self.red_d.begin()

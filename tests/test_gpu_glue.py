@@ -142,3 +142,45 @@ def test_modulated_transformation_module_matches_torch_ops(monkeypatch):
     assert _rel(xc.grad, xr.grad) < 1e-4 and _rel(wc.grad, wr.grad) < 1e-4
     for n, p in mtm.named_parameters():
         assert _rel(p.grad, ref[n]) < 2e-4, n
+
+
+def test_layernorm_bf16_output_and_bf16_gradient():
+    """norm1 / norm2 under autocast: bf16 in, bf16 out (= the rounding the consuming matmul applies), bf16 upstream gradient."""
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2050, 256, generator=g).bfloat16(); w = torch.rand(256, generator=g) + 0.5; b = torch.randn(256, generator=g) * 0.1
+    gy = torch.randn(2050, 256, generator=g).bfloat16()
+    xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (256,), wr, br, 1e-5); yr.backward(gy.double())
+    xc = x.cuda().requires_grad_(True); wc = w.cuda().requires_grad_(True); bc = b.cuda().requires_grad_(True)
+    yc = glue.layer_norm(xc, wc, bc, 1e-5, torch.bfloat16)
+    assert yc.dtype == torch.bfloat16
+    assert torch.equal(yc, glue.layer_norm(x.cuda(), w.cuda(), b.cuda(), 1e-5).bfloat16())     # exactly the rounded fp32 result
+    yc.backward(gy.cuda())
+    assert _rel(yc, yr) < 1e-2 and _rel(xc.grad, xr.grad) < 2e-2
+    assert _rel(wc.grad, wr.grad) < 1e-4 and _rel(bc.grad, br.grad) < 1e-4
+
+
+def test_fused_real_pass_matches_reference_formulation_on_gpu(monkeypatch):
+    """Trainer D-step with the shared-feature / explicit-adjoint real pass vs the reference's three discriminator calls +
+    autograd.grad(create_graph=True): identical discriminator gradients (fp32, TF32 off)."""
+    pkg = G_.pkg(); hm = pkg.host_model
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    torch.manual_seed(0)
+    D = hm.AuroraDiscriminator().cuda()
+    real = torch.randn(4, 3, 64, 64, device="cuda").clamp(-1, 1); text = torch.randn(4, 512, device="cuda"); mis = text[[1, 2, 3, 0]]
+    res = []
+    for fused in (True, False):
+        D.zero_grad(set_to_none=True)
+        if fused:
+            rp, mp, r1 = hm.discriminator_real_pass(D, real, text, mis, 10.0)
+        else:
+            r = real.clone().requires_grad_(True)
+            rp = D(r, text); r1 = hm.r1_penalty(rp, r, 10.0); mp = D(r.detach(), mis)
+        (F.softplus(-rp).mean() + F.softplus(mp).mean() + r1).backward()
+        res.append((rp.detach(), mp.detach(), r1.detach(), {n: p.grad.clone() for n, p in D.named_parameters()}))
+    a, b = res
+    assert _rel(a[0], b[0]) < 1e-5 and _rel(a[1], b[1]) < 1e-5 and _rel(a[2], b[2]) < 1e-4
+    for n in a[3]:
+        assert _rel(a[3][n], b[3][n]) < 1e-3, n

@@ -61,3 +61,32 @@ def test_generator_and_discriminator_match_reference(pkg):
             assert p1.grad.abs().max() < 1e-8, n1
             continue
         assert (p1.grad - p2.grad).abs().max() / p2.grad.abs().max() < 2e-3, n1
+
+
+def test_fused_real_pass_equals_reference_formulation(pkg):
+    """host_model.discriminator_real_pass (shared features + explicit adjoint for R1) against the reference's formulation
+    (t2i_moe_gan.py:1278-1306: three discriminator calls, autograd.grad(create_graph=True)): values and every gradient."""
+    import torch
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    D = hm.AuroraDiscriminator().double()
+    real = torch.randn(3, 3, 64, 64, dtype=torch.float64).clamp(-1, 1)
+    text = torch.randn(3, 512, dtype=torch.float64); mis = text[[2, 0, 1]]
+
+    def run(fused):
+        D.zero_grad(set_to_none=True)
+        if fused:
+            rp, mp, r1 = hm.discriminator_real_pass(D, real, text, mis, 10.0)
+        else:
+            r = real.clone().requires_grad_(True)
+            rp = D(r, text); r1 = hm.r1_penalty(rp, r, 10.0); mp = D(r.detach(), mis)
+        loss = torch.nn.functional.softplus(-rp).mean() + torch.nn.functional.softplus(mp).mean() + r1
+        loss.backward()
+        return rp.detach(), mp.detach(), r1.detach(), {n: p.grad.clone() for n, p in D.named_parameters()}
+
+    a, b = run(True), run(False)
+    for x, y in zip(a[:3], b[:3]):
+        assert float((x - y).abs().max()) <= 1e-10 * max(1.0, float(y.abs().max()))
+    assert a[3].keys() == b[3].keys()
+    for n in a[3]:
+        assert float((a[3][n] - b[3][n]).abs().max()) <= 1e-9 * max(1e-3, float(b[3][n].abs().max())), n
