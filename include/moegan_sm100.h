@@ -275,7 +275,7 @@ int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, cons
 /* replaces: the learned-offset resampling of ModulatedTransformationModule (t2i_moe_gan.py:219-240):
  * grid = clamp(meshgrid(linspace(-1,1)) + 0.05 * off, -1, 1);  out = F.grid_sample(x, grid, bilinear, zeros,
  * align_corners=False).  x / out / g / dx: NHWC [B,H,W,C] fp32 or bf16; off / doff: fp32 [B,H,W,2] = (x, y) offsets
- * as produced by offset_net (before the 0.05 scale).  C: multiple of 128; H*W <= 512 for the backward. */
+ * as produced by offset_net (before the 0.05 scale).  C: multiple of 128; H*W <= 256 for the backward. */
 int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H, int32_t W, int32_t C,
                              void* out, void* stream);
 int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H,

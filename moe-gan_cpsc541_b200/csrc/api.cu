@@ -794,7 +794,7 @@ int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, i
 int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H, int32_t W, int32_t C,
                              void* dx, float* doff, void* stream) {
     RUN(check_nhwc("offset_sample_bwd", B, H * W, C));
-    MOEGAN_REQUIRE(H >= 1 && W >= 1 && H * W <= 512, MOEGAN_ERR_BAD_SHAPE, "offset_sample_bwd: H x W (%d x %d) must be in [1, 512] pixels", H, W);
+    MOEGAN_REQUIRE(H >= 1 && W >= 1 && H * W <= 256, MOEGAN_ERR_BAD_SHAPE, "offset_sample_bwd: H x W (%d x %d) must be in [1, 256] pixels", H, W);
     REQ_PTR(g); REQ_PTR(x); REQ_PTR(off); REQ_PTR(dx); REQ_PTR(doff);
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
                    MOEGAN_ERR_MISALIGNED, "offset_sample_bwd: pointers must be 16-byte aligned");

@@ -40,90 +40,127 @@ template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16*
 // =====================================================================================================
 // LayerNorm over the last dimension (d = 128 * nseg <= 1024), eps inside the sqrt (nn.LayerNorm)
 // =====================================================================================================
-constexpr int LN_MAX_SEG = 8;
-
-template <typename TIN, typename TOUT>
+// NSEG = 128-column segments held per lane (compile time: the per-row state lives in registers); R = rows a warp works on at
+// once - for small d a single row is 256-512 bytes, far too little in flight per warp to cover DRAM latency.
+template <typename TIN, typename TOUT, int NSEG, int R>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int d,
                      float eps, TOUT* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
     const int lane = threadIdx.x & 31;
-    if (r >= rows) return;
+    if (r0 >= rows) return;
     const int nseg = d / 128;
-    float4 v[LN_MAX_SEG];
-    float sum = 0.f;
+    float4 v[R][NSEG];
+    float sum[R];
 #pragma unroll
-    for (int s = 0; s < LN_MAX_SEG; ++s)
-        if (s < nseg) { v[s] = Vec4<TIN>::load(x + r * d + s * 128 + lane * 4); sum += (v[s].x + v[s].y) + (v[s].z + v[s].w); }
-    const float mean = warp_sum(sum) / (float)d;
-    float sq = 0.f;
+    for (int i = 0; i < R; ++i) {
+        sum[i] = 0.f;
 #pragma unroll
-    for (int s = 0; s < LN_MAX_SEG; ++s)
-        if (s < nseg) {
-            const float a = v[s].x - mean, b = v[s].y - mean, c = v[s].z - mean, e = v[s].w - mean;
-            sq += (a * a + b * b) + (c * c + e * e);
+        for (int s = 0; s < NSEG; ++s) {
+            v[i][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < nseg && r0 + i < rows) v[i][s] = Vec4<TIN>::load(x + (r0 + i) * d + s * 128 + lane * 4);
+            sum[i] += (v[i][s].x + v[i][s].y) + (v[i][s].z + v[i][s].w);
         }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+    }
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int s = 0; s < LN_MAX_SEG; ++s)
+    for (int i = 0; i < R; ++i) mean[i] = warp_sum(sum[i]) / (float)d;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        float sq = 0.f;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s)
+            if (s < nseg) {
+                const float a = v[i][s].x - mean[i], b = v[i][s].y - mean[i], c = v[i][s].z - mean[i], e = v[i][s].w - mean[i];
+                sq += (a * a + b * b) + (c * c + e * e);
+            }
+        sum[i] = sq;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) rstd[i] = rsqrtf(warp_sum(sum[i]) / (float)d + eps);
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s)
         if (s < nseg) {
             const int c = s * 128 + lane * 4;
             const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), b = __ldg(reinterpret_cast<const float4*>(beta + c));
-            float4 o;
-            o.x = (v[s].x - mean) * rstd * g.x + b.x; o.y = (v[s].y - mean) * rstd * g.y + b.y;
-            o.z = (v[s].z - mean) * rstd * g.z + b.z; o.w = (v[s].w - mean) * rstd * g.w + b.w;
-            Vec4<TOUT>::store(y + r * d + c, o);
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (r0 + i < rows) {
+                    float4 o;
+                    o.x = (v[i][s].x - mean[i]) * rstd[i] * g.x + b.x; o.y = (v[i][s].y - mean[i]) * rstd[i] * g.y + b.y;
+                    o.z = (v[i][s].z - mean[i]) * rstd[i] * g.z + b.z; o.w = (v[i][s].w - mean[i]) * rstd[i] * g.w + b.w;
+                    Vec4<TOUT>::store(y + (r0 + i) * d + c, o);
+                }
         }
-    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+    if (lane < R && r0 + lane < rows) {
+        float m = mean[0], q = rstd[0];
+#pragma unroll
+        for (int i = 1; i < R; ++i) if (lane == i) { m = mean[i]; q = rstd[i]; }
+        mean_out[r0 + lane] = m; rstd_out[r0 + lane] = q;
+    }
 }
 
 // dx = rstd * (gamma*g - mean_d(gamma*g) - xhat * mean_d(gamma*g*xhat)); per-CTA partial column sums of g*xhat and g.
-// Each warp walks rows r = warp_global, += total_warps; the CTA's 8 warps are combined through shared memory.
-template <typename TG, typename TIN>
+// Each warp walks groups of R rows (group index = warp_global, += total_warps); the CTA's 8 warps are combined through
+// shared memory; dx is written in x's storage type.
+template <typename TG, typename TIN, int NSEG, int R>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows, int d,
                      TIN* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
-    __shared__ float4 red[8][LN_MAX_SEG * 32];
+    __shared__ float4 red[8][NSEG * 32];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nseg = d / 128;
-    float4 gam[LN_MAX_SEG], dg[LN_MAX_SEG], db[LN_MAX_SEG];
+    float4 gam[NSEG], dg[NSEG], db[NSEG];
 #pragma unroll
-    for (int s = 0; s < LN_MAX_SEG; ++s) {
+    for (int s = 0; s < NSEG; ++s) {
         dg[s] = make_float4(0.f, 0.f, 0.f, 0.f); db[s] = dg[s]; gam[s] = dg[s];
         if (s < nseg) gam[s] = __ldg(reinterpret_cast<const float4*>(gamma + s * 128 + lane * 4));
     }
     const float inv_d = 1.0f / (float)d;
-    for (long long r = (long long)blockIdx.x * 8 + wid; r < rows; r += (long long)gridDim.x * 8) {
-        const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
-        float4 xh[LN_MAX_SEG], gg[LN_MAX_SEG];
-        float s1 = 0.f, s2 = 0.f;
+    for (long long r0 = ((long long)blockIdx.x * 8 + wid) * R; r0 < rows; r0 += (long long)gridDim.x * 8 * R) {
+        float4 xh[R][NSEG], gg[R][NSEG];
+        float s1[R], s2[R], rs[R];
 #pragma unroll
-        for (int s = 0; s < LN_MAX_SEG; ++s)
-            if (s < nseg) {
-                const long long o = r * d + s * 128 + lane * 4;
-                const float4 xv = Vec4<TIN>::load(x + o);
-                const float4 gv = Vec4<TG>::load(g + o);
-                xh[s] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-                dg[s].x += gv.x * xh[s].x; dg[s].y += gv.y * xh[s].y; dg[s].z += gv.z * xh[s].z; dg[s].w += gv.w * xh[s].w;
-                db[s].x += gv.x; db[s].y += gv.y; db[s].z += gv.z; db[s].w += gv.w;
-                gg[s] = make_float4(gv.x * gam[s].x, gv.y * gam[s].y, gv.z * gam[s].z, gv.w * gam[s].w);
-                s1 += (gg[s].x + gg[s].y) + (gg[s].z + gg[s].w);
-                s2 += (gg[s].x * xh[s].x + gg[s].y * xh[s].y) + (gg[s].z * xh[s].z + gg[s].w * xh[s].w);
+        for (int i = 0; i < R; ++i) {
+            const bool ok = r0 + i < rows;
+            const float mean = ok ? __ldg(mean_in + r0 + i) : 0.f;
+            rs[i] = ok ? __ldg(rstd_in + r0 + i) : 0.f;
+            s1[i] = 0.f; s2[i] = 0.f;
+#pragma unroll
+            for (int s = 0; s < NSEG; ++s) {
+                xh[i][s] = make_float4(0.f, 0.f, 0.f, 0.f); gg[i][s] = xh[i][s];
+                if (s < nseg && ok) {
+                    const long long o = (r0 + i) * d + s * 128 + lane * 4;
+                    const float4 xv = Vec4<TIN>::load(x + o);
+                    const float4 gv = Vec4<TG>::load(g + o);
+                    xh[i][s] = make_float4((xv.x - mean) * rs[i], (xv.y - mean) * rs[i], (xv.z - mean) * rs[i], (xv.w - mean) * rs[i]);
+                    dg[s].x += gv.x * xh[i][s].x; dg[s].y += gv.y * xh[i][s].y; dg[s].z += gv.z * xh[i][s].z; dg[s].w += gv.w * xh[i][s].w;
+                    db[s].x += gv.x; db[s].y += gv.y; db[s].z += gv.z; db[s].w += gv.w;
+                    gg[i][s] = make_float4(gv.x * gam[s].x, gv.y * gam[s].y, gv.z * gam[s].z, gv.w * gam[s].w);
+                    s1[i] += (gg[i][s].x + gg[i][s].y) + (gg[i][s].z + gg[i][s].w);
+                    s2[i] += (gg[i][s].x * xh[i][s].x + gg[i][s].y * xh[i][s].y) + (gg[i][s].z * xh[i][s].z + gg[i][s].w * xh[i][s].w);
+                }
             }
-        s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+        }
 #pragma unroll
-        for (int s = 0; s < LN_MAX_SEG; ++s)
-            if (s < nseg) {
-                float4 o;
-                o.x = rstd * (gg[s].x - s1 - xh[s].x * s2); o.y = rstd * (gg[s].y - s1 - xh[s].y * s2);
-                o.z = rstd * (gg[s].z - s1 - xh[s].z * s2); o.w = rstd * (gg[s].w - s1 - xh[s].w * s2);
-                Vec4<TIN>::store(dx + r * d + s * 128 + lane * 4, o);
+        for (int i = 0; i < R; ++i) { s1[i] = warp_sum(s1[i]) * inv_d; s2[i] = warp_sum(s2[i]) * inv_d; }
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (r0 + i < rows) {
+#pragma unroll
+                for (int s = 0; s < NSEG; ++s)
+                    if (s < nseg) {
+                        float4 o;
+                        o.x = rs[i] * (gg[i][s].x - s1[i] - xh[i][s].x * s2[i]); o.y = rs[i] * (gg[i][s].y - s1[i] - xh[i][s].y * s2[i]);
+                        o.z = rs[i] * (gg[i][s].z - s1[i] - xh[i][s].z * s2[i]); o.w = rs[i] * (gg[i][s].w - s1[i] - xh[i][s].w * s2[i]);
+                        Vec4<TIN>::store(dx + (r0 + i) * d + s * 128 + lane * 4, o);
+                    }
             }
     }
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int s = 0; s < LN_MAX_SEG; ++s)
+        for (int s = 0; s < NSEG; ++s)
             if (s < nseg) red[wid][s * 32 + lane] = pass == 0 ? dg[s] : db[s];
         __syncthreads();
         for (int j = threadIdx.x; j < nseg * 32; j += 256) {
@@ -146,6 +183,27 @@ partial_sum_kernel(const float* __restrict__ part, int n, int nparts, TOUT* __re
     for (; b + 1 < nparts; b += 2) { s0 += part[(size_t)b * n + i]; s1 += part[(size_t)(b + 1) * n + i]; }
     if (b < nparts) s0 += part[(size_t)b * n + i];
     store1<TOUT>(out + i, s0 + s1);
+}
+// the same for MANY partials (hundreds of CTAs): CTA = 32 columns x 8 row lanes, combined through shared memory in a fixed order
+__global__ void __launch_bounds__(256)
+partial_sum_tall_kernel(const float* __restrict__ part, int n, int nparts, float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cx;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < n) {
+        int b = ry;
+        for (; b + 8 < nparts; b += 16) { s0 += part[(size_t)b * n + i]; s1 += part[(size_t)(b + 8) * n + i]; }
+        if (b < nparts) s0 += part[(size_t)b * n + i];
+    }
+    red[ry][cx] = s0 + s1;
+    __syncthreads();
+    if (ry == 0 && i < n) {
+        float a = red[0][cx];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) a += red[w][cx];
+        out[i] = a;
+    }
 }
 
 // =====================================================================================================
@@ -283,44 +341,81 @@ offset_sample_bwd_off_kernel(const T* __restrict__ g, const T* __restrict__ x, c
     gix = warp_sum(gix); giy = warp_sum(giy);
     if (lane == 0) { doff[p * 2] = gix * t.sx; doff[p * 2 + 1] = giy * t.sy; }
 }
-// backward w.r.t. the input: CTA = (sample, group of CC channels); THREAD = one channel, which it owns exclusively, so the
-// scatter into the sample's [HW, CC] accumulator tile in shared memory needs no atomics and runs in a fixed order.
-template <typename T, int CC>
-__global__ void __launch_bounds__(CC)
+// backward w.r.t. the input, as a deterministic GATHER.  CTA = one sample.  The scatter pattern (which output pixels touch
+// which input pixel, with which weight) is the same for every channel, so it is inverted once per sample in shared memory:
+//   1. every output pixel p computes its 4 taps;  2. per-input-pixel counts (integer atomics: order-free) and an exclusive scan;
+//   3. input pixel q scans the tap table in (p, tap) order and writes its contributor list -> fixed accumulation order;
+//   4. warp per input pixel, lanes over channels: dx[q, :] = sum_e w_e * g[p_e, :]  (coalesced row reads, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(256)
 offset_sample_bwd_in_kernel(const T* __restrict__ g, const float* __restrict__ off, int H, int W, int C, T* __restrict__ dx) {
     extern __shared__ float smem[];
-    const int HW = H * W;
-    float* acc = smem;                                   // [HW][CC]
-    int* tidx = reinterpret_cast<int*>(smem + HW * CC);  // [HW][4]
-    float* tw = reinterpret_cast<float*>(tidx + HW * 4); // [HW][4]
-    const int b = blockIdx.y, c = blockIdx.x * CC + threadIdx.x;
-    for (int p = threadIdx.x; p < HW; p += CC) {
-        const Tap t = make_tap(__ldg(off + ((size_t)b * HW + p) * 2), __ldg(off + ((size_t)b * HW + p) * 2 + 1), p / W, p % W, H, W);
+    const int HW = H * W;                                 // <= 256
+    int* tidx = reinterpret_cast<int*>(smem);             // [HW][4]
+    float* tw = smem + HW * 4;                            // [HW][4]
+    int* cnt = reinterpret_cast<int*>(smem + HW * 8);     // [HW]
+    int* start = cnt + HW;                                // [HW + 1] (+ padding to a multiple of 4 ints)
+    int* ent_p = start + ((HW + 1 + 3) & ~3);             // [4 * HW]
+    float* ent_w = reinterpret_cast<float*>(ent_p + 4 * HW);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid < HW) {
+        const Tap t = make_tap(__ldg(off + ((size_t)b * HW + tid) * 2), __ldg(off + ((size_t)b * HW + tid) * 2 + 1), tid / W, tid % W, H, W);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { tidx[p * 4 + k] = t.idx[k]; tw[p * 4 + k] = t.w[k]; }
+        for (int k = 0; k < 4; ++k) { tidx[tid * 4 + k] = t.idx[k]; tw[tid * 4 + k] = t.w[k]; }
+        cnt[tid] = 0;
     }
-    for (int p = 0; p < HW; ++p) acc[p * CC + threadIdx.x] = 0.0f;
     __syncthreads();
-    const T* gb = g + (size_t)b * HW * C + c;
-    constexpr int U = 8;
-    for (int p0 = 0; p0 < HW; p0 += U) {
-        float gv[U];
+    if (tid < HW) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) gv[u] = (p0 + u < HW) ? load1<T>(gb + (size_t)(p0 + u) * C) : 0.0f;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (p0 + u < HW) {
-                const int4 id = *reinterpret_cast<const int4*>(tidx + (p0 + u) * 4);
-                const float4 w = *reinterpret_cast<const float4*>(tw + (p0 + u) * 4);
-                if (id.x >= 0) acc[id.x * CC + threadIdx.x] += w.x * gv[u];
-                if (id.y >= 0) acc[id.y * CC + threadIdx.x] += w.y * gv[u];
-                if (id.z >= 0) acc[id.z * CC + threadIdx.x] += w.z * gv[u];
-                if (id.w >= 0) acc[id.w * CC + threadIdx.x] += w.w * gv[u];
-            }
+        for (int k = 0; k < 4; ++k) { const int q = tidx[tid * 4 + k]; if (q >= 0) atomicAdd(&cnt[q], 1); }
+    }
+    __syncthreads();
+    // exclusive scan of cnt (Hillis-Steele over 256 slots, in place in start[1..])
+    __shared__ int scan[256];
+    scan[tid] = tid < HW ? cnt[tid] : 0;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int add = tid >= o ? scan[tid - o] : 0;
+        __syncthreads();
+        scan[tid] += add;
+        __syncthreads();
+    }
+    if (tid == 0) start[0] = 0;
+    if (tid < HW) start[tid + 1] = scan[tid];
+    __syncthreads();
+    if (tid < HW) {
+        int pos = start[tid];
+        for (int p = 0; p < HW; ++p) {
+            const int4 id = *reinterpret_cast<const int4*>(tidx + p * 4);     // broadcast read
+            if (id.x == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 0]; ++pos; }
+            if (id.y == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 1]; ++pos; }
+            if (id.z == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 2]; ++pos; }
+            if (id.w == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 3]; ++pos; }
         }
     }
-    T* db = dx + (size_t)b * HW * C + c;
-    for (int p = 0; p < HW; ++p) store1<T>(db + (size_t)p * C, acc[p * CC + threadIdx.x]);
+    __syncthreads();
+    const int wid = tid >> 5, lane = tid & 31;
+    const T* gb = g + (size_t)b * HW * C;
+    T* db = dx + (size_t)b * HW * C;
+    for (int q = wid; q < HW; q += 8) {
+        const int e0 = start[q], e1 = start[q + 1];
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            int e = e0;
+            for (; e + 1 < e1; e += 2) {                  // two rows in flight
+                const float4 v0 = Vec4<T>::load(gb + (size_t)ent_p[e] * C + c), v1 = Vec4<T>::load(gb + (size_t)ent_p[e + 1] * C + c);
+                const float w0 = ent_w[e], w1 = ent_w[e + 1];
+                a.x = fmaf(w0, v0.x, a.x); a.y = fmaf(w0, v0.y, a.y); a.z = fmaf(w0, v0.z, a.z); a.w = fmaf(w0, v0.w, a.w);
+                a.x = fmaf(w1, v1.x, a.x); a.y = fmaf(w1, v1.y, a.y); a.z = fmaf(w1, v1.z, a.z); a.w = fmaf(w1, v1.w, a.w);
+            }
+            if (e < e1) {
+                const float4 v0 = Vec4<T>::load(gb + (size_t)ent_p[e] * C + c);
+                const float w0 = ent_w[e];
+                a.x = fmaf(w0, v0.x, a.x); a.y = fmaf(w0, v0.y, a.y); a.z = fmaf(w0, v0.z, a.z); a.w = fmaf(w0, v0.w, a.w);
+            }
+            Vec4<T>::store(db + (size_t)q * C + c, a);
+        }
+    }
 }
 
 inline int grid_cap(long long blocks) {
@@ -337,15 +432,24 @@ int ln_bwd_blocks(long long rows) {
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// (NSEG, R) by segment count: 1 -> (1, 4), 2 -> (2, 2), 3..4 -> (4, 1), 5..8 -> (8, 1)
 int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
                          int y_bf16, float* mean, float* rstd, cudaStream_t st) {
     if (rows == 0) return MOEGAN_OK;
-    const int blocks = (int)((rows + 7) / 8);
     typedef __nv_bfloat16 bf;
-#define MOEGAN_LN_FWD(TI, TO) layernorm_fwd_kernel<TI, TO><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), mean, rstd)
+    const int nseg = d / 128;
+#define MOEGAN_LN_FWD2(TI, TO, NS, RR)                                                                                         \
+    layernorm_fwd_kernel<TI, TO, NS, RR><<<(int)((rows + 8 * RR - 1) / (8 * RR)), 256, 0, st>>>(                              \
+        reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), mean, rstd)
+#define MOEGAN_LN_FWD(TI, TO)                                                                                                  \
+    do {                                                                                                                       \
+        if (nseg == 1) MOEGAN_LN_FWD2(TI, TO, 1, 4); else if (nseg == 2) MOEGAN_LN_FWD2(TI, TO, 2, 2);                         \
+        else if (nseg <= 4) MOEGAN_LN_FWD2(TI, TO, 4, 1); else MOEGAN_LN_FWD2(TI, TO, 8, 1);                                   \
+    } while (0)
     if (x_bf16) { if (y_bf16) MOEGAN_LN_FWD(bf, bf); else MOEGAN_LN_FWD(bf, float); }
     else        { if (y_bf16) MOEGAN_LN_FWD(float, bf); else MOEGAN_LN_FWD(float, float); }
 #undef MOEGAN_LN_FWD
+#undef MOEGAN_LN_FWD2
     MOEGAN_CHECK_LAUNCH("layernorm_fwd_kernel");
     return MOEGAN_OK;
 }
@@ -358,14 +462,23 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
     }
     const int blocks = ln_bwd_blocks(rows);
     typedef __nv_bfloat16 bf;
-#define MOEGAN_LN_BWD(TG, TI) layernorm_bwd_kernel<TG, TI><<<blocks, 256, 0, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, mean, rstd, rows, d, reinterpret_cast<TI*>(dx), scratch)
+    const int nseg = d / 128;
+#define MOEGAN_LN_BWD2(TG, TI, NS, RR)                                                                                         \
+    layernorm_bwd_kernel<TG, TI, NS, RR><<<blocks, 256, 0, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, mean, \
+                                                                 rstd, rows, d, reinterpret_cast<TI*>(dx), scratch)
+#define MOEGAN_LN_BWD(TG, TI)                                                                                                  \
+    do {                                                                                                                       \
+        if (nseg == 1) MOEGAN_LN_BWD2(TG, TI, 1, 4); else if (nseg == 2) MOEGAN_LN_BWD2(TG, TI, 2, 2);                         \
+        else if (nseg <= 4) MOEGAN_LN_BWD2(TG, TI, 4, 1); else MOEGAN_LN_BWD2(TG, TI, 8, 1);                                   \
+    } while (0)
     if (g_bf16) { if (x_bf16) MOEGAN_LN_BWD(bf, bf); else MOEGAN_LN_BWD(bf, float); }
     else        { if (x_bf16) MOEGAN_LN_BWD(float, bf); else MOEGAN_LN_BWD(float, float); }
 #undef MOEGAN_LN_BWD
+#undef MOEGAN_LN_BWD2
     MOEGAN_CHECK_LAUNCH("layernorm_bwd_kernel");
     // scratch = [blocks][2][d] = [blocks][2d]  ->  [dgamma | dbeta]
-    partial_sum_kernel<float><<<ceil_div(2 * d, 256), 256, 0, st>>>(scratch, 2 * d, blocks, dgamma_dbeta);
-    MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
+    partial_sum_tall_kernel<<<ceil_div(2 * d, 32), 256, 0, st>>>(scratch, 2 * d, blocks, dgamma_dbeta);
+    MOEGAN_CHECK_LAUNCH("partial_sum_tall_kernel");
     return MOEGAN_OK;
 }
 
@@ -420,15 +533,9 @@ int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, i
 
 template <typename T>
 static int launch_bwd_in(const T* g, const float* off, int B, int H, int W, int C, T* dx, cudaStream_t st) {
-    constexpr int CC = 64;
-    const size_t smem = (size_t)H * W * (CC * 4 + 32);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(offset_sample_bwd_in_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    dim3 grid(C / CC, B);
-    offset_sample_bwd_in_kernel<T, CC><<<grid, CC, smem, st>>>(g, off, H, W, C, dx);
+    const int HW = H * W;
+    const size_t smem = (size_t)4 * (HW * 8 + HW + ((HW + 1 + 3) & ~3) + HW * 8);
+    offset_sample_bwd_in_kernel<T><<<B, 256, smem, st>>>(g, off, H, W, C, dx);
     MOEGAN_CHECK_LAUNCH("offset_sample_bwd_in_kernel");
     return MOEGAN_OK;
 }

@@ -156,6 +156,6 @@ def offset_sample_reference(x: torch.Tensor, off_raw: torch.Tensor) -> torch.Ten
 
 def offset_sample(x: torch.Tensor, off_raw: torch.Tensor) -> torch.Tensor:
     """x [B,C,H,W] resampled at meshgrid + 0.05 * off_raw (off_raw [B,2,H,W] = offset_net(x): channel 0 = x, 1 = y)."""
-    if x.is_cuda and x.shape[1] % 128 == 0 and x.shape[2] * x.shape[3] <= 512:
+    if x.is_cuda and x.shape[1] % 128 == 0 and x.shape[2] * x.shape[3] <= 256:
         return _OffsetSampleFn.apply(x, off_raw)
     return offset_sample_reference(x, off_raw)
