@@ -287,6 +287,9 @@ int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, cons
  * kind 2: A [K,S*M] (M contiguous), B [K,S*N].    precision as above.  Used by tests and bench only. */
 int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K,
                      const void* A, const void* B, float* C, void* stream);
+/* id of the CUDA-graph capture `stream` is part of (0: not capturing, -1: query failed): lets the host-side weight cache
+ * share one conversion between the forward passes of ONE captured step. */
+int64_t moegan_stream_capture_id(void* stream);
 /* instrumentation for bench.py: number of kernel launches this library has enqueued so far (all threads) */
 int64_t moegan_debug_launch_count(void);
 /* GEMM profiling: when enabled, every tcgen05 GEMM launch is bracketed by cudaEventRecord on its own stream.

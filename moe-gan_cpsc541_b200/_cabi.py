@@ -97,6 +97,7 @@ SIGNATURES = {
     "moegan_umma_gemm": (c_int32, [c_int32] * 5 + [_P] * 3 + [_P]),
     "moegan_debug_set_mn_desc": (c_int32, [c_int32] * 3),
     "moegan_debug_launch_count": (c_int64, []),
+    "moegan_stream_capture_id": (c_int64, [_P]),
     "moegan_debug_profile_enable": (c_int32, [c_int32]),
     "moegan_debug_profile_read": (c_int32, [_P, _P, c_int32]),
     "moegan_to_operand": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P]),

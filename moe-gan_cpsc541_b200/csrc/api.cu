@@ -178,6 +178,12 @@ int64_t moegan_ffn_bwd_scratch_bytes(const moegan_shape* s) {
     return (int64_t)ffn_bwd_scratch_bytes_impl(s);
 }
 int64_t moegan_debug_launch_count(void) { return g_launches.load(); }
+int64_t moegan_stream_capture_id(void* stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &st, &id) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return st == cudaStreamCaptureStatusActive ? (int64_t)id : 0;
+}
 int moegan_debug_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;
@@ -211,7 +217,7 @@ int moegan_router_sample_kl_fwd(const moegan_shape* s, const float* mu_f, const 
     REQ_PTR(Wf); REQ_PTR(Wt); REQ_PTR(Wc); REQ_PTR(kl_out);
     if (sampling) { REQ_PTR(eps_f); REQ_PTR(eps_t); REQ_PTR(eps_c); }
     return launch_sample_kl(s, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, sampling, Wf, Wt, Wc, Wf_op, Wt_op, kl_out,
-                            (cudaStream_t)stream);
+                            nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int moegan_router_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, void* stream) {
@@ -342,9 +348,12 @@ int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
     return launch_combine_bwd(s, plan, dout, y, row_token, row_gate, gates, dy_op, dgate_row, dy_slab_sums, (cudaStream_t)stream);
 }
 
-int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
-                   const void* pre, const void* h_op, const void* dy_op, const float* dy_slab_sums, void* dpre_op, void* dx_rows,
-                   float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream) {
+// defer_bias: the caller (moegan_block_bwd) runs the two bias-gradient slab sums itself on its side stream, off the critical
+// path of the GEMM chain; dgrad2_done is recorded on `stream` right after the dgrad2 launch (the db1 slab sums depend on it).
+static int ffn_bwd_core(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
+                        const void* pre, const void* h_op, const void* dy_op, const float* dy_slab_sums, void* dpre_op, void* dx_rows,
+                        float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream,
+                        bool defer_bias, cudaEvent_t dgrad2_done) {
     CHECK_SHAPE(s);
     const FfnBwdScratch SL = ffn_bwd_scratch_layout(s);
     MOEGAN_REQUIRE(scratch_bytes >= (int64_t)SL.total && scratch != nullptr,
@@ -380,9 +389,13 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         RUN(launch_umma_gemm(GEMM_ROWS_BMN, 256, A, B, p, m_blocks * (hid / 256), st));
     }
     // bias gradients = per-expert sums of the 32-row slab sums (dy: from combine_bwd; dpre: from the epilogue above)
-    RUN(launch_slab_sum(s, plan, dpre_slabs, hid, slab_stage, db1, st));
-    if (dy_slab_sums != nullptr) RUN(launch_slab_sum(s, plan, dy_slab_sums, d, slab_stage, db2, st));
-    else                         RUN(launch_colsum_grouped(s, plan, dy_op, d, dW2, db2, st));   // partials in dW2 (written further down)
+    if (defer_bias) {
+        MOEGAN_CHECK_CUDA(cudaEventRecord(dgrad2_done, st));
+    } else {
+        RUN(launch_slab_sum(s, plan, dpre_slabs, hid, slab_stage, db1, st));
+        if (dy_slab_sums != nullptr) RUN(launch_slab_sum(s, plan, dy_slab_sums, d, slab_stage, db2, st));
+        else                         RUN(launch_colsum_grouped(s, plan, dy_op, d, dW2, db2, st));   // partials in dW2 (written further down)
+    }
     {   // dgrad1: dx_rows = dpre W1
         GemmOperand A{dpre_op, S * hid, (uint64_t)s->m_cap, S * hid};
         GemmOperand B{W1_op, S * d, (uint64_t)s->E * hid, S * d};
@@ -417,6 +430,13 @@ int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
         if (ks > 1) RUN(launch_sum_partials(reinterpret_cast<const float*>(splitk), (long long)s->E * d * hid, ks, dW1, st));
     }
     return MOEGAN_OK;
+}
+
+int moegan_ffn_bwd(const moegan_shape* s, const int32_t* plan, const void* a_op, const void* W1_op, const void* W2_op,
+                   const void* pre, const void* h_op, const void* dy_op, const float* dy_slab_sums, void* dpre_op, void* dx_rows,
+                   float* dW1, float* db1, float* dW2, float* db2, void* scratch, int64_t scratch_bytes, void* stream) {
+    return ffn_bwd_core(s, plan, a_op, W1_op, W2_op, pre, h_op, dy_op, dy_slab_sums, dpre_op, dx_rows, dW1, db1, dW2, db2, scratch,
+                        scratch_bytes, stream, false, nullptr);
 }
 
 int moegan_uncombine_bwd(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
@@ -469,7 +489,7 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
     const int d = s->d, Dt = s->Dt;
 
     RUN(launch_router_bwd_logits(s, raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, annealing_factor,
-                                 draw, dfp_op, dtau_part, st));
+                                 fp, draw, dfp_op, dtau_part, dwc_part, st));
     RUN(launch_router_bwd_small(s, fp, draw, tp, Wc, dtau_part, temperature, annealing_factor, dtl, dwc_part, dWc, dtp, dtp_op,
                                 dtemperature, st));
     const bool text_simt = router_bwd_text_simt_ok(s);     // tiny batches: one SIMT kernel instead of two tensor-core GEMMs
@@ -539,13 +559,23 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
 // ---- side stream: independent sub-chains of a block call run concurrently with the expert GEMMs ----------
 // (the router's backward chain / the weight conversion are many small launches that leave most SMs idle).  Fork and join
 // are cudaEventRecord / cudaStreamWaitEvent pairs, so the pattern is legal inside CUDA-graph capture too.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false, tried = false; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr; bool ok = false, tried = false; };
 static SideStream g_side;
 static std::mutex g_side_mu;
 static bool side_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MOEGAN_DISABLE_SIDE_STREAM"); v = (e != nullptr && e[0] == '1') ? 0 : 1; }
     return v == 1;
+}
+// Overlap only pays while the expert GEMMs leave SMs idle (configs[1]: 8 192 dispatched rows, 353 -> 323 us).  At the train-step
+// shapes (16 K - 262 K rows) every GEMM fills the chip with one 225 KB CTA per SM, nothing can co-reside, and the fork / join
+// edges plus the contention cost 0.7 ms per step (measured) - there the block runs on the caller's stream alone.
+static bool side_pays(const moegan_shape* s) {
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("MOEGAN_FORCE_SIDE_STREAM"); force = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    if (force == 1) return true;
+    const long long rows = s->dense ? (long long)s->T * s->E : (long long)s->T * s->k;
+    return rows * s->d <= 6LL * 1024 * 1024;
 }
 static SideStream* side_stream() {
     if (!side_enabled()) return nullptr;
@@ -554,7 +584,8 @@ static SideStream* side_stream() {
         g_side.tried = true;
         g_side.ok = cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) == cudaSuccess;
+                    cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&g_side.mid, cudaEventDisableTiming) == cudaSuccess;
         if (!g_side.ok) cudaGetLastError();
     }
     return g_side.ok ? &g_side : nullptr;
@@ -658,14 +689,18 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
     if (s->T == 0) return MOEGAN_OK;
     // weight conversion (only when the caller's cache is stale) overlaps the router / dispatch kernels
-    SideStream* ss = (a->prep_w1 != nullptr) ? side_stream() : nullptr;
+    SideStream* ss = (a->prep_w1 != nullptr && side_pays(s)) ? side_stream() : nullptr;
     if (a->prep_w1 != nullptr) {
         if (ss != nullptr) RUN(side_fork(ss, (cudaStream_t)stream));
         RUN(moegan_prep_weights(s, a->prep_w1, a->prep_b1, a->prep_w2, a->prep_b2, const_cast<void*>(a->W1_op), const_cast<float*>(a->b1s),
                                 const_cast<void*>(a->W2_op), const_cast<float*>(a->b2s), ss != nullptr ? (void*)ss->s : stream));
     }
-    RUN(moegan_router_sample_kl_fwd(s, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c, a->sampled,
-                                    F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), a->kl_out, stream));
+    REQ_PTR(a->mu_f); REQ_PTR(a->rho_f); REQ_PTR(a->mu_t); REQ_PTR(a->rho_t); REQ_PTR(a->mu_c); REQ_PTR(a->rho_c);
+    if (a->sampled) { REQ_PTR(a->eps_f); REQ_PTR(a->eps_t); REQ_PTR(a->eps_c); }
+    const bool keep_eps = a->need_backward && a->sampled;      // the eps consumed here, kept inside the workspace for the backward
+    RUN(launch_sample_kl(s, a->mu_f, a->rho_f, a->eps_f, a->mu_t, a->rho_t, a->eps_t, a->mu_c, a->rho_c, a->eps_c, a->sampled,
+                         F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), a->kl_out,
+                         keep_eps ? F(L.eps_f) : nullptr, keep_eps ? F(L.eps_t) : nullptr, keep_eps ? F(L.eps_c) : nullptr, (cudaStream_t)stream));
     RUN(moegan_router_text_fwd(s, a->w, F(L.Wt), F(L.Wc), F(L.tp), F(L.tl), stream));
     RUN(moegan_router_fwd(s, a->x, F(L.Wf), F(L.Wc), F(L.tl), a->temperature, a->annealing_factor, F(L.fp), F(L.raw), a->probs,
                           I(L.topk_idx), F(L.gates), I(L.chunk_counts), F(L.chunk_colsum), stream));
@@ -679,12 +714,6 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
     RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
     RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->out, stream));
-    if (a->need_backward && a->sampled) {
-        cudaStream_t st = (cudaStream_t)stream;
-        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_f), a->eps_f, (size_t)s->d * MOEGAN_ROUTER_HID * 4, cudaMemcpyDeviceToDevice, st));
-        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_t), a->eps_t, (size_t)s->Dt * MOEGAN_ROUTER_HID * 4, cudaMemcpyDeviceToDevice, st));
-        MOEGAN_CHECK_CUDA(cudaMemcpyAsync(P(L.eps_c), a->eps_c, (size_t)2 * MOEGAN_ROUTER_HID * s->E * 4, cudaMemcpyDeviceToDevice, st));
-    }
     return MOEGAN_OK;
 }
 
@@ -709,11 +738,15 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dy_slabs = reinterpret_cast<float*>(ws + W.dy_slabs);
     RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, dy_slabs, stream));
     // the router's backward only needs dgate_row: run it on the side stream while the expert GEMMs own the main stream
-    SideStream* ss = s->hard ? nullptr : side_stream();
+    SideStream* ss = (s->hard || !side_pays(s)) ? nullptr : side_stream();
     void* rstream = stream;
     if (ss != nullptr) { RUN(side_fork(ss, (cudaStream_t)stream)); rstream = ss->s; }
-    RUN(moegan_ffn_bwd(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
-                       a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream));
+    // with a side stream the bias-gradient slab sums leave the GEMM chain (they run after the router chain, db1 once dgrad2 is done)
+    const FfnBwdScratch SL = ffn_bwd_scratch_layout(s);
+    float* slab_stage = reinterpret_cast<float*>(ws + W.ffn_scratch + SL.slab_stage);
+    RUN(ffn_bwd_core(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
+                     a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream, ss != nullptr,
+                     ss != nullptr ? ss->mid : nullptr));
     if (!s->hard) {
         RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
                               I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
@@ -721,7 +754,12 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
                               a->kl_out, a->sampled ? a->dkl : nullptr,
                               a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
                               ws + W.router_ws, (int64_t)router_bwd_layout(s).total, rstream));
-        if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
+    }
+    if (ss != nullptr) {
+        RUN(launch_slab_sum(s, I(L.plan), dy_slabs, s->d, slab_stage, a->db2, ss->s));      // after the router chain: nothing waits for it
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s, ss->mid, 0));
+        RUN(launch_slab_sum(s, I(L.plan), reinterpret_cast<const float*>(ws + W.ffn_scratch + SL.dpre_slabs), 4 * s->d, slab_stage, a->db1, ss->s));
+        RUN(side_join(ss, (cudaStream_t)stream));
     }
     RUN(moegan_uncombine_bwd(s, ws + W.dx_rows, I(L.token_rows), dx_router, a->dx, stream));
     return MOEGAN_OK;

@@ -477,7 +477,8 @@ int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* 
 
 int slab_sum_splits(const moegan_shape* s) {
     const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;   // mean rows per expert
-    long long ns = rows / 32 / 16;                     // >= 16 slabs per split
+    const long long slabs = rows / 32;
+    long long ns = slabs <= 64 ? 1 : slabs / 16;       // few slabs: one pass, no finishing kernel; else >= 16 slabs per split
     if (ns < 1) ns = 1;
     if (ns > 32) ns = 32;
     return (int)ns;

@@ -8,14 +8,17 @@ namespace moegan {
 int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_f, const float* eps_f,
                      const float* mu_t, const float* rho_t, const float* eps_t,
                      const float* mu_c, const float* rho_c, const float* eps_c, int sampling,
-                     float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out, cudaStream_t st);
+                     float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out,
+                     float* keep_f, float* keep_t, float* keep_c, cudaStream_t st);
 int launch_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, cudaStream_t st);
 int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
                       const float* temperature, float af, float* fp, float* raw, float* probs, int32_t* topk_idx, float* gates,
                       int32_t* chunk_counts, float* chunk_colsum, cudaStream_t st);
 int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const float* Wc, const int32_t* topk_idx,
                              const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
-                             const float* temperature, float af, float* draw, void* dfp_op, float* dtau_part, cudaStream_t st);
+                             const float* temperature, float af, const float* fp, float* draw, void* dfp_op, float* dtau_part,
+                             float* dwc_part, cudaStream_t st);
+bool router_bwd_dwc_fused(const moegan_shape* s);
 int router_bwd_logits_blocks(const moegan_shape* s);
 int router_bwd_dwc_parts(const moegan_shape* s);
 int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,

@@ -22,19 +22,22 @@ sample_kl_kernel(const float* __restrict__ mu_f, const float* __restrict__ rho_f
                  const float* __restrict__ mu_c, const float* __restrict__ rho_c, const float* __restrict__ eps_c,
                  int n_f, int n_t, int n_c, int sampling, int split,
                  float* __restrict__ Wf, float* __restrict__ Wt, float* __restrict__ Wc,
-                 __nv_bfloat16* __restrict__ Wf_op, __nv_bfloat16* __restrict__ Wt_op, float* __restrict__ kl_part) {
+                 __nv_bfloat16* __restrict__ Wf_op, __nv_bfloat16* __restrict__ Wt_op, float* __restrict__ kl_part,
+                 float* __restrict__ keep_f, float* __restrict__ keep_t, float* __restrict__ keep_c) {
     const int n = n_f + n_t + n_c;
     float kl = 0.0f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float *mu, *rho, *eps; float* W; __nv_bfloat16* op; int j;
-        if (i < n_f)            { j = i;             mu = mu_f; rho = rho_f; eps = eps_f; W = Wf; op = Wf_op; }
-        else if (i < n_f + n_t) { j = i - n_f;       mu = mu_t; rho = rho_t; eps = eps_t; W = Wt; op = Wt_op; }
-        else                    { j = i - n_f - n_t; mu = mu_c; rho = rho_c; eps = eps_c; W = Wc; op = nullptr; }
+        const float *mu, *rho, *eps; float* W; __nv_bfloat16* op; float* keep; int j;
+        if (i < n_f)            { j = i;             mu = mu_f; rho = rho_f; eps = eps_f; W = Wf; op = Wf_op; keep = keep_f; }
+        else if (i < n_f + n_t) { j = i - n_f;       mu = mu_t; rho = rho_t; eps = eps_t; W = Wt; op = Wt_op; keep = keep_t; }
+        else                    { j = i - n_f - n_t; mu = mu_c; rho = rho_c; eps = eps_c; W = Wc; op = nullptr; keep = keep_c; }
         const float m = mu[j], r = rho[j];
         float w;
         if (sampling) {
             const float sigma = clampf(softplus_ref(clampf(r, -8.0f, 4.0f)), 1e-6f, 10.0f);
-            w = clampf(m, -10.0f, 10.0f) + sigma * clampf(eps[j], -2.0f, 2.0f);
+            const float ev = eps[j];
+            if (keep != nullptr) keep[j] = ev;     // the backward needs the eps this forward consumed (the buffers get redrawn)
+            w = clampf(m, -10.0f, 10.0f) + sigma * clampf(ev, -2.0f, 2.0f);
         } else {
             w = m;   // eval: raw mu, no clamp (:357-361)
         }
@@ -98,11 +101,17 @@ text_fwd_kernel(const float* __restrict__ w, const float* __restrict__ Wt, const
     const int k0 = q * kper, k1 = min(k0 + kper, Dt);
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     int k = k0;
-    for (; k + 3 < k1; k += 4) {       // 4 independent loads in flight
-        a0 = fmaf(ws[k], Wt[(size_t)k * HID + j], a0);
-        a1 = fmaf(ws[k + 1], Wt[(size_t)(k + 1) * HID + j], a1);
-        a2 = fmaf(ws[k + 2], Wt[(size_t)(k + 2) * HID + j], a2);
-        a3 = fmaf(ws[k + 3], Wt[(size_t)(k + 3) * HID + j], a3);
+    for (; k + 15 < k1; k += 16) {     // 16 independent loads in flight: the kernel is a chain of L2 round trips otherwise
+        float wv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) wv[u] = __ldg(Wt + (size_t)(k + u) * HID + j);
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+            a0 = fmaf(ws[k + u], wv[u], a0);
+            a1 = fmaf(ws[k + u + 1], wv[u + 1], a1);
+            a2 = fmaf(ws[k + u + 2], wv[u + 2], a2);
+            a3 = fmaf(ws[k + u + 3], wv[u + 3], a3);
+        }
     }
     for (; k < k1; ++k) a0 = fmaf(ws[k], Wt[(size_t)k * HID + j], a0);
     part[q * HID + j] = (a0 + a1) + (a2 + a3);
@@ -319,16 +328,25 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
 constexpr int RB_THREADS = 256;
 constexpr int RB_TOK = 16;   // tokens per CTA (8 warps x 2)
 
+// FUSE_DWC (E <= 8): the CTA also accumulates its share of dWc[0:128] = fp^T draw (lane = 4 of the 128 rows, 8 experts in
+// registers) while the draw values are in flight anyway, and writes ONE partial [128][E] per CTA - the separate pass over
+// fp / draw (router_bwd_dwc_part_kernel, 30-90 us of the router's backward chain) disappears.  The grid is persistent
+// (<= RB_MAX_BLOCKS CTAs walk the 16-token groups) so that the finishing sums stay short however large T is.
+constexpr int RB_MAX_BLOCKS = 296;
+constexpr int RB_FUSE_MAX_E = 8;
+template <bool FUSE_DWC>
 __global__ void __launch_bounds__(RB_THREADS)
 router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict__ Wc, const int* __restrict__ topk_idx,
                          const int* __restrict__ token_rows, const float* __restrict__ dgate_row,
                          const float* __restrict__ dprobs_ext, const float* __restrict__ dload,
                          const float* __restrict__ temperature, float af,
-                         int T, int T_pad, int E, int k, int dense, int split,
-                         float* __restrict__ draw, __nv_bfloat16* __restrict__ dfp_op, float* __restrict__ dtau_part) {
+                         int T, int T_pad, int E, int k, int dense, int split, const float* __restrict__ fp,
+                         float* __restrict__ draw, __nv_bfloat16* __restrict__ dfp_op, float* __restrict__ dtau_part,
+                         float* __restrict__ dwc_part) {
     extern __shared__ __align__(16) float bsm[];
     float* WcT = bsm;                 // [E][128]
     float* red = bsm + E * HID;       // [8]
+    float* wred = red + 8;            // FUSE_DWC: [8 warps][128 * E]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < HID * E; i += RB_THREADS) {
         const int j = i / E, e = i - j * E;
@@ -340,8 +358,15 @@ router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict_
     const float dl_add = (act && dload != nullptr) ? __ldg(dload + lane) : 0.0f;
     float dtau_acc = 0.0f;
     const int ldop = split ? 2 * HID : HID;
+    float4 wacc[RB_FUSE_MAX_E];
+#pragma unroll
+    for (int e = 0; e < RB_FUSE_MAX_E; ++e) wacc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ngroups = (T + RB_TOK - 1) / RB_TOK;
+    const int gpb = (ngroups + gridDim.x - 1) / gridDim.x;
+    const int g_end = min(ngroups, (int)(blockIdx.x + 1) * gpb);
+    for (int grp = blockIdx.x * gpb; grp < g_end; ++grp)
     for (int a = wid; a < RB_TOK; a += RB_THREADS / 32) {
-        const int t = blockIdx.x * RB_TOK + a;
+        const int t = grp * RB_TOK + a;
         if (t >= T) break;
         // recompute the forward chain exactly as router_fwd_kernel does
         const float r = act ? raw[(size_t)t * E + lane] : 0.0f;
@@ -377,10 +402,24 @@ router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict_
         if (act) draw[(size_t)t * E + lane] = dr;
         // dfp[t, j] = sum_e draw[e] * Wc[j, e]
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = 0; e < E; ++e) {
-            const float de = __shfl_sync(0xffffffffu, dr, e);
-            const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
-            o.x = fmaf(de, wc.x, o.x); o.y = fmaf(de, wc.y, o.y); o.z = fmaf(de, wc.z, o.z); o.w = fmaf(de, wc.w, o.w);
+        if (FUSE_DWC) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(fp + (size_t)t * HID + lane * 4));
+#pragma unroll
+            for (int e = 0; e < RB_FUSE_MAX_E; ++e) {
+                if (e < E) {
+                    const float de = __shfl_sync(0xffffffffu, dr, e);
+                    const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+                    o.x = fmaf(de, wc.x, o.x); o.y = fmaf(de, wc.y, o.y); o.z = fmaf(de, wc.z, o.z); o.w = fmaf(de, wc.w, o.w);
+                    wacc[e].x = fmaf(f4.x, de, wacc[e].x); wacc[e].y = fmaf(f4.y, de, wacc[e].y);
+                    wacc[e].z = fmaf(f4.z, de, wacc[e].z); wacc[e].w = fmaf(f4.w, de, wacc[e].w);
+                }
+            }
+        } else {
+            for (int e = 0; e < E; ++e) {
+                const float de = __shfl_sync(0xffffffffu, dr, e);
+                const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+                o.x = fmaf(de, wc.x, o.x); o.y = fmaf(de, wc.y, o.y); o.z = fmaf(de, wc.z, o.z); o.w = fmaf(de, wc.w, o.w);
+            }
         }
         __nv_bfloat16* dst = dfp_op + (size_t)t * ldop + lane * 4;
         float h0, h1, h2, h3, l0, l1, l2, l3;
@@ -395,6 +434,22 @@ router_bwd_logits_kernel(const float* __restrict__ raw, const float* __restrict_
         float s = 0.0f;
         for (int w = 0; w < RB_THREADS / 32; ++w) s += red[w];
         dtau_part[blockIdx.x] = s;
+    }
+    if (FUSE_DWC) {
+        // part[blk][j][e], j = lane * 4 + c: the 8 warps are summed in a fixed order
+#pragma unroll
+        for (int e = 0; e < RB_FUSE_MAX_E; ++e)
+            if (e < E) {
+                float* dst = wred + (size_t)wid * HID * E + (lane * 4) * E + e;
+                dst[0] = wacc[e].x; dst[E] = wacc[e].y; dst[2 * E] = wacc[e].z; dst[3 * E] = wacc[e].w;
+            }
+        __syncthreads();
+        for (int i = tid; i < HID * E; i += RB_THREADS) {
+            float a = wred[i];
+#pragma unroll
+            for (int w = 1; w < RB_THREADS / 32; ++w) a += wred[(size_t)w * HID * E + i];
+            dwc_part[(size_t)blockIdx.x * HID * E + i] = a;
+        }
     }
 }
 
@@ -620,14 +675,16 @@ __global__ void balance_loss_kernel(const float* __restrict__ load, int E, int T
 int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_f, const float* eps_f,
                      const float* mu_t, const float* rho_t, const float* eps_t,
                      const float* mu_c, const float* rho_c, const float* eps_c, int sampling,
-                     float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out, cudaStream_t st) {
+                     float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out,
+                     float* keep_f, float* keep_t, float* keep_c, cudaStream_t st) {
     const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
     const int n = n_f + n_t + n_c;
     int blocks = ceil_div(n, 256 * 4);
     if (blocks > MOEGAN_KL_PARTS) blocks = MOEGAN_KL_PARTS;
     sample_kl_kernel<<<blocks, 256, 0, st>>>(mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, n_f, n_t, n_c,
                                              sampling, s->precision == 1, Wf, Wt, Wc,
-                                             reinterpret_cast<__nv_bfloat16*>(Wf_op), reinterpret_cast<__nv_bfloat16*>(Wt_op), kl_out + 2);
+                                             reinterpret_cast<__nv_bfloat16*>(Wf_op), reinterpret_cast<__nv_bfloat16*>(Wt_op), kl_out + 2,
+                                             keep_f, keep_t, keep_c);
     MOEGAN_CHECK_LAUNCH("sample_kl_kernel");
     kl_finalize_kernel<<<1, 32, 0, st>>>(kl_out + 2, blocks, kl_out);
     MOEGAN_CHECK_LAUNCH("kl_finalize_kernel");
@@ -663,21 +720,35 @@ int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, co
 
 int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const float* Wc, const int32_t* topk_idx,
                              const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
-                             const float* temperature, float af, float* draw, void* dfp_op, float* dtau_part, cudaStream_t st) {
-    const int blocks = ceil_div(s->T, RB_TOK);
+                             const float* temperature, float af, const float* fp, float* draw, void* dfp_op, float* dtau_part,
+                             float* dwc_part, cudaStream_t st) {
+    const int blocks = router_bwd_logits_blocks(s);
     const int T_pad = row_pad(s->T);
-    router_bwd_logits_kernel<<<blocks, RB_THREADS, (s->E * HID + 8) * sizeof(float), st>>>(
-        raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, af, s->T, T_pad, s->E, s->k, s->dense,
-        s->precision == 1, draw, reinterpret_cast<__nv_bfloat16*>(dfp_op), dtau_part);
+    if (router_bwd_dwc_fused(s)) {
+        const size_t smem = ((size_t)s->E * HID + 8 + (size_t)(RB_THREADS / 32) * HID * s->E) * sizeof(float);
+        router_bwd_logits_kernel<true><<<blocks, RB_THREADS, smem, st>>>(
+            raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, af, s->T, T_pad, s->E, s->k, s->dense,
+            s->precision == 1, fp, draw, reinterpret_cast<__nv_bfloat16*>(dfp_op), dtau_part, dwc_part);
+    } else {
+        router_bwd_logits_kernel<false><<<blocks, RB_THREADS, (s->E * HID + 8) * sizeof(float), st>>>(
+            raw, Wc, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature, af, s->T, T_pad, s->E, s->k, s->dense,
+            s->precision == 1, fp, draw, reinterpret_cast<__nv_bfloat16*>(dfp_op), dtau_part, nullptr);
+    }
     MOEGAN_CHECK_LAUNCH("router_bwd_logits_kernel");
     return MOEGAN_OK;
 }
-int router_bwd_logits_blocks(const moegan_shape* s) { return ceil_div(s->T, RB_TOK); }
+bool router_bwd_dwc_fused(const moegan_shape* s) { return s->E <= RB_FUSE_MAX_E; }
+int router_bwd_logits_blocks(const moegan_shape* s) {
+    const int groups = ceil_div(s->T, RB_TOK);
+    return groups < RB_MAX_BLOCKS ? (groups > 0 ? groups : 1) : RB_MAX_BLOCKS;
+}
 static int dwc_tok_per_block(const moegan_shape* s) {
     const int chunks = ceil_div(s->T, WC_TOK);
     return ceil_div(chunks, WC_MAX_PARTS) * WC_TOK;
 }
-int router_bwd_dwc_parts(const moegan_shape* s) { return ceil_div(s->T, dwc_tok_per_block(s)); }
+int router_bwd_dwc_parts(const moegan_shape* s) {
+    return router_bwd_dwc_fused(s) ? router_bwd_logits_blocks(s) : ceil_div(s->T, dwc_tok_per_block(s));
+}
 
 int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,
                             const float* dtau_part, const float* temperature, float af,
@@ -685,8 +756,10 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
     router_bwd_dtl_kernel<<<s->B, 256, 0, st>>>(draw, s->tokens_per_sample, s->E, dtl);
     MOEGAN_CHECK_LAUNCH("router_bwd_dtl_kernel");
     const int nparts = router_bwd_dwc_parts(s);
-    router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_tok_per_block(s), dwc_part);
-    MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
+    if (!router_bwd_dwc_fused(s)) {          // E <= 8: the logits kernel has already written the partials
+        router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_tok_per_block(s), dwc_part);
+        MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
+    }
     router_bwd_small_kernel<<<1 + s->B + s->E, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
                                                      temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
                                                      reinterpret_cast<__nv_bfloat16*>(dtp_op), dtemperature);

@@ -82,13 +82,15 @@ class WeightCache:
 
     The reference re-casts every nn.Linear weight on every autocast forward; here both generator forwards
     of a train step (D-step under no_grad, G-step with grad) share one conversion.  While a CUDA graph is
-    being captured the conversion is always enqueued (a replay must re-convert the then-current weights).
+    being captured the conversion is enqueued once per (capture, parameter versions): a replay must re-convert the
+    then-current weights, but the forward passes of one captured step still share it.
     """
 
     def __init__(self):
         self.key = None
         self.bufs = None
         self.capture_bufs = None
+        self.capture_key = None
 
     def get(self, cfg: MoEConfig, w1: Sequence[torch.Tensor], b1, w2, b2):
         """Returns (buffers, stale).  When `stale`, the caller passes the parameter pointer tables to moegan_block_fwd,
@@ -98,6 +100,11 @@ class WeightCache:
                tuple((p.data_ptr(), p._version) for group in (w1, b1, w2, b2) for p in group))
         if not capturing and key == self.key and self.bufs is not None:
             return self.bufs, False
+        if capturing:
+            cid = int(C.lib().moegan_stream_capture_id(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            ckey = (cid, key)
+            if cid > 0 and ckey == self.capture_key and self.capture_bufs is not None:
+                return self.capture_bufs, False
         dev = w1[0].device
         S = 2 if cfg.precision == 1 else 1
         hid = 4 * cfg.d
@@ -106,7 +113,7 @@ class WeightCache:
                 torch.empty((cfg.E * cfg.d, S * hid), dtype=torch.bfloat16, device=dev),
                 torch.empty((cfg.E, cfg.d), dtype=torch.float32, device=dev))
         if capturing:
-            self.capture_bufs = bufs
+            self.capture_bufs, self.capture_key = bufs, ckey
         else:
             self.key, self.bufs = key, bufs
         return bufs, True
