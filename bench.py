@@ -415,8 +415,10 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     if os.environ.get("MOEGAN_BENCH_CHANNELS_LAST", "1") == "1":
         real = real.contiguous(memory_format=torch.channels_last)
 
+    bucket_mb = float(os.environ.get("MOEGAN_BENCH_BUCKET_MB", "25"))
+
     def make_trainer(graph):
-        return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph)
+        return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph, bucket_bytes=int(bucket_mb * (1 << 20)))
 
     launch_mode = "eager"
     trainer = make_trainer(False)
@@ -539,7 +541,7 @@ def run_b200_arm(args, rank, world, local_rank):
         "config": {"workload": train_workload_name(world), "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * world,
                    "image": "real 64x64 -> D; G emits 16x16 (+8x8)", "l2": "256 MiB buffer zeroed between timed iterations",
                    "parallelism": f"dp{world}" if world > 1 else "single", "launch": r["launch"],
-                   "allreduce": "NCCL, 25 MB buckets from grad-ready hooks on a comm stream" if world > 1 else None},
+                   "allreduce": f"NCCL, {os.environ.get('MOEGAN_BENCH_BUCKET_MB', '25')} MB buckets from grad-ready hooks on a comm stream" if world > 1 else None},
         "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "cpu_baseline": cpu,
         "host_enqueue_us_per_step": r["host_enqueue_us_per_step"], "inference": r.get("inference"),
     }

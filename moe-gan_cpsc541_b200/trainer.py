@@ -26,6 +26,17 @@ from .functional import BalanceLossFunction
 # --------------------------------------------------------------------------------------------------
 # bucketed, overlapped gradient all-reduce
 # --------------------------------------------------------------------------------------------------
+def _flat_storage_view(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """1-D view of a dense tensor in STORAGE order (no copy): contiguous tensors and channels-last 4-D tensors (the conv
+    weights / gradients of a channels_last model).  An all-reduce is element-wise, so any order works as long as pack
+    and unpack use the same one and every rank has the same layout.  None if the tensor is not dense in either format."""
+    if t.is_contiguous():
+        return t.view(-1)
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t.permute(0, 2, 3, 1).view(-1)
+    return None
+
+
 class GradReducer:
     """Averages .grad of `params` across the process group, bucket by bucket, as soon as a bucket's gradients exist.
 
@@ -54,6 +65,8 @@ class GradReducer:
         self.launched = [False] * len(self.buckets)
         self.comm_stream = None
         self.enabled = False
+        # NCCL averages inside the collective (ReduceOp.AVG); other backends (gloo in the CPU tests) sum, then scale
+        self.avg_in_collective = bool(self.world > 1 and dist.get_backend(group) == "nccl")
         self._handles = []
         if self.world > 1:
             for p in self.params:
@@ -89,13 +102,16 @@ class GradReducer:
         flat = self._flat(bi)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
         views = flat.split([p.numel() for p in self.buckets[bi]])
-        torch._foreach_copy_(list(views), [g.reshape(-1) for g in grads])
+        srcs = [_flat_storage_view(g) for g in grads]
+        srcs = [s if s is not None else g.reshape(-1) for s, g in zip(srcs, grads)]
+        torch._foreach_copy_(list(views), srcs)
+        op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(flat, group=self.group)
+                dist.all_reduce(flat, op=op, group=self.group)
         else:
-            dist.all_reduce(flat, group=self.group)
+            dist.all_reduce(flat, op=op, group=self.group)
 
     def finish(self) -> None:
         """Call after backward: reduces stragglers, joins the comm stream, writes the averaged gradients back."""
@@ -108,18 +124,23 @@ class GradReducer:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         inv = 1.0 / self.world
         for bi, b in enumerate(self.buckets):
-            views = self._flat(bi).split([p.numel() for p in b])
+            views = list(self._flat(bi).split([p.numel() for p in b]))
             outs = []
             for p in b:
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
-                outs.append(p.grad.reshape(-1) if p.grad.is_contiguous() else None)
-            if all(o is not None for o in outs):
-                torch._foreach_copy_(outs, list(views))
-                torch._foreach_mul_(outs, inv)
-            else:
-                for p, v in zip(b, views):
-                    p.grad.copy_(v.view_as(p)).mul_(inv)
+                outs.append(_flat_storage_view(p.grad))
+            fast = [(o, v) for o, v in zip(outs, views) if o is not None]
+            if fast:                                   # two multi-tensor launches per bucket, whatever the memory format
+                fo, fv = [o for o, _ in fast], [v for _, v in fast]
+                torch._foreach_copy_(fo, fv)
+                if not self.avg_in_collective:
+                    torch._foreach_mul_(fo, inv)
+            for p, o, v in zip(b, outs, views):        # gradients that are dense in neither format (none in this model)
+                if o is None:
+                    p.grad.copy_(v.view_as(p))
+                    if not self.avg_in_collective:
+                        p.grad.mul_(inv)
         self.enabled = False
 
 

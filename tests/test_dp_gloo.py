@@ -54,6 +54,29 @@ def _worker(rank, world, port, q):
             assert torch.allclose(g, want, atol=1e-6), i
         assert torch.count_nonzero(unused.grad) == 0
 
+        # channels-last conv weights (the bench's model layout): gradients are dense but not row-major contiguous; they
+        # are packed / unpacked through storage-order views, never through per-parameter copies
+        def conv_net():
+            torch.manual_seed(1)
+            return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.LeakyReLU(0.2),
+                                       torch.nn.Conv2d(8, 4, 3, padding=1)).to(memory_format=torch.channels_last)
+        net = conv_net()
+        redc = pkg.GradReducer(list(net.parameters()), bucket_bytes=512)
+        torch.manual_seed(200 + rank)
+        xi = torch.randn(2, 3, 6, 6).contiguous(memory_format=torch.channels_last)
+        redc.begin(); net(xi).square().mean().backward(); redc.finish()
+        assert any(not p.grad.is_contiguous() for p in net.parameters()), "test needs a channels-last gradient"
+        for i, p in enumerate(net.parameters()):
+            want = 0
+            for r in range(world):
+                n2 = conv_net()
+                torch.manual_seed(200 + r)
+                n2(torch.randn(2, 3, 6, 6).contiguous(memory_format=torch.channels_last)).square().mean().backward()
+                want = want + list(n2.parameters())[i].grad
+            assert torch.allclose(p.grad, want / world, atol=1e-6), i
+        v = pkg.trainer._flat_storage_view(torch.empty(4, 3, 2, 2).to(memory_format=torch.channels_last))
+        assert v is not None and v.numel() == 48 and pkg.trainer._flat_storage_view(torch.empty(4, 6)[:, ::2]) is None
+
         # exact balance loss under DP: loss(global load) and its gradient after DP averaging
         torch.manual_seed(7)
         probs_all = torch.softmax(torch.randn(world * 10, 4) * 2, dim=1)
