@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define MOEGAN_ABI_VERSION 2
+#define MOEGAN_ABI_VERSION 3
 #define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
@@ -143,16 +143,17 @@ int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
                    const void* W2_op, const float* b2s, void* pre, void* h_op, void* y, void* stream);
 
 /* replaces: `combined_output += probs[:, i:i+1] * expert_output` (t2i_moe_gan.py:462,470) and
- * `combined_output[mask] = expert_output` (:483).  out [T,d] fp32. */
+ * `combined_output[mask] = expert_output` (:483); with `residual` ([T,d] fp32 or bf16, may be NULL) also the
+ * `x_spatial + moe_out` of AttentionBlock (:571) in the same pass.  out [T,d] fp32 or bf16. */
 int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows,
-                       float* out, void* stream);
+                       const void* residual, int32_t residual_is_bf16, void* out, int32_t out_is_bf16, void* stream);
 
 /* ---- backward ------------------------------------------------------------------------------- */
 /* autograd of the combine: dy_op[r] = gate * dout[token(r)] (zero on padding rows),
- * dgate_row[r] = <dout[token(r)], y[r]>.  gates: [T,k] (dense: the probs, k == E).
+ * dgate_row[r] = <dout[token(r)], y[r]>.  dout [T,d] fp32 or bf16.  gates: [T,k] (dense: the probs, k == E).
  * dy_slab_sums (may be NULL): [m_cap/32, d] fp32 column sums of every 32 consecutive dy rows - moegan_ffn_bwd turns them
  * into the second Linear's bias gradient without reading dy again. */
-int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y,
+int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int32_t dout_is_bf16, const void* y,
                        const int32_t* row_token, const float* row_gate, const float* gates,
                        void* dy_op, float* dgate_row, float* dy_slab_sums, void* stream);
 
@@ -216,11 +217,14 @@ typedef struct {
     float annealing_factor;
     int32_t sampled;            /* 1: training (weights sampled, KL computed) */
     int32_t need_backward;      /* 1: keep what moegan_block_bwd needs */
-    float* out;                 /* [T,d] */
+    void* out;                  /* [T,d] fp32, or bf16 when out_is_bf16 */
     float* probs;               /* [T,E] */
     float* load;                /* [E] */
     float* kl_out;              /* [MOEGAN_KL_OUT_FLOATS] */
     void* workspace; int64_t workspace_bytes;
+    const void* residual;       /* [T,d] fp32 / bf16 or NULL: out = residual + moe(x)  (AttentionBlock :571 fused) */
+    int32_t residual_is_bf16;
+    int32_t out_is_bf16;
 } moegan_block_fwd_args;
 
 typedef struct {
@@ -229,7 +233,7 @@ typedef struct {
     const float *mu_f, *rho_f, *eps_f, *mu_t, *rho_t, *eps_t, *mu_c, *rho_c, *eps_c, *temperature;   /* eps_* may be NULL: the forward
                                    call keeps its own copy of the eps it consumed inside fwd_workspace */
     const void* W1_op; const void* W2_op; const float* kl_out;
-    const float* dout;          /* [T,d] */
+    const void* dout;           /* [T,d] fp32, or bf16 when dout_is_bf16 */
     const float* dkl;           /* [1] or NULL */
     const float* dprobs;        /* [T,E] or NULL */
     const float* dload;         /* [E] or NULL */
@@ -240,6 +244,8 @@ typedef struct {
     float *dmu_f, *drho_f, *dmu_t, *drho_t, *dmu_c, *drho_c, *dtemperature;   /* NULL in hard mode */
     float *dW1, *db1, *dW2, *db2;   /* [E,4d,d] [E,4d] [E,d,4d] [E,d] */
     void* workspace; int64_t workspace_bytes;
+    int32_t dout_is_bf16;
+    int32_t reserved;
 } moegan_block_bwd_args;
 
 int64_t moegan_block_fwd_workspace(const moegan_shape* s, int32_t need_backward, moegan_block_layout* layout /* may be NULL */);

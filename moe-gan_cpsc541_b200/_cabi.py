@@ -17,7 +17,7 @@ MAX_EXPERTS = 32
 MAX_TOPK = 8
 CHUNK = 32
 KL_OUT_FLOATS = 2 + 256
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Shape(ctypes.Structure):
@@ -41,7 +41,7 @@ class BlockFwdArgs(ctypes.Structure):
                   "W1_op", "b1s", "W2_op", "b2s", "prep_w1", "prep_b1", "prep_w2", "prep_b2")]
                 + [("annealing_factor", c_float), ("sampled", c_int32), ("need_backward", c_int32)]
                 + [(n, c_void_p) for n in ("out", "probs", "load", "kl_out", "workspace")]
-                + [("workspace_bytes", c_int64)])
+                + [("workspace_bytes", c_int64), ("residual", c_void_p), ("residual_is_bf16", c_int32), ("out_is_bf16", c_int32)])
 
 
 class BlockBwdArgs(ctypes.Structure):
@@ -53,7 +53,7 @@ class BlockBwdArgs(ctypes.Structure):
                 + [(n, c_void_p) for n in
                    ("dx", "dw", "dmu_f", "drho_f", "dmu_t", "drho_t", "dmu_c", "drho_c", "dtemperature", "dW1", "db1", "dW2", "db2",
                     "workspace")]
-                + [("workspace_bytes", c_int64)])
+                + [("workspace_bytes", c_int64), ("dout_is_bf16", c_int32), ("reserved", c_int32)])
 
 
 _P = c_void_p
@@ -74,8 +74,8 @@ SIGNATURES = {
     "moegan_convert_tokens": (c_int32, [_SP, _P, _P, _P]),
     "moegan_prep_weights": (c_int32, [_SP] + [POINTER(c_void_p)] * 4 + [_P] * 4 + [_P]),
     "moegan_ffn_fwd": (c_int32, [_SP] + [_P] * 9 + [_P]),
-    "moegan_combine_fwd": (c_int32, [_SP] + [_P] * 4 + [_P]),
-    "moegan_combine_bwd": (c_int32, [_SP] + [_P] * 9 + [_P]),
+    "moegan_combine_fwd": (c_int32, [_SP, _P, _P, _P, _P, c_int32, _P, c_int32, _P]),
+    "moegan_combine_bwd": (c_int32, [_SP, _P, _P, c_int32] + [_P] * 7 + [_P]),
     "moegan_ffn_bwd": (c_int32, [_SP] + [_P] * 14 + [_P, c_int64] + [_P]),
     "moegan_ffn_bwd_scratch_bytes": (c_int64, [_SP]),
     "moegan_uncombine_bwd": (c_int32, [_SP] + [_P] * 4 + [_P]),

@@ -330,22 +330,26 @@ int moegan_ffn_fwd(const moegan_shape* s, const int32_t* plan, const void* a_op,
     return MOEGAN_OK;
 }
 
-int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, void* stream) {
+int moegan_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
+                       int32_t residual_is_bf16, void* out, int32_t out_is_bf16, void* stream) {
     CHECK_SHAPE(s);
     if (s->T == 0) return MOEGAN_OK;
     REQ_PTR(y); REQ_PTR(gates); REQ_PTR(out);
     if (!s->dense) REQ_PTR(token_rows);
-    return launch_combine_fwd(s, y, gates, token_rows, out, (cudaStream_t)stream);
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                   "combine_fwd: out / residual must be 16-byte aligned");
+    return launch_combine_fwd(s, y, gates, token_rows, residual, residual_is_bf16, out, out_is_bf16, (cudaStream_t)stream);
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
-                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_slab_sums, void* stream) {
+int moegan_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int32_t dout_is_bf16, const void* y,
+                       const int32_t* row_token, const float* row_gate, const float* gates, void* dy_op, float* dgate_row,
+                       float* dy_slab_sums, void* stream) {
     CHECK_SHAPE(s);
     if (s->T == 0) return MOEGAN_OK;
     REQ_PTR(plan); REQ_PTR(dout); REQ_PTR(y); REQ_PTR(dy_op); REQ_PTR(dgate_row);
     if (s->dense) { REQ_PTR(gates); } else { REQ_PTR(row_token); REQ_PTR(row_gate); }
-    return launch_combine_bwd(s, plan, dout, y, row_token, row_gate, gates, dy_op, dgate_row, dy_slab_sums, (cudaStream_t)stream);
+    return launch_combine_bwd(s, plan, dout, dout_is_bf16, y, row_token, row_gate, gates, dy_op, dgate_row, dy_slab_sums, (cudaStream_t)stream);
 }
 
 // defer_bias: the caller (moegan_block_bwd) runs the two bias-gradient slab sums itself on its side stream, off the critical
@@ -713,7 +717,7 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     }
     if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
     RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
-    RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->out, stream));
+    RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->residual, a->residual_is_bf16, a->out, a->out_is_bf16, stream));
     return MOEGAN_OK;
 }
 
@@ -736,7 +740,8 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dgate_row = reinterpret_cast<float*>(ws + W.dgate_row);
     float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
     float* dy_slabs = reinterpret_cast<float*>(ws + W.dy_slabs);
-    RUN(moegan_combine_bwd(s, I(L.plan), a->dout, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row, dy_slabs, stream));
+    RUN(moegan_combine_bwd(s, I(L.plan), a->dout, a->dout_is_bf16, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row,
+                           dy_slabs, stream));
     // the router's backward only needs dgate_row: run it on the side stream while the expert GEMMs own the main stream
     SideStream* ss = (s->hard || !side_pays(s)) ? nullptr : side_stream();
     void* rstream = stream;

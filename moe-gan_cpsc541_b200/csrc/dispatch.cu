@@ -208,10 +208,21 @@ __device__ __forceinline__ float4 load_row4(const void* base, size_t elem_off) {
     return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
 }
 
-template <bool Y_F32>
+// 4 consecutive fp32 / bf16 values -> float4, and back (residual, upstream gradient and output of the combine may be either)
+template <bool BF16>
+__device__ __forceinline__ float4 load4_any(const void* base, size_t elem_off) { return load_row4<!BF16>(base, elem_off); }
+template <bool BF16>
+__device__ __forceinline__ void store4_any(void* base, size_t elem_off, float4 v) {
+    if (BF16) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    else      *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off) = v;
+}
+
+// RES: 0 = no residual, 1 = fp32 residual, 2 = bf16 residual (`x_spatial + moe_out`, t2i_moe_gan.py:571, in the
+// combine's epilogue); OUT_BF16: write the result in bf16 (the dtype of the residual stream under autocast)
+template <bool Y_F32, int RES, bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, const int* __restrict__ token_rows,
-                   int T, int T_pad, int d, int k, int dense, float* __restrict__ out) {
+                   int T, int T_pad, int d, int k, int dense, const void* __restrict__ residual, void* __restrict__ out) {
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
@@ -233,15 +244,22 @@ combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, 
     }
 #pragma unroll
     for (int s = 0; s < MAX_SEG; ++s)
-        if (s < nseg) *reinterpret_cast<float4*>(out + (size_t)t * d + s * 128 + lane * 4) = acc[s];
+        if (s < nseg) {
+            const size_t o = (size_t)t * d + s * 128 + lane * 4;
+            if (RES != 0) {
+                const float4 r = load4_any<RES == 2>(residual, o);
+                acc[s].x += r.x; acc[s].y += r.y; acc[s].z += r.z; acc[s].w += r.w;
+            }
+            store4_any<OUT_BF16>(out, o, acc[s]);
+        }
 }
 
 // combine backward: CTA = 32 consecutive dispatched rows (never straddles experts: segments are 256-row aligned), 4 rows per
 // warp.  Also emits the column sums of the CTA's 32 dy rows (colpart [m_cap / 32, d]) - the second Linear's bias gradient
 // is their per-expert sum, so dy is never re-read for it.
-template <bool Y_F32>
+template <bool Y_F32, bool DOUT_BF16>
 __global__ void __launch_bounds__(256)
-combine_bwd_kernel(const int* __restrict__ plan, const float* __restrict__ dout, const void* __restrict__ y,
+combine_bwd_kernel(const int* __restrict__ plan, const void* __restrict__ dout, const void* __restrict__ y,
                    const int* __restrict__ row_token, const float* __restrict__ row_gate, const float* __restrict__ gates,
                    int T, int T_pad, int d, int E, int dense, int split,
                    __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row, float* __restrict__ colpart) {
@@ -275,7 +293,7 @@ combine_bwd_kernel(const int* __restrict__ plan, const float* __restrict__ dout,
         for (int s = 0; s < MAX_SEG; ++s) {
             if (s < nseg) {
                 const int col = s * 128 + lane * 4;
-                const float4 go = __ldg(reinterpret_cast<const float4*>(dout + (size_t)t * d + col));
+                const float4 go = load4_any<DOUT_BF16>(dout, (size_t)t * d + col);
                 const float4 yv = load_row4<Y_F32>(y, (size_t)r * d + col);
                 dot = fmaf(go.x, yv.x, fmaf(go.y, yv.y, fmaf(go.z, yv.z, fmaf(go.w, yv.w, dot))));
                 const float4 dv = make_float4(g * go.x, g * go.y, g * go.z, g * go.w);
@@ -451,26 +469,30 @@ int launch_prep_weights(const moegan_shape* s, const float* const* w1, const flo
     return MOEGAN_OK;
 }
 
-int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, cudaStream_t st) {
+int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
+                       int residual_bf16, void* out, int out_bf16, cudaStream_t st) {
     const int T_pad = row_pad(s->T);
     const int blocks = ceil_div(s->T, 8);
-    if (s->precision == 1) combine_fwd_kernel<true><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
-    else                   combine_fwd_kernel<false><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, out);
+    const int res = residual == nullptr ? 0 : (residual_bf16 ? 2 : 1);
+#define MOEGAN_CF(YF, RS, OB) combine_fwd_kernel<YF, RS, OB><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, residual, out)
+#define MOEGAN_CF_R(YF, OB) do { if (res == 0) MOEGAN_CF(YF, 0, OB); else if (res == 1) MOEGAN_CF(YF, 1, OB); else MOEGAN_CF(YF, 2, OB); } while (0)
+    if (s->precision == 1) { if (out_bf16) MOEGAN_CF_R(true, true); else MOEGAN_CF_R(true, false); }
+    else                   { if (out_bf16) MOEGAN_CF_R(false, true); else MOEGAN_CF_R(false, false); }
+#undef MOEGAN_CF_R
+#undef MOEGAN_CF
     MOEGAN_CHECK_LAUNCH("combine_fwd_kernel");
     return MOEGAN_OK;
 }
 
-int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
+int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int dout_bf16, const void* y, const int32_t* row_token,
                        const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st) {
     const int T_pad = row_pad(s->T);
     const int blocks = s->m_cap / 32;
     __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
-    if (s->precision == 1)
-        combine_bwd_kernel<true><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 1, dy,
-                                                         dgate_row, dy_colpart);
-    else
-        combine_bwd_kernel<false><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, 0, dy,
-                                                          dgate_row, dy_colpart);
+#define MOEGAN_CB(YF, DB, SP) combine_bwd_kernel<YF, DB><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, SP, dy, dgate_row, dy_colpart)
+    if (s->precision == 1) { if (dout_bf16) MOEGAN_CB(true, true, 1); else MOEGAN_CB(true, false, 1); }
+    else                   { if (dout_bf16) MOEGAN_CB(false, true, 0); else MOEGAN_CB(false, false, 0); }
+#undef MOEGAN_CB
     MOEGAN_CHECK_LAUNCH("combine_bwd_kernel");
     return MOEGAN_OK;
 }

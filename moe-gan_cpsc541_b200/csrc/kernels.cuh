@@ -43,8 +43,9 @@ int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx
 int launch_to_operand(const float* src, int64_t rows, int64_t cols, int split, int sanitize, void* dst, cudaStream_t st);
 int launch_prep_weights(const moegan_shape* s, const float* const* w1, const float* const* b1, const float* const* w2,
                         const float* const* b2, void* W1_op, float* b1s, void* W2_op, float* b2s, cudaStream_t st);
-int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, float* out, cudaStream_t st);
-int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const float* dout, const void* y, const int32_t* row_token,
+int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
+                       int residual_bf16, void* out, int out_bf16, cudaStream_t st);
+int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int dout_bf16, const void* y, const int32_t* row_token,
                        const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st);
 int slab_sum_splits(const moegan_shape* s);
 int launch_slab_sum(const moegan_shape* s, const int32_t* plan, const float* part, int cols, float* scratch, float* out, cudaStream_t st);

@@ -146,7 +146,9 @@ def workspace_views(ws: torch.Tensor, layout: "C.BlockLayout", cfg: MoEConfig) -
 
 
 class MoEBlockFunction(torch.autograd.Function):
-    """(x_tok [T,d], w [B,Dt], eps x3, router params x7, expert params x4E) -> (out [T,d], kl [], probs [T,E], load [E])."""
+    """(x_tok [T,d], w [B,Dt], eps x3, router params x7, residual [T,d] | None, expert params x4E)
+    -> (out [T,d], kl [], probs [T,E], load [E]).  With a residual, out = residual + moe(x) in the residual's dtype (the
+    `x_spatial + moe_out` of AttentionBlock, t2i_moe_gan.py:571, done in the combine kernel's epilogue)."""
 
     _last = None   # (workspace, layout, cfg) of the most recent forward, for tests / diagnostics
 
@@ -157,7 +159,7 @@ class MoEBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg: MoEConfig, wcache: WeightCache, x_tok, w, eps_f, eps_t, eps_c,
-                mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature, *expert_params):
+                mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature, residual, *expert_params):
         lib = C.lib()
         E, d, T = cfg.E, cfg.d, cfg.T
         _require_cuda(x_tok, "x"); _require_cuda(w, "w"); _require_cuda(mu_f, "router.feature_mu")
@@ -172,7 +174,13 @@ class MoEBlockFunction(torch.autograd.Function):
         (W1_op, b1s, W2_op, b2s), stale = wcache.get(cfg, w1, b1, w2, b2)
 
         ws = torch.empty((plan.fwd_bytes if need_bwd else plan.fwd_bytes_nobwd,), dtype=torch.uint8, device=dev)
-        out = torch.empty((T, d), dtype=f32, device=dev)
+        if residual is not None:
+            if residual.dtype not in (torch.float32, torch.bfloat16):
+                residual = residual.float()
+            residual = residual.contiguous()
+            if residual.shape != (T, d):
+                raise ValueError(f"residual must be [T, d] = [{T}, {d}], got {tuple(residual.shape)}")
+        out = torch.empty((T, d), dtype=f32 if residual is None else residual.dtype, device=dev)
         probs = torch.empty((T, E), dtype=f32, device=dev)
         small = torch.empty((E + C.KL_OUT_FLOATS,), dtype=f32, device=dev)     # [load | kl_out]
 
@@ -191,6 +199,9 @@ class MoEBlockFunction(torch.autograd.Function):
         a.load = small.data_ptr()
         a.kl_out = small.data_ptr() + 4 * E
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.residual = _dp(residual)
+        a.residual_is_bf16 = 1 if (residual is not None and residual.dtype == torch.bfloat16) else 0
+        a.out_is_bf16 = 1 if out.dtype == torch.bfloat16 else 0
         C.check(lib.moegan_block_fwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_fwd")
 
         load = small[:E]
@@ -201,6 +212,7 @@ class MoEBlockFunction(torch.autograd.Function):
             ctx.w = w
             ctx.router_params = router_params
             ctx.wops = (W1_op, W2_op)
+            ctx.has_residual = residual is not None
         MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
         return out, kl, probs, load
 
@@ -212,7 +224,10 @@ class MoEBlockFunction(torch.autograd.Function):
         dev = ctx.w.device
         f32 = torch.float32
         hid = 4 * d
-        dout = torch.zeros((T, d), dtype=f32, device=dev) if dout is None else dout.contiguous().float()
+        if dout is None:
+            dout = torch.zeros((T, d), dtype=f32, device=dev)
+        else:
+            dout = (dout if dout.dtype in (f32, torch.bfloat16) else dout.float()).contiguous()   # bf16 is read as such by combine_bwd
         dprobs = None if dprobs is None else dprobs.contiguous().float()
         dload = None if dload is None else dload.contiguous().float()
         dkl = None if dkl is None else dkl.reshape(1).contiguous().float()
@@ -232,6 +247,7 @@ class MoEBlockFunction(torch.autograd.Function):
         a.dout, a.dkl, a.dprobs, a.dload = dout.data_ptr(), _dp(dkl), _dp(dprobs), _dp(dload)
         a.annealing_factor = float(cfg.annealing_factor)
         a.sampled = 1 if cfg.sampled else 0
+        a.dout_is_bf16 = 1 if dout.dtype == torch.bfloat16 else 0
         a.dx = dx.data_ptr()
         a.dW1, a.db1, a.dW2, a.db2 = dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), db2.data_ptr()
         router_grads = [None] * 7
@@ -247,7 +263,8 @@ class MoEBlockFunction(torch.autograd.Function):
         C.check(lib.moegan_block_bwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_bwd")
         expert_grads = [t for quad in zip(dW1.unbind(0), db1.unbind(0), dW2.unbind(0), db2.unbind(0)) for t in quad]
         ctx.ws = None
-        return (None, None, dx, dw, None, None, None, *router_grads, *expert_grads)
+        d_res = dout if ctx.has_residual else None     # d(residual + moe) / d residual = identity
+        return (None, None, dx, dw, None, None, None, *router_grads, d_res, *expert_grads)
 
 
 class BalanceLossFunction(torch.autograd.Function):

@@ -112,10 +112,15 @@ class AttentionBlock(nn.Module):
         t = t + self.cross_attn(ln(self.norm2, t, mm), tp, tp, need_weights=False)[0]
         x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
         x_norm = ln(self.norm3, t).reshape(B, H, W, C).permute(0, 3, 1, 2)  # NCHW view of NHWC memory (:561)
-        moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
+        if getattr(self.moe, "fuses_residual", False):
+            # B200 block: `x_spatial + moe_out` (:571) happens in the combine kernel, in x_spatial's dtype
+            h, moe_kl, probs = self.moe(x_norm, w, annealing_factor, residual=x_spatial)
+        else:
+            moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
+            h = x_spatial + moe_out.to(x_spatial.dtype)
         if kl_losses is not None:
             kl_losses.append(moe_kl)
-        return self.proj_out(x_spatial + moe_out.to(x_spatial.dtype), w), probs
+        return self.proj_out(h, w), probs
 
 
 class GenerativeBlock(nn.Module):

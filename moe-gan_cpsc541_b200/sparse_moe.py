@@ -128,6 +128,7 @@ class SparseMoE(nn.Module):
         self.experts = nn.ModuleList([SparseExpertFFN(dim) for _ in range(num_experts)])
         self.router = BayesianRouter(dim, text_dim, num_experts)
         self._wcache = WeightCache()
+        self.fuses_residual = True   # forward(..., residual=) adds the skip connection inside the combine kernel
         self.redraw_eps = True    # False = parity mode "use the epsilon_* buffers as they are" 
         self.last_load: Optional[torch.Tensor] = None   # fused per-expert prob column sums of the last forward
 
@@ -150,7 +151,10 @@ class SparseMoE(nn.Module):
         return 0 if torch.is_autocast_enabled() else 1
 
     def forward(self, x: torch.Tensor, w: torch.Tensor, annealing_factor: float = 1.0, *,
-                eps: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+                eps: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None, residual: Optional[torch.Tensor] = None):
+        """Reference contract (t2i_moe_gan.py:444-491).  `residual` (optional, [B,d,H,W], same memory layout as x): return
+        `residual + moe(x)` in the residual's dtype - the skip connection of AttentionBlock (:571) fused into the combine
+        kernel."""
         if not x.is_cuda:
             raise RuntimeError("SparseMoE (B200 path) needs CUDA tensors: there is no CPU fallback")
         batch_size, channels, height, width = x.shape
@@ -182,11 +186,16 @@ class SparseMoE(nn.Module):
         cfg = MoEConfig(B=batch_size, tokens_per_sample=height * width, d=channels, Dt=w.shape[1], E=E, k=k,
                         dense=dense, hard=hard, precision=precision, sampled=training, annealing_factor=af,
                         need_backward=need_bwd)
+        res_tok = None
+        if residual is not None:
+            if residual.shape != x.shape:
+                raise ValueError(f"residual {tuple(residual.shape)} must have the shape of x {tuple(x.shape)}")
+            res_tok = residual.permute(0, 2, 3, 1).contiguous().view(-1, channels)      # a view for NHWC memory
         with torch.autocast(device_type="cuda", enabled=False):
-            out, kl, probs, load = MoEBlockFunction.apply(cfg, self._wcache, x_tok, w, eps[0], eps[1], eps[2], *params, *expert_params)
+            out, kl, probs, load = MoEBlockFunction.apply(cfg, self._wcache, x_tok, w, eps[0], eps[1], eps[2], *params, res_tok, *expert_params)
         self.last_load = load
         probs._moegan_load = load          # lets moe_balance_loss() use the fused column sums
-        if out.dtype != x.dtype:
+        if residual is None and out.dtype != x.dtype:
             out = out.to(x.dtype)
         output = out.reshape(batch_size, height, width, channels).permute(0, 3, 1, 2)   # (:486)
         return output, kl, probs

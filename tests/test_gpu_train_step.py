@@ -164,3 +164,39 @@ def test_bayesian_router_forward_matches_block_probs():
     text = w.repeat_interleave(16, dim=0)                 # the reference's per-token expansion (:456)
     probs, logits = moe.router(feat, text, sampling=False, annealing_factor=1.5)
     assert torch.equal(probs, probs_blk) and logits.shape == (32, 4) and float(logits.abs().max()) <= 20.0
+
+
+@pytest.mark.parametrize("res_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("top_k", [None, 2])
+def test_fused_residual_equals_separate_add(res_dtype, top_k):
+    """forward(..., residual=r) == r + forward(...) (t2i_moe_gan.py:571), outputs and every gradient; the
+    upstream gradient arrives in the residual's dtype and is consumed as such by the combine backward."""
+    pkg = G_.pkg()
+    torch.manual_seed(0)
+    moe = pkg.SparseMoE(128, 64, 4, top_k=top_k, precision="fp32").cuda()
+    moe.redraw_eps = False
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    x0 = nhwc(torch.randn(3, 128, 8, 8, device="cuda")); w0 = torch.randn(3, 64, device="cuda")
+    r0 = nhwc(torch.randn(3, 128, 8, 8, device="cuda")).to(res_dtype)
+    go = nhwc(torch.randn(3, 128, 8, 8, device="cuda")).to(res_dtype)
+    res = []
+    for fused in (True, False):
+        moe.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True); w = w0.clone().requires_grad_(True); r = r0.clone().requires_grad_(True)
+        if fused:
+            out, kl, probs = moe(x, w, 1.5, residual=r)
+        else:
+            o, kl, probs = moe(x, w, 1.5)
+            out = r + o.to(res_dtype)
+        assert out.dtype == res_dtype and out.shape == x.shape
+        torch.autograd.backward([out, kl], [go, torch.full((), 1e-3, device="cuda")])
+        res.append((out.detach().float(), x.grad.clone(), w.grad.clone(), r.grad.float().clone(),
+                    {n: p.grad.clone() for n, p in moe.named_parameters() if p.grad is not None}))
+    a, b = res
+    tol = 0.0 if res_dtype == torch.float32 else 2e-2
+    rel = lambda u, v: float((u - v).abs().max() / v.abs().max().clamp_min(1e-30))
+    assert rel(a[0], b[0]) <= tol
+    assert torch.equal(a[3], b[3])                               # d residual = upstream gradient, untouched
+    assert rel(a[1], b[1]) <= 1e-6 and rel(a[2], b[2]) <= 1e-5   # same dout values reach the block either way
+    for n in a[4]:
+        assert rel(a[4][n], b[4][n]) <= 1e-5, n
