@@ -173,29 +173,43 @@ struct WeightPtrs {
     const float* w2[MOEGAN_MAX_EXPERTS];
     const float* b2[MOEGAN_MAX_EXPERTS];
 };
+// grid (x, 2E): blockIdx.y = (which, expert) selects one [rows, cols] fp32 matrix; it is a plain linear fp32 -> bf16 copy in bf16
+// mode (same row-major layout on both sides), so the inner loop has no index arithmetic beyond the grid stride; 4 independent
+// 16-byte loads per thread and iteration.  (The first version decoded (which, e, row, col) from a flat index with three 64-bit
+// divisions per element and ran at 2.9 TB/s.)
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const WeightPtrs ptrs, int E, int d, int split, __nv_bfloat16* __restrict__ W1_op, float* __restrict__ b1s,
                     __nv_bfloat16* __restrict__ W2_op, float* __restrict__ b2s) {
     const int hid = 4 * d;
-    const long long per = (long long)hid * d / 4;          // float4 per weight matrix
-    const long long total = 2 * per * E;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int which = (int)(i / (per * E));            // 0: W1 [4d, d], 1: W2 [d, 4d]
-        const long long r = i - (long long)which * per * E;
-        const int e = (int)(r / per);
-        const long long q = r - (long long)e * per;
-        const int cols = which == 0 ? d : hid, rows = which == 0 ? hid : d;
-        const int c4 = cols / 4;
-        const int row = (int)(q / c4), c = (int)(q - (long long)row * c4) * 4;
-        const float* src = (which == 0 ? ptrs.w1[e] : ptrs.w2[e]) + (long long)row * cols + c;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-        __nv_bfloat16* dst = (which == 0 ? W1_op : W2_op) + ((long long)e * rows + row) * (split ? 2 * cols : cols) + c;
-        store_operand4(dst, cols, split, v);
+    const int which = blockIdx.y / E, e = blockIdx.y - which * E;      // 0: W1 [4d, d], 1: W2 [d, 4d]
+    const int cols = which == 0 ? d : hid, rows = which == 0 ? hid : d;
+    const int per = rows * (cols / 4);                                  // float4 per matrix
+    const float4* src = reinterpret_cast<const float4*>(which == 0 ? ptrs.w1[e] : ptrs.w2[e]);
+    __nv_bfloat16* dstm = (which == 0 ? W1_op : W2_op) + (size_t)e * rows * (split ? 2 * cols : cols);
+    const int stride = gridDim.x * blockDim.x;
+    for (int q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < per; q0 += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int q = q0 + u * stride; if (q < per) v[u] = __ldg(src + q); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * stride;
+            if (q < per) {
+                if (!split) {
+                    *reinterpret_cast<uint2*>(dstm + (size_t)q * 4) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+                } else {
+                    const int c4 = cols / 4;
+                    const int row = q / c4, c = (q - row * c4) * 4;
+                    store_operand4(dstm + (size_t)row * 2 * cols + c, cols, true, v[u]);
+                }
+            }
+        }
     }
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gsz = gridDim.x * blockDim.x;
-    for (int i = gtid; i < E * hid; i += gsz) b1s[i] = ptrs.b1[i / hid][i % hid];
-    for (int i = gtid; i < E * d; i += gsz) b2s[i] = ptrs.b2[i / d][i % d];
+    if (blockIdx.y == 0) {
+        const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+        for (int i = gtid; i < E * hid; i += stride) b1s[i] = ptrs.b1[i / hid][i % hid];
+        for (int i = gtid; i < E * d; i += stride) b2s[i] = ptrs.b2[i / d][i % d];
+    }
 }
 
 // =====================================================================================================
@@ -459,11 +473,12 @@ int launch_prep_weights(const moegan_shape* s, const float* const* w1, const flo
         const int q = e < s->E ? e : 0;
         p.w1[e] = w1[q]; p.b1[e] = b1[q]; p.w2[e] = w2[q]; p.b2[e] = b2[q];
     }
-    const long long total = 2LL * s->E * 4 * s->d * s->d / 4;
-    long long blocks = ceil_div64(total, 256);
-    const long long cap = (long long)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    prep_weights_kernel<<<(int)blocks, 256, 0, st>>>(p, s->E, s->d, s->precision == 1, reinterpret_cast<__nv_bfloat16*>(W1_op), b1s,
+    const long long per = 4LL * s->d * s->d / 4;                        // float4 per matrix
+    long long bx = ceil_div64(per, 256 * 4);                            // 4 float4 per thread
+    const long long cap = ceil_div64((long long)num_sms() * 8, 2 * s->E);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    prep_weights_kernel<<<dim3((unsigned)bx, (unsigned)(2 * s->E)), 256, 0, st>>>(p, s->E, s->d, s->precision == 1, reinterpret_cast<__nv_bfloat16*>(W1_op), b1s,
                                                      reinterpret_cast<__nv_bfloat16*>(W2_op), b2s);
     MOEGAN_CHECK_LAUNCH("prep_weights_kernel");
     return MOEGAN_OK;

@@ -35,10 +35,14 @@ g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g): step()
 for _ in range(5): g.replay()
 torch.cuda.synchronize()
+NREP = 4
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    g.replay(); torch.cuda.synchronize()
+    for _ in range(NREP): g.replay()
+    torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
+per = len(evs) // NREP
+evs = evs[(NREP - 1) * per:]                 # the last of NREP back-to-back replays (no profiler start-up effects)
 t0 = evs[0].time_range.start
 print(f"{len(evs)} kernels, span {(max(e.time_range.end for e in evs) - t0):.1f} us")
 for e in evs:
