@@ -278,6 +278,13 @@ int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, cons
                              int32_t P, int32_t C, float slope, void* dx, void* ds, void* scratch, int64_t scratch_bytes,
                              void* stream);
 
+/* replaces: the bias gradient `grad_output.sum(0)` of the nn.Linear projections applied to all T tokens inside
+ * AttentionBlock (nn.MultiheadAttention in_proj / out_proj, t2i_moe_gan.py:516-517, used :545,:557): out[c] = sum_r x[r,c].
+ * x [rows, cols] fp32 or bf16, cols % 4 == 0; out fp32 [cols]; deterministic. */
+int64_t moegan_colsum_scratch_bytes(int64_t rows, int32_t cols);
+int moegan_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, float* out, void* scratch, int64_t scratch_bytes,
+                  void* stream);
+
 /* replaces: the learned-offset resampling of ModulatedTransformationModule (t2i_moe_gan.py:219-240):
  * grid = clamp(meshgrid(linspace(-1,1)) + 0.05 * off, -1, 1);  out = F.grid_sample(x, grid, bilinear, zeros,
  * align_corners=False).  x / out / g / dx: NHWC [B,H,W,C] fp32 or bf16; off / doff: fp32 [B,H,W,2] = (x, y) offsets

@@ -92,6 +92,8 @@ SIGNATURES = {
     "moegan_channel_scale_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "moegan_channel_scale_bwd_scratch_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "moegan_channel_scale_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),
+    "moegan_colsum_scratch_bytes": (c_int64, [c_int64, c_int32]),
+    "moegan_colsum": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, c_int64, _P]),
     "moegan_offset_sample_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "moegan_offset_sample_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "moegan_umma_gemm": (c_int32, [c_int32] * 5 + [_P] * 3 + [_P]),

@@ -825,6 +825,19 @@ int moegan_channel_scale_bwd(const void* g, const void* x, int32_t is_bf16, cons
                    MOEGAN_ERR_MISALIGNED, "channel_scale_bwd: pointers must be 16-byte aligned");
     return launch_channel_scale_bwd(g, x, is_bf16, s, s_is_bf16, B, P, C, slope, dx, ds, reinterpret_cast<float*>(scratch), (cudaStream_t)stream);
 }
+int64_t moegan_colsum_scratch_bytes(int64_t rows, int32_t cols) {
+    if (rows <= 0 || cols <= 0) return 256;
+    return (int64_t)colsum_splits(rows, cols) * cols * 4 + 256;
+}
+int moegan_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, float* out, void* scratch, int64_t scratch_bytes, void* stream) {
+    MOEGAN_REQUIRE(rows >= 0 && cols >= 0 && cols % 4 == 0, MOEGAN_ERR_BAD_SHAPE, "colsum: cols (%d) must be a multiple of 4, rows (%lld) >= 0",
+                   cols, (long long)rows);
+    REQ_PTR(x); REQ_PTR(out); REQ_PTR(scratch);
+    MOEGAN_REQUIRE(scratch_bytes >= moegan_colsum_scratch_bytes(rows, cols), MOEGAN_ERR_BAD_SHAPE, "colsum: scratch too small");
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0,
+                   MOEGAN_ERR_MISALIGNED, "colsum: pointers must be 16-byte aligned");
+    return launch_colsum(x, is_bf16, rows, cols, out, reinterpret_cast<float*>(scratch), (cudaStream_t)stream);
+}
 int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H, int32_t W, int32_t C, void* out,
                              void* stream) {
     RUN(check_nhwc("offset_sample_fwd", B, H * W, C));

@@ -207,6 +207,40 @@ partial_sum_tall_kernel(const float* __restrict__ part, int n, int nparts, float
 }
 
 // =====================================================================================================
+// column sums of a tall matrix: out[c] = sum_r x[r, c]  (bias gradient of a Linear applied to [T, d] tokens; ATen's generic
+// reduction needs ~80 us for a bf16 [65 536, 128] input).  CTA = 128 columns x one row split; thread = 4 columns, 8 row lanes,
+// 4 rows in flight; partials [nsplit][cols] are summed in a fixed order -> deterministic.
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const T* __restrict__ x, long long rows, int cols, int nsplit, float* __restrict__ part) {
+    __shared__ float4 red[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + cx * 4;
+    const long long per = (rows + nsplit - 1) / nsplit;
+    const long long r0 = (long long)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    if (c < cols) {
+        long long r = r0 + ry;
+        for (; r + 24 < r1; r += 32) {
+            const float4 v0 = Vec4<T>::load(x + r * cols + c), v1 = Vec4<T>::load(x + (r + 8) * cols + c);
+            const float4 v2 = Vec4<T>::load(x + (r + 16) * cols + c), v3 = Vec4<T>::load(x + (r + 24) * cols + c);
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;  a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;  a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        }
+        for (; r < r1; r += 8) { const float4 v0 = Vec4<T>::load(x + r * cols + c); a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w; }
+    }
+    red[ry][cx] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float4 a = red[0][cx];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { const float4 b = red[w][cx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * cols + c) = a;
+    }
+}
+
+// =====================================================================================================
 // channel_scale: out[b, p, c] = lrelu(x[b, p, c] * s[b, c], slope)      x: [B, P, C] (NHWC), s: [B, C] fp32
 // =====================================================================================================
 // forward: grid-stride over groups of 4 channels
@@ -518,6 +552,29 @@ int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const void*
     if (s_bf16) partial_sum_kernel<bf><<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, reinterpret_cast<bf*>(ds));
     else        partial_sum_kernel<float><<<ceil_div(B * C, 256), 256, 0, st>>>(scratch, B * C, ps, reinterpret_cast<float*>(ds));
     MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
+    return MOEGAN_OK;
+}
+
+int colsum_splits(long long rows, int cols) {
+    const long long col_ctas = (cols + 127) / 128;
+    long long ns = ((long long)num_sms() * 4 + col_ctas - 1) / col_ctas;     // ~4 CTAs per SM in total
+    const long long max_ns = rows / 64 > 1 ? rows / 64 : 1;                  // >= 64 rows per split
+    if (ns > max_ns) ns = max_ns;
+    return (int)(ns < 1 ? 1 : ns);
+}
+int launch_colsum(const void* x, int bf16, long long rows, int cols, float* out, float* scratch, cudaStream_t st) {
+    if (cols == 0) return MOEGAN_OK;
+    if (rows == 0) { MOEGAN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * 4, st)); return MOEGAN_OK; }
+    const int ns = colsum_splits(rows, cols);
+    dim3 grid((cols + 127) / 128, ns);
+    float* part = ns == 1 ? out : scratch;
+    if (bf16) colsum_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ns, part);
+    else      colsum_rows_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, cols, ns, part);
+    MOEGAN_CHECK_LAUNCH("colsum_rows_kernel");
+    if (ns > 1) {
+        partial_sum_kernel<float><<<ceil_div(cols, 256), 256, 0, st>>>(scratch, cols, ns, out);
+        MOEGAN_CHECK_LAUNCH("partial_sum_kernel");
+    }
     return MOEGAN_OK;
 }
 

@@ -66,6 +66,8 @@ int channel_scale_psplit(int B, int P, int C);
 int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st);
 int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* dx,
                              void* ds, float* scratch, cudaStream_t st);
+int colsum_splits(long long rows, int cols);
+int launch_colsum(const void* x, int bf16, long long rows, int cols, float* out, float* scratch, cudaStream_t st);
 int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, int H, int W, int C, void* out, cudaStream_t st);
 int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float* off, int B, int H, int W, int C, void* dx, float* doff,
                              cudaStream_t st);

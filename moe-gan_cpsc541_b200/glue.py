@@ -118,6 +118,75 @@ def channel_scale(x: torch.Tensor, s: torch.Tensor, slope: float = 1.0) -> torch
 
 
 # --------------------------------------------------------------------------------------------------
+# Linear over all tokens with a fast bias gradient; nn.MultiheadAttention evaluated through it (t2i_moe_gan.py:516-517,:545,:557)
+# --------------------------------------------------------------------------------------------------
+def colsum(x2: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a contiguous [rows, cols] fp32 / bf16 CUDA matrix (deterministic)."""
+    rows, cols = x2.shape
+    lib = C.lib()
+    out = torch.empty(cols, device=x2.device, dtype=torch.float32)
+    nbytes = int(lib.moegan_colsum_scratch_bytes(rows, cols))
+    scratch = torch.empty(nbytes, device=x2.device, dtype=torch.uint8)
+    C.check(lib.moegan_colsum(C.ptr(x2), _is_bf16(x2), rows, cols, C.ptr(out), C.ptr(scratch), nbytes, _stream()), "moegan_colsum")
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b as autocast would compute it (operands in the autocast dtype, cuBLAS), with the bias gradient
+    `grad_y.sum(0)` - a [T, d] -> [d] reduction that ATen runs at a few percent of HBM bandwidth - by the library's kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        xc, wc = x.to(dt), weight.to(dt)
+        with torch.autocast("cuda", enabled=False):
+            y = F.linear(xc, wc, bias.to(dt))
+        ctx.save_for_backward(xc, wc)
+        ctx.dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, wc = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if g2.dtype not in (torch.float32, torch.bfloat16):
+            g2 = g2.float()
+        g2 = g2.contiguous()
+        gm = g2 if g2.dtype == wc.dtype else g2.to(wc.dtype)
+        x2 = xc.reshape(-1, xc.shape[-1])
+        gx = (gm @ wc).view(xc.shape).to(ctx.dtypes[0])
+        gw = (gm.t() @ x2).to(ctx.dtypes[1])
+        gb = colsum(g2).to(ctx.dtypes[2])
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """`F.linear(x, weight, bias)`; on CUDA the bias gradient comes from `moegan_colsum`."""
+    if x.is_cuda and bias is not None and weight.shape[0] % 4 == 0 and x.dtype in (torch.float32, torch.bfloat16):
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+def multihead_attention(m: torch.nn.MultiheadAttention, query: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
+    """`m(query, key, key, need_weights=False)[0]` for a batch_first nn.MultiheadAttention without masks or dropout - the same
+    packed in-projection, scaled_dot_product_attention and out-projection `F.multi_head_attention_forward` performs, with the
+    token-wide projections going through `linear` above.  Parameters (and state_dict keys) stay those of the module."""
+    d, h = m.embed_dim, m.num_heads
+    W, bvec = m.in_proj_weight, m.in_proj_bias
+    if query is key:
+        q, k, v = linear(query, W, bvec).chunk(3, dim=-1)
+    else:
+        q = linear(query, W[:d], bvec[:d])
+        k, v = F.linear(key, W[d:], bvec[d:]).chunk(2, dim=-1)
+    B, L, S = q.shape[0], q.shape[1], k.shape[1]
+    q = q.reshape(B, L, h, d // h).transpose(1, 2)
+    k = k.reshape(B, S, h, d // h).transpose(1, 2)
+    v = v.reshape(B, S, h, d // h).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, d)
+    return linear(o, m.out_proj.weight, m.out_proj.bias)
+
+
+# --------------------------------------------------------------------------------------------------
 # learned-offset bilinear resampling (ModulatedTransformationModule, t2i_moe_gan.py:219-240)
 # --------------------------------------------------------------------------------------------------
 class _OffsetSampleFn(torch.autograd.Function):

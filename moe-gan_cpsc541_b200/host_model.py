@@ -51,7 +51,8 @@ class ModulatedConv(nn.Module):
         slope = 1.0 if act_slope is None else float(act_slope)
         if self.demodulate:
             wsq = self.weight.float().pow(2).sum(dim=(2, 3))              # [out, in]
-            d = torch.rsqrt(s.float().pow(2) @ wsq.t() + 1e-8)            # [B, out]
+            with torch.autocast(x.device.type, enabled=False):            # fp32 as in the reference; no bf16 round trips of s^2 / wsq
+                d = torch.rsqrt(s.float().pow(2) @ wsq.t() + 1e-8)        # [B, out]
             return glue.channel_scale(y, d, slope)
         return y if act_slope is None else F.leaky_relu(y, slope)
 
@@ -107,9 +108,9 @@ class AttentionBlock(nn.Module):
         ln = lambda m, v, dt=torch.float32: glue.layer_norm(v, m.weight, m.bias, m.eps, dt)
         t = self.proj_in(x, w).permute(0, 2, 3, 1).reshape(B, H * W, C)
         n = ln(self.norm1, t, mm)
-        t = t + self.self_attn(n, n, n, need_weights=False)[0]
+        t = t + glue.multihead_attention(self.self_attn, n, n)            # = self.self_attn(n, n, n, need_weights=False)[0]
         tp = self.text_proj(text_seq)
-        t = t + self.cross_attn(ln(self.norm2, t, mm), tp, tp, need_weights=False)[0]
+        t = t + glue.multihead_attention(self.cross_attn, ln(self.norm2, t, mm), tp)
         x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
         x_norm = ln(self.norm3, t).reshape(B, H, W, C).permute(0, 3, 1, 2)  # NCHW view of NHWC memory (:561)
         if getattr(self.moe, "fuses_residual", False):

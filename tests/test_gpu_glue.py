@@ -184,3 +184,45 @@ def test_fused_real_pass_matches_reference_formulation_on_gpu(monkeypatch):
     assert _rel(a[0], b[0]) < 1e-5 and _rel(a[1], b[1]) < 1e-5 and _rel(a[2], b[2]) < 1e-4
     for n in a[3]:
         assert _rel(a[3][n], b[3][n]) < 1e-3, n
+
+
+@pytest.mark.parametrize("rows,cols", [(65536, 128), (16384, 768), (300, 384), (1, 128), (70001, 4), (5000, 1000)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum_matches_torch(rows, cols, dtype):
+    glue = G_.pkg().glue
+    x = torch.randn(rows, cols, generator=torch.Generator().manual_seed(rows + cols)).to(dtype)
+    got = glue.colsum(x.cuda())
+    assert got.dtype == torch.float32 and got.shape == (cols,)
+    assert _rel(got, x.double().sum(0)) < 2e-5
+    assert torch.equal(got, glue.colsum(x.cuda()))          # deterministic
+
+
+def test_linear_and_multihead_attention_match_torch(monkeypatch):
+    """glue.linear == F.linear (values, all gradients); glue.multihead_attention == nn.MultiheadAttention(need_weights=False),
+    self- and cross-attention (key length 1, as AttentionBlock uses it), fp32 with TF32 off."""
+    glue = G_.pkg().glue
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(256, 384).cuda()
+    x = torch.randn(5, 77, 256, device="cuda", requires_grad=True); go = torch.randn(5, 77, 384, device="cuda")
+    y = glue.linear(x, lin.weight, lin.bias); y.backward(go)
+    got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None; lin.zero_grad()
+    yr = torch.nn.functional.linear(x, lin.weight, lin.bias); yr.backward(go)
+    for a, b in zip(got, (yr.detach(), x.grad, lin.weight.grad, lin.bias.grad)):
+        assert _rel(a, b) < 1e-5
+    mha = torch.nn.MultiheadAttention(256, 8, batch_first=True).cuda()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(); mha.out_proj.bias.normal_()
+    for cross in (False, True):
+        q = torch.randn(3, 64, 256, device="cuda", requires_grad=True)
+        kv = torch.randn(3, 1, 256, device="cuda", requires_grad=True) if cross else q
+        g = torch.randn(3, 64, 256, device="cuda")
+        res = []
+        for fn in (lambda: glue.multihead_attention(mha, q, kv), lambda: mha(q, kv, kv, need_weights=False)[0]):
+            mha.zero_grad(); q.grad = None
+            if cross: kv.grad = None
+            o = fn(); o.backward(g)
+            res.append([o.detach(), q.grad.clone(), kv.grad.clone()] + [p.grad.clone() for p in mha.parameters()])
+        for a, b in zip(*res):
+            assert _rel(a, b) < 2e-5
