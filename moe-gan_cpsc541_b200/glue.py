@@ -167,6 +167,27 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.T
     return F.linear(x, weight, bias)
 
 
+class _ChannelBiasFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, bias):
+        ctx.bias_dtype = bias.dtype
+        return y + bias.to(y.dtype).view(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        gc = _nhwc(g if g.dtype in (torch.float32, torch.bfloat16) else g.float())
+        gb = colsum(gc.permute(0, 2, 3, 1).reshape(-1, gc.shape[1]))          # NHWC memory = a [B*H*W, C] matrix
+        return g, gb.to(ctx.bias_dtype)
+
+
+def add_channel_bias(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """`y + bias[None, :, None, None]` (the bias of a convolution evaluated without one); on CUDA its gradient
+    `grad.sum((0, 2, 3))` comes from `moegan_colsum` over the NHWC view instead of ATen's strided reduction."""
+    if y.is_cuda and y.dim() == 4 and y.shape[1] % 4 == 0:
+        return _ChannelBiasFn.apply(y, bias)
+    return y + bias.to(y.dtype).view(1, -1, 1, 1)
+
+
 def multihead_attention(m: torch.nn.MultiheadAttention, query: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
     """`m(query, key, key, need_weights=False)[0]` for a batch_first nn.MultiheadAttention without masks or dropout - the same
     packed in-projection, scaled_dot_product_attention and out-projection `F.multi_head_attention_forward` performs, with the

@@ -260,9 +260,9 @@ def discriminator_real_pass(D: "AuroraDiscriminator", real, text, text_mismatche
     c1, c2, c3 = D.conv_layers[0], D.conv_layers[2], D.output_layer[0]
     slope = D.conv_layers[1].negative_slope
     W1, W2, W3 = c1.weight, c2.weight, c3.weight        # weight_norm parametrisations: evaluate once
-    a1 = F.conv2d(real, W1, c1.bias, stride=2, padding=1)
+    a1 = glue.add_channel_bias(F.conv2d(real, W1, None, stride=2, padding=1), c1.bias)     # bias gradient by the library's column sum
     h1 = F.leaky_relu(a1, slope)
-    a2 = F.conv2d(h1, W2, c2.bias, stride=2, padding=1)
+    a2 = glue.add_channel_bias(F.conv2d(h1, W2, None, stride=2, padding=1), c2.bias)
     f = F.leaky_relu(a2, slope)
 
     def head(txt):
