@@ -274,10 +274,10 @@ def discriminator_real_pass(D: "AuroraDiscriminator", real, text, text_mismatche
     # adjoint of real_pred.sum(): the seed is all-ones and identical for every sample
     seed = torch.ones(1, 1, out_real.shape[2], out_real.shape[3], device=real.device, dtype=out_real.dtype)
     d_f = F.conv_transpose2d(seed, W3)[:, : f.shape[1]]                          # [1,256,16,16]
-    one, sl = torch.ones((), device=real.device, dtype=d_f.dtype), torch.full((), slope, device=real.device, dtype=d_f.dtype)
-    d_a2 = d_f * torch.where(a2 > 0, one, sl)                                    # [B,256,16,16]
+    lrelu_adj = torch.ops.aten.leaky_relu_backward                               # grad * (x > 0 ? 1 : slope): one kernel, differentiable
+    d_a2 = lrelu_adj(d_f.expand_as(a2), a2, slope, False)                        # [B,256,16,16]
     d_h1 = F.conv_transpose2d(d_a2, W2, stride=2, padding=1)
-    d_a1 = d_h1 * torch.where(a1 > 0, one, sl)
+    d_a1 = lrelu_adj(d_h1, a1, slope, False)
     grad_real = F.conv_transpose2d(d_a1, W1, stride=2, padding=1)                # = d real_pred.sum() / d real
     r1 = (r1_gamma / 2) * grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1).pow(2).mean()
     return real_pred, mismatched_pred, r1
