@@ -260,7 +260,19 @@ class Timer:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item()), int(n1 - n0), host_ms
 
-    def gemm_profile(self, fn, steps):
+    def lead(self, lead_ms):
+        """Keep the GPU busy for ~lead_ms (a spin kernel) so that the host enqueues the profiled step AHEAD of the device: eager
+        launches are host-bound here (~5 us of Python per launch), and an event pair around a kernel that the GPU has to wait for
+        measures the wait, not the kernel.  With the queue full, begin -> end is the kernel plus the inter-kernel gap only."""
+        if lead_ms <= 0:
+            return
+        try:
+            khz = self.torch.cuda.get_device_properties(self.dev).clock_rate
+        except Exception:
+            khz = 1965000
+        self.torch.cuda._sleep(int(lead_ms * khz))
+
+    def gemm_profile(self, fn, steps, lead_ms=0.0):
         """Durations (ms) of every tcgen05 GEMM launch in `steps` eager steps, measured by CUDA events the library
         records around the launch on its own stream."""
         C = importlib.import_module(PKG)._cabi
@@ -268,6 +280,7 @@ class Timer:
         self.barrier()
         for _ in range(steps):
             self.flush.zero_()
+            self.lead(lead_ms)
             fn()
         self.barrier()
         cap = 4096 * max(steps, 1)
@@ -276,6 +289,158 @@ class Timer:
         n = self.lib.moegan_debug_profile_read(ms_buf, tag_buf, cap)
         self.lib.moegan_debug_profile_enable(0)
         return [ms_buf[i] for i in range(n)], [tag_buf[i] for i in range(n)]
+
+    def kernel_profile(self, fn, steps, lead_ms=0.0):
+        """[(ms, tag, meta8)] of EVERY launch of the library in `steps` eager steps (level-2 profiling: CUDA events recorded by
+        the library on the launching stream around each kernel)."""
+        C = importlib.import_module(PKG)._cabi
+        self.lib.moegan_debug_profile_enable(2)
+        self.barrier()
+        for _ in range(steps):
+            self.flush.zero_()
+            self.lead(lead_ms)
+            fn()
+        self.barrier()
+        cap = 8192 * max(steps, 1)
+        ms_buf, tag_buf, meta_buf = (C.c_float * cap)(), (C.c_int32 * cap)(), (C.c_int32 * (8 * cap))()
+        n = self.lib.moegan_debug_profile_read_ex(ms_buf, tag_buf, meta_buf, cap)
+        self.lib.moegan_debug_profile_enable(0)
+        return [(ms_buf[i], tag_buf[i], tuple(meta_buf[8 * i: 8 * i + 8])) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------------------
+# per-kernel roofline table (SURVEY 8(d)): algorithmic bytes / flops of every launcher of the library, from the
+# shape metadata the library attaches to its profiling records (include/moegan_sm100.h, MOEGAN_PROF_*)
+# --------------------------------------------------------------------------------------------------
+PROF_BASE = 2000000
+PROF_NAMES = {1: "sample_kl(+kl_finalize)", 2: "text_fwd", 3: "router_fwd", 4: "plan", 5: "gather", 6: "to_operand", 7: "prep_weights",
+              8: "combine_fwd", 9: "combine_bwd", 10: "slab_sum", 11: "uncombine", 12: "router_bwd_logits(+dtl)", 13: "router_bwd_small",
+              14: "router_bwd_text", 15: "reparam_kl_bwd", 16: "sum_partials", 17: "colsum_grouped", 18: "balance_loss",
+              20: "layernorm_fwd", 21: "layernorm_bwd", 22: "channel_scale_fwd", 23: "channel_scale_bwd", 24: "offset_sample_fwd",
+              25: "offset_sample_bwd", 26: "colsum"}
+GEMM_KINDS = {0: "rows x W^T (K-major B)", 1: "rows x W (MN-major B)", 2: "wgrad A^T B"}
+GEMM_EPI = {0: "f32", 1: "bf16", 2: "bias+bf16", 3: "bias+f32", 4: "bias+GELU", 5: "bias+GELU fp32x3", 6: "xGELU'", 7: "xGELU' fp32x3"}
+NOMINAL_HBM_GBS = 8000.0     # the figure north_star quotes
+
+
+def fp32_fma_peak_tflops(pk):
+    """148 SMs x 128 fp32 lanes x 2 flop x max SM clock: the CUDA-core bound of the fp32 router projection (nominal, not measured)."""
+    return 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+
+
+def kernel_model(tag, meta, Dt=512):
+    """(name, shape label, algorithmic bytes, algorithmic flops, bound) of one profiling record; bytes / flops None = latency-bound."""
+    m = list(meta)
+    H = 128
+    if tag < PROF_BASE:                                          # tcgen05 GEMM: meta[4..7] = N, K | dimA, host rows | -1, group size
+        kind, BN, epi, cta2 = (tag % 10000) // 1000, tag % 1000, (tag // 10000) % 10, tag // 100000
+        T, d, E, fl = m[0], m[1], m[2], m[3]
+        k, dense = fl & 0xff, bool(fl & 0x100)
+        N, K, rows, grp, two_out = m[4], m[5], m[6], m[7] & 0xffff, bool(m[7] & 0x10000)
+        R = rows if rows >= 0 else (T * E if dense else T * k)   # grouped GEMMs: the dispatched rows (padding rows are not work)
+        flops = 2.0 * R * N * K
+        S = 2 if fl & 0x400 else 1
+        # operand bytes: A rows x K (or rows x dimA for wgrad) + B (weights, or rows x N for wgrad) + the output
+        if kind == 2:
+            byt = R * K * 2 * S + R * N * 2 * S + max(grp, 1) * K * N * 4
+        else:
+            out_b = {0: 4, 1: 2, 2: 2, 3: 4, 4: 2 * (2 if two_out else 1), 5: 8, 6: 2 + 2, 7: 4 + 4}.get(epi, 4)   # outputs (+ the aux tile read)
+            byt = R * K * 2 * S + max(grp, 1) * N * K * 2 * S + R * N * out_b + (R // 32 * N * 4 if epi in (6, 7) else 0)
+        name = f"umma_gemm<{BN},{kind},{'pair' if cta2 else '1cta'},{epi}> {GEMM_EPI.get(epi, epi)}{' +GELU\' out' if (epi == 4 and two_out) else ''}"
+        return name, f"R={R} N={N} K={K} groups={grp}", float(byt), flops, "tensor"
+    kid = tag - PROF_BASE
+    name = PROF_NAMES.get(kid, f"kernel{kid}")
+    if kid >= 20 or kid in (6, 10, 16, 17, 18):                  # layers around the block and helpers with their own metadata
+        a, b, c, bits = m[0], m[1], m[2], m[3]
+        sz = lambda bit: 2 if bits & bit else 4
+        if kid == 20: return name, f"rows={a} d={b}", float(a * b * (sz(1) + sz(2)) + a * 8), None, "hbm"
+        if kid == 21: return name, f"rows={a} d={b}", float(a * b * (sz(1) + 2 * sz(2)) + a * 8), None, "hbm"
+        if kid == 22: return name, f"B={a} P={b} C={c}", float(a * b * c * 2 * sz(1) + a * c * sz(2)), None, "hbm"
+        if kid == 23: return name, f"B={a} P={b} C={c}", float(a * b * c * 3 * sz(1) + 2 * a * c * sz(2)), None, "hbm"
+        if kid == 24: return name, f"B={a} P={b} C={c}", float(a * b * c * 2 * sz(1) + a * b * 8), None, "hbm"
+        if kid == 25: return name, f"B={a} P={b} C={c}", float(a * b * c * 3 * sz(1) + 2 * a * b * 8), None, "hbm"
+        if kid == 26: return name, f"rows={a} cols={b}", float(a * b * sz(1)), None, "hbm"
+        if kid == 6:  return name, f"rows={a} cols={b}", float(a * b * (4 + (4 if bits & 0x400 else 2))), None, "hbm"
+        if kid == 10: return name, f"m_cap={a} cols={b}", float(a // 32 * b * 4 + c * b * 4), None, "hbm"
+        if kid == 16: return name, f"n={a} splits={b}", float(a * (b + 1) * 4), None, "hbm"
+        if kid == 17: return name, f"m_cap={a} cols={b}", float(a * b * 2), None, "hbm"
+        return name, "", None, None, "latency"
+    T, d, E, fl = m[0], m[1], m[2], m[3]
+    k, dense, fp32 = fl & 0xff, bool(fl & 0x100), bool(fl & 0x400)
+    R = T * E if dense else T * k
+    kk = E if dense else k
+    S = 2 if fp32 else 1
+    act = 4 if fp32 else 2                                       # y / dx rows
+    nrt = H * (d + Dt) + 2 * H * E                               # router weight elements
+    label = f"T={T} d={d} E={E} k={kk}{' dense' if dense else ''}"
+    if kid == 1:  return name, label, float(5 * nrt * 4), None, "hbm"
+    if kid == 3:
+        byt = T * d * 4 + H * d * 4 + T * (2 * E + 2 * kk) * 4 + (T * H * 4 if fl & 0x1000 else 0)
+        return name, label, float(byt), 2.0 * T * d * H + 2.0 * T * H * E, "fp32"
+    if kid == 5:  return name, label, float(T * d * 4 + T * k * 8 + R * d * 2 * S + (T * d * 2 * S if fl & 0x1000 else 0) + R * 8 + T * k * 4), None, "hbm"
+    if kid == 7:  return name, label, float(E * 8 * d * d * (4 + 2 * S) + 2 * E * 5 * d * 4), None, "hbm"
+    if kid == 8:
+        res = 4 if fl & 0x1000 else (2 if fl & 0x2000 else 0)
+        return name, label, float(R * d * act + T * kk * 4 * (1 if dense else 2) + T * d * res + T * d * (2 if fl & 0x4000 else 4)), None, "hbm"
+    if kid == 9:  return name, label, float(T * d * (2 if fl & 0x1000 else 4) + R * d * act + R * d * 2 * S + R * 8 + R // 32 * d * 4), None, "hbm"
+    if kid == 11: return name, label, float(R * d * act + (T * d * 4 if fl & 0x1000 else 0) + T * d * 4), None, "hbm"
+    if kid == 12: return name, label, float(T * (H * 4 + H * 2 * S + 3 * E * 4) + R * 4), None, "hbm"
+    if kid == 15: return name, label, float(7 * nrt * 4), None, "hbm"
+    return name, label, None, None, "latency"                    # text_fwd, plan, router_bwd_small / text: a few KB, latency-bound
+
+
+def kernel_table(records, steps, pk):
+    """records: [(ms, tag, meta8)] of `steps` eager steps -> rows sorted by time per step.  GB/s against the measured copy
+    bandwidth (MEASURED_PEAKS.json) and against the 8 TB/s nominal; TFLOP/s against the measured bf16 peak (tensor) or the
+    nominal fp32 FMA peak (router projection).  Event-bracketed durations include the ~1-2 us gap between queued launches."""
+    groups = {}
+    for ms, tag, meta in records:
+        groups.setdefault((tag, tuple(meta)), []).append(ms)
+    hbm = float(pk.get("hbm_gbs", 6453.7))
+    tens = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+    f32 = fp32_fma_peak_tflops(pk)
+    rows = []
+    for (tag, meta), v in groups.items():
+        name, label, byt, flops, bound = kernel_model(tag, meta)
+        us = 1e3 * sum(v) / len(v)
+        row = {"kernel": name, "shape": label, "launches_per_step": round(len(v) / max(steps, 1), 2), "us": round(us, 2),
+               "us_per_step": round(1e3 * sum(v) / max(steps, 1), 1), "bound": bound}
+        if byt is not None and us > 0:
+            gbs = byt / (us * 1e-6) / 1e9
+            row.update({"bytes": int(byt), "GBps": round(gbs, 1), "frac_hbm_measured": round(gbs / hbm, 3), "frac_hbm_8TBps": round(gbs / NOMINAL_HBM_GBS, 3)})
+        if flops is not None and us > 0:
+            tf = flops / (us * 1e-6) / 1e12
+            row.update({"flops": flops, "TFLOPps": round(tf, 2), "frac_compute": round(tf / (tens if bound == "tensor" else f32), 3)})
+        if bound == "tensor" and byt is not None and flops is not None:
+            # which roof is lower for this instance: time at the measured tensor peak vs time at the measured HBM bandwidth
+            t_t, t_m = flops / (tens * 1e12), byt / (hbm * 1e9)
+            row["roof"] = "hbm" if t_m > t_t else "tensor"
+            row["frac_of_roof"] = round(max(t_t, t_m) / (us * 1e-6), 3)
+        elif bound == "hbm" and "frac_hbm_measured" in row:
+            row["roof"], row["frac_of_roof"] = "hbm", row["frac_hbm_measured"]
+        elif bound == "fp32" and "frac_compute" in row:
+            row["roof"], row["frac_of_roof"] = "fp32_fma", row["frac_compute"]
+        rows.append(row)
+    rows.sort(key=lambda r: -r["us_per_step"])
+    return rows
+
+
+def write_kernel_table(path, title, rows, append=False):
+    if not path:
+        return
+    with open(path, "a" if append else "w") as f:
+        f.write(f"### per-kernel roofline: {title}\n\n")
+        f.write("CUDA events recorded by the library around each launch on its stream (eager pass, L2 flushed between steps; ~1-2 us of "
+                "launch gap inside every figure).  bytes / flops = ALGORITHMIC (DESIGN.md section 4); GB/s against the measured copy bandwidth "
+                "of MEASURED_PEAKS.json and the 8 TB/s nominal; `frac of roof` = time at the lower of the two roofs / measured time.\n\n")
+        f.write("| kernel | shape | n/step | us | us/step | MB | GB/s | of measured HBM | of 8 TB/s | TFLOP/s | roof | frac of roof |\n")
+        f.write("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|\n")
+        g = lambda r, k, fmt="{}": fmt.format(r[k]) if k in r else ""
+        for r in rows:
+            f.write(f"| `{r['kernel']}` | {r['shape']} | {r['launches_per_step']} | {r['us']} | {r['us_per_step']} | "
+                    f"{(r['bytes'] / 1e6 if 'bytes' in r else 0):.1f} | {g(r, 'GBps')} | {g(r, 'frac_hbm_measured')} | {g(r, 'frac_hbm_8TBps')} | "
+                    f"{g(r, 'TFLOPps')} | {r.get('roof', r['bound'])} | {g(r, 'frac_of_roof')} |\n")
+        f.write("\n")
 
 
 def traffic_from_profiles(key):
@@ -357,7 +522,9 @@ def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
     if launches_per_graph is not None:
         launches = launches_per_graph * steps
     e2e_ms, _, _ = T_.run(step_e2e, steps, max(2, warmup // 2))
-    ms_list, _ = T_.gemm_profile(step_device, steps)
+    ms_list, _ = T_.gemm_profile(step_device, steps, lead_ms=2.0)
+    nk = max(2, min(steps, 10))
+    kernels = kernel_table(T_.kernel_profile(step_device, nk, lead_ms=3.0), nk, peaks())
     per_step = len(ms_list) // steps if steps else 0
     names = ["ffn1_fwd", "ffn2_fwd", "dgrad2", "dgrad1", "wgrad2", "wgrad1"]     # the six expert GEMMs lead each step's router GEMMs
     by_kernel = {}
@@ -381,7 +548,7 @@ def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernels timed individually)" if pk else "fallback 1590 (B200_PROFILING.md)",
                      "traffic": traffic_from_profiles("umma_gemm_moe_block"), "flops_per_launch": flops_per_launch,
                      "mean_launch_us": mean_ms * 1e3, "per_kernel_us": {k: 1e3 * sum(v) / len(v) for k, v in by_kernel.items()}},
-        "tokens": T,
+        "tokens": T, "kernels": kernels,
     }
 
 
@@ -446,7 +613,8 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     # roofline of the tcgen05 grouped GEMM family inside the step (eager pass; events recorded by the library)
     eager = trainer if launch_mode == "eager" else make_trainer(False)
     nprof = max(2, min(steps, 4))
-    ms_list, tags = T_.gemm_profile(lambda: eager._step_impl(real, text), nprof)
+    ms_list, tags = T_.gemm_profile(lambda: eager._step_impl(real, text), nprof, lead_ms=15.0)
+    kernels = kernel_table(T_.kernel_profile(lambda: eager._step_impl(real, text), nprof, lead_ms=25.0), nprof, peaks())
     per_step = len(ms_list) // nprof if nprof else 0
     # every expert GEMM of every block has the same algorithmic flops: 2*M*N*K with M = E*T, {N,K} = {4d, d} -> 8*E*T*d^2,
     # and T*d^2 = 16*B*512^2 is the same for the three blocks.  Per step: 3 blocks x (2 forwards x 2 GEMMs +
@@ -470,6 +638,7 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
                      "traffic": traffic_from_profiles("umma_gemm_train_step"), "flops_per_launch": flops_per_launch,
                      "gemm_ms_per_step": step_gemm_ms, "gemm_launches_per_step": per_step,
                      "gemm_share_of_step": step_gemm_ms / ms_per_step if ms_per_step else None},
+        "kernels": kernels,
     }
     # ---- inference (configs[4]): generate_images semantics, eval-mode hard top-1 routing ----
     try:
@@ -516,7 +685,9 @@ def run_b200_arm(args, rank, world, local_rank):
             "cpu_baseline": {"value": units / sec, "unit": "tokens/s", "cores": cpu_threads(), "kind": "port",
                              "sample": f"full step (T={units}) x 5 reps, median {sec * 1e3:.0f} ms; numpy fp32 oracle port"},
             "moe_block_fwd_bwd_us": r["ms_per_step"] * 1e3, "host_enqueue_us_per_step": r["host_enqueue_us_per_step"],
+            "kernels": r["kernels"],
         }
+        write_kernel_table(args.kernels_out, line["config"]["workload"], r["kernels"])
         print(json.dumps(line), flush=True)
         return
 
@@ -544,10 +715,15 @@ def run_b200_arm(args, rank, world, local_rank):
                    "allreduce": f"NCCL, {os.environ.get('MOEGAN_BENCH_BUCKET_MB', '25')} MB buckets from grad-ready hooks on a comm stream" if world > 1 else None},
         "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "cpu_baseline": cpu,
         "host_enqueue_us_per_step": r["host_enqueue_us_per_step"], "inference": r.get("inference"),
+        # per-kernel roofline of the library's launches inside the step (eager pass, library-recorded CUDA events): the 24 largest
+        "kernels": r["kernels"][:24],
+        "library_us_per_step": round(sum(k["us_per_step"] for k in r["kernels"]), 1),
     }
+    write_kernel_table(args.kernels_out, line["config"]["workload"], r["kernels"])
     if mb is not None and "error" not in mb:
         line["moe_block"] = {"fwd_bwd_us": mb["ms_per_step"] * 1e3, "tokens_per_s": mb["tokens_per_s"], "launch": mb["launch"],
-                             "workload": moe_block_workload_name(), "roofline": mb["roofline"], "e2e": mb["e2e"]}
+                             "workload": moe_block_workload_name(), "roofline": mb["roofline"], "e2e": mb["e2e"], "kernels": mb["kernels"]}
+        write_kernel_table(args.kernels_out, moe_block_workload_name(), mb["kernels"], append=True)
     elif mb is not None:
         line["moe_block"] = mb
     print(json.dumps(line), flush=True)
@@ -563,6 +739,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-extras", action="store_true", help="skip the embedded moe_block microbench")
+    ap.add_argument("--kernels-out", default=None, help="also write the per-kernel roofline table(s) as markdown to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define MOEGAN_ABI_VERSION 3
+#define MOEGAN_ABI_VERSION 4
 #define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
@@ -305,11 +305,28 @@ int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int3
 int64_t moegan_stream_capture_id(void* stream);
 /* instrumentation for bench.py: number of kernel launches this library has enqueued so far (all threads) */
 int64_t moegan_debug_launch_count(void);
-/* GEMM profiling: when enabled, every tcgen05 GEMM launch is bracketed by cudaEventRecord on its own stream.
- * moegan_debug_profile_read synchronises those events and returns up to max_n (ms, flops-tag) records in
- * launch order, then clears the list.  tag = the `kind * 1000 + BN` of the launch. */
-int moegan_debug_profile_enable(int32_t on);
+/* Profiling for bench.py: CUDA events recorded by the library around its own launches, on the stream of the launch.
+ *   level 0 off; 1 = the tcgen05 GEMMs only; 2 = every kernel launcher (not during CUDA-graph capture).
+ * GEMM records carry tag = kind * 1000 + BN + 100000 * cta_pair + 10000 * epilogue (< MOEGAN_PROF_KERNEL_BASE); the other
+ * launchers tag = MOEGAN_PROF_KERNEL_BASE + MOEGAN_PROF_<kernel>.  meta[0..3] = {T, d, E, flags} of the block call the launch
+ * belongs to (flags: bits 0-7 k, 0x100 dense, 0x200 hard, 0x400 fp32 mode, 0x1000.. kernel-specific dtype bits, see
+ * bench.py), or {rows / B, d / P, C, dtype bits} for the layers around the block; meta[4..7] = {N, K (or the A dimension of a
+ * weight-gradient GEMM), host-known rows or -1, experts in the group} for GEMM records, 0 otherwise.
+ * moegan_debug_profile_read returns the GEMM records only (ms, tag), moegan_debug_profile_read_ex all records (ms, tag,
+ * meta[8]) in launch order; both synchronise the events and clear the list. */
+#define MOEGAN_PROF_KERNEL_BASE 2000000
+enum {
+    MOEGAN_PROF_SAMPLE_KL = 1, MOEGAN_PROF_TEXT_FWD = 2, MOEGAN_PROF_ROUTER_FWD = 3, MOEGAN_PROF_PLAN = 4, MOEGAN_PROF_GATHER = 5,
+    MOEGAN_PROF_TO_OPERAND = 6, MOEGAN_PROF_PREP_WEIGHTS = 7, MOEGAN_PROF_COMBINE_FWD = 8, MOEGAN_PROF_COMBINE_BWD = 9,
+    MOEGAN_PROF_SLAB_SUM = 10, MOEGAN_PROF_UNCOMBINE = 11, MOEGAN_PROF_ROUTER_BWD_LOGITS = 12, MOEGAN_PROF_ROUTER_BWD_SMALL = 13,
+    MOEGAN_PROF_ROUTER_BWD_TEXT = 14, MOEGAN_PROF_REPARAM_KL_BWD = 15, MOEGAN_PROF_SUM_PARTIALS = 16, MOEGAN_PROF_COLSUM_GROUPED = 17,
+    MOEGAN_PROF_BALANCE = 18,
+    MOEGAN_PROF_LAYERNORM_FWD = 20, MOEGAN_PROF_LAYERNORM_BWD = 21, MOEGAN_PROF_CHANNEL_SCALE_FWD = 22, MOEGAN_PROF_CHANNEL_SCALE_BWD = 23,
+    MOEGAN_PROF_OFFSET_SAMPLE_FWD = 24, MOEGAN_PROF_OFFSET_SAMPLE_BWD = 25, MOEGAN_PROF_COLSUM = 26
+};
+int moegan_debug_profile_enable(int32_t level);
 int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n);
+int moegan_debug_profile_read_ex(float* ms_out, int32_t* tag_out, int32_t* meta_out, int32_t max_n);
 /* debug: override the MN-major shared-memory descriptor parameters of the GEMM (0 = built-in defaults) */
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes);
 /* fp32 [rows, cols] -> bf16 operand [rows, S*cols] */

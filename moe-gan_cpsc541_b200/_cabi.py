@@ -17,7 +17,7 @@ MAX_EXPERTS = 32
 MAX_TOPK = 8
 CHUNK = 32
 KL_OUT_FLOATS = 2 + 256
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Shape(ctypes.Structure):
@@ -102,6 +102,7 @@ SIGNATURES = {
     "moegan_stream_capture_id": (c_int64, [_P]),
     "moegan_debug_profile_enable": (c_int32, [c_int32]),
     "moegan_debug_profile_read": (c_int32, [_P, _P, c_int32]),
+    "moegan_debug_profile_read_ex": (c_int32, [_P, _P, _P, c_int32]),
     "moegan_to_operand": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P]),
 }
 

@@ -36,16 +36,26 @@ int num_sms() {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// ---- optional GEMM profiling (bench.py) ----
-struct ProfRec { cudaEvent_t beg, end; int tag; };
+// ---- optional profiling (bench.py): see common.cuh ----
+struct ProfRec { cudaEvent_t beg, end; int tag; int meta[8]; };
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
-static bool g_prof_on = false;
-bool profile_begin(cudaStream_t st, int tag, void** handle) {
+static std::atomic<int> g_prof_level{0};
+static thread_local int t_prof_shape[4] = {0, 0, 0, 0};
+int profile_level() { return g_prof_level.load(std::memory_order_relaxed); }
+void profile_note_shape(const moegan_shape* s) {
+    if (g_prof_level.load(std::memory_order_relaxed) == 0 || s == nullptr) return;
+    t_prof_shape[0] = s->T; t_prof_shape[1] = s->d; t_prof_shape[2] = s->E; t_prof_shape[3] = prof_shape_flags(s);
+}
+bool profile_begin(cudaStream_t st, int tag, const int* meta_lo, const int* meta_hi, void** handle) {
     *handle = nullptr;
-    if (!g_prof_on) return false;
+    if (profile_level() == 0) return false;
     ProfRec* r = new ProfRec;
     r->tag = tag;
+    for (int i = 0; i < 4; ++i) {
+        r->meta[i] = meta_lo != nullptr ? meta_lo[i] : t_prof_shape[i];
+        r->meta[4 + i] = meta_hi != nullptr ? meta_hi[i] : 0;
+    }
     if (cudaEventCreate(&r->beg) != cudaSuccess || cudaEventCreate(&r->end) != cudaSuccess) { delete r; return false; }
     cudaEventRecord(r->beg, st);
     *handle = r;
@@ -151,6 +161,7 @@ using namespace moegan;
     do {                                                      \
         int _rc = validate_shape(s);                          \
         if (_rc != MOEGAN_OK) return _rc;                     \
+        profile_note_shape(s);                                \
     } while (0)
 #define RUN(expr)                                             \
     do {                                                      \
@@ -184,23 +195,34 @@ int64_t moegan_stream_capture_id(void* stream) {
     if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &st, &id) != cudaSuccess) { cudaGetLastError(); return -1; }
     return st == cudaStreamCaptureStatusActive ? (int64_t)id : 0;
 }
-int moegan_debug_profile_enable(int32_t on) {
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof_on = on != 0;
+int moegan_debug_profile_enable(int32_t level) {
+    g_prof_level.store(level < 0 ? 0 : level);
     return MOEGAN_OK;
 }
-int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n) {
+// gemm_only: drop (and free) the records of the other kernels - the contract of the original moegan_debug_profile_read
+static int profile_drain(float* ms_out, int32_t* tag_out, int32_t* meta_out, int32_t max_n, bool gemm_only) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     int n = 0;
     for (auto& r : g_prof) {
-        cudaEventSynchronize(r.end);
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, r.beg, r.end);
-        if (n < max_n) { if (ms_out) ms_out[n] = ms; if (tag_out) tag_out[n] = r.tag; ++n; }
+        const bool keep = !gemm_only || r.tag < MOEGAN_PROF_KERNEL_BASE;
+        if (keep && n < max_n) {
+            cudaEventSynchronize(r.end);
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, r.beg, r.end);
+            if (ms_out) ms_out[n] = ms;
+            if (tag_out) tag_out[n] = r.tag;
+            if (meta_out) for (int i = 0; i < 8; ++i) meta_out[8 * n + i] = r.meta[i];
+            ++n;
+        }
         cudaEventDestroy(r.beg); cudaEventDestroy(r.end);
     }
     g_prof.clear();
+    cudaGetLastError();
     return n;
+}
+int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n) { return profile_drain(ms_out, tag_out, nullptr, max_n, true); }
+int moegan_debug_profile_read_ex(float* ms_out, int32_t* tag_out, int32_t* meta_out, int32_t max_n) {
+    return profile_drain(ms_out, tag_out, meta_out, max_n, false);
 }
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes) {
     g_mn_lbo = lbo_bytes; g_mn_sbo = sbo_bytes; g_mn_kadv = kadv_bytes;
@@ -452,7 +474,9 @@ int moegan_uncombine_bwd(const moegan_shape* s, const void* dx_rows, const int32
     return launch_uncombine(s, dx_rows, token_rows, dx_router, dx, (cudaStream_t)stream);
 }
 
-int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w, const float* Wf, const float* Wt, const float* Wc,
+// dx_router_done (optional): recorded on `stream` right after the GEMM that produces dx_router - the un-permute of the block's
+// backward waits for that, not for the rest of the chain
+static int router_bwd_core(const moegan_shape* s, const void* x_copy, const float* w, const float* Wf, const float* Wt, const float* Wc,
                       const void* Wf_op, const void* Wt_op, const float* fp, const float* tp, const float* raw,
                       const int32_t* topk_idx, const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext,
                       const float* dload, const float* temperature, float annealing_factor, int32_t sampled,
@@ -460,7 +484,8 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
                       const float* eps_t, const float* mu_c, const float* rho_c, const float* eps_c,
                       const float* kl_out, const float* dkl,
                       float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c,
-                      float* dtemperature, float* dx_router, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+                      float* dtemperature, float* dx_router, float* dw, void* workspace, int64_t workspace_bytes, void* stream,
+                           cudaEvent_t dx_router_done) {
     CHECK_SHAPE(s);
     MOEGAN_REQUIRE(!s->hard, MOEGAN_ERR_UNSUPPORTED, "router_bwd: hard (eval) routing has no gradient");
     MOEGAN_REQUIRE(s->T > 0, MOEGAN_ERR_BAD_SHAPE, "router_bwd: T must be positive");
@@ -513,6 +538,7 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
         p.m_blocks_host = ceil_div(s->T, 128); p.out_rows_valid = s->T;
         p.out0 = dx_router; p.ld_out0 = d;
         RUN(launch_umma_gemm(GEMM_ROWS_BK, BN, A, B, p, (long long)p.m_blocks_host * (d / BN), st));
+        if (dx_router_done != nullptr) MOEGAN_CHECK_CUDA(cudaEventRecord(dx_router_done, st));
     }
     {   // dWf [d, 128] = x^T dfp
         GemmOperand A{x_copy, S * d, (uint64_t)s->T, S * d};
@@ -549,6 +575,20 @@ int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w,
     return MOEGAN_OK;
 }
 
+int moegan_router_bwd(const moegan_shape* s, const void* x_copy, const float* w, const float* Wf, const float* Wt, const float* Wc,
+                      const void* Wf_op, const void* Wt_op, const float* fp, const float* tp, const float* raw,
+                      const int32_t* topk_idx, const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext,
+                      const float* dload, const float* temperature, float annealing_factor, int32_t sampled,
+                      const float* mu_f, const float* rho_f, const float* eps_f, const float* mu_t, const float* rho_t,
+                      const float* eps_t, const float* mu_c, const float* rho_c, const float* eps_c,
+                      const float* kl_out, const float* dkl,
+                      float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c,
+                      float* dtemperature, float* dx_router, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+    return router_bwd_core(s, x_copy, w, Wf, Wt, Wc, Wf_op, Wt_op, fp, tp, raw, topk_idx, token_rows, dgate_row, dprobs_ext, dload, temperature,
+                           annealing_factor, sampled, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c, kl_out, dkl,
+                           dmu_f, drho_f, dmu_t, drho_t, dmu_c, drho_c, dtemperature, dx_router, dw, workspace, workspace_bytes, stream, nullptr);
+}
+
 int moegan_balance_loss_fwd(const float* load, int32_t E, int32_t T, float balance_weight, float* loss, void* stream) {
     REQ_PTR(load); REQ_PTR(loss);
     MOEGAN_REQUIRE(E >= 1 && E <= MOEGAN_MAX_EXPERTS && T > 0, MOEGAN_ERR_BAD_SHAPE, "balance_loss: bad E (%d) or T (%d)", E, T);
@@ -563,7 +603,8 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
 // ---- side stream: independent sub-chains of a block call run concurrently with the expert GEMMs ----------
 // (the router's backward chain / the weight conversion are many small launches that leave most SMs idle).  Fork and join
 // are cudaEventRecord / cudaStreamWaitEvent pairs, so the pattern is legal inside CUDA-graph capture too.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr; bool ok = false, tried = false; };
+struct SideStream { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, join2 = nullptr, dxr = nullptr;
+                    bool ok = false, tried = false; };
 static SideStream g_side;
 static std::mutex g_side_mu;
 static bool side_enabled() {
@@ -587,6 +628,9 @@ static SideStream* side_stream() {
     if (!g_side.tried) {
         g_side.tried = true;
         g_side.ok = cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&g_side.s2, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&g_side.join2, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&g_side.dxr, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) == cudaSuccess &&
                     cudaEventCreateWithFlags(&g_side.mid, cudaEventDisableTiming) == cudaSuccess;
@@ -742,31 +786,43 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dy_slabs = reinterpret_cast<float*>(ws + W.dy_slabs);
     RUN(moegan_combine_bwd(s, I(L.plan), a->dout, a->dout_is_bf16, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row,
                            dy_slabs, stream));
-    // the router's backward only needs dgate_row: run it on the side stream while the expert GEMMs own the main stream
+    // Small blocks (side_pays): three concurrent chains after combine_bwd -
+    //   caller's stream : dgrad2 -> dgrad1 -> wgrad2 -> wgrad1 -> [dx_router ready] -> uncombine
+    //   side stream 1   : the router's backward (it only needs dgate_row); signals `dxr` once dx_router exists
+    //   side stream 2   : the two bias-gradient slab sums (db2 at once, db1 once dgrad2 is done) - nothing waits for them
+    // so the tail after the last weight-gradient GEMM is one un-permute, not five serial launches.
     SideStream* ss = (s->hard || !side_pays(s)) ? nullptr : side_stream();
     void* rstream = stream;
-    if (ss != nullptr) { RUN(side_fork(ss, (cudaStream_t)stream)); rstream = ss->s; }
-    // with a side stream the bias-gradient slab sums leave the GEMM chain (they run after the router chain, db1 once dgrad2 is done)
+    if (ss != nullptr) {
+        RUN(side_fork(ss, (cudaStream_t)stream));
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s2, ss->fork, 0));
+        rstream = ss->s;
+    }
     const FfnBwdScratch SL = ffn_bwd_scratch_layout(s);
     float* slab_stage = reinterpret_cast<float*>(ws + W.ffn_scratch + SL.slab_stage);
     RUN(ffn_bwd_core(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
                      a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream, ss != nullptr,
                      ss != nullptr ? ss->mid : nullptr));
     if (!s->hard) {
-        RUN(moegan_router_bwd(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
-                              I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
-                              a->sampled, a->mu_f, a->rho_f, F(L.eps_f), a->mu_t, a->rho_t, F(L.eps_t), a->mu_c, a->rho_c, F(L.eps_c),
-                              a->kl_out, a->sampled ? a->dkl : nullptr,
-                              a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
-                              ws + W.router_ws, (int64_t)router_bwd_layout(s).total, rstream));
+        RUN(router_bwd_core(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
+                            I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
+                            a->sampled, a->mu_f, a->rho_f, F(L.eps_f), a->mu_t, a->rho_t, F(L.eps_t), a->mu_c, a->rho_c, F(L.eps_c),
+                            a->kl_out, a->sampled ? a->dkl : nullptr,
+                            a->dmu_f, a->drho_f, a->dmu_t, a->drho_t, a->dmu_c, a->drho_c, a->dtemperature, dx_router, a->dw,
+                            ws + W.router_ws, (int64_t)router_bwd_layout(s).total, rstream, ss != nullptr ? ss->dxr : nullptr));
     }
     if (ss != nullptr) {
-        RUN(launch_slab_sum(s, I(L.plan), dy_slabs, s->d, slab_stage, a->db2, ss->s));      // after the router chain: nothing waits for it
-        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s, ss->mid, 0));
-        RUN(launch_slab_sum(s, I(L.plan), reinterpret_cast<const float*>(ws + W.ffn_scratch + SL.dpre_slabs), 4 * s->d, slab_stage, a->db1, ss->s));
-        RUN(side_join(ss, (cudaStream_t)stream));
+        RUN(launch_slab_sum(s, I(L.plan), dy_slabs, s->d, slab_stage, a->db2, ss->s2));
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s2, ss->mid, 0));
+        RUN(launch_slab_sum(s, I(L.plan), reinterpret_cast<const float*>(ws + W.ffn_scratch + SL.dpre_slabs), 4 * s->d, slab_stage, a->db1, ss->s2));
+        MOEGAN_CHECK_CUDA(cudaEventRecord(ss->join2, ss->s2));
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->dxr, 0));
     }
     RUN(moegan_uncombine_bwd(s, ws + W.dx_rows, I(L.token_rows), dx_router, a->dx, stream));
+    if (ss != nullptr) {
+        RUN(side_join(ss, (cudaStream_t)stream));
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->join2, 0));
+    }
     return MOEGAN_OK;
 }
 

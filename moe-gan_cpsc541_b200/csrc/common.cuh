@@ -50,6 +50,38 @@ void count_launch();
 
 int validate_shape(const moegan_shape* s);
 
+// ---- bench instrumentation (api.cu): CUDA events around launches, recorded on the launching stream ----------
+// level 0: off; 1: the tcgen05 GEMMs only; 2: every kernel launcher of the library (MOEGAN_PROF_* ids, include/moegan_sm100.h).
+// A record carries 8 ints of metadata (4: shape of the block call / of the layer, 4: GEMM dimensions) so that bench.py can attach
+// algorithmic bytes / flops to it.
+int profile_level();
+void profile_note_shape(const moegan_shape* s);                       // shape of the block call the following launches belong to
+bool profile_begin(cudaStream_t st, int tag, const int* meta_lo, const int* meta_hi, void** handle);   // 4 + 4 ints; lo == nullptr: the noted shape
+void profile_end(cudaStream_t st, void* handle);
+inline int prof_shape_flags(const moegan_shape* s) {
+    return (s->k & 0xff) | (s->dense ? 0x100 : 0) | (s->hard ? 0x200 : 0) | (s->precision == 1 ? 0x400 : 0);
+}
+struct ProfScope {
+    void* h = nullptr;
+    cudaStream_t st;
+    ProfScope(cudaStream_t s, int id, const moegan_shape* sh, int extra_flags = 0) : st(s) {
+        if (profile_level() >= 2) {
+            const int m[4] = {sh->T, sh->d, sh->E, prof_shape_flags(sh) | extra_flags};
+            profile_begin(s, MOEGAN_PROF_KERNEL_BASE + id, m, nullptr, &h);
+        }
+    }
+    ProfScope(cudaStream_t s, int id, long long m0, int m1, int m2, int m3) : st(s) {
+        if (profile_level() >= 2) {
+            const int m[4] = {(int)m0, m1, m2, m3};
+            profile_begin(s, MOEGAN_PROF_KERNEL_BASE + id, m, nullptr, &h);
+        }
+    }
+    ~ProfScope() { if (h != nullptr) profile_end(st, h); }
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+};
+
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int row_pad(int rows) { return (rows + MOEGAN_ROW_ALIGN - 1) / MOEGAN_ROW_ALIGN * MOEGAN_ROW_ALIGN; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

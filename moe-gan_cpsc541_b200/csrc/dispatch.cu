@@ -9,7 +9,6 @@ namespace moegan {
 
 namespace {
 
-constexpr int MAX_SEG = 8;   // d <= 1024: a warp covers 128 columns per segment (32 lanes x 4)
 
 // =====================================================================================================
 // plan: histogram totals -> padded expert offsets, block->expert map, per-chunk bases, balance load
@@ -231,99 +230,169 @@ __device__ __forceinline__ void store4_any(void* base, size_t elem_off, float4 v
     else      *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off) = v;
 }
 
+// loads kept in their storage format until use (a pending bf16 load holds 2 registers, not 4)
+template <bool F32> struct Raw4 { typedef uint2 type; };
+template <> struct Raw4<true> { typedef float4 type; };
+template <bool F32>
+__device__ __forceinline__ typename Raw4<F32>::type raw_load4(const void* base, size_t elem_off) {
+    if constexpr (F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    else               return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+}
+__device__ __forceinline__ float4 raw_to_float4(float4 v) { return v; }
+__device__ __forceinline__ float4 raw_to_float4(uint2 u) {
+    return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
+}
+
+// Memory-level parallelism: these kernels only move bytes, so what bounds them is how many loads a warp keeps in flight
+// (B200 needs ~30 KB outstanding per SM to saturate HBM).  NSEG (= d / 128) is a template parameter, the slot / row loops are
+// processed in batches whose loads are ALL issued before the first use (batch x NSEG = 8 independent 8/16-byte loads per lane),
+// and the arithmetic keeps the reference's accumulation order (slot order == expert order), so results do not depend on the batch.
+// TokBatch consecutive tokens per warp x SlotBatch slots per pass x NSEG segments = 16 independent loads per lane: with d = 128 a
+// token's rows are only 256 B each, and a warp that handles ONE token lives for a single memory round trip (18 waves of such CTAs at
+// T = 65 536 ran at 0.3 of the HBM roof).  Consecutive tokens are adjacent rows of every expert segment in dense mode.
+template <int NSEG> struct TokBatch { static constexpr int value = NSEG == 1 ? 4 : (NSEG == 2 ? 2 : 1); };
+template <int NSEG> struct SlotBatch { static constexpr int value = NSEG >= 8 ? 2 : (NSEG >= 4 ? 16 / NSEG : 4); };
+
 // RES: 0 = no residual, 1 = fp32 residual, 2 = bf16 residual (`x_spatial + moe_out`, t2i_moe_gan.py:571, in the
 // combine's epilogue); OUT_BF16: write the result in bf16 (the dtype of the residual stream under autocast)
-template <bool Y_F32, int RES, bool OUT_BF16>
-__global__ void __launch_bounds__(256)
+template <bool Y_F32, int RES, bool OUT_BF16, int NSEG>
+__global__ void __launch_bounds__(256, 2)
 combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, const int* __restrict__ token_rows,
                    int T, int T_pad, int d, int k, int dense, const void* __restrict__ residual, void* __restrict__ out) {
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    constexpr int JB = SlotBatch<NSEG>::value, TB = TokBatch<NSEG>::value;
+    const int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * TB;
     const int lane = threadIdx.x & 31;
-    if (t >= T) return;
-    const int nseg = d / 128;
-    float4 acc[MAX_SEG];
+    if (t0 >= T) return;
+    typename Raw4<RES != 2>::type res[TB][NSEG];
+    if (RES != 0) {
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < k; ++j) {                     // slot order == expert order in dense mode (:467)
-        const int row = dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j);
-        const float g = __ldg(gates + (size_t)t * k + j);
+        for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int s = 0; s < MAX_SEG; ++s) {
-            if (s < nseg) {
-                const float4 v = load_row4<Y_F32>(y, (size_t)row * d + s * 128 + lane * 4);
-                acc[s].x = fmaf(g, v.x, acc[s].x); acc[s].y = fmaf(g, v.y, acc[s].y);
-                acc[s].z = fmaf(g, v.z, acc[s].z); acc[s].w = fmaf(g, v.w, acc[s].w);
+            for (int s = 0; s < NSEG; ++s)
+                if (t0 + i < T) res[i][s] = raw_load4<RES != 2>(residual, (size_t)(t0 + i) * d + s * 128 + lane * 4);
+    }
+    float4 acc[TB][NSEG];
+#pragma unroll
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) acc[i][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < k; j0 += JB) {              // slot order == expert order in dense mode (:467)
+        int row[TB][JB]; float g[TB][JB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) {
+                const int j = j0 + jj, t = t0 + i;
+                const bool ok = j < k && t < T;
+                row[i][jj] = ok ? (dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j)) : -1;
+                g[i][jj] = ok ? __ldg(gates + (size_t)t * k + j) : 0.0f;
             }
-        }
+        typename Raw4<Y_F32>::type v[TB][JB][NSEG];
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+                for (int s = 0; s < NSEG; ++s)
+                    if (row[i][jj] >= 0) v[i][jj][s] = raw_load4<Y_F32>(y, (size_t)row[i][jj] * d + s * 128 + lane * 4);
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+                if (row[i][jj] >= 0) {
+#pragma unroll
+                    for (int s = 0; s < NSEG; ++s) {
+                        const float4 f = raw_to_float4(v[i][jj][s]);
+                        acc[i][s].x = fmaf(g[i][jj], f.x, acc[i][s].x); acc[i][s].y = fmaf(g[i][jj], f.y, acc[i][s].y);
+                        acc[i][s].z = fmaf(g[i][jj], f.z, acc[i][s].z); acc[i][s].w = fmaf(g[i][jj], f.w, acc[i][s].w);
+                    }
+                }
     }
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s)
-        if (s < nseg) {
-            const size_t o = (size_t)t * d + s * 128 + lane * 4;
-            if (RES != 0) {
-                const float4 r = load4_any<RES == 2>(residual, o);
-                acc[s].x += r.x; acc[s].y += r.y; acc[s].z += r.z; acc[s].w += r.w;
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s)
+            if (t0 + i < T) {
+                float4 a = acc[i][s];
+                if (RES != 0) { const float4 r = raw_to_float4(res[i][s]); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+                store4_any<OUT_BF16>(out, (size_t)(t0 + i) * d + s * 128 + lane * 4, a);
             }
-            store4_any<OUT_BF16>(out, o, acc[s]);
-        }
 }
 
 // combine backward: CTA = 32 consecutive dispatched rows (never straddles experts: segments are 256-row aligned), 4 rows per
 // warp.  Also emits the column sums of the CTA's 32 dy rows (colpart [m_cap / 32, d]) - the second Linear's bias gradient
 // is their per-expert sum, so dy is never re-read for it.
-template <bool Y_F32, bool DOUT_BF16>
+template <bool Y_F32, bool DOUT_BF16, int NSEG>
 __global__ void __launch_bounds__(256)
 combine_bwd_kernel(const int* __restrict__ plan, const void* __restrict__ dout, const void* __restrict__ y,
                    const int* __restrict__ row_token, const float* __restrict__ row_gate, const float* __restrict__ gates,
                    int T, int T_pad, int d, int E, int dense, int split,
                    __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row, float* __restrict__ colpart) {
-    __shared__ float4 red[8][MAX_SEG * 32];
+    constexpr int IB = NSEG == 1 ? 4 : (NSEG == 2 ? 2 : 1);     // rows whose loads are in flight together (2 * IB * NSEG per lane)
+    __shared__ float4 red[8][NSEG * 32];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x * 32 >= __ldg(plan + 1)) return;    // rows in use (a multiple of 128)
     const int ld = split ? 2 * d : d;
-    const int nseg = d / 128;
-    float4 cs[MAX_SEG];
+    float4 cs[NSEG];
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s) cs[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < 4; ++i) {
-        const int r = blockIdx.x * 32 + i * 8 + wid;
-        int t; float g;
-        if (dense) {
-            const int e = r / T_pad; t = r - e * T_pad;
-            if (t >= T) t = -1;
-            g = t >= 0 ? __ldg(gates + (size_t)t * E + e) : 0.0f;
-        } else {
-            t = __ldg(row_token + r);
-            g = t >= 0 ? __ldg(row_gate + r) : 0.0f;
-        }
-        __nv_bfloat16* dst = dy_op + (size_t)r * ld;
-        if (t < 0) {                                   // padding row: zero (the wgrad GEMMs sum over it)
-            for (int j = lane; j < ld / 4; j += 32) reinterpret_cast<uint2*>(dst)[j] = make_uint2(0u, 0u);
-            if (lane == 0) dgate_row[r] = 0.0f;
-            continue;
-        }
-        float dot = 0.0f;
+    for (int s = 0; s < NSEG; ++s) cs[s] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < MAX_SEG; ++s) {
-            if (s < nseg) {
+    for (int i0 = 0; i0 < 4; i0 += IB) {
+        int tok[IB]; float g[IB];
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) {
+            const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
+            int t;
+            if (dense) {
+                const int e = r / T_pad; t = r - e * T_pad;
+                if (t >= T) t = -1;
+                g[ii] = t >= 0 ? __ldg(gates + (size_t)t * E + e) : 0.0f;
+            } else {
+                t = __ldg(row_token + r);
+                g[ii] = t >= 0 ? __ldg(row_gate + r) : 0.0f;
+            }
+            tok[ii] = t;
+        }
+        typename Raw4<!DOUT_BF16>::type go[IB][NSEG];
+        typename Raw4<Y_F32>::type yv[IB][NSEG];
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii)
+#pragma unroll
+            for (int s = 0; s < NSEG; ++s)
+                if (tok[ii] >= 0) {
+                    const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
+                    const int col = s * 128 + lane * 4;
+                    go[ii][s] = raw_load4<!DOUT_BF16>(dout, (size_t)tok[ii] * d + col);
+                    yv[ii][s] = raw_load4<Y_F32>(y, (size_t)r * d + col);
+                }
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) {
+            const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
+            __nv_bfloat16* dst = dy_op + (size_t)r * ld;
+            if (tok[ii] < 0) {                             // padding row: zero (the wgrad GEMMs sum over it)
+                for (int j = lane; j < ld / 4; j += 32) reinterpret_cast<uint2*>(dst)[j] = make_uint2(0u, 0u);
+                if (lane == 0) dgate_row[r] = 0.0f;
+                continue;
+            }
+            float dot = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NSEG; ++s) {
                 const int col = s * 128 + lane * 4;
-                const float4 go = load4_any<DOUT_BF16>(dout, (size_t)t * d + col);
-                const float4 yv = load_row4<Y_F32>(y, (size_t)r * d + col);
-                dot = fmaf(go.x, yv.x, fmaf(go.y, yv.y, fmaf(go.z, yv.z, fmaf(go.w, yv.w, dot))));
-                const float4 dv = make_float4(g * go.x, g * go.y, g * go.z, g * go.w);
+                const float4 a = raw_to_float4(go[ii][s]), b = raw_to_float4(yv[ii][s]);
+                dot = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, dot))));
+                const float4 dv = make_float4(g[ii] * a.x, g[ii] * a.y, g[ii] * a.z, g[ii] * a.w);
                 store_operand4(dst + col, d, split != 0, dv);
                 cs[s].x += dv.x; cs[s].y += dv.y; cs[s].z += dv.z; cs[s].w += dv.w;
             }
+            dot = warp_sum(dot);
+            if (lane == 0) dgate_row[r] = dot;
         }
-        dot = warp_sum(dot);
-        if (lane == 0) dgate_row[r] = dot;
     }
     if (colpart == nullptr) return;
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s)
-        if (s < nseg) red[wid][s * 32 + lane] = cs[s];
+    for (int s = 0; s < NSEG; ++s) red[wid][s * 32 + lane] = cs[s];
     __syncthreads();
-    for (int j = threadIdx.x; j < nseg * 32; j += 256) {           // float4 index: columns 4j .. 4j+3 (j = seg * 32 + lane)
+    for (int j = threadIdx.x; j < NSEG * 32; j += 256) {           // float4 index: columns 4j .. 4j+3 (j = seg * 32 + lane)
         float4 a = red[0][j];
 #pragma unroll
         for (int w = 1; w < 8; ++w) { const float4 b = red[w][j]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
@@ -332,33 +401,57 @@ combine_bwd_kernel(const int* __restrict__ plan, const void* __restrict__ dout, 
 }
 
 // dx[t] = sum_j dx_rows[row(t, j)] (+ dx_router[t])
-template <bool R_F32>
-__global__ void __launch_bounds__(256)
+template <bool R_F32, int NSEG>
+__global__ void __launch_bounds__(256, 2)
 uncombine_kernel(const void* __restrict__ dx_rows, const int* __restrict__ token_rows, const float* __restrict__ dx_router,
                  int T, int T_pad, int d, int k, int dense, float* __restrict__ dx) {
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    constexpr int JB = SlotBatch<NSEG>::value, TB = TokBatch<NSEG>::value;
+    const int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * TB;
     const int lane = threadIdx.x & 31;
-    if (t >= T) return;
-    const int nseg = d / 128;
-    float4 acc[MAX_SEG];
+    if (t0 >= T) return;
+    float4 acc[TB][NSEG];
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s) {
-        acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < nseg && dx_router != nullptr) acc[s] = __ldg(reinterpret_cast<const float4*>(dx_router + (size_t)t * d + s * 128 + lane * 4));
-    }
-    for (int j = 0; j < k; ++j) {
-        const int row = dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j);
+    for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int s = 0; s < MAX_SEG; ++s) {
-            if (s < nseg) {
-                const float4 v = load_row4<R_F32>(dx_rows, (size_t)row * d + s * 128 + lane * 4);
-                acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w;
-            }
+        for (int s = 0; s < NSEG; ++s) {
+            acc[i][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dx_router != nullptr && t0 + i < T)
+                acc[i][s] = __ldg(reinterpret_cast<const float4*>(dx_router + (size_t)(t0 + i) * d + s * 128 + lane * 4));
         }
+    for (int j0 = 0; j0 < k; j0 += JB) {
+        int row[TB][JB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) {
+                const int j = j0 + jj, t = t0 + i;
+                row[i][jj] = (j < k && t < T) ? (dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j)) : -1;
+            }
+        typename Raw4<R_F32>::type v[TB][JB][NSEG];
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+                for (int s = 0; s < NSEG; ++s)
+                    if (row[i][jj] >= 0) v[i][jj][s] = raw_load4<R_F32>(dx_rows, (size_t)row[i][jj] * d + s * 128 + lane * 4);
+#pragma unroll
+        for (int i = 0; i < TB; ++i)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+                if (row[i][jj] >= 0) {
+#pragma unroll
+                    for (int s = 0; s < NSEG; ++s) {
+                        const float4 f = raw_to_float4(v[i][jj][s]);
+                        acc[i][s].x += f.x; acc[i][s].y += f.y; acc[i][s].z += f.z; acc[i][s].w += f.w;
+                    }
+                }
     }
 #pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s)
-        if (s < nseg) *reinterpret_cast<float4*>(dx + (size_t)t * d + s * 128 + lane * 4) = acc[s];
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s)
+            if (t0 + i < T) *reinterpret_cast<float4*>(dx + (size_t)(t0 + i) * d + s * 128 + lane * 4) = acc[i][s];
 }
 
 // bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c].
@@ -437,6 +530,7 @@ colsum_finish_kernel(const float* __restrict__ part, int n, int nsplit, float* _
 // =====================================================================================================
 int launch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float* chunk_colsum, int32_t* plan,
                 int32_t* chunk_base, float* load, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_PLAN, s);
     plan_kernel<<<1, 1024, 0, st>>>(chunk_counts, chunk_colsum, ceil_div(s->T, MOEGAN_CHUNK), s->T, s->E, s->dense, s->m_cap, plan,
                                     chunk_base, load);
     MOEGAN_CHECK_LAUNCH("plan_kernel");
@@ -446,6 +540,7 @@ int launch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float*
 int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates, const int32_t* plan,
                   const int32_t* chunk_base, void* x_op, void* x_copy, int32_t* row_token, float* row_gate, int32_t* token_rows,
                   cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_GATHER, s, x_copy != nullptr ? 0x1000 : 0);
     const int nchunks = ceil_div(s->T, MOEGAN_CHUNK);
     gather_kernel<<<nchunks + s->E, 256, 0, st>>>(x, topk_idx, gates, plan, chunk_base, nchunks, s->T, s->d, s->E, s->k,
                                                   s->precision == 1, reinterpret_cast<__nv_bfloat16*>(x_op),
@@ -455,6 +550,7 @@ int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx
 }
 
 int launch_to_operand(const float* src, int64_t rows, int64_t cols, int split, int sanitize, void* dst, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_TO_OPERAND, (long long)rows, (int)cols, 0, split ? 0x400 : 0);
     if (rows * cols == 0) return MOEGAN_OK;
     MOEGAN_REQUIRE(cols % 4 == 0, MOEGAN_ERR_BAD_SHAPE, "to_operand: cols (%lld) must be a multiple of 4", (long long)cols);
     const long long n4 = rows * cols / 4;
@@ -468,6 +564,7 @@ int launch_to_operand(const float* src, int64_t rows, int64_t cols, int split, i
 
 int launch_prep_weights(const moegan_shape* s, const float* const* w1, const float* const* b1, const float* const* w2,
                         const float* const* b2, void* W1_op, float* b1s, void* W2_op, float* b2s, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_PREP_WEIGHTS, s);
     WeightPtrs p;
     for (int e = 0; e < MOEGAN_MAX_EXPERTS; ++e) {
         const int q = e < s->E ? e : 0;
@@ -484,30 +581,56 @@ int launch_prep_weights(const moegan_shape* s, const float* const* w1, const flo
     return MOEGAN_OK;
 }
 
+// NSEG = d / 128 as a compile-time constant (d is validated as a multiple of 128 in [128, 1024])
+#define MOEGAN_NSEG_SWITCH(nseg, CALL) \
+    switch (nseg) { case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; \
+                    case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; default: CALL(8); break; }
+
+template <bool YF, int RS, bool OB>
+static void combine_fwd_dispatch(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
+                                 void* out, cudaStream_t st) {
+    const int T_pad = row_pad(s->T);
+#define MOEGAN_CF(NS) combine_fwd_kernel<YF, RS, OB, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, residual, out)
+    MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_CF)
+#undef MOEGAN_CF
+}
+
 int launch_combine_fwd(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
                        int residual_bf16, void* out, int out_bf16, cudaStream_t st) {
-    const int T_pad = row_pad(s->T);
-    const int blocks = ceil_div(s->T, 8);
+    ProfScope _ps(st, MOEGAN_PROF_COMBINE_FWD, s, (residual == nullptr ? 0 : (residual_bf16 ? 0x2000 : 0x1000)) | (out_bf16 ? 0x4000 : 0));
     const int res = residual == nullptr ? 0 : (residual_bf16 ? 2 : 1);
-#define MOEGAN_CF(YF, RS, OB) combine_fwd_kernel<YF, RS, OB><<<blocks, 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, residual, out)
-#define MOEGAN_CF_R(YF, OB) do { if (res == 0) MOEGAN_CF(YF, 0, OB); else if (res == 1) MOEGAN_CF(YF, 1, OB); else MOEGAN_CF(YF, 2, OB); } while (0)
+#define MOEGAN_CF_R(YF, OB) do { if (res == 0) combine_fwd_dispatch<YF, 0, OB>(s, y, gates, token_rows, residual, out, st); \
+                                 else if (res == 1) combine_fwd_dispatch<YF, 1, OB>(s, y, gates, token_rows, residual, out, st); \
+                                 else combine_fwd_dispatch<YF, 2, OB>(s, y, gates, token_rows, residual, out, st); } while (0)
     if (s->precision == 1) { if (out_bf16) MOEGAN_CF_R(true, true); else MOEGAN_CF_R(true, false); }
     else                   { if (out_bf16) MOEGAN_CF_R(false, true); else MOEGAN_CF_R(false, false); }
 #undef MOEGAN_CF_R
-#undef MOEGAN_CF
     MOEGAN_CHECK_LAUNCH("combine_fwd_kernel");
     return MOEGAN_OK;
 }
 
-int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int dout_bf16, const void* y, const int32_t* row_token,
-                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st) {
+template <bool YF, bool DB>
+static void combine_bwd_dispatch(const moegan_shape* s, const int32_t* plan, const void* dout, const void* y, const int32_t* row_token,
+                                 const float* row_gate, const float* gates, int split, __nv_bfloat16* dy, float* dgate_row, float* dy_colpart,
+                                 cudaStream_t st) {
     const int T_pad = row_pad(s->T);
     const int blocks = s->m_cap / 32;
-    __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
-#define MOEGAN_CB(YF, DB, SP) combine_bwd_kernel<YF, DB><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, SP, dy, dgate_row, dy_colpart)
-    if (s->precision == 1) { if (dout_bf16) MOEGAN_CB(true, true, 1); else MOEGAN_CB(true, false, 1); }
-    else                   { if (dout_bf16) MOEGAN_CB(false, true, 0); else MOEGAN_CB(false, false, 0); }
+#define MOEGAN_CB(NS) combine_bwd_kernel<YF, DB, NS><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, split, dy, dgate_row, dy_colpart)
+    MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_CB)
 #undef MOEGAN_CB
+}
+
+int launch_combine_bwd(const moegan_shape* s, const int32_t* plan, const void* dout, int dout_bf16, const void* y, const int32_t* row_token,
+                       const float* row_gate, const float* gates, void* dy_op, float* dgate_row, float* dy_colpart, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_COMBINE_BWD, s, dout_bf16 ? 0x1000 : 0);
+    __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(dy_op);
+    if (s->precision == 1) {
+        if (dout_bf16) combine_bwd_dispatch<true, true>(s, plan, dout, y, row_token, row_gate, gates, 1, dy, dgate_row, dy_colpart, st);
+        else           combine_bwd_dispatch<true, false>(s, plan, dout, y, row_token, row_gate, gates, 1, dy, dgate_row, dy_colpart, st);
+    } else {
+        if (dout_bf16) combine_bwd_dispatch<false, true>(s, plan, dout, y, row_token, row_gate, gates, 0, dy, dgate_row, dy_colpart, st);
+        else           combine_bwd_dispatch<false, false>(s, plan, dout, y, row_token, row_gate, gates, 0, dy, dgate_row, dy_colpart, st);
+    }
     MOEGAN_CHECK_LAUNCH("combine_bwd_kernel");
     return MOEGAN_OK;
 }
@@ -523,6 +646,7 @@ int slab_sum_splits(const moegan_shape* s) {
 
 // out[e, c] = sum of expert e's slab sums part[m_cap / 32, cols];  scratch: slab_sum_splits() * E * cols floats
 int launch_slab_sum(const moegan_shape* s, const int32_t* plan, const float* part, int cols, float* scratch, float* out, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_SLAB_SUM, (long long)s->m_cap, cols, s->E, prof_shape_flags(s));
     const int nsplit = slab_sum_splits(s);
     dim3 grid(ceil_div(cols, 128), s->E, nsplit);
     slab_sum_kernel<<<grid, 128, 0, st>>>(plan, part, cols, s->T, s->dense, s->E, nsplit, nsplit == 1 ? out : scratch);
@@ -537,16 +661,21 @@ int launch_slab_sum(const moegan_shape* s, const int32_t* plan, const float* par
 
 int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* token_rows, const float* dx_router, float* dx,
                      cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_UNCOMBINE, s, dx_router != nullptr ? 0x1000 : 0);
     const int T_pad = row_pad(s->T);
-    const int blocks = ceil_div(s->T, 8);
-    if (s->precision == 1) uncombine_kernel<true><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);
-    else                   uncombine_kernel<false><<<blocks, 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx);
+#define MOEGAN_UC32(NS) uncombine_kernel<true, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
+#define MOEGAN_UC16(NS) uncombine_kernel<false, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
+    if (s->precision == 1) { MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_UC32) }
+    else                   { MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_UC16) }
+#undef MOEGAN_UC32
+#undef MOEGAN_UC16
     MOEGAN_CHECK_LAUNCH("uncombine_kernel");
     return MOEGAN_OK;
 }
 
 int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void* src_op, int cols, float* scratch, float* out,
                           cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_COLSUM_GROUPED, (long long)s->m_cap, cols, s->E, prof_shape_flags(s));
     // rows per expert are only known on the device; size the split from the mean (dense: exact)
     const long long rows = s->dense ? s->T : ((long long)s->T * s->k + s->E - 1) / s->E;
     int nsplit = (int)(rows / 1024);
@@ -566,6 +695,7 @@ int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void
 
 // out[i] = sum_s part[s * n + i], fixed order (deterministic split-K / split-row finish)
 int launch_sum_partials(const float* part, long long n, int nsplit, float* out, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_SUM_PARTIALS, n, nsplit, 0, 0);
     if (n <= 0) return MOEGAN_OK;
     colsum_finish_kernel<<<(int)ceil_div64(n, 256), 256, 0, st>>>(part, (int)n, nsplit, out);
     MOEGAN_CHECK_LAUNCH("sum_partials");

@@ -469,6 +469,7 @@ int ln_bwd_blocks(long long rows) {
 // (NSEG, R) by segment count: 1 -> (1, 4), 2 -> (2, 2), 3..4 -> (4, 1), 5..8 -> (8, 1)
 int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
                          int y_bf16, float* mean, float* rstd, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_FWD, rows, d, 0, (x_bf16 ? 1 : 0) | (y_bf16 ? 2 : 0));
     if (rows == 0) return MOEGAN_OK;
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
@@ -490,6 +491,7 @@ int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const fl
 
 int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd,
                          long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_BWD, rows, d, 0, (g_bf16 ? 1 : 0) | (x_bf16 ? 2 : 0));
     if (rows == 0) {
         MOEGAN_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, (size_t)2 * d * 4, st));
         return MOEGAN_OK;
@@ -517,6 +519,7 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
 }
 
 int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_CHANNEL_SCALE_FWD, (long long)B, P, C, (bf16 ? 1 : 0) | (s_bf16 ? 2 : 0));
     const long long n4 = (long long)B * P * C / 4;
     if (n4 == 0) return MOEGAN_OK;
     const int blocks = grid_cap((n4 + 255) / 256);
@@ -539,6 +542,7 @@ int channel_scale_psplit(int B, int P, int C) {
 
 int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* dx,
                              void* ds, float* scratch, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_CHANNEL_SCALE_BWD, (long long)B, P, C, (bf16 ? 1 : 0) | (s_bf16 ? 2 : 0));
     if ((long long)B * P * C == 0) return MOEGAN_OK;
     const int ps = channel_scale_psplit(B, P, C);
     dim3 grid(C / 128, B, ps);
@@ -563,6 +567,7 @@ int colsum_splits(long long rows, int cols) {
     return (int)(ns < 1 ? 1 : ns);
 }
 int launch_colsum(const void* x, int bf16, long long rows, int cols, float* out, float* scratch, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_COLSUM, rows, cols, 0, bf16 ? 1 : 0);
     if (cols == 0) return MOEGAN_OK;
     if (rows == 0) { MOEGAN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * 4, st)); return MOEGAN_OK; }
     const int ns = colsum_splits(rows, cols);
@@ -579,6 +584,7 @@ int launch_colsum(const void* x, int bf16, long long rows, int cols, float* out,
 }
 
 int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, int H, int W, int C, void* out, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_OFFSET_SAMPLE_FWD, (long long)B, H * W, C, bf16 ? 1 : 0);
     const long long npix = (long long)B * H * W;
     if (npix == 0) return MOEGAN_OK;
     const int blocks = (int)((npix + 7) / 8);
@@ -599,6 +605,7 @@ static int launch_bwd_in(const T* g, const float* off, int B, int H, int W, int 
 
 int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float* off, int B, int H, int W, int C, void* dx, float* doff,
                              cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_OFFSET_SAMPLE_BWD, (long long)B, H * W, C, bf16 ? 1 : 0);
     const long long npix = (long long)B * H * W;
     if (npix == 0) return MOEGAN_OK;
     const int blocks = (int)((npix + 7) / 8);

@@ -549,23 +549,43 @@ router_bwd_small_kernel(const float* __restrict__ dwc_part, int nparts, const fl
             if (split) dtp_op[(size_t)b * ld + HID + tid] = __float2bfloat16_rn(lo);
         }
     } else {
-        const int o = (blockIdx.x - 1 - B) * 128 + (tid & 127);   // flat index into [128][E]
-        const int h = tid >> 7;
-        float a0 = 0.0f, a1 = 0.0f;
-        int pz = h;
-        for (; pz + 2 < nparts; pz += 4) {                          // two independent chains per thread
-            a0 += dwc_part[(size_t)pz * HID * E + o];
-            a1 += dwc_part[(size_t)(pz + 2) * HID * E + o];
+        // dWc: CTA = 32 consecutive entries of the flat [128][E] matrix, 8 threads per entry.  Both sums are long and thin (up to
+        // 296 partials / B samples per entry): every thread walks its eighth with four independent chains so that the L2 round
+        // trips overlap (one serial chain per entry made this kernel ~65 us at every shape), then a fixed-order sum in smem.
+        const int oo = tid & 31, h = tid >> 5;
+        const int o = (blockIdx.x - 1 - B) * 32 + oo;
+        const size_t ps = (size_t)HID * E;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        for (int pz = h; pz < nparts; pz += 32) {
+            a0 += dwc_part[(size_t)pz * ps + o];
+            if (pz + 8 < nparts)  a1 += dwc_part[(size_t)(pz + 8) * ps + o];
+            if (pz + 16 < nparts) a2 += dwc_part[(size_t)(pz + 16) * ps + o];
+            if (pz + 24 < nparts) a3 += dwc_part[(size_t)(pz + 24) * ps + o];
         }
-        for (; pz < nparts; pz += 2) a0 += dwc_part[(size_t)pz * HID * E + o];
-        red[tid] = a0 + a1;
+        red[tid] = (a0 + a1) + (a2 + a3);
         __syncthreads();
         if (h == 0) {
-            dWc[o] = red[tid] + red[tid + 128];
-            const int j = o / E, e = o - j * E;                     // bottom rows
-            float s = 0.0f;
-            for (int b = 0; b < B; ++b) s = fmaf(tp[(size_t)b * HID + j], dtl[(size_t)b * E + e], s);
-            dWc[HID * E + o] = s;
+            float v = red[oo];
+#pragma unroll
+            for (int w8 = 1; w8 < 8; ++w8) v += red[w8 * 32 + oo];
+            dWc[o] = v;
+        }
+        __syncthreads();
+        const int j = o / E, e = o - j * E;                         // bottom rows: dWc[128 + j][e] = sum_b tp[b, j] dtl[b, e]
+        a0 = a1 = a2 = a3 = 0.0f;
+        for (int b = h; b < B; b += 32) {
+            a0 = fmaf(tp[(size_t)b * HID + j], dtl[(size_t)b * E + e], a0);
+            if (b + 8 < B)  a1 = fmaf(tp[(size_t)(b + 8) * HID + j], dtl[(size_t)(b + 8) * E + e], a1);
+            if (b + 16 < B) a2 = fmaf(tp[(size_t)(b + 16) * HID + j], dtl[(size_t)(b + 16) * E + e], a2);
+            if (b + 24 < B) a3 = fmaf(tp[(size_t)(b + 24) * HID + j], dtl[(size_t)(b + 24) * E + e], a3);
+        }
+        red[tid] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (h == 0) {
+            float v = red[oo];
+#pragma unroll
+            for (int w8 = 1; w8 < 8; ++w8) v += red[w8 * 32 + oo];
+            dWc[HID * E + o] = v;
         }
     }
 }
@@ -677,6 +697,7 @@ int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_
                      const float* mu_c, const float* rho_c, const float* eps_c, int sampling,
                      float* Wf, float* Wt, float* Wc, void* Wf_op, void* Wt_op, float* kl_out,
                      float* keep_f, float* keep_t, float* keep_c, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_SAMPLE_KL, s);
     const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
     const int n = n_f + n_t + n_c;
     int blocks = ceil_div(n, 256 * 4);
@@ -692,6 +713,7 @@ int launch_sample_kl(const moegan_shape* s, const float* mu_f, const float* rho_
 }
 
 int launch_text_fwd(const moegan_shape* s, const float* w, const float* Wt, const float* Wc, float* tp, float* tl, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_TEXT_FWD, s);
     text_fwd_kernel<<<s->B, HID * TX_SPLIT, (s->Dt + (TX_SPLIT + 1) * HID) * sizeof(float), st>>>(w, Wt, Wc, s->Dt, s->E, tp, tl);
     MOEGAN_CHECK_LAUNCH("text_fwd_kernel");
     return MOEGAN_OK;
@@ -704,6 +726,7 @@ static size_t router_fwd_smem(int E) {
 int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, const float* Wc, const float* tl,
                       const float* temperature, float af, float* fp, float* raw, float* probs, int32_t* topk_idx, float* gates,
                       int32_t* chunk_counts, float* chunk_colsum, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_ROUTER_FWD, s, fp != nullptr ? 0x1000 : 0);
     static bool attr = false;
     if (!attr) {
         MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(router_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -722,6 +745,7 @@ int launch_router_bwd_logits(const moegan_shape* s, const float* raw, const floa
                              const int32_t* token_rows, const float* dgate_row, const float* dprobs_ext, const float* dload,
                              const float* temperature, float af, const float* fp, float* draw, void* dfp_op, float* dtau_part,
                              float* dwc_part, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_ROUTER_BWD_LOGITS, s);
     const int blocks = router_bwd_logits_blocks(s);
     const int T_pad = row_pad(s->T);
     if (router_bwd_dwc_fused(s)) {
@@ -753,6 +777,7 @@ int router_bwd_dwc_parts(const moegan_shape* s) {
 int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float* draw, const float* tp, const float* Wc,
                             const float* dtau_part, const float* temperature, float af,
                             float* dtl, float* dwc_part, float* dWc, float* dtp, void* dtp_op, float* dtemperature, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_ROUTER_BWD_SMALL, s);
     router_bwd_dtl_kernel<<<s->B, 256, 0, st>>>(draw, s->tokens_per_sample, s->E, dtl);
     MOEGAN_CHECK_LAUNCH("router_bwd_dtl_kernel");
     const int nparts = router_bwd_dwc_parts(s);
@@ -760,7 +785,7 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
         router_bwd_dwc_part_kernel<<<nparts, HID, 0, st>>>(fp, draw, s->T, s->E, dwc_tok_per_block(s), dwc_part);
         MOEGAN_CHECK_LAUNCH("router_bwd_dwc_part_kernel");
     }
-    router_bwd_small_kernel<<<1 + s->B + s->E, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
+    router_bwd_small_kernel<<<1 + s->B + 4 * s->E, 256, 0, st>>>(dwc_part, nparts, tp, dtl, Wc, dtau_part, router_bwd_logits_blocks(s),
                                                      temperature, af, s->B, s->E, s->precision == 1, dWc, dtp,
                                                      reinterpret_cast<__nv_bfloat16*>(dtp_op), dtemperature);
     MOEGAN_CHECK_LAUNCH("router_bwd_small_kernel");
@@ -769,6 +794,7 @@ int launch_router_bwd_small(const moegan_shape* s, const float* fp, const float*
 
 bool router_bwd_text_simt_ok(const moegan_shape* s) { return s->B <= TXB_MAX_B; }
 int launch_router_bwd_text(const moegan_shape* s, const float* w, const float* dtp, const float* Wt, float* dw, float* dWt, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_ROUTER_BWD_TEXT, s);
     router_bwd_text_kernel<<<s->Dt, HID, 0, st>>>(w, dtp, Wt, s->B, s->Dt, dw, dWt);
     MOEGAN_CHECK_LAUNCH("router_bwd_text_kernel");
     return MOEGAN_OK;
@@ -780,6 +806,7 @@ int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* 
                           const float* mu_c, const float* rho_c, const float* eps_c, int sampled, int f_splits,
                           const float* kl_out, const float* dkl,
                           float* dmu_f, float* drho_f, float* dmu_t, float* drho_t, float* dmu_c, float* drho_c, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_REPARAM_KL_BWD, s);
     const int n_f = s->d * HID, n_t = s->Dt * HID, n_c = 2 * HID * s->E;
     const int blocks = ceil_div(n_f + n_t + n_c, 256 * 2);
     reparam_kl_bwd_kernel<<<blocks, 256, 0, st>>>(dWf, dWt, dWc, mu_f, rho_f, eps_f, mu_t, rho_t, eps_t, mu_c, rho_c, eps_c,
@@ -789,6 +816,7 @@ int launch_reparam_kl_bwd(const moegan_shape* s, const float* dWf, const float* 
 }
 
 int launch_balance_loss(const float* load, int E, int T, float bw, const float* dloss, float* loss, float* dload, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_BALANCE, (long long)T, 0, E, 0);
     balance_loss_kernel<<<1, 32, 0, st>>>(load, E, T, bw, dloss, loss, dload);
     MOEGAN_CHECK_LAUNCH("balance_loss_kernel");
     return MOEGAN_OK;

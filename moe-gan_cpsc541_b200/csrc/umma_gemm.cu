@@ -621,7 +621,11 @@ int launch_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
         attr_set = true;
     }
     void* prof = nullptr;
-    profile_begin(stream, KIND * 1000 + BN + (CTA2 ? 100000 : 0), &prof);
+    if (profile_level() >= 1) {
+        const int dims[4] = {p.N, KIND == GEMM_WGRAD ? p.dimA : p.K, KIND == GEMM_WGRAD ? p.k_rows_host : p.m_blocks_host * 128,
+                             p.E | (p.out1 != nullptr ? 0x10000 : 0)};
+        profile_begin(stream, KIND * 1000 + BN + (CTA2 ? 100000 : 0) + EPI * 10000, nullptr, dims, &prof);
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

@@ -56,9 +56,6 @@ struct GemmParams {
     int mn_lbo, mn_sbo, mn_kadv;  // MN-major smem descriptor parameters (bytes); 0 -> defaults
 };
 
-bool profile_begin(cudaStream_t st, int tag, void** handle);   // api.cu (bench instrumentation)
-void profile_end(cudaStream_t st, void* handle);
-
 // max_tiles: upper bound on the number of output tiles (sizes the persistent grid).
 int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& B, GemmParams p, long long max_tiles,
                      cudaStream_t stream);
