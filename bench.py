@@ -290,11 +290,13 @@ class Timer:
         self.lib.moegan_debug_profile_enable(0)
         return [ms_buf[i] for i in range(n)], [tag_buf[i] for i in range(n)]
 
-    def kernel_profile(self, fn, steps, lead_ms=0.0):
+    def kernel_profile(self, fn, steps, lead_ms=0.0, serial=True):
         """[(ms, tag, meta8)] of EVERY launch of the library in `steps` eager steps (level-2 profiling: CUDA events recorded by
         the library on the launching stream around each kernel)."""
         C = importlib.import_module(PKG)._cabi
         self.lib.moegan_debug_profile_enable(2)
+        if serial:      # one stream: a bracket around a side-stream kernel would include its wait for SMs held by a GEMM
+            self.lib.moegan_debug_set_side_streams(0)
         self.barrier()
         for _ in range(steps):
             self.flush.zero_()
@@ -305,6 +307,7 @@ class Timer:
         ms_buf, tag_buf, meta_buf = (C.c_float * cap)(), (C.c_int32 * cap)(), (C.c_int32 * (8 * cap))()
         n = self.lib.moegan_debug_profile_read_ex(ms_buf, tag_buf, meta_buf, cap)
         self.lib.moegan_debug_profile_enable(0)
+        self.lib.moegan_debug_set_side_streams(-1)
         return [(ms_buf[i], tag_buf[i], tuple(meta_buf[8 * i: 8 * i + 8])) for i in range(n)]
 
 

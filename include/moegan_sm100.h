@@ -327,6 +327,9 @@ enum {
 int moegan_debug_profile_enable(int32_t level);
 int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n);
 int moegan_debug_profile_read_ex(float* ms_out, int32_t* tag_out, int32_t* meta_out, int32_t max_n);
+/* debug / bench: 0 = keep every kernel of a block call on the caller's stream (per-kernel timing without concurrency), 1 = allow the
+ * library's side streams, -1 = default (on, unless MOEGAN_DISABLE_SIDE_STREAM=1) */
+int moegan_debug_set_side_streams(int32_t mode);
 /* debug: override the MN-major shared-memory descriptor parameters of the GEMM (0 = built-in defaults) */
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes);
 /* fp32 [rows, cols] -> bf16 operand [rows, S*cols] */

@@ -103,6 +103,7 @@ SIGNATURES = {
     "moegan_debug_profile_enable": (c_int32, [c_int32]),
     "moegan_debug_profile_read": (c_int32, [_P, _P, c_int32]),
     "moegan_debug_profile_read_ex": (c_int32, [_P, _P, _P, c_int32]),
+    "moegan_debug_set_side_streams": (c_int32, [c_int32]),
     "moegan_to_operand": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P]),
 }
 

@@ -607,10 +607,17 @@ struct SideStream { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = n
                     bool ok = false, tried = false; };
 static SideStream g_side;
 static std::mutex g_side_mu;
+static std::atomic<int> g_side_override{-1};     // moegan_debug_set_side_streams: -1 = environment / default
 static bool side_enabled() {
+    const int o = g_side_override.load(std::memory_order_relaxed);
+    if (o >= 0) return o == 1;
     static int v = -1;
     if (v < 0) { const char* e = getenv("MOEGAN_DISABLE_SIDE_STREAM"); v = (e != nullptr && e[0] == '1') ? 0 : 1; }
     return v == 1;
+}
+int moegan_debug_set_side_streams(int32_t mode) {
+    g_side_override.store(mode < 0 ? -1 : (mode != 0 ? 1 : 0));
+    return MOEGAN_OK;
 }
 // Overlap only pays while the expert GEMMs leave SMs idle (configs[1]: 8 192 dispatched rows, 353 -> 323 us).  At the train-step
 // shapes (16 K - 262 K rows) every GEMM fills the chip with one 225 KB CTA per SM, nothing can co-reside, and the fork / join

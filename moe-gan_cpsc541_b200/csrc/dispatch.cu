@@ -247,101 +247,145 @@ __device__ __forceinline__ float4 raw_to_float4(uint2 u) {
 // (B200 needs ~30 KB outstanding per SM to saturate HBM).  NSEG (= d / 128) is a template parameter, the slot / row loops are
 // processed in batches whose loads are ALL issued before the first use (batch x NSEG = 8 independent 8/16-byte loads per lane),
 // and the arithmetic keeps the reference's accumulation order (slot order == expert order), so results do not depend on the batch.
-// TokBatch consecutive tokens per warp x SlotBatch slots per pass x NSEG segments = 16 independent loads per lane: with d = 128 a
-// token's rows are only 256 B each, and a warp that handles ONE token lives for a single memory round trip (18 waves of such CTAs at
-// T = 65 536 ran at 0.3 of the HBM roof).  Consecutive tokens are adjacent rows of every expert segment in dense mode.
-template <int NSEG> struct TokBatch { static constexpr int value = NSEG == 1 ? 4 : (NSEG == 2 ? 2 : 1); };
-template <int NSEG> struct SlotBatch { static constexpr int value = NSEG >= 8 ? 2 : (NSEG >= 4 ? 16 / NSEG : 4); };
+// combine_fwd / uncombine are flat over 8-column chunks (16 B of bf16, 32 B of fp32): thread f owns chunk (t, c) = (f / CPR, f % CPR),
+// CPR = d / 8, CHUNKS_PER_THREAD chunks 256 apart, and issues the loads of SLOTS slots of all its chunks before the first use.
+// Measured on B200 (ncu, T = 65 536, d = 128): what bounds these kernels is the number of outstanding load REQUESTS per SM, not
+// bytes - a warp-per-token version with 8-byte lanes ran at 2.9 TB/s; 16-byte lanes move twice the bytes per request.
+constexpr int CHUNKS_PER_THREAD = 2;
+template <bool F32> struct Chunk8 { uint4 a; };                       // 8 bf16
+template <> struct Chunk8<true> { float4 a, b; };                      // 8 fp32
+template <bool F32>
+__device__ __forceinline__ Chunk8<F32> chunk_load(const void* base, size_t elem_off) {
+    Chunk8<F32> c;
+    if constexpr (F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+        c.a = __ldg(p); c.b = __ldg(p + 1);
+    } else {
+        c.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+    }
+    return c;
+}
+__device__ __forceinline__ void chunk_unpack(const Chunk8<true>& c, float (&f)[8]) {
+    f[0] = c.a.x; f[1] = c.a.y; f[2] = c.a.z; f[3] = c.a.w; f[4] = c.b.x; f[5] = c.b.y; f[6] = c.b.z; f[7] = c.b.w;
+}
+__device__ __forceinline__ void chunk_unpack(const Chunk8<false>& c, float (&f)[8]) {
+    f[0] = bf16_lo_to_float(c.a.x); f[1] = bf16_hi_to_float(c.a.x); f[2] = bf16_lo_to_float(c.a.y); f[3] = bf16_hi_to_float(c.a.y);
+    f[4] = bf16_lo_to_float(c.a.z); f[5] = bf16_hi_to_float(c.a.z); f[6] = bf16_lo_to_float(c.a.w); f[7] = bf16_hi_to_float(c.a.w);
+}
+template <bool BF16>
+__device__ __forceinline__ void chunk_store(void* base, size_t elem_off, const float (&f)[8]) {
+    if constexpr (BF16) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    } else {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+        p[0] = make_float4(f[0], f[1], f[2], f[3]); p[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+}
 
 // RES: 0 = no residual, 1 = fp32 residual, 2 = bf16 residual (`x_spatial + moe_out`, t2i_moe_gan.py:571, in the
 // combine's epilogue); OUT_BF16: write the result in bf16 (the dtype of the residual stream under autocast)
 template <bool Y_F32, int RES, bool OUT_BF16, int NSEG>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 combine_fwd_kernel(const void* __restrict__ y, const float* __restrict__ gates, const int* __restrict__ token_rows,
                    int T, int T_pad, int d, int k, int dense, const void* __restrict__ residual, void* __restrict__ out) {
-    constexpr int JB = SlotBatch<NSEG>::value, TB = TokBatch<NSEG>::value;
-    const int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * TB;
-    const int lane = threadIdx.x & 31;
-    if (t0 >= T) return;
-    typename Raw4<RES != 2>::type res[TB][NSEG];
+    constexpr int CPR = NSEG * 16, U = CHUNKS_PER_THREAD, JB = Y_F32 ? 2 : 4;
+    const long long f0 = (long long)blockIdx.x * (256 * U) + threadIdx.x;
+    int t[U], col[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long f = f0 + u * 256;
+        const int tt = (int)(f / CPR);
+        t[u] = tt < T ? tt : -1;
+        col[u] = (int)(f - (long long)tt * CPR) * 8;
+    }
+    Chunk8<RES != 2> res[U];
     if (RES != 0) {
 #pragma unroll
-        for (int i = 0; i < TB; ++i)
-#pragma unroll
-            for (int s = 0; s < NSEG; ++s)
-                if (t0 + i < T) res[i][s] = raw_load4<RES != 2>(residual, (size_t)(t0 + i) * d + s * 128 + lane * 4);
+        for (int u = 0; u < U; ++u)
+            if (t[u] >= 0) res[u] = chunk_load<RES != 2>(residual, (size_t)t[u] * d + col[u]);
     }
-    float4 acc[TB][NSEG];
+    float acc[U][8];
 #pragma unroll
-    for (int i = 0; i < TB; ++i)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int s = 0; s < NSEG; ++s) acc[i][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = 0; e < 8; ++e) acc[u][e] = 0.0f;
     for (int j0 = 0; j0 < k; j0 += JB) {              // slot order == expert order in dense mode (:467)
-        int row[TB][JB]; float g[TB][JB];
+        int row[U][JB]; float g[U][JB];
 #pragma unroll
-        for (int i = 0; i < TB; ++i)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-                const int j = j0 + jj, t = t0 + i;
-                const bool ok = j < k && t < T;
-                row[i][jj] = ok ? (dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j)) : -1;
-                g[i][jj] = ok ? __ldg(gates + (size_t)t * k + j) : 0.0f;
+                const int j = j0 + jj;
+                const bool ok = j < k && t[u] >= 0;
+                row[u][jj] = ok ? (dense ? j * T_pad + t[u] : __ldg(token_rows + (size_t)t[u] * k + j)) : -1;
+                g[u][jj] = ok ? __ldg(gates + (size_t)t[u] * k + j) : 0.0f;
             }
-        typename Raw4<Y_F32>::type v[TB][JB][NSEG];
+        Chunk8<Y_F32> v[U][JB];
 #pragma unroll
-        for (int i = 0; i < TB; ++i)
-#pragma unroll
-            for (int jj = 0; jj < JB; ++jj)
-#pragma unroll
-                for (int s = 0; s < NSEG; ++s)
-                    if (row[i][jj] >= 0) v[i][jj][s] = raw_load4<Y_F32>(y, (size_t)row[i][jj] * d + s * 128 + lane * 4);
-#pragma unroll
-        for (int i = 0; i < TB; ++i)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj)
-                if (row[i][jj] >= 0) {
+                if (row[u][jj] >= 0) v[u][jj] = chunk_load<Y_F32>(y, (size_t)row[u][jj] * d + col[u]);
 #pragma unroll
-                    for (int s = 0; s < NSEG; ++s) {
-                        const float4 f = raw_to_float4(v[i][jj][s]);
-                        acc[i][s].x = fmaf(g[i][jj], f.x, acc[i][s].x); acc[i][s].y = fmaf(g[i][jj], f.y, acc[i][s].y);
-                        acc[i][s].z = fmaf(g[i][jj], f.z, acc[i][s].z); acc[i][s].w = fmaf(g[i][jj], f.w, acc[i][s].w);
-                    }
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+                if (row[u][jj] >= 0) {
+                    float f[8];
+                    chunk_unpack(v[u][jj], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[u][e] = fmaf(g[u][jj], f[e], acc[u][e]);
                 }
     }
 #pragma unroll
-    for (int i = 0; i < TB; ++i)
+    for (int u = 0; u < U; ++u)
+        if (t[u] >= 0) {
+            if (RES != 0) {
+                float r[8];
+                chunk_unpack(res[u], r);
 #pragma unroll
-        for (int s = 0; s < NSEG; ++s)
-            if (t0 + i < T) {
-                float4 a = acc[i][s];
-                if (RES != 0) { const float4 r = raw_to_float4(res[i][s]); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
-                store4_any<OUT_BF16>(out, (size_t)(t0 + i) * d + s * 128 + lane * 4, a);
+                for (int e = 0; e < 8; ++e) acc[u][e] += r[e];
             }
+            chunk_store<OUT_BF16>(out, (size_t)t[u] * d + col[u], acc[u]);
+        }
 }
 
-// combine backward: CTA = 32 consecutive dispatched rows (never straddles experts: segments are 256-row aligned), 4 rows per
-// warp.  Also emits the column sums of the CTA's 32 dy rows (colpart [m_cap / 32, d]) - the second Linear's bias gradient
-// is their per-expert sum, so dy is never re-read for it.
+// combine backward: CTA = 32 consecutive dispatched rows (never straddles experts: segments are 256-row aligned).  Thread = one
+// 8-column chunk (c = tid % CPR) of the rows rg, rg + RG, ... (rg = tid / CPR; RG row groups of CPR threads each), 16-byte accesses.
+// Also emits the column sums of the CTA's 32 dy rows (colpart [m_cap / 32, d]) - the second Linear's bias gradient is their
+// per-expert sum, so dy is never re-read for it.  Every reduction runs in a fixed order (bit-identical reruns).
+template <int NSEG> struct CbRowGroups { static constexpr int value = NSEG == 1 ? 16 : (NSEG == 2 ? 8 : (NSEG <= 4 ? 4 : 2)); };
+__device__ __forceinline__ void store_operand8(__nv_bfloat16* dst, int lo_off, bool split, const float (&v)[8]) {
+    float h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    if (split) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
 template <bool Y_F32, bool DOUT_BF16, int NSEG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NSEG * 16 * CbRowGroups<NSEG>::value)
 combine_bwd_kernel(const int* __restrict__ plan, const void* __restrict__ dout, const void* __restrict__ y,
                    const int* __restrict__ row_token, const float* __restrict__ row_gate, const float* __restrict__ gates,
                    int T, int T_pad, int d, int E, int dense, int split,
                    __nv_bfloat16* __restrict__ dy_op, float* __restrict__ dgate_row, float* __restrict__ colpart) {
-    constexpr int IB = NSEG == 1 ? 4 : (NSEG == 2 ? 2 : 1);     // rows whose loads are in flight together (2 * IB * NSEG per lane)
-    __shared__ float4 red[8][NSEG * 32];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CPR = NSEG * 16, RG = CbRowGroups<NSEG>::value, RPT = 32 / RG;     // rows per thread
+    constexpr int IB = (Y_F32 || !DOUT_BF16) ? (RPT < 2 ? RPT : 2) : (RPT < 4 ? RPT : 4);   // rows whose loads are in flight together
+    __shared__ float red[RG][NSEG * 128];
+    __shared__ float dot_part[32][NSEG];
+    const int tid = threadIdx.x, c = tid % CPR, rg = tid / CPR, col = c * 8;
     if (blockIdx.x * 32 >= __ldg(plan + 1)) return;    // rows in use (a multiple of 128)
     const int ld = split ? 2 * d : d;
-    float4 cs[NSEG];
+    float cs[8];
 #pragma unroll
-    for (int s = 0; s < NSEG; ++s) cs[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < 8; ++e) cs[e] = 0.0f;
 #pragma unroll
-    for (int i0 = 0; i0 < 4; i0 += IB) {
+    for (int i0 = 0; i0 < RPT; i0 += IB) {
         int tok[IB]; float g[IB];
 #pragma unroll
         for (int ii = 0; ii < IB; ++ii) {
-            const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
+            const int r = blockIdx.x * 32 + rg + RG * (i0 + ii);
             int t;
             if (dense) {
                 const int e = r / T_pad; t = r - e * T_pad;
@@ -353,105 +397,106 @@ combine_bwd_kernel(const int* __restrict__ plan, const void* __restrict__ dout, 
             }
             tok[ii] = t;
         }
-        typename Raw4<!DOUT_BF16>::type go[IB][NSEG];
-        typename Raw4<Y_F32>::type yv[IB][NSEG];
+        Chunk8<!DOUT_BF16> go[IB];
+        Chunk8<Y_F32> yv[IB];
 #pragma unroll
         for (int ii = 0; ii < IB; ++ii)
-#pragma unroll
-            for (int s = 0; s < NSEG; ++s)
-                if (tok[ii] >= 0) {
-                    const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
-                    const int col = s * 128 + lane * 4;
-                    go[ii][s] = raw_load4<!DOUT_BF16>(dout, (size_t)tok[ii] * d + col);
-                    yv[ii][s] = raw_load4<Y_F32>(y, (size_t)r * d + col);
-                }
+            if (tok[ii] >= 0) {
+                const int r = blockIdx.x * 32 + rg + RG * (i0 + ii);
+                go[ii] = chunk_load<!DOUT_BF16>(dout, (size_t)tok[ii] * d + col);
+                yv[ii] = chunk_load<Y_F32>(y, (size_t)r * d + col);
+            }
 #pragma unroll
         for (int ii = 0; ii < IB; ++ii) {
-            const int r = blockIdx.x * 32 + (i0 + ii) * 8 + wid;
-            __nv_bfloat16* dst = dy_op + (size_t)r * ld;
-            if (tok[ii] < 0) {                             // padding row: zero (the wgrad GEMMs sum over it)
-                for (int j = lane; j < ld / 4; j += 32) reinterpret_cast<uint2*>(dst)[j] = make_uint2(0u, 0u);
-                if (lane == 0) dgate_row[r] = 0.0f;
-                continue;
-            }
+            const int rl = rg + RG * (i0 + ii);
+            const int r = blockIdx.x * 32 + rl;
+            __nv_bfloat16* dst = dy_op + (size_t)r * ld + col;
             float dot = 0.0f;
+            if (tok[ii] < 0) {                             // padding row: zero (the wgrad GEMMs sum over it)
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                if (split) *reinterpret_cast<uint4*>(dst + d) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                float a[8], b[8], dv[8];
+                chunk_unpack(go[ii], a);
+                chunk_unpack(yv[ii], b);
 #pragma unroll
-            for (int s = 0; s < NSEG; ++s) {
-                const int col = s * 128 + lane * 4;
-                const float4 a = raw_to_float4(go[ii][s]), b = raw_to_float4(yv[ii][s]);
-                dot = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, dot))));
-                const float4 dv = make_float4(g[ii] * a.x, g[ii] * a.y, g[ii] * a.z, g[ii] * a.w);
-                store_operand4(dst + col, d, split != 0, dv);
-                cs[s].x += dv.x; cs[s].y += dv.y; cs[s].z += dv.z; cs[s].w += dv.w;
+                for (int e = 7; e >= 0; --e) dot = fmaf(a[e], b[e], dot);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { dv[e] = g[ii] * a[e]; cs[e] += dv[e]; }
+                store_operand8(dst, d, split != 0, dv);
             }
-            dot = warp_sum(dot);
-            if (lane == 0) dgate_row[r] = dot;
+            // <dout_t, y_r>: 16-lane groups never straddle rows (CPR is a multiple of 16); the NSEG group sums are added in order
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if ((c & 15) == 0) dot_part[rl][c >> 4] = dot;
         }
     }
-    if (colpart == nullptr) return;
 #pragma unroll
-    for (int s = 0; s < NSEG; ++s) red[wid][s * 32 + lane] = cs[s];
+    for (int e = 0; e < 8; ++e) red[rg][col + e] = cs[e];
     __syncthreads();
-    for (int j = threadIdx.x; j < NSEG * 32; j += 256) {           // float4 index: columns 4j .. 4j+3 (j = seg * 32 + lane)
-        float4 a = red[0][j];
+    if (tid < 32) {
+        float v = dot_part[tid][0];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) { const float4 b = red[w][j]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-        reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * d)[j] = a;
+        for (int q = 1; q < NSEG; ++q) v += dot_part[tid][q];
+        dgate_row[blockIdx.x * 32 + tid] = v;
+    }
+    if (colpart == nullptr) return;
+    for (int j = tid; j < NSEG * 128; j += CPR * RG) {
+        float a = red[0][j];
+#pragma unroll
+        for (int w = 1; w < RG; ++w) a += red[w][j];
+        colpart[(size_t)blockIdx.x * d + j] = a;
     }
 }
 
-// dx[t] = sum_j dx_rows[row(t, j)] (+ dx_router[t])
+// dx[t] = sum_j dx_rows[row(t, j)] (+ dx_router[t])      (same flat chunk layout as combine_fwd)
 template <bool R_F32, int NSEG>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 uncombine_kernel(const void* __restrict__ dx_rows, const int* __restrict__ token_rows, const float* __restrict__ dx_router,
                  int T, int T_pad, int d, int k, int dense, float* __restrict__ dx) {
-    constexpr int JB = SlotBatch<NSEG>::value, TB = TokBatch<NSEG>::value;
-    const int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * TB;
-    const int lane = threadIdx.x & 31;
-    if (t0 >= T) return;
-    float4 acc[TB][NSEG];
+    constexpr int CPR = NSEG * 16, U = CHUNKS_PER_THREAD, JB = R_F32 ? 2 : 4;
+    const long long f0 = (long long)blockIdx.x * (256 * U) + threadIdx.x;
+    int t[U], col[U];
+    float acc[U][8];
 #pragma unroll
-    for (int i = 0; i < TB; ++i)
+    for (int u = 0; u < U; ++u) {
+        const long long f = f0 + u * 256;
+        const int tt = (int)(f / CPR);
+        t[u] = tt < T ? tt : -1;
+        col[u] = (int)(f - (long long)tt * CPR) * 8;
 #pragma unroll
-        for (int s = 0; s < NSEG; ++s) {
-            acc[i][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (dx_router != nullptr && t0 + i < T)
-                acc[i][s] = __ldg(reinterpret_cast<const float4*>(dx_router + (size_t)(t0 + i) * d + s * 128 + lane * 4));
-        }
+        for (int e = 0; e < 8; ++e) acc[u][e] = 0.0f;
+        if (dx_router != nullptr && t[u] >= 0) chunk_unpack(chunk_load<true>(dx_router, (size_t)t[u] * d + col[u]), acc[u]);
+    }
     for (int j0 = 0; j0 < k; j0 += JB) {
-        int row[TB][JB];
+        int row[U][JB];
 #pragma unroll
-        for (int i = 0; i < TB; ++i)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-                const int j = j0 + jj, t = t0 + i;
-                row[i][jj] = (j < k && t < T) ? (dense ? j * T_pad + t : __ldg(token_rows + (size_t)t * k + j)) : -1;
+                const int j = j0 + jj;
+                row[u][jj] = (j < k && t[u] >= 0) ? (dense ? j * T_pad + t[u] : __ldg(token_rows + (size_t)t[u] * k + j)) : -1;
             }
-        typename Raw4<R_F32>::type v[TB][JB][NSEG];
+        Chunk8<R_F32> v[U][JB];
 #pragma unroll
-        for (int i = 0; i < TB; ++i)
-#pragma unroll
-            for (int jj = 0; jj < JB; ++jj)
-#pragma unroll
-                for (int s = 0; s < NSEG; ++s)
-                    if (row[i][jj] >= 0) v[i][jj][s] = raw_load4<R_F32>(dx_rows, (size_t)row[i][jj] * d + s * 128 + lane * 4);
-#pragma unroll
-        for (int i = 0; i < TB; ++i)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj)
-                if (row[i][jj] >= 0) {
+                if (row[u][jj] >= 0) v[u][jj] = chunk_load<R_F32>(dx_rows, (size_t)row[u][jj] * d + col[u]);
 #pragma unroll
-                    for (int s = 0; s < NSEG; ++s) {
-                        const float4 f = raw_to_float4(v[i][jj][s]);
-                        acc[i][s].x += f.x; acc[i][s].y += f.y; acc[i][s].z += f.z; acc[i][s].w += f.w;
-                    }
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj)
+                if (row[u][jj] >= 0) {
+                    float f[8];
+                    chunk_unpack(v[u][jj], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[u][e] += f[e];
                 }
     }
 #pragma unroll
-    for (int i = 0; i < TB; ++i)
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s)
-            if (t0 + i < T) *reinterpret_cast<float4*>(dx + (size_t)(t0 + i) * d + s * 128 + lane * 4) = acc[i][s];
+    for (int u = 0; u < U; ++u)
+        if (t[u] >= 0) chunk_store<false>(dx, (size_t)t[u] * d + col[u], acc[u]);
 }
 
 // bias gradients: out[e, c] = sum over real rows of expert e of (hi + lo)[row, c].
@@ -590,7 +635,7 @@ template <bool YF, int RS, bool OB>
 static void combine_fwd_dispatch(const moegan_shape* s, const void* y, const float* gates, const int32_t* token_rows, const void* residual,
                                  void* out, cudaStream_t st) {
     const int T_pad = row_pad(s->T);
-#define MOEGAN_CF(NS) combine_fwd_kernel<YF, RS, OB, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, residual, out)
+#define MOEGAN_CF(NS) combine_fwd_kernel<YF, RS, OB, NS><<<(unsigned)ceil_div64((int64_t)s->T * NS * 16, 256 * CHUNKS_PER_THREAD), 256, 0, st>>>(y, gates, token_rows, s->T, T_pad, s->d, s->k, s->dense, residual, out)
     MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_CF)
 #undef MOEGAN_CF
 }
@@ -615,7 +660,7 @@ static void combine_bwd_dispatch(const moegan_shape* s, const int32_t* plan, con
                                  cudaStream_t st) {
     const int T_pad = row_pad(s->T);
     const int blocks = s->m_cap / 32;
-#define MOEGAN_CB(NS) combine_bwd_kernel<YF, DB, NS><<<blocks, 256, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, split, dy, dgate_row, dy_colpart)
+#define MOEGAN_CB(NS) combine_bwd_kernel<YF, DB, NS><<<blocks, NS * 16 * CbRowGroups<NS>::value, 0, st>>>(plan, dout, y, row_token, row_gate, gates, s->T, T_pad, s->d, s->E, s->dense, split, dy, dgate_row, dy_colpart)
     MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_CB)
 #undef MOEGAN_CB
 }
@@ -663,8 +708,8 @@ int launch_uncombine(const moegan_shape* s, const void* dx_rows, const int32_t* 
                      cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_UNCOMBINE, s, dx_router != nullptr ? 0x1000 : 0);
     const int T_pad = row_pad(s->T);
-#define MOEGAN_UC32(NS) uncombine_kernel<true, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
-#define MOEGAN_UC16(NS) uncombine_kernel<false, NS><<<ceil_div(s->T, 8 * TokBatch<NS>::value), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
+#define MOEGAN_UC32(NS) uncombine_kernel<true, NS><<<(unsigned)ceil_div64((int64_t)s->T * NS * 16, 256 * CHUNKS_PER_THREAD), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
+#define MOEGAN_UC16(NS) uncombine_kernel<false, NS><<<(unsigned)ceil_div64((int64_t)s->T * NS * 16, 256 * CHUNKS_PER_THREAD), 256, 0, st>>>(dx_rows, token_rows, dx_router, s->T, T_pad, s->d, s->k, s->dense, dx)
     if (s->precision == 1) { MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_UC32) }
     else                   { MOEGAN_NSEG_SWITCH(s->d / 128, MOEGAN_UC16) }
 #undef MOEGAN_UC32

@@ -332,7 +332,7 @@ constexpr int RB_TOK = 16;   // tokens per CTA (8 warps x 2)
 // registers) while the draw values are in flight anyway, and writes ONE partial [128][E] per CTA - the separate pass over
 // fp / draw (router_bwd_dwc_part_kernel, 30-90 us of the router's backward chain) disappears.  The grid is persistent
 // (<= RB_MAX_BLOCKS CTAs walk the 16-token groups) so that the finishing sums stay short however large T is.
-constexpr int RB_MAX_BLOCKS = 296;
+constexpr int RB_MAX_BLOCKS = 592;   // 4 CTAs per SM (64 registers): the per-token chain is latency-bound, occupancy is what hides it
 constexpr int RB_FUSE_MAX_E = 8;
 template <bool FUSE_DWC>
 __global__ void __launch_bounds__(RB_THREADS)
