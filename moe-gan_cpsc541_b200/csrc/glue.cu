@@ -37,6 +37,30 @@ template <typename T> __device__ __forceinline__ void store1(T* p, float v);
 template <> __device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// ---- 8 consecutive channels (16 B of bf16 / 32 B of fp32): what bounds these kernels on B200 is the number of outstanding load
+// REQUESTS per SM, so the wider the per-lane access the closer to the HBM roof (ncu on the combine kernels, dispatch.cu) ----
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        f[0] = bf16_lo_to_float(u.x); f[1] = bf16_hi_to_float(u.x); f[2] = bf16_lo_to_float(u.y); f[3] = bf16_hi_to_float(u.y);
+        f[4] = bf16_lo_to_float(u.z); f[5] = bf16_hi_to_float(u.z); f[6] = bf16_lo_to_float(u.w); f[7] = bf16_hi_to_float(u.w);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+};
+
 // =====================================================================================================
 // LayerNorm over the last dimension (d = 128 * nseg <= 1024), eps inside the sqrt (nn.LayerNorm)
 // =====================================================================================================
@@ -243,53 +267,86 @@ colsum_rows_kernel(const T* __restrict__ x, long long rows, int cols, int nsplit
 // =====================================================================================================
 // channel_scale: out[b, p, c] = lrelu(x[b, p, c] * s[b, c], slope)      x: [B, P, C] (NHWC), s: [B, C] fp32
 // =====================================================================================================
-// forward: grid-stride over groups of 4 channels
+// forward: flat over groups of 8 channels, CS_U groups (256 apart) per thread, all loads issued before the first use
+constexpr int CS_U = 2;
 template <typename T, typename TS>
 __global__ void __launch_bounds__(256)
-channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, long long n4, int P, int C, float slope, T* __restrict__ out) {
-    const int c4 = C / 4;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-        const long long bp = i / c4;
-        const int c = (int)(i - bp * c4) * 4;
-        const long long b = bp / P;
-        const float4 v = Vec4<T>::load(x + i * 4);
-        const float4 sc = Vec4<TS>::load(s + b * C + c);
-        float4 o = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
-        o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
-        o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
-        Vec4<T>::store(out + i * 4, o);
+channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, long long n8, int P, int C, float slope, T* __restrict__ out) {
+    const int c8 = C / 8;
+    const long long i0 = (long long)blockIdx.x * (256 * CS_U) + threadIdx.x;
+    float v[CS_U][8], sc[CS_U][8];
+#pragma unroll
+    for (int u = 0; u < CS_U; ++u) {
+        const long long i = i0 + u * 256;
+        if (i < n8) {
+            const long long bp = i / c8;
+            const int c = (int)(i - bp * c8) * 8;
+            const long long b = bp / P;
+            Vec8<T>::load(x + i * 8, v[u]);
+            Vec8<TS>::load(s + b * C + c, sc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < CS_U; ++u) {
+        const long long i = i0 + u * 256;
+        if (i < n8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float t = v[u][e] * sc[u][e]; o[e] = t > 0.f ? t : t * slope; }
+            Vec8<T>::store(out + i * 8, o);
+        }
     }
 }
-// backward: CTA = (sample b, 128-channel group, pixel split); warp w takes pixels w, w+8, ...; lane = 4 channels.
+// backward: CTA = (sample b, 128-channel group, pixel split); half-warp = one pixel (16 lanes x 8 channels), so the 16 half-warps
+// take pixels h, h + 16, ... two at a time.
 //   m = g * (x*s > 0 ? 1 : slope);  dx = m * s;  ds[b, c] = sum_p m * x   (partials over the pixel splits, summed in order)
 template <typename T, typename TS>
 __global__ void __launch_bounds__(256)
 channel_scale_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const TS* __restrict__ s, int P, int C, float slope,
                          int psplit, T* __restrict__ dx, float* __restrict__ ds_part /* [psplit][B][C] */, int Bn) {
-    __shared__ float4 red[8][32];
+    __shared__ float red[16][128];
     const int b = blockIdx.y, cgp = blockIdx.x, sp = blockIdx.z;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = cgp * 128 + lane * 4;
-    const float4 sc = Vec4<TS>::load(s + (size_t)b * C + c);
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int c = cgp * 128 + l16 * 8;
+    float sc[8];
+    Vec8<TS>::load(s + (size_t)b * C + c, sc);
     const int per = (P + psplit - 1) / psplit;
     const int p0 = sp * per, p1 = min(P, p0 + per);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = p0 + wid; p < p1; p += 8) {
-        const size_t o = ((size_t)b * P + p) * C + c;
-        const float4 gv = Vec4<T>::load(g + o), xv = Vec4<T>::load(x + o);
-        float4 m;
-        m.x = xv.x * sc.x > 0.f ? gv.x : gv.x * slope; m.y = xv.y * sc.y > 0.f ? gv.y : gv.y * slope;
-        m.z = xv.z * sc.z > 0.f ? gv.z : gv.z * slope; m.w = xv.w * sc.w > 0.f ? gv.w : gv.w * slope;
-        Vec4<T>::store(dx + o, make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w));
-        acc.x += m.x * xv.x; acc.y += m.y * xv.y; acc.z += m.z * xv.z; acc.w += m.w * xv.w;
-    }
-    red[wid][lane] = acc;
-    __syncthreads();
-    if (wid == 0) {
-        float4 a = red[0][lane];
+    float acc[8];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) { const float4 t = red[w][lane]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-        *reinterpret_cast<float4*>(ds_part + ((size_t)sp * Bn + b) * C + c) = a;
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int p = p0 + hw; p < p1; p += 32) {
+        const bool two = p + 16 < p1;
+        const size_t o0 = ((size_t)b * P + p) * C + c, o1 = o0 + (size_t)16 * C;
+        float g0[8], x0[8], g1[8], x1[8];
+        Vec8<T>::load(g + o0, g0); Vec8<T>::load(x + o0, x0);
+        if (two) { Vec8<T>::load(g + o1, g1); Vec8<T>::load(x + o1, x1); }
+        float d0[8], d1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float m = x0[e] * sc[e] > 0.f ? g0[e] : g0[e] * slope;
+            d0[e] = m * sc[e];
+            acc[e] += m * x0[e];
+        }
+        Vec8<T>::store(dx + o0, d0);
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float m = x1[e] * sc[e] > 0.f ? g1[e] : g1[e] * slope;
+                d1[e] = m * sc[e];
+                acc[e] += m * x1[e];
+            }
+            Vec8<T>::store(dx + o1, d1);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[hw][l16 * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float a = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) a += red[w][threadIdx.x];
+        ds_part[((size_t)sp * Bn + b) * C + cgp * 128 + threadIdx.x] = a;
     }
 }
 
@@ -520,11 +577,11 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
 
 int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_CHANNEL_SCALE_FWD, (long long)B, P, C, (bf16 ? 1 : 0) | (s_bf16 ? 2 : 0));
-    const long long n4 = (long long)B * P * C / 4;
-    if (n4 == 0) return MOEGAN_OK;
-    const int blocks = grid_cap((n4 + 255) / 256);
+    const long long n8 = (long long)B * P * C / 8;
+    if (n8 == 0) return MOEGAN_OK;
+    const unsigned blocks = (unsigned)((n8 + 256 * CS_U - 1) / (256 * CS_U));
     typedef __nv_bfloat16 bf;
-#define MOEGAN_CS_FWD(T, TS) channel_scale_fwd_kernel<T, TS><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), n4, P, C, slope, reinterpret_cast<T*>(out))
+#define MOEGAN_CS_FWD(T, TS) channel_scale_fwd_kernel<T, TS><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), n8, P, C, slope, reinterpret_cast<T*>(out))
     if (bf16) { if (s_bf16) MOEGAN_CS_FWD(bf, bf); else MOEGAN_CS_FWD(bf, float); }
     else      { if (s_bf16) MOEGAN_CS_FWD(float, bf); else MOEGAN_CS_FWD(float, float); }
 #undef MOEGAN_CS_FWD
@@ -533,10 +590,10 @@ int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16,
 }
 
 int channel_scale_psplit(int B, int P, int C) {
-    // enough CTAs to fill the chip: B * C/128 * psplit >= ~4 per SM, at least 8 pixels (one per warp) per split
+    // enough CTAs to fill the chip: B * C/128 * psplit >= ~4 per SM, at least 16 pixels (one per half-warp) per split
     long long ctas = (long long)B * (C / 128);
     int ps = 1;
-    while (ctas * ps < (long long)num_sms() * 4 && ps * 2 * 8 <= P && ps < 64) ps *= 2;
+    while (ctas * ps < (long long)num_sms() * 4 && ps * 2 * 16 <= P && ps < 64) ps *= 2;
     return ps;
 }
 
