@@ -294,6 +294,12 @@ int moegan_offset_sample_fwd(const void* x, int32_t is_bf16, const float* off, i
 int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, const float* off, int32_t B, int32_t H,
                              int32_t W, int32_t C, void* dx, float* doff, void* stream);
 
+/* replaces: F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) at the head of GenerativeBlock.forward
+ * (t2i_moe_gan.py:646-648).  x / dx: NHWC [B,H,W,C], out / g: NHWC [B,2H,2W,C], fp32 or bf16; C: multiple of 8.  The backward is
+ * a deterministic gather (no atomics). */
+int moegan_upsample2x_fwd(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* out, void* stream);
+int moegan_upsample2x_bwd(const void* g, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* dx, void* stream);
+
 /* ---- test / bench hook ---------------------------------------------------------------------- */
 /* Plain (ungrouped) GEMM on the same tcgen05 kernel, fp32 out:  C[M,N] = op(A) * op(B).
  * kind 0: A [M,S*K] K-major, B [N,S*K] K-major.   kind 1: A [M,S*K] K-major, B [K,S*N] (N contiguous).
@@ -322,7 +328,8 @@ enum {
     MOEGAN_PROF_ROUTER_BWD_TEXT = 14, MOEGAN_PROF_REPARAM_KL_BWD = 15, MOEGAN_PROF_SUM_PARTIALS = 16, MOEGAN_PROF_COLSUM_GROUPED = 17,
     MOEGAN_PROF_BALANCE = 18,
     MOEGAN_PROF_LAYERNORM_FWD = 20, MOEGAN_PROF_LAYERNORM_BWD = 21, MOEGAN_PROF_CHANNEL_SCALE_FWD = 22, MOEGAN_PROF_CHANNEL_SCALE_BWD = 23,
-    MOEGAN_PROF_OFFSET_SAMPLE_FWD = 24, MOEGAN_PROF_OFFSET_SAMPLE_BWD = 25, MOEGAN_PROF_COLSUM = 26
+    MOEGAN_PROF_OFFSET_SAMPLE_FWD = 24, MOEGAN_PROF_OFFSET_SAMPLE_BWD = 25, MOEGAN_PROF_COLSUM = 26,
+    MOEGAN_PROF_UPSAMPLE2X_FWD = 27, MOEGAN_PROF_UPSAMPLE2X_BWD = 28
 };
 int moegan_debug_profile_enable(int32_t level);
 int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n);

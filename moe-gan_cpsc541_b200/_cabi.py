@@ -96,6 +96,8 @@ SIGNATURES = {
     "moegan_colsum": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, c_int64, _P]),
     "moegan_offset_sample_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "moegan_offset_sample_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "moegan_upsample2x_fwd": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "moegan_upsample2x_bwd": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "moegan_umma_gemm": (c_int32, [c_int32] * 5 + [_P] * 3 + [_P]),
     "moegan_debug_set_mn_desc": (c_int32, [c_int32] * 3),
     "moegan_debug_launch_count": (c_int64, []),

@@ -920,6 +920,23 @@ int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, cons
     return launch_offset_sample_bwd(g, x, is_bf16, off, B, H, W, C, dx, doff, (cudaStream_t)stream);
 }
 
+int moegan_upsample2x_fwd(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
+    MOEGAN_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, MOEGAN_ERR_BAD_SHAPE,
+                   "upsample2x: B (%d) >= 0, H x W (%d x %d) >= 1, C (%d) a positive multiple of 8", B, H, W, C);
+    REQ_PTR(x); REQ_PTR(out);
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                   "upsample2x_fwd: pointers must be 16-byte aligned");
+    return launch_upsample2x_fwd(x, is_bf16, B, H, W, C, out, (cudaStream_t)stream);
+}
+int moegan_upsample2x_bwd(const void* g, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* dx, void* stream) {
+    MOEGAN_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, MOEGAN_ERR_BAD_SHAPE,
+                   "upsample2x: B (%d) >= 0, H x W (%d x %d) >= 1, C (%d) a positive multiple of 8", B, H, W, C);
+    REQ_PTR(g); REQ_PTR(dx);
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                   "upsample2x_bwd: pointers must be 16-byte aligned");
+    return launch_upsample2x_bwd(g, is_bf16, B, H, W, C, dx, (cudaStream_t)stream);
+}
+
 // ---- test / bench hooks ----------------------------------------------------------------------------
 int moegan_umma_gemm(int32_t kind, int32_t precision, int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* C, void* stream) {
     REQ_PTR(A); REQ_PTR(B); REQ_PTR(C);

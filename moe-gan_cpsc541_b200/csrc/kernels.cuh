@@ -72,6 +72,9 @@ int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, i
 int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float* off, int B, int H, int W, int C, void* dx, float* doff,
                              cudaStream_t st);
 
+int launch_upsample2x_fwd(const void* x, int bf16, int B, int H, int W, int C, void* out, cudaStream_t st);
+int launch_upsample2x_bwd(const void* g, int bf16, int B, int H, int W, int C, void* dx, cudaStream_t st);
+
 int launch_sum_partials(const float* part, long long n, int nsplit, float* out, cudaStream_t st);
 
 }  // namespace moegan

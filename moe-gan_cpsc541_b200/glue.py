@@ -208,6 +208,36 @@ def multihead_attention(m: torch.nn.MultiheadAttention, query: torch.Tensor, key
 
 
 # --------------------------------------------------------------------------------------------------
+# 2x bilinear upsampling at the head of a GenerativeBlock (t2i_moe_gan.py:646-648)
+# --------------------------------------------------------------------------------------------------
+class _Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, Cn, H, W = x.shape
+        xc = _nhwc(x if x.dtype in (torch.float32, torch.bfloat16) else x.float())
+        out = torch.empty((B, Cn, 2 * H, 2 * W), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
+        C.check(C.lib().moegan_upsample2x_fwd(C.ptr(xc), _is_bf16(xc), B, H, W, Cn, C.ptr(out), _stream()), "moegan_upsample2x_fwd")
+        ctx.in_shape, ctx.x_dtype = (B, Cn, H, W), x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cn, H, W = ctx.in_shape
+        gc = _nhwc(g if g.dtype in (torch.float32, torch.bfloat16) else g.float())
+        dx = torch.empty((B, Cn, H, W), device=g.device, dtype=gc.dtype, memory_format=torch.channels_last)
+        C.check(C.lib().moegan_upsample2x_bwd(C.ptr(gc), _is_bf16(gc), B, H, W, Cn, C.ptr(dx), _stream()), "moegan_upsample2x_bwd")
+        return dx.to(ctx.x_dtype)
+
+
+def upsample2x_bilinear(x: torch.Tensor) -> torch.Tensor:
+    """`F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)` for x [B,C,H,W]; on CUDA (C a multiple of 8) through
+    the library's NHWC kernels - same tap formula and evaluation order as ATen, deterministic gather in the backward."""
+    if x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16):
+        return _Upsample2xFn.apply(x)
+    return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+
+
+# --------------------------------------------------------------------------------------------------
 # learned-offset bilinear resampling (ModulatedTransformationModule, t2i_moe_gan.py:219-240)
 # --------------------------------------------------------------------------------------------------
 class _OffsetSampleFn(torch.autograd.Function):

@@ -226,3 +226,30 @@ def test_linear_and_multihead_attention_match_torch(monkeypatch):
             res.append([o.detach(), q.grad.clone(), kv.grad.clone()] + [p.grad.clone() for p in mha.parameters()])
         for a, b in zip(*res):
             assert _rel(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 256, 8, 8), (2, 512, 4, 4), (2, 8, 1, 3), (1, 128, 5, 7), (300, 16, 2, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample2x_matches_interpolate(B, C, H, W, dtype):
+    """The 2x bilinear upsampling at the head of GenerativeBlock (t2i_moe_gan.py:646-648) against F.interpolate in fp64:
+    border clamps on both sides (H = 1, odd sizes), NCHW and channels-last inputs, the gather backward."""
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(B * 1000 + C + H)
+    x = torch.randn(B, C, H, W, generator=g).to(dtype)
+    gy = torch.randn(B, C, 2 * H, 2 * W, generator=g).to(dtype)
+    xr = x.double().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    yr.backward(gy.double())
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        xc = x.cuda().contiguous(memory_format=fmt).requires_grad_(True)
+        yc = glue.upsample2x_bilinear(xc)
+        assert yc.dtype == dtype and yc.shape == yr.shape and yc.is_contiguous(memory_format=torch.channels_last)
+        yc.backward(gy.cuda())
+        tol = 1e-6 if dtype == torch.float32 else 1e-2
+        assert _rel(yc, yr) < tol
+        assert _rel(xc.grad, xr.grad) < tol
+        y2 = glue.upsample2x_bilinear(xc.detach())
+        assert torch.equal(y2, yc.detach())
+    if dtype == torch.float32:      # same taps, same evaluation order as ATen's kernel
+        ya = F.interpolate(x.cuda().contiguous(memory_format=torch.channels_last), scale_factor=2, mode="bilinear", align_corners=False)
+        assert _rel(yc, ya) < 1e-6
