@@ -431,6 +431,18 @@ def kernel_table(records, steps, pk):
     return rows
 
 
+def gemm_roof_summary(rows):
+    """Time-weighted position of the tcgen05 GEMM instances against the LOWER of their two roofs (per-instance `roof` / `frac_of_roof` of
+    kernel_table): sum of roof times / sum of measured times, and the share of GEMM time spent in HBM-bound instances."""
+    g = [r for r in rows if r["bound"] == "tensor" and "frac_of_roof" in r]
+    tot = sum(r["us_per_step"] for r in g)
+    if tot <= 0:
+        return None
+    return {"frac_of_lower_roof": round(sum(r["us_per_step"] * r["frac_of_roof"] for r in g) / tot, 3),
+            "hbm_bound_share_of_gemm_time": round(sum(r["us_per_step"] for r in g if r.get("roof") == "hbm") / tot, 3),
+            "note": "per instance: max(flops / measured bf16 peak, algorithmic bytes / measured HBM bandwidth) / event-bracketed duration"}
+
+
 def write_kernel_table(path, title, rows, append=False):
     if not path:
         return
@@ -553,7 +565,8 @@ def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
                      "unit": "TFLOP/s", "frac": ach / peak_tf,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernels timed individually)" if pk else "fallback 1590 (B200_PROFILING.md)",
                      "traffic": traffic_from_profiles("umma_gemm_moe_block"), "flops_per_launch": flops_per_launch,
-                     "mean_launch_us": mean_ms * 1e3, "per_kernel_us": {k: 1e3 * sum(v) / len(v) for k, v in by_kernel.items()}},
+                     "mean_launch_us": mean_ms * 1e3, "per_kernel_us": {k: 1e3 * sum(v) / len(v) for k, v in by_kernel.items()},
+                     "by_instance": gemm_roof_summary(kernels)},
         "tokens": T, "kernels": kernels,
     }
 
@@ -643,7 +656,8 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels inside a long step)" if pk else "fallback 1590 (B200_PROFILING.md)",
                      "traffic": traffic_from_profiles("umma_gemm_train_step"), "flops_per_launch": flops_per_launch,
                      "gemm_ms_per_step": step_gemm_ms, "gemm_launches_per_step": per_step,
-                     "gemm_share_of_step": step_gemm_ms / ms_per_step if ms_per_step else None},
+                     "gemm_share_of_step": step_gemm_ms / ms_per_step if ms_per_step else None,
+                     "by_instance": gemm_roof_summary(kernels)},
         "kernels": kernels,
     }
     # ---- inference (configs[4]): generate_images semantics, eval-mode hard top-1 routing ----

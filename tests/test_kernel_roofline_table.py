@@ -96,3 +96,12 @@ def test_level2_profiling_brackets_every_launcher(pkg):
         assert any(r["kernel"] == "combine_fwd" and r["bytes"] == T * k * d * 2 + T * k * 8 + T * d * 4 for r in rows)
     # nothing left behind
     assert lib.moegan_debug_profile_read_ex(ms, tag, meta, cap) == 0
+
+
+def test_gemm_roof_summary_weights_by_time():
+    rows = [{"bound": "tensor", "roof": "hbm", "frac_of_roof": 0.8, "us_per_step": 300.0},
+            {"bound": "tensor", "roof": "tensor", "frac_of_roof": 0.5, "us_per_step": 100.0},
+            {"bound": "hbm", "roof": "hbm", "frac_of_roof": 0.3, "us_per_step": 1000.0}]
+    s = bench.gemm_roof_summary(rows)
+    assert s["frac_of_lower_roof"] == 0.725 and s["hbm_bound_share_of_gemm_time"] == 0.75
+    assert bench.gemm_roof_summary([rows[2]]) is None
