@@ -768,6 +768,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if world > 1:
+        # NCCL writes its version / warning lines to stdout when NCCL_DEBUG is set in the environment: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
