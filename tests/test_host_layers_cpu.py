@@ -1,0 +1,36 @@
+"""CPU checks of host-model re-formulations that need neither the reference tree nor a GPU."""
+import torch
+
+
+def test_text_conditioned_head_equals_cat_then_conv(pkg):
+    """The discriminator's output layer without the concatenated tensor (host_model.text_conditioned_head) against
+    conv2d(cat([f, tiled text])) (t2i_moe_gan.py:899-907): values and every gradient, fp64, both input sizes of the train loop."""
+    import torch.nn.functional as F
+    hm = pkg.host_model
+    torch.manual_seed(0)
+    for hw in (16, 4):                                   # features of a 64x64 real image / of a 16x16 generated one
+        f = torch.randn(3, 256, hw, hw, dtype=torch.float64, requires_grad=True)
+        t = torch.randn(3, 128, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(1, 384, 4, 4, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(1, dtype=torch.float64, requires_grad=True)
+        ref = F.conv2d(torch.cat([f, t[:, :, None, None].expand(-1, -1, hw, hw)], dim=1), w, b)
+        gy = torch.randn_like(ref)
+        g_ref = torch.autograd.grad(ref, (f, t, w, b), gy)
+        out = hm.text_conditioned_head(f, t, w, b)
+        assert out.shape == ref.shape and torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+        for a, r in zip(torch.autograd.grad(out, (f, t, w, b), gy), g_ref):
+            assert torch.allclose(a, r, rtol=1e-11, atol=1e-11)
+
+
+def test_glue_cpu_definitions(pkg):
+    """On CPU tensors the glue functions ARE the torch formulas they replace (the definition the CPU arm uses)."""
+    import torch.nn.functional as F
+    glue = pkg.glue
+    torch.manual_seed(1)
+    x = torch.randn(2, 16, 3, 5)
+    assert torch.equal(glue.upsample2x_bilinear(x), F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+    s = torch.randn(2, 16)
+    assert torch.allclose(glue.channel_scale(x, s, 0.2), F.leaky_relu(x * s[:, :, None, None], 0.2))
+    t = torch.randn(7, 128)
+    w, b = torch.randn(128), torch.randn(128)
+    assert torch.allclose(glue.layer_norm(t, w, b, 1e-5), F.layer_norm(t, (128,), w, b, 1e-5))

@@ -90,3 +90,4 @@ def test_fused_real_pass_equals_reference_formulation(pkg):
     assert a[3].keys() == b[3].keys()
     for n in a[3]:
         assert float((a[3][n] - b[3][n]).abs().max()) <= 1e-9 * max(1e-3, float(b[3][n].abs().max())), n
+
