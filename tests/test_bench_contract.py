@@ -1,0 +1,33 @@
+"""The JSON contract of bench.py's reference arm (the one leg that runs without a GPU): one line on stdout with the keys the
+driver reads, the CPU port described in `cpu_baseline`, `e2e` repeating the line's own value with zero copy bytes."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "train_imgs_per_s" and d["unit"] == "imgs/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_defaults_and_workload_names():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.TRAIN_BATCH == 256 and bench.CPU_BATCH == 8 and bench.INFER_BATCH == 1024
+    assert bench.WL["E"] == 8 and bench.WL["k"] == 2 and bench.WL["B"] * bench.WL["H"] * bench.WL["W"] == 4096 and bench.WL["d"] == 512
+    assert "configs[1]" in bench.moe_block_workload_name() and "configs[2]" in bench.train_workload_name(1)
