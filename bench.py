@@ -39,6 +39,12 @@ WL = dict(B=8, H=16, W=32, d=512, Dt=512, E=8, k=2, mu_scale=8.0, af=1.0)
 TRAIN_BATCH = 256          # per GPU (configs[2]); 8 GPUs -> global 2048 (configs[3])
 CPU_BATCH = 8              # configs[0]: the reference's own CPU-runnable case
 INFER_BATCH = 1024         # configs[4]
+GLOBAL_BATCH_DP = 2048      # configs[3]
+# how the parity the numbers rest on is defined (tests/, -m gpu): stated in the bench line so a reader need not open the tests
+PARITY_NOTE = {"metric": "max|a-b| / max|b| per tensor (max-norm relative error)", "fp32_mode_bar": 1e-4, "bf16_mode_bar": 2e-2,
+               "routing": "top-k indices / permutation bit-exact; tokens whose top-k logit gap is < 1e-6 are listed and excluded",
+               "exception": "scalar router.temperature gradient is allowed 3x the bar in bf16 mode (a cancelling sum over all tokens)",
+               "against": "unmodified reference on the same GPU (tests/test_gpu_reference_dropin.py), golden fixtures from the reference (tests/golden), numpy oracle"}
 
 
 def peaks():
@@ -48,9 +54,10 @@ def peaks():
         return {}
 
 
-def make_numpy_case(seed):
+def make_numpy_case(seed, WL=None):
     import numpy as np
     from oracle import moe_oracle as O   # parameter shapes / init helper only; the oracle is never on the measured GPU path
+    WL = WL or globals()["WL"]
     rng = np.random.RandomState(seed)
     params = O.init_params(rng, WL["d"], WL["Dt"], WL["E"], mu_scale=WL["mu_scale"])
     x = rng.standard_normal((WL["B"], WL["d"], WL["H"], WL["W"])).astype(np.float32)
@@ -118,15 +125,78 @@ def cpu_threads():
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the reference's train iteration restated with the numpy oracle as the MoE block
+# CPU arm: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) through one iteration of its own batch loop
+# (oracle/ref_step.py restates t2i_moe_gan.py:1262-1421 around the reference's own modules); the torch-CPU port is only the
+# fallback for a tree that was never built next to /root/reference
 # --------------------------------------------------------------------------------------------------
+def reference_available():
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:
+        return False
+
+
+def pick_cpu_threads(make_step, candidates=None):
+    """The reference arm gets the thread count that is FASTEST for it on this host: batch-8 fp32 ops do not scale to hundreds of
+    hardware threads, so "all the host threads it can use" is found by timing one step at a few settings (launchers such as
+    torch.distributed.run export OMP_NUM_THREADS=1 - the count is always set explicitly here)."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (candidates or (ncpu, ncpu // 2, 64, 32, 16, 8)) if 1 <= c <= ncpu}, reverse=True)
+    best, best_t, tried = cands[-1], float("inf"), {}
+    step = make_step()
+    torch.set_num_threads(cands[0]); step()                # warm-up (allocator, lazy inits)
+    for c in cands:
+        torch.set_num_threads(c)
+        step()
+        t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
+        tried[c] = round(t, 3)
+        if t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best, tried, step
+
+
 def cpu_train_step_time(reps, batch=CPU_BATCH, warmup=1):
-    """One iteration of t2i_moe_gan.py:1262-1421 (no CLIP terms) on the host cores, fp32, batch 8 (configs[0])."""
+    """One iteration of t2i_moe_gan.py:1262-1421 (no CLIP terms) on the host cores, fp32, batch 8 (configs[0]).
+    Returns (median seconds, batch, info dict with kind / cores / threads tried)."""
+    import torch
+    if reference_available():
+        from oracle.ref_step import ReferenceTrainStep
+        real = torch.randn(batch, 3, 64, 64).clamp(-1, 1)
+        text = torch.randn(batch, 512)
+
+        def make_step():
+            tr = ReferenceTrainStep("cpu", amp_dtype=None, checkpoint_activation=False, seed=0)
+            return lambda: tr.step(real, text)
+        cores, tried, step = pick_cpu_threads(make_step)
+        kind = "reference"
+        what = ("the UNMODIFIED reference (oracle/_ref/t2i_moe_gan.py: AuroraGenerator / AuroraDiscriminator / AuroraGANLoss) through one iteration of "
+                "its own batch loop (t2i_moe_gan.py:1262-1421 restated in oracle/ref_step.py, CLIP terms :1384-1387 omitted as in the B200 arm), "
+                "activation checkpointing off")
+    else:
+        step = _port_train_step(batch)
+        cores, tried, kind = cpu_threads(), {}, "port"
+        what = ("oracle/_ref not staged in this tree: torch-CPU PORT of the reference step (host model + oracle/torch_bridge.py), not the reference itself")
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2], batch, {"kind": kind, "cores": cores, "cores_available": os.cpu_count(), "threads_tried_s_per_step": tried, "what": what}
+
+
+def _port_train_step(batch):
     import torch
     pkg = importlib.import_module(PKG)
     hm = pkg.host_model
     from oracle.torch_bridge import TorchSparseMoE
     torch.manual_seed(0)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
     G, D = hm.AuroraGenerator(), hm.AuroraDiscriminator()
     for blk in (G.gen_block_4, G.gen_block_8, G.gen_block_16):
         o = TorchSparseMoE(blk.attn_block.moe.dim, 512)
@@ -163,16 +233,14 @@ def cpu_train_step_time(reps, batch=CPU_BATCH, warmup=1):
         g_loss.backward()
         torch.nn.utils.clip_grad_norm_(G.parameters(), 0.8)
         opt_g.step()
+    return step
 
-    for _ in range(warmup):
-        step()
-    times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        step()
-        times.append(time.perf_counter() - t0)
-    times.sort()
-    return times[len(times) // 2], batch
+
+def cpu_baseline_record(sec, units, info, reps):
+    return {"value": units / sec, "unit": "imgs/s", "cores": info["cores"], "cores_available": info["cores_available"], "kind": info["kind"],
+            "threads_tried_s_per_step": info["threads_tried_s_per_step"],
+            "sample": (f"batch {units} (BASELINE configs[0]) x {reps} reps, median {sec * 1e3:.0f} ms/step, fp32, {info['cores']} host threads "
+                       f"(fastest of those tried): {info['what']}")}
 
 
 def cpu_moe_block_time(reps):
@@ -190,8 +258,10 @@ def cpu_moe_block_time(reps):
     return times[len(times) // 2], xt.shape[0]
 
 
-def moe_block_workload_name():
-    return (f"MoE block microbench (BASELINE configs[1]): E={WL['E']} top-{WL['k']}, T={WL['B'] * WL['H'] * WL['W']} tokens x "
+def moe_block_workload_name(WL=None):
+    WL = WL or globals()["WL"]
+    route = f"top-{WL['k']}" if WL.get("k") else "dense-soft k=E (reference training path)"
+    return (f"MoE block microbench ({WL.get('tag', 'BASELINE configs[1]')}): E={WL['E']} {route}, T={WL['B'] * WL['H'] * WL['W']} tokens x "
             f"d={WL['d']}, fwd+bwd, synthetic tokens, router mu x{WL['mu_scale']:g}")
 
 
@@ -201,24 +271,32 @@ def train_workload_name(world):
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only; the other
+    ranks of a torchrun launch exit 0 without work).  Same metric / unit / workload family as the B200 arm; each step is a BOUNDED
+    SAMPLE of that workload (batch 8 = BASELINE configs[0], fp32) so the run ends within a few minutes - stated in `config`."""
     if rank != 0:
         return
     if args.workload == "moe_block":
         sec, units = cpu_moe_block_time(max(1, args.steps))
-        metric, unit, wl = "moe_block_fwd_bwd_tokens_per_s", "tokens/s", moe_block_workload_name()
-        sample = f"full step (T={units}) x {args.steps} reps, median; numpy fp32 oracle port of t2i_moe_gan.py:249-491"
+        metric, unit = "moe_block_fwd_bwd_tokens_per_s", "tokens/s"
+        config = {"workload": moe_block_workload_name(), "reference_arm": "numpy fp32 oracle port of t2i_moe_gan.py:249-491 (the reference has no top-k)",
+                  "same_config": True}
+        cpu = {"value": units / sec, "unit": unit, "cores": cpu_threads(), "kind": "port",
+               "sample": f"full step (T={units}) x {args.steps} reps, median; numpy fp32 oracle port of t2i_moe_gan.py:249-491"}
     else:
-        sec, units = cpu_train_step_time(max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-        metric, unit, wl = "train_imgs_per_s", "imgs/s", train_workload_name(1)
-        sample = (f"batch {units} (BASELINE configs[0]) x {args.steps} reps, median {sec * 1e3:.0f} ms/step; fp32; the reference's train iteration "
-                  "(t2i_moe_gan.py:1262-1421, no CLIP terms) restated on the PyTorch host model with a torch-CPU port of the reference MoE block (oracle/torch_bridge.py) - "
-                  "the reference tree itself is pure Python and does not travel to the GPU box")
+        reps = max(1, args.steps)
+        sec, units, info = cpu_train_step_time(reps, warmup=max(1, min(args.warmup, 2)))
+        metric, unit = "train_imgs_per_s", "imgs/s"
+        cpu = cpu_baseline_record(sec, units, info, reps)
+        config = {"workload": train_workload_name(world),
+                  "reference_arm": (f"host CPU, fp32, batch {units} per step (BASELINE configs[0]) = a bounded sample of the B200 arm's batch-{TRAIN_BATCH} bf16 workload; "
+                                    f"kind '{info['kind']}', {info['cores']} threads on rank 0 only"),
+                  "same_config": False, "batch_per_step": units, "device": "cpu", "precision": "fp32"}
     val = units / sec
     line = {
         "impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": wl},
-        "cpu_baseline": {"value": val, "unit": unit, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -471,12 +549,14 @@ def traffic_from_profiles(key):
 # --------------------------------------------------------------------------------------------------
 # workload: MoE block microbench (configs[1])
 # --------------------------------------------------------------------------------------------------
-def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
+def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph, WL=None, light=False):
+    """light: block time + e2e only (the companion lines of SURVEY 8(d) config 2), no per-kernel profiling passes."""
     import torch
+    WL = WL or globals()["WL"]
     pkg = importlib.import_module(PKG)
     lib = pkg._cabi.lib()
-    params, x_np, w_np, dout_np, eps_np = make_numpy_case(1000 + rank)          # rank-offset data ...
-    params, _, _, _, _ = make_numpy_case(0)                                      # ... identical weights on every rank
+    params, x_np, w_np, dout_np, eps_np = make_numpy_case(1000 + rank, WL)      # rank-offset data ...
+    params, _, _, _, _ = make_numpy_case(0, WL)                                  # ... identical weights on every rank
     moe = pkg.SparseMoE(WL["d"], WL["Dt"], WL["E"], top_k=WL["k"], precision="bf16")
     sd = {k: torch.from_numpy(v) for k, v in params.items()}
     for k in ("epsilon_f", "epsilon_t", "epsilon_c"):
@@ -540,6 +620,12 @@ def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph):
     if launches_per_graph is not None:
         launches = launches_per_graph * steps
     e2e_ms, _, _ = T_.run(step_e2e, steps, max(2, warmup // 2))
+    if light:
+        ms_per_step = total_ms / steps
+        return {"ms_per_step": ms_per_step, "fwd_bwd_us": ms_per_step * 1e3, "tokens_per_s": T * world / (ms_per_step * 1e-3), "launch": launch_mode,
+                "gpu_launches": launches, "tokens": T, "workload": moe_block_workload_name(WL),
+                "e2e_tokens_per_s": T * world / (e2e_ms / steps * 1e-3),
+                "tensor_floor_us": 48.0 * T * (WL["k"] or WL["E"]) * WL["d"] ** 2 / (float(peaks().get("bf16_tflops", 1590.0)) * 1e12) * 1e6}
     ms_list, _ = T_.gemm_profile(step_device, steps, lead_ms=2.0)
     nk = max(2, min(steps, 10))
     kernels = kernel_table(T_.kernel_profile(step_device, nk, lead_ms=3.0), nk, peaks())
@@ -678,6 +764,105 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
 
 
 # --------------------------------------------------------------------------------------------------
+# the UNMODIFIED reference on the SAME B200 (SURVEY 8(d) "reference on GPU" companion rows): PyTorch-CUDA eager, stock code path
+# --------------------------------------------------------------------------------------------------
+# companion microbench shapes of SURVEY 8(d) config 2: the reference-native E=4, k=E blocks at batch 256, and configs[1] with mu x30
+NATIVE_WLS = [dict(tag="reference-native block 4x4 @ batch 256", B=256, H=4, W=4, d=512, Dt=512, E=4, k=None, mu_scale=8.0, af=1.0),
+              dict(tag="reference-native block 8x8 @ batch 256", B=256, H=8, W=8, d=256, Dt=512, E=4, k=None, mu_scale=8.0, af=1.0),
+              dict(tag="reference-native block 16x16 @ batch 256", B=256, H=16, W=16, d=128, Dt=512, E=4, k=None, mu_scale=8.0, af=1.0)]
+WL_MU30 = dict(WL, mu_scale=30.0, tag="BASELINE configs[1], non-uniform routing")
+
+
+def reference_gpu_train_rows(dev, batch, steps, warmup=2):
+    """Full train step of the unmodified reference modules (oracle/_ref) on this GPU, fp32 and bf16 autocast, batch 256:
+    the number the B200 arm's `value` should be read against (same device, same batch, same losses)."""
+    import torch
+    from oracle.ref_step import ReferenceTrainStep
+    rows = {}
+    torch.manual_seed(4321)
+    real = torch.randn(batch, 3, 64, 64, device=dev).clamp(-1, 1)
+    text = torch.randn(batch, 512, device=dev)
+    for name, dt in (("bf16_autocast", torch.bfloat16), ("fp32", None)):
+        try:
+            tr = ReferenceTrainStep(dev, amp_dtype=dt, checkpoint_activation=False, seed=0)
+            for _ in range(warmup):
+                tr.step(real, text)
+            torch.cuda.synchronize()
+            with ClockSampler(dev.index) as clk:
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                h0 = time.perf_counter()
+                a.record()
+                for _ in range(steps):
+                    out = tr.step(real, text)
+                b.record()
+                torch.cuda.synchronize()
+                wall = (time.perf_counter() - h0) * 1e3 / steps
+            ms = a.elapsed_time(b) / steps
+            rows[name] = {"imgs_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "host_wall_ms_per_step": wall, "batch": batch, "steps": steps,
+                          "clocks": clk.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
+                          "losses": {k: float(v) for k, v in out.items()}}
+            del tr, out
+        except Exception as e:  # noqa
+            rows[name] = {"error": f"{type(e).__name__}: {e}"}
+        import gc
+        gc.collect(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats(dev)
+    rows["what"] = ("unmodified reference (oracle/_ref/t2i_moe_gan.py) AuroraGenerator/AuroraDiscriminator, PyTorch-CUDA eager on this same GPU, one iteration of "
+                    "its batch loop (oracle/ref_step.py = t2i_moe_gan.py:1262-1421 without the CLIP terms), checkpointing off, CUDA events around "
+                    f"{steps} steps after {warmup} warm-ups; the reference's host syncs (.item()) are inside")
+    return rows
+
+
+def reference_gpu_moe_block_us(dev, wl, reps=10, warmup=3):
+    """fwd+bwd of the unmodified reference SparseMoE (dense-soft, E=4) on this GPU at one reference-native shape; fp32 and bf16 autocast."""
+    import torch
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    moe = ref.SparseMoE(wl["d"], wl["Dt"], num_experts=wl["E"]).to(dev).train()
+    with torch.no_grad():
+        for n in ("feature_mu", "text_mu", "combined_mu"):
+            getattr(moe.router, n).mul_(wl["mu_scale"])
+    x = torch.randn(wl["B"], wl["H"], wl["W"], wl["d"], device=dev).permute(0, 3, 1, 2).requires_grad_(True)
+    w = torch.randn(wl["B"], wl["Dt"], device=dev, requires_grad=True)
+    dout = torch.randn(wl["B"], wl["H"], wl["W"], wl["d"], device=dev).permute(0, 3, 1, 2)
+    res = {}
+    for name, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        def step():
+            moe.zero_grad(set_to_none=True); x.grad = None; w.grad = None
+            with torch.autocast("cuda", dtype=dt, enabled=dt is not None):
+                out, kl, probs = moe(x, w, wl["af"])
+            torch.autograd.backward([out, kl], [dout.to(out.dtype), torch.full((), 1e-3, device=dev)])
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            step()
+        b.record(); torch.cuda.synchronize()
+        res[name + "_us"] = a.elapsed_time(b) / reps * 1e3
+    return res
+
+
+def bench_strong_scaling(args, rank, world, dev, T_, steps):
+    """configs[3] as written: GLOBAL batch 2048 split over the ranks (1024 / 512 / 256 per GPU at N = 2 / 4 / 8)."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    per = GLOBAL_BATCH_DP // world
+    G, D = build_models(pkg, dev)
+    torch.manual_seed(99 + rank)
+    real = torch.randn(per, 3, 64, 64, device=dev).clamp(-1, 1).contiguous(memory_format=torch.channels_last)
+    text = torch.randn(per, 512, device=dev)
+    tr = pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=not args.no_graph)
+    total_ms, _, _ = T_.run(lambda: tr.step(real, text), steps, 3)
+    ms = total_ms / steps
+    del tr, G, D
+    torch.cuda.empty_cache()
+    return {"global_batch": GLOBAL_BATCH_DP, "batch_per_gpu": per, "ms_per_step": ms, "imgs_per_s": GLOBAL_BATCH_DP / (ms * 1e-3), "scaling": "strong",
+            "workload": f"BASELINE configs[3] as written: global batch {GLOBAL_BATCH_DP} sharded over {world} GPUs, NCCL gradient all-reduce"}
+
+
+# --------------------------------------------------------------------------------------------------
 def run_b200_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -718,14 +903,35 @@ def run_b200_arm(args, rank, world, local_rank):
             mb = bench_moe_block(args, T_, rank, world, dev, max(10, args.steps), 5, use_graph)
         except Exception as e:  # noqa
             mb = {"error": f"{type(e).__name__}: {e}"}
+    companions, strong = None, None
+    if not args.skip_extras:
+        # SURVEY 8(d) config 2 companion lines: configs[1] with non-uniform routing (mu x30) and the reference-native E=4, k=E blocks
+        companions = []
+        for wl in [WL_MU30] + NATIVE_WLS:
+            try:
+                c = bench_moe_block(args, T_, rank, world, dev, 10, 3, use_graph, WL=wl, light=True)
+                if world == 1 and wl.get("k") is None and reference_available():
+                    c["reference_gpu_eager"] = reference_gpu_moe_block_us(dev, wl)      # the unmodified SparseMoE on this GPU, same shape
+                    c["speedup_vs_reference_gpu_bf16"] = c["reference_gpu_eager"]["bf16_autocast_us"] / c["fwd_bwd_us"]
+                companions.append(c)
+            except Exception as e:  # noqa
+                companions.append({"workload": moe_block_workload_name(wl), "error": f"{type(e).__name__}: {e}"})
+            torch.cuda.empty_cache()
+        if world in (2, 4):
+            try:
+                strong = bench_strong_scaling(args, rank, world, dev, T_, max(5, args.steps // 2))
+            except Exception as e:  # noqa
+                strong = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         return
+    ref_gpu = None
+    if world == 1 and not args.skip_extras and reference_available():
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_train_rows(dev, TRAIN_BATCH, steps=3, warmup=2)
     cpu = None
     if not args.skip_cpu:
-        sec, units = cpu_train_step_time(3, warmup=1)
-        cpu = {"value": units / sec, "unit": "imgs/s", "cores": cpu_threads(), "kind": "port",
-               "sample": (f"batch {units} (BASELINE configs[0]) x 3 reps, median {sec * 1e3:.0f} ms/step, fp32: the reference train iteration "
-                          "(t2i_moe_gan.py:1262-1421, no CLIP terms) on the PyTorch host model with a torch-CPU port of the reference MoE block")}
+        sec, units, info = cpu_train_step_time(3, warmup=1)
+        cpu = cpu_baseline_record(sec, units, info, 3)
     line = {
         "metric": "train_imgs_per_s", "value": r["imgs_per_s"], "unit": "imgs/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -740,6 +946,16 @@ def run_b200_arm(args, rank, world, local_rank):
         "library_us_per_step": round(sum(k["us_per_step"] for k in r["kernels"]), 1),
     }
     write_kernel_table(args.kernels_out, line["config"]["workload"], r["kernels"])
+    if ref_gpu is not None:
+        line["reference_gpu_eager"] = ref_gpu
+        bf = ref_gpu.get("bf16_autocast", {})
+        if "imgs_per_s" in bf:
+            line["speedup_vs_reference_gpu_eager_bf16"] = r["e2e"]["value"] / bf["imgs_per_s"]
+    if companions is not None:
+        line["moe_block_companions"] = companions
+    if strong is not None:
+        line["config3_strong_scaling"] = strong
+    line["parity"] = PARITY_NOTE
     if mb is not None and "error" not in mb:
         line["moe_block"] = {"fwd_bwd_us": mb["ms_per_step"] * 1e3, "tokens_per_s": mb["tokens_per_s"], "launch": mb["launch"],
                              "workload": moe_block_workload_name(), "roofline": mb["roofline"], "e2e": mb["e2e"], "kernels": mb["kernels"]}

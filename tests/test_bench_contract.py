@@ -1,5 +1,5 @@
 """The JSON contract of bench.py's reference arm (the one leg that runs without a GPU): one line on stdout with the keys the
-driver reads, the CPU port described in `cpu_baseline`, `e2e` repeating the line's own value with zero copy bytes."""
+driver reads, the CPU arm (unmodified reference, or the port as fallback) described in `cpu_baseline`, `e2e` repeating the line's own value with zero copy bytes."""
 import json
 import os
 import subprocess
@@ -21,7 +21,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "train_imgs_per_s" and d["unit"] == "imgs/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    # the unmodified reference whenever oracle/_ref (or /root/reference) is present; the torch-CPU port is only the fallback
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    assert cb["kind"] == ("reference" if ref_loader.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    # the reference arm must not claim the B200 arm's configuration: batch 8 / fp32 / CPU is stated, same_config is false
+    assert d["config"]["same_config"] is False and d["config"]["batch_per_step"] == 8 and d["config"]["precision"] == "fp32"
+    assert "bounded sample" in d["config"]["reference_arm"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -31,3 +38,19 @@ def test_bench_defaults_and_workload_names():
     assert bench.TRAIN_BATCH == 256 and bench.CPU_BATCH == 8 and bench.INFER_BATCH == 1024
     assert bench.WL["E"] == 8 and bench.WL["k"] == 2 and bench.WL["B"] * bench.WL["H"] * bench.WL["W"] == 4096 and bench.WL["d"] == 512
     assert "configs[1]" in bench.moe_block_workload_name() and "configs[2]" in bench.train_workload_name(1)
+
+
+def test_reference_arm_sets_threads_under_a_launcher_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must still use the host's cores (round-1 SCALE runs timed it on 1)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    if (os.cpu_count() or 1) > 1:
+        assert d["cpu_baseline"]["cores"] > 1, d["cpu_baseline"]
+    # the other ranks print nothing and exit 0
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
