@@ -49,19 +49,30 @@ class PinnedPrefetcher:
         mk = lambda shape: torch.empty((batch_size, *shape), dtype=torch.float32, pin_memory=self.cuda)
         self._stage = [(mk(n_img), mk(n_emb)) for _ in range(2)]
         self._stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        # one event per staging slot, recorded after the slot's H2D copies: the HOST waits on it before it overwrites the
+        # pinned buffer (stream ordering alone does not stop the CPU, which can run several steps ahead of the GPU, from
+        # rewriting a buffer whose non_blocking copy is still queued)
+        self._copied = [torch.cuda.Event() if self.cuda else None for _ in range(2)]
+        self._in_flight = [False, False]
 
     def __len__(self) -> int:
         return (len(self.ds) // self.bs) // self.world
 
     def _fill(self, slot: int, idx: np.ndarray):
         img, emb = self._stage[slot]
+        if self.cuda and self._in_flight[slot]:
+            self._copied[slot].synchronize()                   # the previous upload out of this slot has finished
+            self._in_flight[slot] = False
         order = np.sort(idx)                                   # sorted reads are kinder to the memory map
         img.copy_(torch.from_numpy(np.ascontiguousarray(self.ds.images[order], dtype=np.float32)))
         emb.copy_(torch.from_numpy(np.ascontiguousarray(self.ds.embeddings[order], dtype=np.float32)))
         if not self.cuda:
             return img.clone(), emb.clone()
         with torch.cuda.stream(self._stream):
-            return img.to(self.device, non_blocking=True), emb.to(self.device, non_blocking=True)
+            out = img.to(self.device, non_blocking=True), emb.to(self.device, non_blocking=True)
+            self._copied[slot].record(self._stream)
+        self._in_flight[slot] = True
+        return out
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         n = len(self.ds)

@@ -77,6 +77,16 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"moegan: '{name}' must be a CUDA tensor - the B200 path has no CPU fallback")
 
 
+_WEIGHT_GENERATION = 0
+
+
+def bump_weight_generation() -> None:
+    """Invalidate every WeightCache.  Call after anything that changes expert weights WITHOUT bumping `Parameter._version` -
+    i.e. a CUDA-graph replay whose captured optimizer step writes the parameters from inside the graph (MoEGANTrainer.step does)."""
+    global _WEIGHT_GENERATION
+    _WEIGHT_GENERATION += 1
+
+
 class WeightCache:
     """bf16 operand copies of the expert weights, rebuilt only when a parameter changed (optimizer step).
 
@@ -84,6 +94,11 @@ class WeightCache:
     of a train step (D-step under no_grad, G-step with grad) share one conversion.  While a CUDA graph is
     being captured the conversion is enqueued once per (capture, parameter versions): a replay must re-convert the
     then-current weights, but the forward passes of one captured step still share it.
+
+    Validity key = (precision, d, E, weight generation, (data_ptr, _version) of every parameter).  `_version` does not move
+    when a captured optimizer step updates the weights during graph.replay(), hence the generation counter
+    (`bump_weight_generation`).  A key is only recorded by `commit()` AFTER the conversion has been enqueued successfully,
+    so a failed / empty (T == 0) block call never leaves uninitialised buffers marked valid.
     """
 
     def __init__(self):
@@ -91,15 +106,18 @@ class WeightCache:
         self.bufs = None
         self.capture_bufs = None
         self.capture_key = None
+        self._pending = None
 
     def get(self, cfg: MoEConfig, w1: Sequence[torch.Tensor], b1, w2, b2):
         """Returns (buffers, stale).  When `stale`, the caller passes the parameter pointer tables to moegan_block_fwd,
-        which converts on a side stream overlapped with the router kernels."""
+        which converts on a side stream overlapped with the router kernels, and then calls commit()."""
         capturing = torch.cuda.is_current_stream_capturing()
-        key = (cfg.precision, cfg.d, cfg.E,
+        key = (cfg.precision, cfg.d, cfg.E, _WEIGHT_GENERATION,
                tuple((p.data_ptr(), p._version) for group in (w1, b1, w2, b2) for p in group))
+        self._pending = None
         if not capturing and key == self.key and self.bufs is not None:
             return self.bufs, False
+        ckey = None
         if capturing:
             cid = int(C.lib().moegan_stream_capture_id(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
             ckey = (cid, key)
@@ -112,11 +130,22 @@ class WeightCache:
                 torch.empty((cfg.E, hid), dtype=torch.float32, device=dev),
                 torch.empty((cfg.E * cfg.d, S * hid), dtype=torch.bfloat16, device=dev),
                 torch.empty((cfg.E, cfg.d), dtype=torch.float32, device=dev))
+        self._pending = (capturing, ckey if capturing else key, bufs)
+        return bufs, True
+
+    def commit(self) -> None:
+        """The conversion requested by the last stale get() has been enqueued: its buffers are valid from now on."""
+        if self._pending is None:
+            return
+        capturing, key, bufs = self._pending
         if capturing:
-            self.capture_bufs, self.capture_key = bufs, ckey
+            self.capture_bufs, self.capture_key = bufs, key
         else:
             self.key, self.bufs = key, bufs
-        return bufs, True
+        self._pending = None
+
+    def invalidate(self) -> None:
+        self.key = self.bufs = self.capture_key = self.capture_bufs = self._pending = None
 
 
 def _dp(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -150,10 +179,13 @@ class MoEBlockFunction(torch.autograd.Function):
     -> (out [T,d], kl [], probs [T,E], load [E]).  With a residual, out = residual + moe(x) in the residual's dtype (the
     `x_spatial + moe_out` of AttentionBlock, t2i_moe_gan.py:571, done in the combine kernel's epilogue)."""
 
-    _last = None   # (workspace, layout, cfg) of the most recent forward, for tests / diagnostics
+    keep_last = False   # tests / diagnostics: keep (workspace, layout, cfg) of the most recent forward alive for last_aux()
+    _last = None
 
     @staticmethod
     def last_aux() -> dict:
+        if MoEBlockFunction._last is None:
+            raise RuntimeError("MoEBlockFunction.last_aux(): set MoEBlockFunction.keep_last = True before the forward")
         ws, layout, cfg = MoEBlockFunction._last
         return workspace_views(ws, layout, cfg)
 
@@ -167,7 +199,20 @@ class MoEBlockFunction(torch.autograd.Function):
         f32 = torch.float32
         x_tok = x_tok.contiguous().float()
         w = w.contiguous().float()
-        router_params = [p.contiguous() for p in (mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature)]
+        # the kernels read parameters through raw pointers as contiguous fp32 on x's device: anything else (a model after
+        # .half() / .bfloat16(), a parameter on another GPU, a strided view) would be misread silently - refuse it here
+        names = ("router.feature_mu", "router.feature_rho", "router.text_mu", "router.text_rho", "router.combined_mu", "router.combined_rho",
+                 "router.temperature")
+        for n, p in list(zip(names, (mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature))) + \
+                [(f"experts.{i // 4}.net.{(0, 0, 2, 2)[i % 4]}.{('weight', 'bias')[i % 2]}", p) for i, p in enumerate(expert_params)]:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
+                raise RuntimeError(f"moegan: parameter '{n}' must be a contiguous float32 tensor on {dev} "
+                                   f"(got {p.dtype}, contiguous={p.is_contiguous()}, {p.device}); keep the MoE parameters in fp32 - autocast "
+                                   "selects the bf16 tensor-core path, the module's storage stays fp32")
+        for n, e_ in (("eps_f", eps_f), ("eps_t", eps_t), ("eps_c", eps_c)):
+            if e_ is not None and (e_.dtype != torch.float32 or not e_.is_contiguous() or e_.device != dev):
+                raise RuntimeError(f"moegan: '{n}' must be a contiguous float32 tensor on {dev}")
+        router_params = [mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature]
         w1 = expert_params[0::4]; b1 = expert_params[1::4]; w2 = expert_params[2::4]; b2 = expert_params[3::4]
         plan = _plan_for(cfg)
         need_bwd = cfg.need_backward
@@ -202,7 +247,10 @@ class MoEBlockFunction(torch.autograd.Function):
         a.residual = _dp(residual)
         a.residual_is_bf16 = 1 if (residual is not None and residual.dtype == torch.bfloat16) else 0
         a.out_is_bf16 = 1 if out.dtype == torch.bfloat16 else 0
-        C.check(lib.moegan_block_fwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_fwd")
+        with torch.cuda.device(dev):     # launches go to the current stream OF x's DEVICE
+            C.check(lib.moegan_block_fwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_fwd")
+        if stale and T > 0:
+            wcache.commit()              # only now are the converted buffers valid (a failed call raised above)
 
         load = small[:E]
         kl = small[E] if cfg.sampled else torch.zeros((), dtype=f32, device=dev)   # eval: tensor(0.) (:489)
@@ -213,13 +261,17 @@ class MoEBlockFunction(torch.autograd.Function):
             ctx.router_params = router_params
             ctx.wops = (W1_op, W2_op)
             ctx.has_residual = residual is not None
-        MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
+        if MoEBlockFunction.keep_last:
+            MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
         return out, kl, probs, load
 
     @staticmethod
     def backward(ctx, dout, dkl, dprobs, dload):
         lib = C.lib()
         cfg, plan = ctx.cfg, ctx.plan
+        if getattr(ctx, "ws", None) is None:
+            raise RuntimeError("moegan: the MoE block's forward workspace was released by its first backward pass; a second backward "
+                               "through the same forward (retain_graph=True) is not supported - run the forward again")
         E, d, Dt, T, B = cfg.E, cfg.d, cfg.Dt, cfg.T, cfg.B
         dev = ctx.w.device
         f32 = torch.float32
@@ -260,7 +312,8 @@ class MoEBlockFunction(torch.autograd.Function):
             a.dw = dw.data_ptr()
             (a.dmu_f, a.drho_f, a.dmu_t, a.drho_t, a.dmu_c, a.drho_c, a.dtemperature) = [g.data_ptr() for g in router_grads]
         a.workspace, a.workspace_bytes = ws_b.data_ptr(), ws_b.numel()
-        C.check(lib.moegan_block_bwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_bwd")
+        with torch.cuda.device(dev):
+            C.check(lib.moegan_block_bwd(plan.shape, ctypes.byref(a), C.c_void_p(_stream_ptr())), "moegan_block_bwd")
         expert_grads = [t for quad in zip(dW1.unbind(0), db1.unbind(0), dW2.unbind(0), db2.unbind(0)) for t in quad]
         ctx.ws = None
         d_res = dout if ctx.has_residual else None     # d(residual + moe) / d residual = identity

@@ -10,7 +10,20 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+import warnings
+
 from . import _cabi as C
+
+_WARNED = set()
+
+
+def _torch_path(fn: str, why: str) -> None:
+    """A CUDA tensor whose shape the library's kernel does not cover goes through the plain torch op - never silently: one
+    RuntimeWarning per (function, reason), so a model whose layers were expected on the kernels shows where they are not."""
+    key = (fn, why)
+    if key not in _WARNED:
+        _WARNED.add(key)
+        warnings.warn(f"moegan glue.{fn}: CUDA tensor handled by the torch op, not the sm_100a kernel ({why})", RuntimeWarning, stacklevel=3)
 
 
 def _stream():
@@ -111,8 +124,10 @@ class _ChannelScaleFn(torch.autograd.Function):
 
 def channel_scale(x: torch.Tensor, s: torch.Tensor, slope: float = 1.0) -> torch.Tensor:
     """`F.leaky_relu(x * s[:, :, None, None], slope)` for x [B,C,H,W], s [B,C]; slope = 1.0 means no activation."""
-    if x.is_cuda and x.shape[1] % 128 == 0 and x.dim() == 4:
+    if x.is_cuda and x.dim() == 4 and x.shape[1] % 128 == 0:
         return _ChannelScaleFn.apply(x, s, slope)
+    if x.is_cuda:
+        _torch_path("channel_scale", f"channels {x.shape[1]} not a multiple of 128 (e.g. the 3-channel to_rgb layers)")
     y = x * s.to(x.dtype)[:, :, None, None]            # CPU definition; also tiny channel counts (to_rgb: 3 channels)
     return y if slope == 1.0 else F.leaky_relu(y, slope)
 
@@ -164,6 +179,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.T
     """`F.linear(x, weight, bias)`; on CUDA the bias gradient comes from `moegan_colsum`."""
     if x.is_cuda and bias is not None and weight.shape[0] % 4 == 0 and x.dtype in (torch.float32, torch.bfloat16):
         return _LinearFn.apply(x, weight, bias)
+    if x.is_cuda:
+        _torch_path("linear", f"bias {'absent' if bias is None else 'present'}, out features {weight.shape[0]}, dtype {x.dtype}")
     return F.linear(x, weight, bias)
 
 
@@ -185,6 +202,8 @@ def add_channel_bias(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     `grad.sum((0, 2, 3))` comes from `moegan_colsum` over the NHWC view instead of ATen's strided reduction."""
     if y.is_cuda and y.dim() == 4 and y.shape[1] % 4 == 0:
         return _ChannelBiasFn.apply(y, bias)
+    if y.is_cuda:
+        _torch_path("add_channel_bias", f"shape {tuple(y.shape)}")
     return y + bias.to(y.dtype).view(1, -1, 1, 1)
 
 
@@ -234,6 +253,8 @@ def upsample2x_bilinear(x: torch.Tensor) -> torch.Tensor:
     the library's NHWC kernels - same tap formula and evaluation order as ATen, deterministic gather in the backward."""
     if x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16):
         return _Upsample2xFn.apply(x)
+    if x.is_cuda:
+        _torch_path("upsample2x_bilinear", f"shape {tuple(x.shape)}, dtype {x.dtype}")
     return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
 
 
@@ -278,4 +299,6 @@ def offset_sample(x: torch.Tensor, off_raw: torch.Tensor) -> torch.Tensor:
     """x [B,C,H,W] resampled at meshgrid + 0.05 * off_raw (off_raw [B,2,H,W] = offset_net(x): channel 0 = x, 1 = y)."""
     if x.is_cuda and x.shape[1] % 128 == 0 and x.shape[2] * x.shape[3] <= 256:
         return _OffsetSampleFn.apply(x, off_raw)
+    if x.is_cuda:
+        _torch_path("offset_sample", f"channels {x.shape[1]}, {x.shape[2]}x{x.shape[3]} pixels (kernel: C % 128 == 0, <= 256 pixels)")
     return offset_sample_reference(x, off_raw)

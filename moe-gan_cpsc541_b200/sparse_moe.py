@@ -194,7 +194,10 @@ class SparseMoE(nn.Module):
         with torch.autocast(device_type="cuda", enabled=False):
             out, kl, probs, load = MoEBlockFunction.apply(cfg, self._wcache, x_tok, w, eps[0], eps[1], eps[2], *params, res_tok, *expert_params)
         self.last_load = load
-        probs._moegan_load = load          # lets moe_balance_loss() use the fused column sums
+        if not hard:
+            # lets moe_balance_loss() use the fused column sums.  Not in eval mode: there `probs` is one-hot (:392-400) while the
+            # fused load is the soft-probability column sum, and the reference's balance loss is defined on what it is handed
+            probs._moegan_load = load
         if residual is None and out.dtype != x.dtype:
             out = out.to(x.dtype)
         output = out.reshape(batch_size, height, width, channels).permute(0, 3, 1, 2)   # (:486)
@@ -213,7 +216,11 @@ def moe_balance_loss(routing_probs, balance_weight: float = 0.01) -> torch.Tenso
     if last is None or last.numel() == 0:
         return torch.tensor(0.0, device=last.device if last is not None else None)
     load = getattr(last, "_moegan_load", None)
-    if load is None:
+    # The fused load is only a valid stand-in for last.sum(0) when it is on the same autograd graph as `last`.  Under reentrant
+    # activation checkpointing (torch.utils.checkpoint's default when use_reentrant is not given) the block runs under no_grad
+    # and the checkpoint re-attaches a grad_fn to `probs` only - the attribute survives but points at a load without history,
+    # and the balance loss would silently lose its gradient to the router.  Then: column-sum the probs that DO carry the graph.
+    if load is None or load.requires_grad != last.requires_grad or load.shape[0] != last.shape[1]:
         load = last.float().sum(dim=0)
     return BalanceLossFunction.apply(load, last.shape[0], float(balance_weight))
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import host_model as hm
 from .sparse_moe import moe_balance_loss
-from .functional import BalanceLossFunction
+from .functional import BalanceLossFunction, bump_weight_generation
 
 
 # --------------------------------------------------------------------------------------------------
@@ -221,11 +221,12 @@ class MoEGANTrainer:
         return torch.autocast(device_type=dev, dtype=self.amp_dtype, enabled=self.amp_dtype is not None)
 
     # ---- D-step (:1268-1348) ----
-    def d_step(self, real: torch.Tensor, text: torch.Tensor, z: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def d_step(self, real: torch.Tensor, text: torch.Tensor, z: torch.Tensor, perm: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self.opt_d.zero_grad(set_to_none=True)
         real = real.detach()
         with self._autocast():
-            perm = torch.rand(text.shape[0], device=text.device).argsort()          # device-side randperm (:1303)
+            if perm is None:
+                perm = torch.rand(text.shape[0], device=text.device).argsort()      # device-side randperm (:1303)
             if self.fused_real_pass:
                 real_pred, mismatched_pred, r1 = hm.discriminator_real_pass(self.D, real, text, text[perm], self.r1_gamma)
             else:
@@ -271,9 +272,13 @@ class MoEGANTrainer:
         self.opt_g.step()
         return {"g_loss": g_gan.detach(), "kl": kl.detach(), "balance": balance.detach()}
 
-    def _step_impl(self, real: torch.Tensor, text: torch.Tensor) -> Dict[str, torch.Tensor]:
-        z = torch.randn(real.shape[0], hm.LATENT_DIM, device=real.device)           # (:1266)
-        out = self.d_step(real, text, z)
+    def _step_impl(self, real: torch.Tensor, text: torch.Tensor, z: Optional[torch.Tensor] = None,
+                   perm: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """z / perm: caller-supplied latent batch and mismatched-text permutation (parity runs against the reference step, which
+        draws them at :1266 / :1303); None = drawn here on the device."""
+        if z is None:
+            z = torch.randn(real.shape[0], hm.LATENT_DIM, device=real.device)       # (:1266)
+        out = self.d_step(real, text, z, perm)
         out.update(self.g_step(text, z))
         return out
 
@@ -286,6 +291,7 @@ class MoEGANTrainer:
         self._static["real"].copy_(real, non_blocking=True)
         self._static["text"].copy_(text, non_blocking=True)
         self._graph.replay()
+        bump_weight_generation()     # the captured AdamW wrote the expert weights without bumping Parameter._version
         return self._out
 
     def step_from_host(self, real_host: torch.Tensor, text_host: torch.Tensor) -> Dict[str, float]:
@@ -295,14 +301,31 @@ class MoEGANTrainer:
             self._static["real"].copy_(real_host, non_blocking=True)
             self._static["text"].copy_(text_host, non_blocking=True)
             self._graph.replay()
+            bump_weight_generation()
             out = self._out
         else:
             out = self.step(real_host.to(dev, non_blocking=True), text_host.to(dev, non_blocking=True))
         packed = torch.stack([out["d_loss"].float(), out["g_loss"].float()]).cpu()
         return {"d_loss": float(packed[0]), "g_loss": float(packed[1])}
 
+    def _training_state(self) -> List[torch.Tensor]:
+        """Every tensor a train step mutates: parameters and buffers of both networks, and the optimizer states that exist."""
+        ts = [t for m in (self.G, self.D) for t in list(m.parameters()) + list(m.buffers())]
+        for opt in (self.opt_g, self.opt_d):
+            for st in opt.state.values():
+                ts += [v for v in st.values() if torch.is_tensor(v)]
+        return ts
+
     def _capture(self, real: torch.Tensor, text: torch.Tensor) -> None:
+        """Capture one step into a CUDA graph WITHOUT advancing training: the three warm-up steps capture needs (lazy
+        initialisation, cuDNN autotuning, optimizer state allocation, NCCL) run on the live tensors - a graph bakes their
+        addresses in - and are then undone in place: parameters / buffers / existing optimizer state are restored from a
+        snapshot, optimizer state the warm-up created is zeroed (= AdamW's initial state, step 0).  A re-capture after
+        set_epoch() therefore costs no optimizer steps (the reference takes none there either)."""
         self._static = {"real": real.clone(), "text": text.clone()}
+        before = self._training_state()
+        snapshot = [t.detach().clone() for t in before]
+        known = {id(t) for t in before}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -313,4 +336,12 @@ class MoEGANTrainer:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._out = self._step_impl(self._static["real"], self._static["text"])
+        with torch.no_grad():
+            for t, s0 in zip(before, snapshot):
+                t.copy_(s0)
+            for t in self._training_state():
+                if id(t) not in known:
+                    t.zero_()
+        bump_weight_generation()
+        torch.cuda.synchronize()
         self._graph = g

@@ -20,11 +20,11 @@ from oracle import moe_oracle as O  # noqa: E402
 CASES = {
     # name: dict(seed, B, H, W, d, Dt, E, af, mu_scale, rho, mode, temperature)
     "train_d128_E4":     dict(seed=101, B=2, H=8, W=8, d=128, Dt=128, E=4, af=1.0, mu_scale=30.0, rho=-4.0, mode="train", temperature=4.0),
-    "train_af3_d64":     dict(seed=102, B=2, H=4, W=4, d=64,  Dt=32,  E=4, af=3.0, mu_scale=1.0,  rho=-4.0, mode="train", temperature=4.0),
-    "train_klunsat_d64": dict(seed=103, B=2, H=4, W=4, d=64,  Dt=32,  E=4, af=1.0, mu_scale=10.0, rho=0.55, mode="train", temperature=1.5),
+    "train_af3_d128":    dict(seed=102, B=2, H=4, W=4, d=128, Dt=64,  E=4, af=3.0, mu_scale=1.0,  rho=-4.0, mode="train", temperature=4.0),
+    "train_klunsat_d128": dict(seed=103, B=2, H=4, W=4, d=128, Dt=64,  E=4, af=1.0, mu_scale=6.0, rho=0.55, mode="train", temperature=1.5),
     "train_E8_d128":     dict(seed=104, B=1, H=8, W=16, d=128, Dt=64, E=8, af=1.0, mu_scale=30.0, rho=-4.0, mode="train", temperature=2.0),
     "eval_d128_E4":      dict(seed=105, B=2, H=8, W=8, d=128, Dt=128, E=4, af=1.0, mu_scale=30.0, rho=-4.0, mode="eval",  temperature=4.0),
-    "eval_d64_E8":       dict(seed=106, B=3, H=4, W=4, d=64,  Dt=32,  E=8, af=1.0, mu_scale=30.0, rho=-4.0, mode="eval",  temperature=4.0),
+    "eval_d128_E8":      dict(seed=106, B=3, H=4, W=4, d=128, Dt=64,  E=8, af=1.0, mu_scale=30.0, rho=-4.0, mode="eval",  temperature=4.0),
 }
 
 BALANCE_WEIGHT = 0.01

@@ -10,7 +10,9 @@ PKG = "moe-gan_cpsc541_b200"
 
 
 def pkg():
-    return importlib.import_module(PKG)
+    p = importlib.import_module(PKG)
+    p.MoEBlockFunction.keep_last = True      # the parity tests read the routing state out of the last forward workspace
+    return p
 
 
 def rel_err(a, b):

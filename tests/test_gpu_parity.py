@@ -213,8 +213,50 @@ def test_empty_expert_and_eval_topk():
 
 
 # --------------------------------------------------------------------------------------------------
-# full BASELINE sizes: size-independent properties (the oracle is too slow there)
+# full BASELINE sizes against the oracle (numpy fp64; a few seconds per case) and size-independent properties
 # --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("mu_scale", [8.0, 30.0])
+def test_microbench_full_size_vs_oracle(mu_scale, precision):
+    """BASELINE configs[1] as benchmarked: 8 experts top-2, 4096 tokens x 512 dim, fwd+bwd.  Routing / permutation bit-exact against
+    the oracle (tokens under the 1e-6 top-k logit gap listed and excluded), out and ALL gradients within the north_star bars.
+    mu x8 is the router scale bench.py times; mu x30 is the non-uniform companion line (ragged expert loads)."""
+    B, H, W, d, Dt, E, k = 8, 16, 32, 512, 512, 8, 2
+    params, x, w, dout, gp, eps = _random_case(61, B, H, W, d, Dt, E, mu_scale=mu_scale)
+    m = G.build_module(params, d, Dt, E, top_k=k, precision=precision)
+    r = G.run_cuda(m, x, w, eps, 1.0, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    ora = G.run_oracle(params, x, w, eps, 1.0, top_k=k, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    excluded = _check_routing(r, ora, E, k)
+    counts = r["aux"]["plan"][48:48 + E]
+    print(f"configs[1] mu x{mu_scale:g} {precision}: excluded (top-k logit gap < 1e-6) {len(excluded)}/{B * H * W}: {excluded.tolist()}; "
+          f"rows per expert {counts.tolist()}")
+    tol = TOL[precision]
+    assert G.rel_err(r["probs"], ora["probs"]) < 1e-4
+    assert G.rel_err(r["out"], ora["out"]) < tol
+    errs = G.compare_grads(r, ora, params, tol)
+    assert len(errs) == 2 + 7 + 4 * E                                  # dx, dw, 7 router tensors, 4 per expert
+    print(f"  worst gradient error {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dense_block16_batch256_vs_oracle(precision):
+    """The largest block of the benchmarked train step (configs[2]): block 16x16 at batch 256 = 65 536 tokens x 128, E=4 dense-soft,
+    af = 3 (epoch 0: temperature clamp saturated), against the oracle - probabilities, output and all gradients."""
+    B, H, W, d, Dt, E = 256, 16, 16, 128, 512, 4
+    params, x, w, dout, gp, eps = _random_case(62, B, H, W, d, Dt, E, mu_scale=30.0)
+    m = G.build_module(params, d, Dt, E, precision=precision)
+    r = G.run_cuda(m, x, w, eps, 3.0, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    ora = G.run_oracle(params, x, w, eps, 3.0, dout=dout, gp=gp, kl_coef=KL_COEF, bal_coef=BAL_COEF)
+    tol = TOL[precision]
+    assert G.rel_err(r["probs"], ora["probs"]) < 1e-4
+    gap = O.topk_gap(ora["cache"].router.probs_soft, ora["cache"].router.logits, 1)
+    keep = gap >= 1e-6
+    assert np.array_equal(r["probs"].argmax(1)[keep], ora["probs"].argmax(1)[keep])
+    assert G.rel_err(r["out"], ora["out"]) < tol
+    errs = G.compare_grads(r, ora, params, tol)
+    print(f"block16 @ batch 256 {precision}: near-ties excluded {int((~keep).sum())}, worst gradient error {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+
+
 def test_microbench_size_properties():
     """configs[1]: 8 experts top-2, 4096 tokens x 512 dim, fwd+bwd (bf16)."""
     B, H, W, d, Dt, E, k = 8, 16, 32, 512, 512, 8, 2

@@ -1,0 +1,370 @@
+"""The drop-in claim, executed: the B200 blocks against the UNMODIFIED reference on the same GPU (`-m gpu`).
+
+`oracle/_ref/t2i_moe_gan.py` is the byte-for-byte staging copy made by `oracle/make_ref.py` at build time (git-ignored, travels
+with the tree like the built .so).  Everything goes through the package's public surface - `SparseMoE.from_reference`,
+`install`, `moe_balance_loss` - and therefore through the C ABI.
+
+  * block parity at the BASELINE batch-256 geometries (T = 4096 / 16384 / 65536): same weights, inputs and eps (read back from
+    `router.epsilon_*` after the reference forward); out / kl / probs / balance, argmax bit-exact (tokens whose top-2
+    logit gap is < 1e-6 are listed and excluded), every parameter gradient + dx + dw; fp32 mode <= 1e-4, bf16 mode <= 2e-2
+  * eval mode at the same sizes: one-hot probs bit-exact, hard-dispatched output
+  * `install(ref)`: the reference's own AuroraGenerator built around the B200 blocks - forward / backward of the whole generator
+    against the reference generator, plain and under the reference's activation checkpointing
+  * reentrant checkpointing keeps the balance-loss gradient
+  * one full train step of `MoEGANTrainer` against one iteration of the reference loop (oracle/ref_step.py) on identical
+    weights, batch, z, mismatch permutation and eps stream
+Error metric everywhere: max|a-b| / max|b| per tensor.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_utils as G_
+from oracle import ref_loader
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+EPS_NAMES = ("epsilon_f", "epsilon_t", "epsilon_c")
+
+
+def _ref():
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not staged (run `python oracle/make_ref.py` next to /root/reference)")
+    return ref_loader.load_reference()
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double(), b.detach().double()
+    den = float(b.abs().max())
+    if den == 0.0:
+        return float(a.abs().max())
+    return float((a - b).abs().max()) / den
+
+
+def nhwc_tokens(B, H, W, d, gen):
+    """[B,d,H,W] view of NHWC memory, as norm3 hands it to the block (t2i_moe_gan.py:561)."""
+    return torch.randn(B, H, W, d, device="cuda", generator=gen).permute(0, 3, 1, 2)
+
+
+def make_reference_block(ref, d, E=4, mu_scale=30.0, temperature=2.0, seed=0):
+    torch.manual_seed(seed)
+    m = ref.SparseMoE(d, 512, num_experts=E).cuda().train()
+    with torch.no_grad():     # default init gives near-uniform probs (0.24-0.26): spread the routing so that argmax means something
+        for n in ("feature_mu", "text_mu", "combined_mu"):
+            getattr(m.router, n).mul_(mu_scale)
+        m.router.temperature.fill_(temperature)
+    return m
+
+
+def excluded_tokens(probs_ref: torch.Tensor, k: int = 1, gap: float = 1e-6) -> torch.Tensor:
+    """Tokens whose k-th / (k+1)-th logit gap is below `gap` (north_star's exclusion list).  softmax is monotone, so the logit gap
+    equals log(p_k / p_{k+1}) wherever the [1e-6, 1] probability clamp is inactive (where it is active the gap is far above 1e-6)."""
+    srt = probs_ref.double().sort(dim=1, descending=True).values
+    return (srt[:, k - 1].log() - srt[:, k].log()) < gap
+
+
+def loss_of(out, kl, probs, bal, dout, gp):
+    return (out.float() * dout).sum() + 0.37 * kl + 5.0 * bal + (probs * gp).sum()
+
+
+GEOMS = [(512, 4, 4), (256, 8, 8), (128, 16, 16)]      # block 4 / 8 / 16 at batch 256: T = 4096 / 16384 / 65536
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("d,H,W", GEOMS)
+def test_from_reference_block_parity_batch256(d, H, W, precision):
+    ref, pkg = _ref(), G_.pkg()
+    B, E = 256, 4
+    T = B * H * W
+    rm = make_reference_block(ref, d, E, seed=d)
+    gen = torch.Generator(device="cuda").manual_seed(1000 + d)
+    x0 = nhwc_tokens(B, H, W, d, gen); w0 = torch.randn(B, 512, device="cuda", generator=gen)
+    dout = nhwc_tokens(B, H, W, d, gen); gp = torch.randn(T, E, device="cuda", generator=gen)
+    loss_obj = ref_loader.make_loss(ref, torch.device("cuda"))
+
+    xr = x0.clone().requires_grad_(True); wr = w0.clone().requires_grad_(True)
+    torch.manual_seed(7)
+    o_r, kl_r, p_r = rm(xr, wr, 1.0)                               # draws eps into router.epsilon_* (:349-351)
+    bal_r = loss_obj.moe_balance_loss([p_r], balance_weight=0.01)
+    loss_of(o_r, kl_r, p_r, bal_r, dout, gp).backward()
+
+    mine = pkg.SparseMoE.from_reference(rm, precision=precision)   # state_dict copy: weights AND the eps the reference just used
+    assert isinstance(mine, pkg.SparseMoE) and mine.training and next(mine.parameters()).is_cuda
+    for n in EPS_NAMES:
+        assert torch.equal(getattr(mine.router, n), getattr(rm.router, n))
+    mine.redraw_eps = False                                        # parity mode: consume the buffers as they are
+    xm = x0.clone().requires_grad_(True); wm = w0.clone().requires_grad_(True)
+    o_m, kl_m, p_m = mine(xm, wm, 1.0)
+    bal_m = pkg.moe_balance_loss([p_m], 0.01)
+    loss_of(o_m, kl_m, p_m, bal_m, dout, gp).backward()
+    torch.cuda.synchronize()
+
+    tol = TOL[precision]
+    errs = {"out": rel(o_m, o_r), "probs": rel(p_m, p_r), "dx": rel(xm.grad, xr.grad), "dw": rel(wm.grad, wr.grad)}
+    assert o_m.shape == o_r.shape and o_m.stride() == o_r.stride()          # NCHW view of NHWC memory (:486)
+    assert abs(float(kl_m) - float(kl_r)) <= 1e-4 * max(1.0, abs(float(kl_r)))
+    assert abs(float(bal_m) - float(bal_r)) <= 1e-4 * max(abs(float(bal_r)), 1e-3)
+    # routing: bit-exact argmax outside the listed near-ties
+    excl = excluded_tokens(p_r)
+    mism = (p_m.argmax(1) != p_r.argmax(1)) & ~excl
+    assert int(mism.sum()) == 0, f"{int(mism.sum())} routing mismatches (excluded near-ties: {int(excl.sum())})"
+    ref_params = dict(rm.named_parameters())
+    for n, p in mine.named_parameters():
+        gr = ref_params[n].grad
+        gm = p.grad if p.grad is not None else torch.zeros_like(p)
+        errs["grad." + n] = rel(gm, gr if gr is not None else torch.zeros_like(p))
+    worst = max(errs, key=errs.get)
+    print(f"[dropin d={d} T={T} {precision}] excluded={int(excl.sum())} worst={worst} {errs[worst]:.2e} out={errs['out']:.2e} probs={errs['probs']:.2e}")
+    assert errs["probs"] < 1e-4                                    # router is fp32 in both modes
+    for k, v in errs.items():
+        # the scalar temperature gradient is a cancelling sum over all T*E logits: 3x in bf16 mode (as in the golden tests)
+        lim = 3.0 * tol if (k == "grad.router.temperature" and precision == "bf16") else tol
+        assert v < lim, (k, v, errs)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("d,H,W", GEOMS)
+def test_from_reference_eval_batch256(d, H, W, precision):
+    """generator.eval(): hard top-1, weight 1.0, one-hot probs, kl = tensor(0.) (:392-400, :471-483, :489)."""
+    ref, pkg = _ref(), G_.pkg()
+    B, E = 256, 4
+    rm = make_reference_block(ref, d, E, seed=d + 1).eval()
+    gen = torch.Generator(device="cuda").manual_seed(2000 + d)
+    x0 = nhwc_tokens(B, H, W, d, gen); w0 = torch.randn(B, 512, device="cuda", generator=gen)
+    with torch.no_grad():
+        o_r, kl_r, p_r = rm(x0, w0, 1.0)
+        mine = pkg.SparseMoE.from_reference(rm, precision=precision)
+        assert not mine.training
+        o_m, kl_m, p_m = mine(x0, w0, 1.0)
+    assert float(kl_m) == 0.0 and float(kl_r) == 0.0
+    assert set(p_m.unique().tolist()) <= {0.0, 1.0} and bool((p_m.sum(1) == 1).all())
+    same = (p_m == p_r).all(dim=1)
+    n_bad = int((~same).sum())
+    if n_bad:
+        # a token may only differ if its top-2 logits tie within 1e-6 under the MEAN weights (:357-361): list them
+        with torch.no_grad():
+            r = rm.router
+            xt = x0.permute(0, 2, 3, 1).reshape(-1, d).double()
+            lg = torch.cat([xt @ r.feature_mu.double(), (w0.double() @ r.text_mu.double()).repeat_interleave(H * W, 0)], 1) @ r.combined_mu.double()
+            lg = lg / torch.clamp(r.temperature.double() * 1.0, 0.5, 5.0)
+            top2 = lg.topk(2, dim=1).values
+            tie = (top2[:, 0] - top2[:, 1]) < 1e-6
+        assert int((~same & ~tie).sum()) == 0, f"{n_bad} one-hot rows differ, {int((~same & ~tie).sum())} of them are not near-ties"
+    ok_tok = same.view(B, H, W)
+    assert rel(o_m.permute(0, 2, 3, 1)[ok_tok], o_r.permute(0, 2, 3, 1)[ok_tok]) < TOL[precision]
+    print(f"[dropin eval d={d} T={B * H * W} {precision}] one-hot rows equal: {int(same.sum())}/{same.numel()}")
+
+
+def _swap_in(ref, pkg):
+    saved = (ref.SparseMoE, ref.AuroraGANLoss.moe_balance_loss)
+    pkg.install(ref)
+    return saved
+
+
+def _swap_out(ref, saved):
+    ref.SparseMoE, ref.AuroraGANLoss.moe_balance_loss = saved
+
+
+def _moes(G):
+    return [G.gen_block_4.attn_block.moe, G.gen_block_8.attn_block.moe, G.gen_block_16.attn_block.moe]
+
+
+def _generator_pair(ref, pkg, seed=0):
+    """(reference generator, the reference's generator class constructed around the B200 blocks, same weights)."""
+    torch.manual_seed(seed)
+    G_ref = ref.AuroraGenerator(max_resolution=16).cuda().train()
+    saved = _swap_in(ref, pkg)
+    try:
+        assert ref.SparseMoE is pkg.SparseMoE
+        torch.manual_seed(seed)
+        G_new = ref.AuroraGenerator(max_resolution=16).cuda().train()        # AttentionBlock.__init__ (:519) now builds B200 blocks
+    finally:
+        _swap_out(ref, saved)
+    assert all(isinstance(m, pkg.SparseMoE) for m in _moes(G_new)) and not any(isinstance(m, pkg.SparseMoE) for m in _moes(G_ref))
+    missing, unexpected = G_new.load_state_dict(G_ref.state_dict(), strict=True)     # identical key set: checkpoints are interchangeable
+    assert not missing and not unexpected
+    assert [n for n, _ in G_new.named_parameters()] == [n for n, _ in G_ref.named_parameters()]
+    return G_ref, G_new
+
+
+def _run_generator(Gm, z, text, loss_obj, balance_fn, w16, w8, af=3.0, autocast=None):
+    Gm.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=autocast, enabled=autocast is not None):
+        img16, img8, kl, routing = Gm(z, text, return_intermediate=True, return_routing=True, annealing_factor=af)
+        bal = balance_fn(routing)
+    L = (img16.float() * w16).sum() + (img8.float() * w8).sum() + 1e-3 * kl + 5.0 * bal
+    L.backward()
+    return img16.detach().float(), img8.detach().float(), float(kl), float(bal), [p.detach() for p in routing]
+
+
+def _sync_eps(G_src, G_dst):
+    for a, b in zip(_moes(G_src), _moes(G_dst)):
+        for n in EPS_NAMES:
+            getattr(b.router, n).copy_(getattr(a.router, n))
+        b.redraw_eps = False
+
+
+@pytest.mark.parametrize("B", [8, 64])
+def test_install_whole_generator_fp32(B):
+    """`b200.install(t2i_moe_gan)` then `AuroraGenerator()`: the reference's generator code around the B200 blocks gives the reference's
+    images, KL, routing probabilities, balance loss and the gradient of EVERY generator parameter (fp32, no autocast)."""
+    ref, pkg = _ref(), G_.pkg()
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False            # both generators run the same cuDNN convolutions: keep them fp32-exact
+    try:
+        G_ref, G_new = _generator_pair(ref, pkg)
+        gen = torch.Generator(device="cuda").manual_seed(B)
+        z = torch.randn(B, 512, device="cuda", generator=gen); text = torch.randn(B, 512, device="cuda", generator=gen)
+        w16 = torch.randn(B, 3, 16, 16, device="cuda", generator=gen); w8 = torch.randn(B, 3, 8, 8, device="cuda", generator=gen)
+        loss_obj = ref_loader.make_loss(ref, torch.device("cuda"))
+        torch.manual_seed(11)
+        r = _run_generator(G_ref, z, text, loss_obj, lambda rp: loss_obj.moe_balance_loss(rp, balance_weight=0.01), w16, w8)
+        _sync_eps(G_ref, G_new)
+        n = _run_generator(G_new, z, text, loss_obj, lambda rp: pkg.moe_balance_loss(rp, 0.01), w16, w8)
+        assert rel(n[0], r[0]) < 1e-3 and rel(n[1], r[1]) < 1e-3
+        assert n[2] == pytest.approx(r[2], rel=1e-5) and n[3] == pytest.approx(r[3], rel=1e-3, abs=1e-7)
+        for pn, pr in zip(n[4], r[4]):
+            assert rel(pn, pr) < 1e-4
+        worst = ("", 0.0)
+        gr = dict(G_ref.named_parameters())
+        for name, p in G_new.named_parameters():
+            g_ref = gr[name].grad
+            if g_ref is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+                continue
+            e = rel(p.grad, g_ref)
+            worst = max(worst, (name, e), key=lambda t: t[1])
+            assert e < 2e-3, (name, e)                 # a 3-block deep generator: block-level bar is 1e-4, errors compound through conv / attention
+        print(f"[install fp32 B={B}] worst whole-generator gradient error {worst[1]:.2e} ({worst[0]})")
+
+        # the reference's own activation checkpointing (non-reentrant, :734-760) around the B200 blocks: same gradients
+        base = {name: p.grad.clone() for name, p in G_new.named_parameters() if p.grad is not None}
+        G_new.enable_checkpointing()
+        c = _run_generator(G_new, z, text, loss_obj, lambda rp: pkg.moe_balance_loss(rp, 0.01), w16, w8)
+        assert rel(c[0], n[0]) < 1e-6
+        for name, p in G_new.named_parameters():
+            if name in base:
+                assert rel(p.grad, base[name]) < 1e-5, name
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+def test_install_whole_generator_bf16_autocast():
+    """Same swap under the train loop's autocast (:1278, :1356): bf16 tensor-core experts + fp32 router against the fp32 reference."""
+    ref, pkg = _ref(), G_.pkg()
+    B = 32
+    G_ref, G_new = _generator_pair(ref, pkg, seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(B, 512, device="cuda", generator=gen); text = torch.randn(B, 512, device="cuda", generator=gen)
+    w16 = torch.randn(B, 3, 16, 16, device="cuda", generator=gen); w8 = torch.randn(B, 3, 8, 8, device="cuda", generator=gen)
+    loss_obj = ref_loader.make_loss(ref, torch.device("cuda"))
+    torch.manual_seed(12)
+    r = _run_generator(G_ref, z, text, loss_obj, lambda rp: loss_obj.moe_balance_loss(rp, balance_weight=0.01), w16, w8)
+    _sync_eps(G_ref, G_new)
+    n = _run_generator(G_new, z, text, loss_obj, lambda rp: pkg.moe_balance_loss(rp, 0.01), w16, w8, autocast=torch.bfloat16)
+    assert rel(n[0], r[0]) < 5e-2 and rel(n[1], r[1]) < 5e-2        # whole bf16 generator (convs, attention, experts) vs fp32
+    assert n[2] == pytest.approx(r[2], rel=1e-5)
+    for pn, pr in zip(n[4], r[4]):
+        assert rel(pn, pr) < 3e-2                                    # router inputs went through bf16 layers upstream
+    gr = dict(G_ref.named_parameters())
+    moe_errs = [rel(p.grad, gr[name].grad) for name, p in G_new.named_parameters() if ".moe.experts." in name and gr[name].grad is not None]
+    assert max(moe_errs) < 0.15, max(moe_errs)                       # sanity bound: every expert gradient has the right scale and sign
+
+
+def test_reentrant_checkpoint_keeps_balance_gradient():
+    """torch.utils.checkpoint(..., use_reentrant=True) runs the block under no_grad and re-attaches autograd to `probs` only: the
+    balance loss must still reach the router (it may not use a fused load that has no history)."""
+    from torch.utils.checkpoint import checkpoint
+    pkg = G_.pkg()
+    torch.manual_seed(0)
+    moe = pkg.SparseMoE(128, 64, 4, precision="fp32").cuda().train()
+    with torch.no_grad():
+        for n in ("feature_mu", "text_mu", "combined_mu"):
+            getattr(moe.router, n).mul_(30.0)
+    moe.router.epsilon_f.normal_(); moe.router.epsilon_t.normal_(); moe.router.epsilon_c.normal_()
+    moe.redraw_eps = False
+    x0 = torch.randn(4, 8, 8, 128, device="cuda").permute(0, 3, 1, 2); w0 = torch.randn(4, 64, device="cuda")
+    grads = []
+    for ckpt in (False, True):
+        moe.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True); w = w0.clone().requires_grad_(True)
+        if ckpt:
+            out, kl, probs = checkpoint(lambda a, b: moe(a, b, 1.0), x, w, use_reentrant=True)
+        else:
+            out, kl, probs = moe(x, w, 1.0)
+        bal = pkg.moe_balance_loss([probs], 1.0)
+        assert bal.requires_grad
+        bal.backward()                                               # ONLY the balance loss: its gradient has to arrive at the router
+        g = moe.router.combined_mu.grad
+        assert g is not None and float(g.abs().max()) > 0.0, "balance loss lost its gradient path to the router"
+        grads.append((g.clone(), moe.router.feature_mu.grad.clone(), x.grad.clone()))
+    for a, b in zip(*grads):
+        assert rel(b, a) < 1e-5
+
+
+def _load_reference_weights(pkg, G_ref, D_ref):
+    """The package's host model (what bench.py's train step runs) with the reference's weights: the checkpoint path of N4."""
+    sd = {"generator": G_ref.state_dict(), "discriminator": D_ref.state_dict()}
+    Gm, Dm = pkg.host_model.AuroraGenerator().cuda(), pkg.host_model.AuroraDiscriminator().cuda()
+    pkg.host_model.load_reference_checkpoint(Gm, Dm, sd)
+    return Gm, Dm
+
+
+@pytest.mark.parametrize("mode,B", [("fp32", 16), ("bf16", 256)])
+def test_train_step_matches_reference_step(mode, B):
+    """One iteration of MoEGANTrainer against one iteration of the reference loop (t2i_moe_gan.py:1262-1421 through oracle/ref_step.py,
+    unmodified reference modules) on identical weights, batch, z, mismatch permutation and - because both sides draw the router eps
+    with the same normal_() calls in the same order from the same CUDA seed - identical eps.  bf16 @ batch 256 is BASELINE configs[2]."""
+    ref, pkg = _ref(), G_.pkg()
+    from oracle.ref_step import ReferenceTrainStep
+    amp = None if mode == "fp32" else torch.bfloat16
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        rs = ReferenceTrainStep("cuda", amp_dtype=amp, seed=21)
+        Gm, Dm = _load_reference_weights(pkg, rs.G, rs.D)
+        tr = pkg.MoEGANTrainer(Gm, Dm, amp_dtype=amp, use_cuda_graph=False)
+        gen = torch.Generator(device="cuda").manual_seed(99)
+        real = torch.randn(B, 3, 64, 64, device="cuda", generator=gen).clamp(-1, 1)
+        text = torch.randn(B, 512, device="cuda", generator=gen)
+        z = torch.randn(B, 512, device="cuda", generator=gen)
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+        torch.manual_seed(1234)
+        o_ref = rs.step(real, text, z=z, shuffled_indices=perm)
+        torch.manual_seed(1234)
+        o_new = tr._step_impl(real, text, z=z, perm=perm.cuda())
+        torch.cuda.synchronize()
+        # the eps streams really were identical (last forward = the G-step's)
+        for a, b in zip(_moes(rs.G), Gm.moe_layers()):
+            for n in EPS_NAMES:
+                assert torch.equal(getattr(a.router, n), getattr(b.router, n)), n
+        lim = 2e-3 if mode == "fp32" else 3e-2
+        got = {k: float(o_new[k]) for k in ("d_loss", "r1", "g_loss", "kl", "balance")}
+        want = {k: float(o_ref[k]) for k in got}
+        print(f"[train step {mode} B={B}] ours {got}  reference {want}")
+        for k in got:
+            assert got[k] == pytest.approx(want[k], rel=lim, abs=lim * 1e-2), (k, got[k], want[k])
+        assert got["kl"] == 50.0 and want["kl"] == 50.0                          # 3 x 120 clamped to 50 (:1369)
+        # the gradients both optimizers consumed (after the reduce / clip_grad_norm_ of :1336 / :1420): direction and norm, whole network
+        for name, net_ref, net_new in (("G", rs.G, Gm), ("D", rs.D, Dm)):
+            new_params = dict(net_new.named_parameters())
+            if name == "D":      # legacy weight_norm names (weight_g / weight_v) -> parametrizations.weight.original0 / 1
+                new_params = {k.replace("parametrizations.weight.original0", "weight_g").replace("parametrizations.weight.original1", "weight_v"): v
+                              for k, v in new_params.items()}
+            dot = nr = nn_ = 0.0
+            for n, p_ref in net_ref.named_parameters():
+                g_ref = p_ref.grad
+                g_new = new_params[n].grad
+                if g_ref is None:
+                    continue
+                g_new = torch.zeros_like(g_ref) if g_new is None else g_new.reshape(g_ref.shape)
+                dot += float((g_ref.double() * g_new.double()).sum()); nr += float(g_ref.double().pow(2).sum()); nn_ += float(g_new.double().pow(2).sum())
+            cos, ratio = dot / max((nr * nn_) ** 0.5, 1e-30), (nn_ / max(nr, 1e-30)) ** 0.5
+            print(f"[train step {mode} B={B}] {name}: cosine(grad ours, grad reference) = {cos:.5f}, norm ratio = {ratio:.4f}")
+            assert cos > (0.999 if mode == "fp32" else 0.95), (name, cos)
+            assert ratio == pytest.approx(1.0, abs=0.01 if mode == "fp32" else 0.1), (name, ratio)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32

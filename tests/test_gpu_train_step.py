@@ -153,17 +153,36 @@ def test_two_forwards_then_backward_of_the_first_uses_its_own_eps():
     assert float((moe.router.feature_rho.grad - g_late).abs().max()) == 0.0
 
 
-def test_bayesian_router_forward_matches_block_probs():
+@pytest.mark.parametrize("training,af", [(False, 1.5), (True, 1.0), (True, 3.0)])
+def test_bayesian_router_forward_vs_oracle(training, af):
+    """BayesianRouter.forward(feature [T,d], text [T,Dt]) -> (probs [T,E], logits [T,E] = clamp(raw / tau, +-20)),
+    both against the oracle's router (t2i_moe_gan.py:335-402) on the eps the call consumed - not against the block's own output."""
+    import numpy as np
+    from oracle import moe_oracle as O
     pkg = G_.pkg()
-    torch.manual_seed(0)
-    moe = pkg.SparseMoE(128, 64, 4, precision="fp32").cuda().eval()
-    x = torch.randn(2, 128, 4, 4, device="cuda"); w = torch.randn(2, 64, device="cuda")
+    rng = np.random.RandomState(3)
+    d, Dt, E, B, HW = 128, 64, 4, 2, 16
+    params = O.init_params(rng, d, Dt, E, mu_scale=30.0)
+    params["router.temperature"][:] = 2.0
+    m = G_.build_module(params, d, Dt, E, precision="fp32", training=training)
+    x = rng.standard_normal((B * HW, d)).astype(np.float32); w = rng.standard_normal((B, Dt)).astype(np.float32)
+    feat = torch.from_numpy(x).cuda()
+    text = torch.from_numpy(w).cuda().repeat_interleave(HW, dim=0)       # the reference's per-token expansion (:456)
+    torch.manual_seed(9)
+    probs, logits = m.router(feat, text, sampling=True, annealing_factor=af)
+    eps = {k: getattr(m.router, k).detach().cpu().numpy() for k in O.EPS_KEYS}
+    p_o, l_o, cache = O.router_forward(x, w, params, eps, af, training, sampling=True, tokens_per_sample=HW)
+    assert logits.shape == (B * HW, E) and probs.shape == (B * HW, E)
+    assert G_.rel_err(logits.cpu().numpy(), l_o) < 1e-4 and float(logits.abs().max()) <= 20.0
+    if training:
+        assert G_.rel_err(probs.cpu().numpy(), p_o) < 1e-4
+    else:
+        assert np.array_equal(probs.cpu().numpy(), p_o)                    # eval: one-hot (:392-400)
+    # and the block reports the same probabilities for the same tokens / eps
+    m.redraw_eps = False
     with torch.no_grad():
-        _, _, probs_blk = moe(x, w, 1.5)
-    feat = x.permute(0, 2, 3, 1).reshape(-1, 128)
-    text = w.repeat_interleave(16, dim=0)                 # the reference's per-token expansion (:456)
-    probs, logits = moe.router(feat, text, sampling=False, annealing_factor=1.5)
-    assert torch.equal(probs, probs_blk) and logits.shape == (32, 4) and float(logits.abs().max()) <= 20.0
+        _, _, probs_blk = m(feat.view(B, HW, 1, d).permute(0, 3, 1, 2), torch.from_numpy(w).cuda(), af)
+    assert torch.equal(probs, probs_blk)
 
 
 @pytest.mark.parametrize("res_dtype", [torch.float32, torch.bfloat16])
@@ -200,3 +219,125 @@ def test_fused_residual_equals_separate_add(res_dtype, top_k):
     assert rel(a[1], b[1]) <= 1e-6 and rel(a[2], b[2]) <= 1e-5   # same dout values reach the block either way
     for n in a[4]:
         assert rel(a[4][n], b[4][n]) <= 1e-5, n
+
+
+def _small_trainer(pkg, use_graph, seed=0, amp=torch.bfloat16):
+    hm = pkg.host_model
+    torch.manual_seed(seed)
+    Gm, Dm = hm.AuroraGenerator().cuda(), hm.AuroraDiscriminator().cuda()
+    return pkg.MoEGANTrainer(Gm, Dm, amp_dtype=amp, use_cuda_graph=use_graph), Gm, Dm
+
+
+def test_graph_capture_does_not_advance_training():
+    """Capturing (or re-capturing after set_epoch) needs three warm-up steps on the live tensors; they are undone in place, so a
+    capture costs no optimizer steps: parameters, buffers and AdamW state are what they were (state the warm-up created is zero)."""
+    pkg = G_.pkg()
+    tr, Gm, Dm = _small_trainer(pkg, True)
+    real = torch.randn(8, 3, 64, 64, device="cuda").clamp(-1, 1); text = torch.randn(8, 512, device="cuda")
+    before = {n: p.detach().clone() for net in (Gm, Dm) for n, p in net.named_parameters()}
+    tr._capture(real, text)
+    after = {n: p.detach() for net in (Gm, Dm) for n, p in net.named_parameters()}
+    assert all(torch.equal(before[n], after[n]) for n in before)
+    for opt in (tr.opt_g, tr.opt_d):
+        for st in opt.state.values():
+            assert all(float(v.abs().max()) == 0.0 for v in st.values() if torch.is_tensor(v))
+    out = tr.step(real, text)                          # first replay = first optimizer step
+    torch.cuda.synchronize()
+    assert all(float(st["step"]) == 1.0 for st in tr.opt_g.state.values())
+    assert any(not torch.equal(before[n], p.detach()) for n, p in Gm.named_parameters())
+    assert np.isfinite(float(out["g_loss"]))
+
+
+def test_weight_cache_is_invalidated_by_graph_replay():
+    """a captured AdamW updates the expert weights without bumping Parameter._version; a non-captured forward after
+    N replays must not be served the bf16 operand copies converted before them."""
+    pkg = G_.pkg()
+    hm = pkg.host_model
+    tr, Gm, Dm = _small_trainer(pkg, True)
+    real = torch.randn(8, 3, 64, 64, device="cuda").clamp(-1, 1); text = torch.randn(8, 512, device="cuda")
+    z, t2 = torch.randn(8, 512, device="cuda"), torch.randn(8, 512, device="cuda")
+
+    def sample():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return hm.sample_images(Gm, z, t2).float().clone()
+    tr._capture(real, text)
+    img0 = sample()                                    # fills every block's WeightCache outside capture
+    for _ in range(5):
+        tr.step(real, text)                            # replays: the weights move, _version does not
+    img1 = sample()
+    for m in Gm.moe_layers():
+        m._wcache.invalidate()
+    img2 = sample()                                    # forced fresh conversion of the current weights
+    torch.cuda.synchronize()
+    assert torch.equal(img1, img2), "stale expert weights were served after graph replays"
+    assert not torch.equal(img0, img1)
+
+
+@pytest.mark.parametrize("top_k,precision", [(None, "bf16"), (2, "bf16"), (None, "fp32")])
+def test_block_graph_replay_equals_eager_bitwise(top_k, precision):
+    """The library's launches are the same in capture and eager mode (side streams, cached weight conversion, workspaces):
+    a CUDA-graph replay of block forward + backward reproduces the eager outputs and every gradient bit for bit."""
+    pkg = G_.pkg()
+    torch.manual_seed(0)
+    E = 8 if top_k else 4
+    moe = pkg.SparseMoE(256, 512, E, top_k=top_k, precision=precision).cuda().train()
+    with torch.no_grad():
+        for n in ("feature_mu", "text_mu", "combined_mu"):
+            getattr(moe.router, n).mul_(20.0)
+    x = torch.randn(16, 8, 8, 256, device="cuda").permute(0, 3, 1, 2).requires_grad_(True)
+    w = torch.randn(16, 512, device="cuda", requires_grad=True)
+    dout = torch.randn(16, 8, 8, 256, device="cuda").permute(0, 3, 1, 2)
+    eps = tuple(torch.randn_like(getattr(moe.router, n)) for n in ("epsilon_f", "epsilon_t", "epsilon_c"))
+    klw = torch.full((), 0.3, device="cuda")
+    params = list(moe.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        x.grad = None; w.grad = None
+        out, kl, probs = moe(x, w, 1.0, eps=eps)
+        bal = pkg.moe_balance_loss([probs], 0.5)
+        torch.autograd.backward([out, kl, bal], [dout, klw, torch.ones((), device="cuda")])
+        return out, kl, probs
+
+    out, kl, probs = step()
+    eager = [out.detach().clone(), kl.detach().clone(), probs.detach().clone(), x.grad.clone(), w.grad.clone()] + [p.grad.clone() for p in params]
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out, kl, probs = step()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    replay = [out, kl, probs, x.grad, w.grad] + [p.grad for p in params]
+    names = ["out", "kl", "probs", "dx", "dw"] + [n for n, _ in moe.named_parameters()]
+    for n, a, b in zip(names, eager, replay):
+        assert torch.equal(a, b), f"{n}: graph replay differs from eager (max |diff| {float((a.float() - b.float()).abs().max()):.3e})"
+
+
+def test_train_step_graph_replay_matches_eager_step():
+    """Whole train step: a CUDA-graph replay and an eager step from the same weights, batch and RNG state report the same losses
+    (graph-safe Philox: the captured random ops consume the generator exactly like the eager ones)."""
+    pkg = G_.pkg()
+    tr_e, Ge, De = _small_trainer(pkg, False, seed=4)
+    tr_g, Gg, Dg = _small_trainer(pkg, True, seed=4)
+    assert all(torch.equal(a, b) for a, b in zip(Ge.parameters(), Gg.parameters()))
+    real = torch.randn(16, 3, 64, 64, device="cuda").clamp(-1, 1); text = torch.randn(16, 512, device="cuda")
+    tr_g._capture(real, text)
+    torch.manual_seed(77); oe = {k: float(v) for k, v in tr_e.step(real, text).items()}
+    torch.manual_seed(77); og = {k: float(v) for k, v in tr_g.step(real, text).items()}
+    torch.cuda.synchronize()
+    print(f"[graph vs eager] eager {oe}  graph {og}")
+    for k in oe:
+        assert og[k] == pytest.approx(oe[k], rel=5e-3, abs=1e-5), (k, oe[k], og[k])
+    # and the update that followed points the same way
+    dot = ne = ng = 0.0
+    for a, b in zip(Ge.parameters(), Gg.parameters()):
+        if a.grad is None or b.grad is None:
+            continue
+        dot += float((a.grad.double() * b.grad.double()).sum()); ne += float(a.grad.double().pow(2).sum()); ng += float(b.grad.double().pow(2).sum())
+    assert dot / max((ne * ng) ** 0.5, 1e-30) > 0.99

@@ -77,14 +77,14 @@ def test_kl_saturated_constant_and_zero_grad():
 
 
 def test_kl_unsaturated_gradient():
-    c, params, eps, g, *_ = run_oracle("train_klunsat_d64")
+    c, params, eps, g, *_ = run_oracle("train_klunsat_d128")
     kl, raw = O.kl_divergence(params)
     assert 0.0 < raw < 120.0 and kl == pytest.approx(float(g["kl"]), rel=1e-5)
 
 
 def test_af3_saturates_temperature_clamp():
     """af=3 with temperature 4 -> tau clamped to 5 -> dtemperature == 0 (SURVEY 7 hard parts)."""
-    g = load_golden("train_af3_d64")
+    g = load_golden("train_af3_d128")
     assert float(np.abs(g["grad.router.temperature"]).max()) == 0.0
 
 
