@@ -300,10 +300,12 @@ def test_block_graph_replay_equals_eager_bitwise(top_k, precision):
         torch.autograd.backward([out, kl, bal], [dout, klw, torch.ones((), device="cuda")])
         return out, kl, probs
 
-    out, kl, probs = step()
-    eager = [out.detach().clone(), kl.detach().clone(), probs.detach().clone(), x.grad.clone(), w.grad.clone()] + [p.grad.clone() for p in params]
+    # every use of the leaves happens on a side stream: autograd pins a leaf's AccumulateGrad node to the stream of its first use, and
+    # a node pinned to the legacy default stream cannot take part in a capture (cudaErrorStreamCaptureImplicit)
     side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
+        out, kl, probs = step()
+        eager = [out.detach().clone(), kl.detach().clone(), probs.detach().clone(), x.grad.clone(), w.grad.clone()] + [p.grad.clone() for p in params]
         for _ in range(2):
             step()
     torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
