@@ -423,6 +423,14 @@ def kernel_model(tag, meta, Dt=512):
         R = rows if rows >= 0 else (T * E if dense else T * k)   # grouped GEMMs: the dispatched rows (padding rows are not work)
         flops = 2.0 * R * N * K
         S = 2 if fl & 0x400 else 1
+        if kind == 3:
+            # fused FFN pair (csrc/ffn_fused.cu): Linear(K -> N) + GELU + Linear(N -> K) per row, H stays on chip.  Algorithmic bytes: the
+            # token rows once (dense-soft: shared by all experts), the expert weights once, the output rows once
+            dense_soft = bool(m[7] & 0x20000)
+            tok = R // max(grp, 1) if dense_soft else R
+            byt = tok * K * 2 + max(grp, 1) * 2 * N * K * 2 + tok * K * (4 if dense_soft else 2)
+            name = f"ffn_fused<{'dense-soft +combine' if dense_soft else 'grouped'}> Linear+GELU+Linear"
+            return name, f"R={R} hidden={N} d={K} experts={grp}", float(byt), 2.0 * flops, "tensor"
         # operand bytes: A rows x K (or rows x dimA for wgrad) + B (weights, or rows x N for wgrad) + the output
         if kind == 2:
             byt = R * K * 2 * S + R * N * 2 * S + max(grp, 1) * K * N * 4

@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define MOEGAN_ABI_VERSION 4
+#define MOEGAN_ABI_VERSION 5
 #define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
@@ -225,6 +225,9 @@ typedef struct {
     const void* residual;       /* [T,d] fp32 / bf16 or NULL: out = residual + moe(x)  (AttentionBlock :571 fused) */
     int32_t residual_is_bf16;
     int32_t out_is_bf16;
+    const void* x_op;           /* optional, bf16 mode only: bf16 [T,d] copy of x that the caller already holds (moegan_layernorm_fwd_dual emits
+                                 * it together with the fp32 rows, t2i_moe_gan.py:561) - the block then runs no fp32 -> bf16 conversion pass
+                                 * over the tokens; pass the same tensor in moegan_block_bwd_args.x_op */
 } moegan_block_fwd_args;
 
 typedef struct {
@@ -246,6 +249,7 @@ typedef struct {
     void* workspace; int64_t workspace_bytes;
     int32_t dout_is_bf16;
     int32_t reserved;
+    const void* x_op;           /* the x_op the forward call was given (NULL if none) */
 } moegan_block_bwd_args;
 
 int64_t moegan_block_fwd_workspace(const moegan_shape* s, int32_t need_backward, moegan_block_layout* layout /* may be NULL */);
@@ -259,6 +263,10 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
  * anyway); mean / rstd [rows] fp32 are what the backward needs.  d: multiple of 128, <= 1024. */
 int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d,
                          float eps, void* y, int32_t y_is_bf16, float* mean, float* rstd, void* stream);
+/* norm3 in front of the MoE block (t2i_moe_gan.py:561), SURVEY 8(f) N1: the same LayerNorm writing BOTH the fp32 rows the router reads
+ * (y [rows,d] fp32) and their bf16 GEMM-operand copy (y_op [rows,d] bf16) in one pass over x. */
+int moegan_layernorm_fwd_dual(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
+                              float* y, void* y_op, float* mean, float* rstd, void* stream);
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d);
 /* dy fp32 or bf16; dx [rows,d] in x's dtype; dgamma_dbeta fp32 [2,d] (row 0 = weight gradient, row 1 = bias gradient),
  * deterministic. */
@@ -337,6 +345,10 @@ int moegan_debug_profile_read_ex(float* ms_out, int32_t* tag_out, int32_t* meta_
 /* debug / bench: 0 = keep every kernel of a block call on the caller's stream (per-kernel timing without concurrency), 1 = allow the
  * library's side streams, -1 = default (on, unless MOEGAN_DISABLE_SIDE_STREAM=1) */
 int moegan_debug_set_side_streams(int32_t mode);
+/* debug / bench / tests: 0 = never use the fused FFN kernel (csrc/ffn_fused.cu) in forward-only block calls, 1 / -1 = default (used in
+ * bf16 mode at d = 128 / 256 unless MOEGAN_DISABLE_FUSED_FFN=1).  The forward workspace layout depends on it: query
+ * moegan_block_fwd_workspace again after changing it. */
+int moegan_debug_set_fused_ffn(int32_t mode);
 /* debug: override the MN-major shared-memory descriptor parameters of the GEMM (0 = built-in defaults) */
 int moegan_debug_set_mn_desc(int32_t lbo_bytes, int32_t sbo_bytes, int32_t kadv_bytes);
 /* fp32 [rows, cols] -> bf16 operand [rows, S*cols] */

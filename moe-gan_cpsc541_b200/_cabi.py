@@ -17,7 +17,7 @@ MAX_EXPERTS = 32
 MAX_TOPK = 8
 CHUNK = 32
 KL_OUT_FLOATS = 2 + 256
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Shape(ctypes.Structure):
@@ -41,7 +41,8 @@ class BlockFwdArgs(ctypes.Structure):
                   "W1_op", "b1s", "W2_op", "b2s", "prep_w1", "prep_b1", "prep_w2", "prep_b2")]
                 + [("annealing_factor", c_float), ("sampled", c_int32), ("need_backward", c_int32)]
                 + [(n, c_void_p) for n in ("out", "probs", "load", "kl_out", "workspace")]
-                + [("workspace_bytes", c_int64), ("residual", c_void_p), ("residual_is_bf16", c_int32), ("out_is_bf16", c_int32)])
+                + [("workspace_bytes", c_int64), ("residual", c_void_p), ("residual_is_bf16", c_int32), ("out_is_bf16", c_int32),
+                   ("x_op", c_void_p)])
 
 
 class BlockBwdArgs(ctypes.Structure):
@@ -53,7 +54,7 @@ class BlockBwdArgs(ctypes.Structure):
                 + [(n, c_void_p) for n in
                    ("dx", "dw", "dmu_f", "drho_f", "dmu_t", "drho_t", "dmu_c", "drho_c", "dtemperature", "dW1", "db1", "dW2", "db2",
                     "workspace")]
-                + [("workspace_bytes", c_int64), ("dout_is_bf16", c_int32), ("reserved", c_int32)])
+                + [("workspace_bytes", c_int64), ("dout_is_bf16", c_int32), ("reserved", c_int32), ("x_op", c_void_p)])
 
 
 _P = c_void_p
@@ -87,6 +88,7 @@ SIGNATURES = {
     "moegan_block_fwd": (c_int32, [_SP, POINTER(BlockFwdArgs), _P]),
     "moegan_block_bwd": (c_int32, [_SP, POINTER(BlockBwdArgs), _P]),
     "moegan_layernorm_fwd": (c_int32, [_P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, c_int32, _P, _P, _P]),
+    "moegan_layernorm_fwd_dual": (c_int32, [_P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, _P, _P, _P, _P]),
     "moegan_layernorm_bwd_scratch_bytes": (c_int64, [c_int64, c_int32]),
     "moegan_layernorm_bwd": (c_int32, [_P, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
     "moegan_channel_scale_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P]),
@@ -106,6 +108,7 @@ SIGNATURES = {
     "moegan_debug_profile_read": (c_int32, [_P, _P, c_int32]),
     "moegan_debug_profile_read_ex": (c_int32, [_P, _P, _P, c_int32]),
     "moegan_debug_set_side_streams": (c_int32, [c_int32]),
+    "moegan_debug_set_fused_ffn": (c_int32, [c_int32]),
     "moegan_to_operand": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P]),
 }
 

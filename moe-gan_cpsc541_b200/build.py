@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libmoegan_sm100.so")
-SOURCES = ["api.cu", "router.cu", "dispatch.cu", "umma_gemm.cu", "glue.cu"]
+SOURCES = ["api.cu", "router.cu", "dispatch.cu", "umma_gemm.cu", "ffn_fused.cu", "glue.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -657,6 +657,16 @@ static int side_join(SideStream* ss, cudaStream_t main_st) {
 }
 
 // ---- whole block in one call -------------------------------------------------------------------------
+// Forward-only calls (the D-step's generator pass under no_grad, eval / inference) in bf16 mode at d = 128 / 256 run the fused
+// FFN kernel (ffn_fused.cu): dense-soft mode also folds the weighted combine + residual into it, so neither H, y nor a combine
+// launch exist; grouped (sparse / hard) mode writes y and keeps the un-permuting combine.
+static std::atomic<int> g_fused_override{-1};      // moegan_debug_set_fused_ffn: -1 = default (on where supported)
+static bool fused_fwd(const moegan_shape* s, int need_bwd) {
+    if (need_bwd) return false;
+    const int o = g_fused_override.load(std::memory_order_relaxed);
+    if (o == 0) return false;
+    return ffn_fused_supported(s->d, s->precision);
+}
 static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layout* L) {
     const size_t S = s->precision == 1 ? 2 : 1, H = MOEGAN_ROUTER_HID;
     const size_t T = s->T, d = s->d, Dt = s->Dt, E = s->E, k = s->k, B = s->B, hid = 4 * d, m_cap = s->m_cap;
@@ -689,9 +699,10 @@ static void block_layout(const moegan_shape* s, int need_bwd, moegan_block_layou
     L->row_token = take(m_cap * 4, !s->dense);
     L->row_gate = take(m_cap * 4, !s->dense);
     L->token_rows = take(T * k * 4, !s->dense);
+    const bool fused = fused_fwd(s, need_bwd);
     L->pre = take(m_cap * hid * act, need_bwd);
-    L->h_op = take(m_cap * S * hid * 2, true);
-    L->y = take(m_cap * d * act, true);
+    L->h_op = take(m_cap * S * hid * 2, !fused);
+    L->y = take(m_cap * d * act, !(fused && s->dense));
     // the eps the forward consumed (the caller's buffers are redrawn by the next training forward)
     L->eps_f = take(d * H * 4, need_bwd);
     L->eps_t = take(Dt * H * 4, need_bwd);
@@ -760,15 +771,40 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     RUN(moegan_router_fwd(s, a->x, F(L.Wf), F(L.Wc), F(L.tl), a->temperature, a->annealing_factor, F(L.fp), F(L.raw), a->probs,
                           I(L.topk_idx), F(L.gates), I(L.chunk_counts), F(L.chunk_colsum), stream));
     RUN(moegan_dispatch_plan(s, I(L.chunk_counts), F(L.chunk_colsum), I(L.plan), I(L.chunk_base), a->load, stream));
+    // a->x_op: the caller already holds the bf16 operand copy of x (emitted by moegan_layernorm_fwd_dual in the same pass as the fp32
+    // rows): no conversion kernel here, and the backward pass reads that tensor too (moegan_block_bwd_args.x_op)
+    MOEGAN_REQUIRE(a->x_op == nullptr || (s->precision == 0 && (reinterpret_cast<uintptr_t>(a->x_op) & 15) == 0), MOEGAN_ERR_UNSUPPORTED,
+                   "block_fwd: x_op is a plain bf16 [T, d] copy of x - bf16 mode only, 16-byte aligned");
+    void* const x_copy = a->x_op != nullptr ? const_cast<void*>(a->x_op) : P(L.x_copy);
+    void* const a_op = s->dense ? x_copy : P(L.a_op);
     if (s->dense) {
-        RUN(moegan_convert_tokens(s, a->x, P(L.x_copy), stream));
+        if (a->x_op == nullptr) RUN(moegan_convert_tokens(s, a->x, x_copy, stream));
     } else {
-        RUN(moegan_dispatch_gather(s, a->x, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), P(L.a_op), P(L.x_copy),
+        RUN(moegan_dispatch_gather(s, a->x, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), a_op, a->x_op != nullptr ? nullptr : x_copy,
                                    I(L.row_token), F(L.row_gate), I(L.token_rows), stream));
     }
     if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
-    RUN(moegan_ffn_fwd(s, I(L.plan), P(L.a_op), a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
+    if (fused_fwd(s, a->need_backward)) {
+        FfnFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.d = s->d; f.E = s->E; f.T = s->T;
+        f.a_op = a_op; f.W1_op = a->W1_op; f.W2_op = a->W2_op; f.b1s = a->b1s; f.b2s = a->b2s;
+        if (s->dense) {
+            f.mode = 1; f.rows = s->T; f.gates = F(L.gates);
+            f.residual = a->residual; f.residual_bf16 = a->residual_is_bf16; f.out = a->out; f.out_bf16 = a->out_is_bf16;
+            return launch_ffn_fused(f, (cudaStream_t)stream);
+        }
+        f.mode = 0; f.rows = s->m_cap; f.plan = I(L.plan); f.out = P(L.y); f.out_bf16 = 1;
+        RUN(launch_ffn_fused(f, (cudaStream_t)stream));
+    } else {
+        RUN(moegan_ffn_fwd(s, I(L.plan), a_op, a->W1_op, a->b1s, a->W2_op, a->b2s, P(L.pre), P(L.h_op), P(L.y), stream));
+    }
     RUN(moegan_combine_fwd(s, P(L.y), F(L.gates), I(L.token_rows), a->residual, a->residual_is_bf16, a->out, a->out_is_bf16, stream));
+    return MOEGAN_OK;
+}
+
+int moegan_debug_set_fused_ffn(int32_t mode) {
+    g_fused_override.store(mode < 0 ? -1 : (mode != 0 ? 1 : 0));
     return MOEGAN_OK;
 }
 
@@ -791,6 +827,9 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     float* dgate_row = reinterpret_cast<float*>(ws + W.dgate_row);
     float* dx_router = s->hard ? nullptr : reinterpret_cast<float*>(ws + W.dx_router);
     float* dy_slabs = reinterpret_cast<float*>(ws + W.dy_slabs);
+    MOEGAN_REQUIRE(a->x_op == nullptr || s->precision == 0, MOEGAN_ERR_UNSUPPORTED, "block_bwd: x_op is bf16 mode only");
+    void* const x_copy = a->x_op != nullptr ? const_cast<void*>(a->x_op) : P(L.x_copy);
+    void* const a_op = s->dense ? x_copy : P(L.a_op);
     RUN(moegan_combine_bwd(s, I(L.plan), a->dout, a->dout_is_bf16, P(L.y), I(L.row_token), F(L.row_gate), F(L.gates), ws + W.dy_op, dgate_row,
                            dy_slabs, stream));
     // Small blocks (side_pays): three concurrent chains after combine_bwd -
@@ -807,11 +846,11 @@ int moegan_block_bwd(const moegan_shape* s, const moegan_block_bwd_args* a, void
     }
     const FfnBwdScratch SL = ffn_bwd_scratch_layout(s);
     float* slab_stage = reinterpret_cast<float*>(ws + W.ffn_scratch + SL.slab_stage);
-    RUN(ffn_bwd_core(s, I(L.plan), P(L.a_op), a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
+    RUN(ffn_bwd_core(s, I(L.plan), a_op, a->W1_op, a->W2_op, P(L.pre), P(L.h_op), ws + W.dy_op, dy_slabs, ws + W.dpre_op, ws + W.dx_rows,
                      a->dW1, a->db1, a->dW2, a->db2, ws + W.ffn_scratch, (int64_t)ffn_bwd_scratch_bytes_impl(s), stream, ss != nullptr,
                      ss != nullptr ? ss->mid : nullptr));
     if (!s->hard) {
-        RUN(router_bwd_core(s, P(L.x_copy), a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
+        RUN(router_bwd_core(s, x_copy, a->w, F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), F(L.fp), F(L.tp), F(L.raw),
                             I(L.topk_idx), I(L.token_rows), dgate_row, a->dprobs, a->dload, a->temperature, a->annealing_factor,
                             a->sampled, a->mu_f, a->rho_f, F(L.eps_f), a->mu_t, a->rho_t, F(L.eps_t), a->mu_c, a->rho_c, F(L.eps_c),
                             a->kl_out, a->sampled ? a->dkl : nullptr,
@@ -845,7 +884,15 @@ int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, c
     REQ_PTR(x); REQ_PTR(gamma); REQ_PTR(beta); REQ_PTR(y); REQ_PTR(mean); REQ_PTR(rstd);
     MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0, MOEGAN_ERR_MISALIGNED, "layernorm_fwd: pointers must be 16-byte aligned");
-    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, y_is_bf16, mean, rstd, (cudaStream_t)stream);
+    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, y_is_bf16, nullptr, mean, rstd, (cudaStream_t)stream);
+}
+int moegan_layernorm_fwd_dual(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
+                              float* y, void* y_op, float* mean, float* rstd, void* stream) {
+    RUN(check_ln(rows, d));
+    REQ_PTR(x); REQ_PTR(gamma); REQ_PTR(beta); REQ_PTR(y); REQ_PTR(y_op); REQ_PTR(mean); REQ_PTR(rstd);
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y_op) | reinterpret_cast<uintptr_t>(gamma) |
+                     reinterpret_cast<uintptr_t>(beta)) & 15) == 0, MOEGAN_ERR_MISALIGNED, "layernorm_fwd_dual: pointers must be 16-byte aligned");
+    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, 0, y_op, mean, rstd, (cudaStream_t)stream);
 }
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d) { return (int64_t)ln_bwd_blocks(rows) * 2 * d * 4 + 256; }
 int moegan_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,

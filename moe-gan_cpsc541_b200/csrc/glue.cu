@@ -69,7 +69,7 @@ template <> struct Vec8<__nv_bfloat16> {
 template <typename TIN, typename TOUT, int NSEG, int R>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int d,
-                     float eps, TOUT* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                     float eps, TOUT* __restrict__ y, __nv_bfloat16* __restrict__ y_op, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     const long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
     const int lane = threadIdx.x & 31;
     if (r0 >= rows) return;
@@ -114,6 +114,9 @@ layernorm_fwd_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma,
                     o.x = (v[i][s].x - mean[i]) * rstd[i] * g.x + b.x; o.y = (v[i][s].y - mean[i]) * rstd[i] * g.y + b.y;
                     o.z = (v[i][s].z - mean[i]) * rstd[i] * g.z + b.z; o.w = (v[i][s].w - mean[i]) * rstd[i] * g.w + b.w;
                     Vec4<TOUT>::store(y + (r0 + i) * d + c, o);
+                    // norm3 -> MoE block: the bf16 GEMM-operand copy of the same row leaves in the same pass, so the
+                    // block needs no separate fp32 -> bf16 conversion kernel over [T, d]
+                    if (y_op != nullptr) Vec4<__nv_bfloat16>::store(y_op + (r0 + i) * d + c, o);
                 }
         }
     if (lane < R && r0 + lane < rows) {
@@ -618,14 +621,14 @@ int ln_bwd_blocks(long long rows) {
 
 // (NSEG, R) by segment count: 1 -> (1, 4), 2 -> (2, 2), 3..4 -> (4, 1), 5..8 -> (8, 1)
 int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
-                         int y_bf16, float* mean, float* rstd, cudaStream_t st) {
-    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_FWD, rows, d, 0, (x_bf16 ? 1 : 0) | (y_bf16 ? 2 : 0));
+                         int y_bf16, void* y_op, float* mean, float* rstd, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_FWD, rows, d, 0, (x_bf16 ? 1 : 0) | (y_bf16 ? 2 : 0) | (y_op != nullptr ? 4 : 0));
     if (rows == 0) return MOEGAN_OK;
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
 #define MOEGAN_LN_FWD2(TI, TO, NS, RR)                                                                                         \
     layernorm_fwd_kernel<TI, TO, NS, RR><<<(int)((rows + 8 * RR - 1) / (8 * RR)), 256, 0, st>>>(                              \
-        reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), mean, rstd)
+        reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), reinterpret_cast<__nv_bfloat16*>(y_op), mean, rstd)
 #define MOEGAN_LN_FWD(TI, TO)                                                                                                  \
     do {                                                                                                                       \
         if (nseg == 1) MOEGAN_LN_FWD2(TI, TO, 1, 4); else if (nseg == 2) MOEGAN_LN_FWD2(TI, TO, 2, 2);                         \

@@ -175,6 +175,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_b
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Cluster-scope release / acquire pair for DATA handed between the CTAs of a pair through shared memory (ffn_fused.cu: the peer's
+// epilogue warps write their half of the GELU tile into their own smem, the leader's MMA reads it through cta_group::2).  The plain
+// arrive above is .release.cta, which does not order the writer's shared-memory stores for an observer in another CTA.
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_acquire_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("moegan: mbarrier watchdog (cluster acquire; block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
 // TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_cta2(uint32_t dst_smem, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
     asm volatile(

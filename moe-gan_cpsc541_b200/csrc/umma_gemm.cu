@@ -663,6 +663,8 @@ bool cta2_enabled() {
 
 }  // namespace
 
+int make_operand_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer) { return make_tmap(m, o, box_outer); }
+
 int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& B, GemmParams p, long long max_tiles,
                      cudaStream_t stream) {
     if (max_tiles <= 0) return MOEGAN_OK;

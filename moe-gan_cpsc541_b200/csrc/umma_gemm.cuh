@@ -1,5 +1,7 @@
 // Host-side interface of the tcgen05 grouped GEMM (implementation in umma_gemm.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace moegan {
@@ -55,6 +57,32 @@ struct GemmParams {
     int out_split_off;      // column offset of the lo half in out0 for the *_X3 epilogues
     int mn_lbo, mn_sbo, mn_kadv;  // MN-major smem descriptor parameters (bytes); 0 -> defaults
 };
+
+// SWIZZLE_128B tensor map of a bf16 operand with boxes of 64 (inner) x box_outer elements (defined in umma_gemm.cu; CUtensorMap is
+// declared by <cuda.h>)
+int make_operand_tmap(CUtensorMap* m, const GemmOperand& o, uint32_t box_outer);
+
+// ---- ffn_fused.cu: Linear -> GELU -> Linear of a 256-row tile pair in ONE kernel; the [rows, 4d] hidden activations never leave the SM ----
+// mode 0 (grouped rows): y[m_cap, d] bf16 = gelu(a W1_e^T + b1_e) W2_e^T + b2_e, expert e of every 128-row block from the plan
+// mode 1 (dense-soft):   out[T, d] = sum_e gates[t, e] * (gelu(x W1_e^T + b1_e) W2_e^T + b2_e) (+ residual), every expert on every token
+struct FfnFusedArgs {
+    int mode;
+    int d, E, T;            // T: token rows (mode 1) / unused (mode 0)
+    int rows;               // rows of the A operand tensor (mode 0: m_cap, mode 1: T)
+    const void* a_op;       // bf16 [rows, d]
+    const void* W1_op;      // bf16 [E * 4d, d]
+    const void* W2_op;      // bf16 [E * d, 4d]
+    const float* b1s;       // [E, 4d]
+    const float* b2s;       // [E, d]
+    const int* plan;        // mode 0
+    const float* gates;     // mode 1: [T, E]
+    const void* residual;   // mode 1, optional: [T, d]
+    int residual_bf16;
+    void* out;              // mode 0: y bf16 [rows, d]; mode 1: out [T, d] fp32 / bf16
+    int out_bf16;
+};
+bool ffn_fused_supported(int d, int precision);
+int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t stream);
 
 // max_tiles: upper bound on the number of output tiles (sizes the persistent grid).
 int launch_umma_gemm(int kind, int BN, const GemmOperand& A, const GemmOperand& B, GemmParams p, long long max_tiles,

@@ -68,6 +68,13 @@ def _plan_for(cfg: MoEConfig) -> _Plan:
     return p
 
 
+def set_fused_ffn(enabled: Optional[bool]) -> None:
+    """Debug / bench / tests: False = forward-only block calls use the separate FFN1 / FFN2 / combine kernels instead of the fused
+    FFN kernel; None = library default.  Drops the cached workspace sizes (the forward layout depends on the choice)."""
+    C.check(C.lib().moegan_debug_set_fused_ffn(-1 if enabled is None else (1 if enabled else 0)), "moegan_debug_set_fused_ffn")
+    _PLANS.clear()
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -175,7 +182,7 @@ def workspace_views(ws: torch.Tensor, layout: "C.BlockLayout", cfg: MoEConfig) -
 
 
 class MoEBlockFunction(torch.autograd.Function):
-    """(x_tok [T,d], w [B,Dt], eps x3, router params x7, residual [T,d] | None, expert params x4E)
+    """(x_tok [T,d], w [B,Dt], eps x3, router params x7, residual [T,d] | None, x_op bf16 [T,d] | None, expert params x4E)
     -> (out [T,d], kl [], probs [T,E], load [E]).  With a residual, out = residual + moe(x) in the residual's dtype (the
     `x_spatial + moe_out` of AttentionBlock, t2i_moe_gan.py:571, done in the combine kernel's epilogue)."""
 
@@ -191,7 +198,7 @@ class MoEBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg: MoEConfig, wcache: WeightCache, x_tok, w, eps_f, eps_t, eps_c,
-                mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature, residual, *expert_params):
+                mu_f, rho_f, mu_t, rho_t, mu_c, rho_c, temperature, residual, x_op, *expert_params):
         lib = C.lib()
         E, d, T = cfg.E, cfg.d, cfg.T
         _require_cuda(x_tok, "x"); _require_cuda(w, "w"); _require_cuda(mu_f, "router.feature_mu")
@@ -245,6 +252,10 @@ class MoEBlockFunction(torch.autograd.Function):
         a.kl_out = small.data_ptr() + 4 * E
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         a.residual = _dp(residual)
+        if x_op is not None:
+            if cfg.precision != 0 or x_op.dtype != torch.bfloat16 or x_op.shape != (T, d) or not x_op.is_contiguous() or x_op.device != dev:
+                raise ValueError(f"x_operand must be a contiguous bf16 [T, d] = [{T}, {d}] copy of x on {dev} and the block must run in bf16 mode")
+            a.x_op = x_op.data_ptr()
         a.residual_is_bf16 = 1 if (residual is not None and residual.dtype == torch.bfloat16) else 0
         a.out_is_bf16 = 1 if out.dtype == torch.bfloat16 else 0
         with torch.cuda.device(dev):     # launches go to the current stream OF x's DEVICE
@@ -261,6 +272,7 @@ class MoEBlockFunction(torch.autograd.Function):
             ctx.router_params = router_params
             ctx.wops = (W1_op, W2_op)
             ctx.has_residual = residual is not None
+            ctx.x_op = x_op
         if MoEBlockFunction.keep_last:
             MoEBlockFunction._last = (ws, plan.layout if need_bwd else plan.layout_nobwd, cfg)
         return out, kl, probs, load
@@ -300,6 +312,7 @@ class MoEBlockFunction(torch.autograd.Function):
         a.annealing_factor = float(cfg.annealing_factor)
         a.sampled = 1 if cfg.sampled else 0
         a.dout_is_bf16 = 1 if dout.dtype == torch.bfloat16 else 0
+        a.x_op = _dp(ctx.x_op)
         a.dx = dx.data_ptr()
         a.dW1, a.db1, a.dW2, a.db2 = dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), db2.data_ptr()
         router_grads = [None] * 7
@@ -317,7 +330,7 @@ class MoEBlockFunction(torch.autograd.Function):
         expert_grads = [t for quad in zip(dW1.unbind(0), db1.unbind(0), dW2.unbind(0), db2.unbind(0)) for t in quad]
         ctx.ws = None
         d_res = dout if ctx.has_residual else None     # d(residual + moe) / d residual = identity
-        return (None, None, dx, dw, None, None, None, *router_grads, d_res, *expert_grads)
+        return (None, None, dx, dw, None, None, None, *router_grads, d_res, None, *expert_grads)
 
 
 class BalanceLossFunction(torch.autograd.Function):

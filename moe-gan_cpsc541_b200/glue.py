@@ -43,7 +43,7 @@ def _is_bf16(t: torch.Tensor) -> int:
 # --------------------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, with_operand=False):
         d = x.shape[-1]
         x2 = x.reshape(-1, d)
         if x2.dtype not in (torch.float32, torch.bfloat16):
@@ -54,14 +54,25 @@ class _LayerNormFn(torch.autograd.Function):
         y = torch.empty(rows, d, device=x.device, dtype=out_dtype)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
-        C.check(C.lib().moegan_layernorm_fwd(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), _is_bf16(y),
-                                             C.ptr(mean), C.ptr(rstd), _stream()), "moegan_layernorm_fwd")
+        y_op = None
+        if with_operand:      # fp32 rows + their bf16 GEMM-operand copy in ONE pass (norm3 -> MoE block)
+            y_op = torch.empty(rows, d, device=x.device, dtype=torch.bfloat16)
+            C.check(C.lib().moegan_layernorm_fwd_dual(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), C.ptr(y_op),
+                                                      C.ptr(mean), C.ptr(rstd), _stream()), "moegan_layernorm_fwd_dual")
+        else:
+            C.check(C.lib().moegan_layernorm_fwd(C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(y), _is_bf16(y),
+                                                 C.ptr(mean), C.ptr(rstd), _stream()), "moegan_layernorm_fwd")
         ctx.save_for_backward(x2, wf, mean, rstd)
         ctx.x_shape, ctx.x_dtype, ctx.w_dtype = x.shape, x.dtype, weight.dtype
+        ctx.with_operand = with_operand
+        if with_operand:
+            y_op = y_op.view(x.shape)
+            ctx.mark_non_differentiable(y_op)     # a rounded copy of y: the gradient flows through y
+            return y.view(x.shape), y_op
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *unused):
         x2, wf, mean, rstd = ctx.saved_tensors
         rows, d = x2.shape
         g = gy.reshape(rows, d)
@@ -75,14 +86,20 @@ class _LayerNormFn(torch.autograd.Function):
         scratch = torch.empty(nbytes, device=g.device, dtype=torch.uint8)
         C.check(lib.moegan_layernorm_bwd(C.ptr(g), _is_bf16(g), C.ptr(x2), _is_bf16(x2), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d,
                                          C.ptr(dx), C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd")
-        return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None, None
+        return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None, None, None
 
 
-def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=torch.float32) -> torch.Tensor:
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=torch.float32, with_operand: bool = False):
     """`nn.LayerNorm(d)(x)` over the last dimension.  Result fp32 (what autocast's LayerNorm returns), or bf16 when the
-    only consumer is an autocast matmul that would round it to bf16 first thing anyway (same values, one pass less)."""
+    only consumer is an autocast matmul that would round it to bf16 first thing anyway (same values, one pass less).
+    with_operand=True (fp32 result only): returns (y fp32, y rounded to bf16) from one pass - what norm3 hands the MoE block."""
     if not x.is_cuda:
-        return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps).to(out_dtype)
+        y = F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps).to(out_dtype)
+        return (y, y.detach().to(torch.bfloat16)) if with_operand else y
+    if with_operand:
+        if out_dtype != torch.float32:
+            raise ValueError("layer_norm(with_operand=True) returns the fp32 rows plus their bf16 copy: out_dtype must be float32")
+        return _LayerNormFn.apply(x, weight, bias, eps, out_dtype, True)
     return _LayerNormFn.apply(x, weight, bias, eps, out_dtype)
 
 

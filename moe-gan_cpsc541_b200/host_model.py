@@ -112,10 +112,18 @@ class AttentionBlock(nn.Module):
         tp = self.text_proj(text_seq)
         t = t + glue.multihead_attention(self.cross_attn, ln(self.norm2, t, mm), tp)
         x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
-        x_norm = ln(self.norm3, t).reshape(B, H, W, C).permute(0, 3, 1, 2)  # NCHW view of NHWC memory (:561)
+        # norm3 (:561): the fp32 rows the router reads and - when the block runs its bf16 tensor-core path - their bf16 operand copy
+        # from the same pass, so the block has no conversion kernel of its own
+        bf16_block = t.is_cuda and getattr(self.moe, "takes_operand", False) and self.moe._precision_code() == 0
+        if bf16_block:
+            x_n, x_op = glue.layer_norm(t, self.norm3.weight, self.norm3.bias, self.norm3.eps, torch.float32, with_operand=True)
+        else:
+            x_n, x_op = ln(self.norm3, t), None
+        x_norm = x_n.reshape(B, H, W, C).permute(0, 3, 1, 2)                # NCHW view of NHWC memory (:561)
         if getattr(self.moe, "fuses_residual", False):
             # B200 block: `x_spatial + moe_out` (:571) happens in the combine kernel, in x_spatial's dtype
-            h, moe_kl, probs = self.moe(x_norm, w, annealing_factor, residual=x_spatial)
+            kw = {"x_operand": x_op} if x_op is not None else {}
+            h, moe_kl, probs = self.moe(x_norm, w, annealing_factor, residual=x_spatial, **kw)
         else:
             moe_out, moe_kl, probs = self.moe(x_norm, w, annealing_factor)
             h = x_spatial + moe_out.to(x_spatial.dtype)

@@ -129,6 +129,7 @@ class SparseMoE(nn.Module):
         self.router = BayesianRouter(dim, text_dim, num_experts)
         self._wcache = WeightCache()
         self.fuses_residual = True   # forward(..., residual=) adds the skip connection inside the combine kernel
+        self.takes_operand = True    # forward(..., x_operand=) consumes the bf16 token copy norm3 emitted (no conversion pass)
         self.redraw_eps = True    # False = parity mode "use the epsilon_* buffers as they are" 
         self.last_load: Optional[torch.Tensor] = None   # fused per-expert prob column sums of the last forward
 
@@ -151,10 +152,12 @@ class SparseMoE(nn.Module):
         return 0 if torch.is_autocast_enabled() else 1
 
     def forward(self, x: torch.Tensor, w: torch.Tensor, annealing_factor: float = 1.0, *,
-                eps: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None, residual: Optional[torch.Tensor] = None):
+                eps: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None, residual: Optional[torch.Tensor] = None,
+                x_operand: Optional[torch.Tensor] = None):
         """Reference contract (t2i_moe_gan.py:444-491).  `residual` (optional, [B,d,H,W], same memory layout as x): return
         `residual + moe(x)` in the residual's dtype - the skip connection of AttentionBlock (:571) fused into the combine
-        kernel."""
+        kernel.  `x_operand` (optional, bf16 mode): the bf16 copy of x's tokens that `glue.layer_norm(...,
+        with_operand=True)` emitted in the same pass as x (norm3, :561) - the block then skips its own conversion pass."""
         if not x.is_cuda:
             raise RuntimeError("SparseMoE (B200 path) needs CUDA tensors: there is no CPU fallback")
         batch_size, channels, height, width = x.shape
@@ -192,7 +195,10 @@ class SparseMoE(nn.Module):
                 raise ValueError(f"residual {tuple(residual.shape)} must have the shape of x {tuple(x.shape)}")
             res_tok = residual.permute(0, 2, 3, 1).contiguous().view(-1, channels)      # a view for NHWC memory
         with torch.autocast(device_type="cuda", enabled=False):
-            out, kl, probs, load = MoEBlockFunction.apply(cfg, self._wcache, x_tok, w, eps[0], eps[1], eps[2], *params, res_tok, *expert_params)
+            x_op = None
+            if x_operand is not None and precision == 0:
+                x_op = x_operand.reshape(-1, channels)
+            out, kl, probs, load = MoEBlockFunction.apply(cfg, self._wcache, x_tok, w, eps[0], eps[1], eps[2], *params, res_tok, x_op, *expert_params)
         self.last_load = load
         if not hard:
             # lets moe_balance_loss() use the fused column sums.  Not in eval mode: there `probs` is one-hot (:392-400) while the

@@ -45,7 +45,8 @@ class GradReducer:
     while the compute stream keeps running backward.  `finish()` joins the streams and scatters the averages back.
     """
 
-    def __init__(self, params: Sequence[nn.Parameter], group=None, bucket_bytes: int = 25 << 20, overlap: bool = True):
+    def __init__(self, params: Sequence[nn.Parameter], group=None, bucket_bytes: int = 25 << 20, overlap: bool = True,
+                 tail_bytes: int = 8 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -59,6 +60,18 @@ class GradReducer:
             cur.append(p); cur_bytes += nbytes
         if cur:
             self.buckets.append(cur)
+        # The LAST bucket holds the first parameters of the model, whose gradients appear at the very end of backward: nothing is left
+        # to overlap its all-reduce with, so it is kept short - its trailing <= tail_bytes are split off into a bucket of their own and
+        # the rest of it can go out (and overlap) earlier.
+        if self.buckets and tail_bytes > 0:
+            last = self.buckets[-1]
+            tail, tb = [], 0
+            while len(last) > 1 and tb + last[-1].numel() * 4 <= tail_bytes:
+                q = last.pop(); tail.insert(0, q); tb += q.numel() * 4
+            if tail and last:
+                self.buckets.append(tail)
+            elif tail:
+                self.buckets[-1] = tail
         self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
         self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
         self.pending = [0] * len(self.buckets)
@@ -68,6 +81,9 @@ class GradReducer:
         # NCCL averages inside the collective (ReduceOp.AVG); other backends (gloo in the CPU tests) sum, then scale
         self.avg_in_collective = bool(self.world > 1 and dist.get_backend(group) == "nccl")
         self._handles = []
+        # profiling (tools/dp_timeline.py): a list to which every bucket appends CUDA events - gradients ready (compute stream),
+        # all-reduce begin / end (comm stream) - so that the exposed part of the collective can be read off one step
+        self.trace: Optional[list] = None
         if self.world > 1:
             for p in self.params:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -97,6 +113,15 @@ class GradReducer:
         if self.pending[bi] == 0:
             self._launch(bi)
 
+    def _grad_view(self, p: nn.Parameter, flat_slice: torch.Tensor) -> Optional[torch.Tensor]:
+        """The slice of a bucket seen as p's gradient (same shape and strides as p), or None if p is dense in neither format."""
+        if p.is_contiguous():
+            return flat_slice.view(p.shape)
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last):
+            n, c, h, w = p.shape
+            return flat_slice.view(n, h, w, c).permute(0, 3, 1, 2)
+        return None
+
     def _launch(self, bi: int) -> None:
         self.launched[bi] = True
         flat = self._flat(bi)
@@ -104,17 +129,35 @@ class GradReducer:
         views = flat.split([p.numel() for p in self.buckets[bi]])
         srcs = [_flat_storage_view(g) for g in grads]
         srcs = [s if s is not None else g.reshape(-1) for s, g in zip(srcs, grads)]
-        torch._foreach_copy_(list(views), srcs)
+        # a gradient that already lives in its bucket slot (left there by the previous finish() and accumulated into in place) needs no copy
+        todo = [(v, s) for v, s in zip(views, srcs) if v.data_ptr() != s.data_ptr()]
+        if todo:
+            torch._foreach_copy_([v for v, _ in todo], [s for _, s in todo])
         op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+        rec = None
+        if self.trace is not None and flat.is_cuda:
+            rec = {"bucket": bi, "bytes": flat.numel() * 4, "ready": torch.cuda.Event(enable_timing=True),
+                   "begin": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
+            rec["ready"].record()
+            self.trace.append(rec)
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
+                if rec is not None:
+                    rec["begin"].record()
                 dist.all_reduce(flat, op=op, group=self.group)
+                if not self.avg_in_collective:
+                    flat.mul_(1.0 / self.world)
+                if rec is not None:
+                    rec["end"].record()
         else:
             dist.all_reduce(flat, op=op, group=self.group)
+            if not self.avg_in_collective:
+                flat.mul_(1.0 / self.world)
 
     def finish(self) -> None:
-        """Call after backward: reduces stragglers, joins the comm stream, writes the averaged gradients back."""
+        """Call after backward: reduces stragglers, joins the comm stream and makes every .grad a VIEW of its (averaged) bucket slot -
+        nothing is copied back: clip_grad_norm_ and the optimizer read the reduced gradients where the collective left them."""
         if self.world == 1 or not self.enabled:
             return
         for bi in range(len(self.buckets)):
@@ -122,25 +165,16 @@ class GradReducer:
                 self._launch(bi)          # parameters that received no gradient this step
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        inv = 1.0 / self.world
         for bi, b in enumerate(self.buckets):
-            views = list(self._flat(bi).split([p.numel() for p in b]))
-            outs = []
-            for p in b:
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-                outs.append(_flat_storage_view(p.grad))
-            fast = [(o, v) for o, v in zip(outs, views) if o is not None]
-            if fast:                                   # two multi-tensor launches per bucket, whatever the memory format
-                fo, fv = [o for o, _ in fast], [v for _, v in fast]
-                torch._foreach_copy_(fo, fv)
-                if not self.avg_in_collective:
-                    torch._foreach_mul_(fo, inv)
-            for p, o, v in zip(b, outs, views):        # gradients that are dense in neither format (none in this model)
-                if o is None:
+            views = self._flat(bi).split([p.numel() for p in b])
+            for p, v in zip(b, views):
+                gv = self._grad_view(p, v)
+                if gv is not None:
+                    p.grad = gv
+                else:                                   # dense in neither memory format (none in this model): copy back
+                    if p.grad is None:
+                        p.grad = torch.empty_like(p)
                     p.grad.copy_(v.view_as(p))
-                    if not self.avg_in_collective:
-                        p.grad.mul_(inv)
         self.enabled = False
 
 

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(pkg._cabi.SIGNATURES) == decl, "ctypes signature table and header disagree"
-    assert lib.moegan_version() == pkg._cabi.ABI_VERSION == 4
+    assert lib.moegan_version() == pkg._cabi.ABI_VERSION == 5
 
 
 def test_sizes_and_error_reporting(pkg):
@@ -45,9 +45,9 @@ def test_ctypes_struct_layouts_match_the_header(pkg):
     C = pkg._cabi
     assert ctypes.sizeof(C.Shape) == 44
     assert ctypes.sizeof(C.BlockLayout) == 216
-    assert ctypes.sizeof(C.BlockFwdArgs) == 240 and C.BlockFwdArgs.out.offset == 176 and C.BlockFwdArgs.residual.offset == 224
+    assert ctypes.sizeof(C.BlockFwdArgs) == 248 and C.BlockFwdArgs.x_op.offset == 240 and C.BlockFwdArgs.out.offset == 176 and C.BlockFwdArgs.residual.offset == 224
     assert C.BlockFwdArgs.out_is_bf16.offset == 236
-    assert ctypes.sizeof(C.BlockBwdArgs) == 288 and C.BlockBwdArgs.dx.offset == 160 and C.BlockBwdArgs.workspace_bytes.offset == 272
+    assert ctypes.sizeof(C.BlockBwdArgs) == 296 and C.BlockBwdArgs.x_op.offset == 288 and C.BlockBwdArgs.dx.offset == 160 and C.BlockBwdArgs.workspace_bytes.offset == 272
     assert C.BlockBwdArgs.dout_is_bf16.offset == 280
     s = C.make_shape(4096, 512, 512, 8, 2, 8, 512, 0, False, False)
     lay = C.BlockLayout()

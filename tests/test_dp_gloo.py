@@ -53,6 +53,19 @@ def _worker(rank, world, port, q):
             want = sum(ref[r][i] for r in range(world)) / world
             assert torch.allclose(g, want, atol=1e-6), i
         assert torch.count_nonzero(unused.grad) == 0
+        # the reduced gradients are VIEWS of the bucket buffers (no copy back), and the last bucket is the short tail
+        spans = [(f.data_ptr(), f.data_ptr() + f.numel() * 4) for f in red.flat]
+        assert all(any(a <= p.grad.data_ptr() < b for a, b in spans) for p in params)
+        assert sum(p.numel() for p in red.buckets[-1]) * 4 <= 8 << 20
+        # a second step: fresh gradients (set_to_none) are packed again; gradients left in place are accumulated into and re-averaged
+        for p in params:
+            p.grad = None
+        red.begin(); model(x).square().mean().backward(); red.finish()
+        for i, (g, p) in enumerate(zip(got, model.parameters())):
+            assert torch.allclose(p.grad, g, atol=1e-6), i
+        red.begin(); model(x).square().mean().backward(); red.finish()          # no zero_grad: avg(avg_prev + local) = avg_prev + avg_new
+        for i, (g, p) in enumerate(zip(got, model.parameters())):
+            assert torch.allclose(p.grad, 2 * g, atol=2e-6), i
 
         # channels-last conv weights (the bench's model layout): gradients are dense but not row-major contiguous; they
         # are packed / unpacked through storage-order views, never through per-parameter copies

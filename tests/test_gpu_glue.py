@@ -253,3 +253,46 @@ def test_upsample2x_matches_interpolate(B, C, H, W, dtype):
     if dtype == torch.float32:      # same taps, same evaluation order as ATen's kernel
         ya = F.interpolate(x.cuda().contiguous(memory_format=torch.channels_last), scale_factor=2, mode="bilinear", align_corners=False)
         assert _rel(yc, ya) < 1e-6
+
+
+@pytest.mark.parametrize("top_k", [None, 2])
+def test_layernorm_with_operand_feeds_the_block_without_a_conversion_pass(top_k):
+    """norm3 emits the fp32 rows and their bf16 operand copy in one pass; the block given `x_operand=` launches one
+    kernel less in dense mode (no to_operand), and output / every gradient are bit-identical to the block converting x itself."""
+    import importlib
+    pkg = importlib.import_module("moe-gan_cpsc541_b200")
+    torch.manual_seed(0)
+    B, HW, d = 6, 64, 256
+    t = torch.randn(B, HW, d, device="cuda")
+    ln = torch.nn.LayerNorm(d).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.2, 0.2)
+    y, y_op = pkg.glue.layer_norm(t, ln.weight, ln.bias, ln.eps, torch.float32, with_operand=True)
+    y_ref = pkg.glue.layer_norm(t, ln.weight, ln.bias, ln.eps)
+    assert y_op.dtype == torch.bfloat16 and y_op.shape == y.shape and torch.equal(y, y_ref) and torch.equal(y_op, y.to(torch.bfloat16))
+    moe = pkg.SparseMoE(d, 512, 8 if top_k else 4, top_k=top_k, precision="bf16").cuda().train()
+    moe.redraw_eps = False
+    for n in ("epsilon_f", "epsilon_t", "epsilon_c"):
+        getattr(moe.router, n).normal_()
+    w = torch.randn(B, 512, device="cuda")
+    go = torch.randn(B, d, 8, 8, device="cuda")
+    res, launches = [], []
+    lib = pkg._cabi.lib()
+    for use_op in (False, True):
+        moe.zero_grad(set_to_none=True)
+        tt = t.clone().requires_grad_(True)
+        if use_op:
+            yy, yo = pkg.glue.layer_norm(tt, ln.weight, ln.bias, ln.eps, torch.float32, with_operand=True)
+        else:
+            yy, yo = pkg.glue.layer_norm(tt, ln.weight, ln.bias, ln.eps), None
+        x = yy.reshape(B, 8, 8, d).permute(0, 3, 1, 2)
+        n0 = lib.moegan_debug_launch_count()
+        out, kl, probs = moe(x, w, 1.0, x_operand=yo) if use_op else moe(x, w, 1.0)
+        launches.append(lib.moegan_debug_launch_count() - n0)
+        (out * go).sum().backward()
+        res.append([out.detach().clone(), tt.grad.clone(), ln.weight.grad.clone()] + [p.grad.clone() for p in moe.parameters()])
+        ln.zero_grad(set_to_none=True)
+    if top_k is None:
+        assert launches[1] == launches[0] - 1, launches          # dense mode: the to_operand launch is gone
+    for a, b in zip(*res):
+        assert torch.equal(a, b)

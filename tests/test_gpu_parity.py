@@ -331,3 +331,64 @@ def test_fp16_autocast_and_bf16_input_follow_the_reference_contract():
     assert G.rel_err(out32.detach().cpu().numpy(), ora["out"]) < 1e-4
     outb, _, _ = m(xt.bfloat16(), wt, 1.0, eps=e)             # low-precision input: output follows x.dtype
     assert outb.dtype == torch.bfloat16 and outb.shape == xt.shape and outb.stride() == out32.stride()
+
+
+# --------------------------------------------------------------------------------------------------
+# fused FFN kernel (csrc/ffn_fused.cu): forward-only block calls in bf16 mode at d = 128 / 256
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [
+    dict(B=3, H=5, W=5, d=128, Dt=64, E=4),                      # ragged dense: T = 75, one half-empty pair tile
+    dict(B=4, H=8, W=8, d=256, Dt=512, E=4),                     # block-8 geometry, T = 256: exactly one pair tile
+    dict(B=5, H=8, W=8, d=256, Dt=512, E=4),                     # T = 320: the peer CTA of the second pair has 64 real rows
+    dict(B=2, H=16, W=16, d=128, Dt=512, E=8),                   # 8 experts x 4 chunks = 32 chunks per tile
+    dict(B=1, H=8, W=8, d=128, Dt=64, E=32, mu_scale=10.0),      # MOEGAN_MAX_EXPERTS: 128 chunks per tile
+    dict(B=256, H=16, W=16, d=128, Dt=512, E=4),                 # block 16x16 at batch 256: 256 pair tiles over 74 CTA pairs
+    dict(B=256, H=8, W=8, d=256, Dt=512, E=4),                   # block 8x8 at batch 256
+    dict(B=2, H=8, W=8, d=128, Dt=64, E=8, k=2),                 # sparse top-k, forward only: grouped mode + combine
+    dict(B=8, H=8, W=8, d=256, Dt=512, E=8, k=2, mu_scale=8.0),
+    dict(B=64, H=8, W=8, d=256, Dt=512, E=4, hard=True),         # eval: hard top-1 (inference path)
+    dict(B=3, H=5, W=5, d=128, Dt=64, E=4, hard=True),
+])
+def test_fused_ffn_forward(shape):
+    """no_grad / eval forward in bf16 mode runs the fused Linear-GELU-Linear(-combine) kernel: against the oracle (2e-2) and against
+    the separate FFN1 / FFN2 / combine kernels on the same inputs (both are bf16 pipelines: 1e-2 of each other)."""
+    s = shape
+    pkg = G.pkg()
+    k, hard = s.get("k"), s.get("hard", False)
+    params, x, w, dout, gp, eps = _random_case(123 + s["d"] + s["E"], s["B"], s["H"], s["W"], s["d"], s["Dt"], s["E"], mu_scale=s.get("mu_scale", 30.0))
+    m = G.build_module(params, s["d"], s["Dt"], s["E"], top_k=k, precision="bf16", training=not hard)
+    n0 = pkg._cabi.lib().moegan_debug_launch_count()
+    r = G.run_cuda(m, x, w, None if hard else eps, 1.0)
+    n_fused = pkg._cabi.lib().moegan_debug_launch_count() - n0
+    try:
+        pkg.functional.set_fused_ffn(False)
+        n0 = pkg._cabi.lib().moegan_debug_launch_count()
+        r_sep = G.run_cuda(m, x, w, None if hard else eps, 1.0)
+        n_sep = pkg._cabi.lib().moegan_debug_launch_count() - n0
+    finally:
+        pkg.functional.set_fused_ffn(None)
+    assert n_fused == n_sep - (2 if (k is None and not hard) else 1), (n_fused, n_sep)     # dense: FFN1+FFN2+combine -> 1 launch; grouped: FFN1+FFN2 -> 1
+    ora = G.run_oracle(params, x, w, None if hard else eps, 1.0, training=not hard, top_k=k)
+    assert np.array_equal(r["probs"], r_sep["probs"])
+    e_o, e_s = G.rel_err(r["out"], ora["out"]), G.rel_err(r["out"], r_sep["out"])
+    print(f"fused FFN {s}: vs oracle {e_o:.2e}, vs separate kernels {e_s:.2e} (separate vs oracle {G.rel_err(r_sep['out'], ora['out']):.2e})")
+    assert e_o < 2e-2 and e_s < 1e-2
+    assert np.isfinite(r["out"]).all()
+
+
+@pytest.mark.parametrize("res_dtype", [torch.float32, torch.bfloat16])
+def test_fused_ffn_forward_residual_and_output_dtype(res_dtype):
+    """The dense-soft fused kernel adds the attention block's skip connection (t2i_moe_gan.py:571) and writes the residual stream's dtype."""
+    pkg = G.pkg()
+    params, x, w, dout, gp, eps = _random_case(321, 6, 8, 8, 256, 512, 4)
+    m = G.build_module(params, 256, 512, 4, precision="bf16")
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    xt, wt = nhwc(torch.from_numpy(x).cuda()), torch.from_numpy(w).cuda()
+    res = nhwc(torch.from_numpy(dout).cuda()).to(res_dtype)
+    e = tuple(torch.from_numpy(eps[kk]).cuda() for kk in O.EPS_KEYS)
+    with torch.no_grad():
+        out_f, _, _ = m(xt, wt, 1.0, eps=e, residual=res)
+        plain, _, _ = m(xt, wt, 1.0, eps=e)
+    assert out_f.dtype == res_dtype and out_f.shape == xt.shape and out_f.stride() == xt.stride()
+    want = res.float() + plain.float()
+    assert float((out_f.float() - want).abs().max() / want.abs().max()) < (1e-6 if res_dtype == torch.float32 else 8e-3)
