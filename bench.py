@@ -469,7 +469,7 @@ def kernel_model(tag, meta, Dt=512):
     if kid == 3:
         byt = T * d * 4 + H * d * 4 + T * (2 * E + 2 * kk) * 4 + (T * H * 4 if fl & 0x1000 else 0)
         return name, label, float(byt), 2.0 * T * d * H + 2.0 * T * H * E, "fp32"
-    if kid == 5:  return name, label, float(T * d * 4 + T * k * 8 + R * d * 2 * S + (T * d * 2 * S if fl & 0x1000 else 0) + R * 8 + T * k * 4), None, "hbm"
+    if kid == 5:  return name, label, float(T * d * (2 if fl & 0x2000 else 4) + T * k * 8 + R * d * 2 * S + (T * d * 2 * S if fl & 0x1000 else 0) + R * 8 + T * k * 4), None, "hbm"
     if kid == 7:  return name, label, float(E * 8 * d * d * (4 + 2 * S) + 2 * E * 5 * d * 4), None, "hbm"
     if kid == 8:
         res = 4 if fl & 0x1000 else (2 if fl & 0x2000 else 0)

@@ -277,7 +277,7 @@ int moegan_dispatch_gather(const moegan_shape* s, const float* x, const int32_t*
     MOEGAN_REQUIRE(!s->dense, MOEGAN_ERR_UNSUPPORTED, "dispatch_gather is for sparse mode; dense mode uses convert_tokens");
     REQ_PTR(x); REQ_PTR(topk_idx); REQ_PTR(gates); REQ_PTR(plan); REQ_PTR(chunk_base); REQ_PTR(x_op); REQ_PTR(row_token);
     REQ_PTR(row_gate); REQ_PTR(token_rows);
-    return launch_gather(s, x, topk_idx, gates, plan, chunk_base, x_op, x_copy, row_token, row_gate, token_rows, (cudaStream_t)stream);
+    return launch_gather(s, x, nullptr, topk_idx, gates, plan, chunk_base, x_op, x_copy, row_token, row_gate, token_rows, (cudaStream_t)stream);
 }
 
 int moegan_convert_tokens(const moegan_shape* s, const float* x, void* x_copy, void* stream) {
@@ -780,8 +780,8 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     if (s->dense) {
         if (a->x_op == nullptr) RUN(moegan_convert_tokens(s, a->x, x_copy, stream));
     } else {
-        RUN(moegan_dispatch_gather(s, a->x, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), a_op, a->x_op != nullptr ? nullptr : x_copy,
-                                   I(L.row_token), F(L.row_gate), I(L.token_rows), stream));
+        RUN(launch_gather(s, a->x, a->x_op, I(L.topk_idx), F(L.gates), I(L.plan), I(L.chunk_base), a_op, a->x_op != nullptr ? nullptr : x_copy,
+                          I(L.row_token), F(L.row_gate), I(L.token_rows), (cudaStream_t)stream));
     }
     if (ss != nullptr) RUN(side_join(ss, (cudaStream_t)stream));
     if (fused_fwd(s, a->need_backward)) {

@@ -85,7 +85,7 @@ __device__ __forceinline__ void store_operand4(__nv_bfloat16* dst, int lo_off, b
 }
 
 __global__ void __launch_bounds__(256)
-gather_kernel(const float* __restrict__ x, const int* __restrict__ topk_idx, const float* __restrict__ gates,
+gather_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_bf16, const int* __restrict__ topk_idx, const float* __restrict__ gates,
               const int* __restrict__ plan, const int* __restrict__ chunk_base, int nchunks, int T, int d, int E, int k, int split,
               __nv_bfloat16* __restrict__ x_op, __nv_bfloat16* __restrict__ x_copy,
               int* __restrict__ row_token, float* __restrict__ row_gate, int* __restrict__ token_rows) {
@@ -137,15 +137,37 @@ gather_kernel(const float* __restrict__ x, const int* __restrict__ topk_idx, con
         }
     }
     __syncthreads();
-    for (int tok = wid; tok < MOEGAN_CHUNK; tok += 8) {
+    // Row copy, flat over (token, 8-column group) so that all 256 threads carry 16-byte accesses whatever d is (a warp per token
+    // with 8-byte lanes left half of every request slot empty: 0.20-0.29 of the HBM roof).  The dispatched row indices come from
+    // shared memory (staged above), the source row is read once and written to its k destinations.
+    const int g8 = d / 8;
+    const int items = MOEGAN_CHUNK * g8;
+    for (int it = tid; it < items; it += 256) {
+        const int tok = it / g8, col = (it - tok * g8) * 8;
         const int t = chunk * MOEGAN_CHUNK + tok;
         if (t >= T) break;
-        for (int seg = 0; seg < d / 128; ++seg) {
-            const int col = seg * 128 + lane * 4;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)t * d + col));
+        if (x_bf16 != nullptr) {              // the caller's bf16 copy of x (norm3 emitted it): a pure 16-byte row copy, half the read bytes
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x_bf16 + (size_t)t * d + col));
             for (int j = 0; j < k; ++j)
-                store_operand4(x_op + (size_t)dst_row[tok * k + j] * ld + col, d, split, v);
-            if (x_copy != nullptr) store_operand4(x_copy + (size_t)t * ld + col, d, split, v);
+                *reinterpret_cast<uint4*>(x_op + (size_t)dst_row[tok * k + j] * d + col) = u;
+            continue;
+        }
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + (size_t)t * d + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + (size_t)t * d + col + 4));
+        if (!split) {
+            const uint4 u = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+            for (int j = 0; j < k; ++j)
+                *reinterpret_cast<uint4*>(x_op + (size_t)dst_row[tok * k + j] * d + col) = u;
+            if (x_copy != nullptr) *reinterpret_cast<uint4*>(x_copy + (size_t)t * d + col) = u;
+        } else {
+            for (int j = 0; j < k; ++j) {
+                store_operand4(x_op + (size_t)dst_row[tok * k + j] * ld + col, d, true, a);
+                store_operand4(x_op + (size_t)dst_row[tok * k + j] * ld + col + 4, d, true, b);
+            }
+            if (x_copy != nullptr) {
+                store_operand4(x_copy + (size_t)t * ld + col, d, true, a);
+                store_operand4(x_copy + (size_t)t * ld + col + 4, d, true, b);
+            }
         }
     }
 }
@@ -582,12 +604,13 @@ int launch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float*
     return MOEGAN_OK;
 }
 
-int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates, const int32_t* plan,
+int launch_gather(const moegan_shape* s, const float* x, const void* x_bf16, const int32_t* topk_idx, const float* gates, const int32_t* plan,
                   const int32_t* chunk_base, void* x_op, void* x_copy, int32_t* row_token, float* row_gate, int32_t* token_rows,
                   cudaStream_t st) {
-    ProfScope _ps(st, MOEGAN_PROF_GATHER, s, x_copy != nullptr ? 0x1000 : 0);
+    ProfScope _ps(st, MOEGAN_PROF_GATHER, s, (x_copy != nullptr ? 0x1000 : 0) | (x_bf16 != nullptr ? 0x2000 : 0));
+    MOEGAN_REQUIRE(x_bf16 == nullptr || s->precision == 0, MOEGAN_ERR_UNSUPPORTED, "gather: a bf16 source is bf16 mode only");
     const int nchunks = ceil_div(s->T, MOEGAN_CHUNK);
-    gather_kernel<<<nchunks + s->E, 256, 0, st>>>(x, topk_idx, gates, plan, chunk_base, nchunks, s->T, s->d, s->E, s->k,
+    gather_kernel<<<nchunks + s->E, 256, 0, st>>>(x, reinterpret_cast<const __nv_bfloat16*>(x_bf16), topk_idx, gates, plan, chunk_base, nchunks, s->T, s->d, s->E, s->k,
                                                   s->precision == 1, reinterpret_cast<__nv_bfloat16*>(x_op),
                                                   reinterpret_cast<__nv_bfloat16*>(x_copy), row_token, row_gate, token_rows);
     MOEGAN_CHECK_LAUNCH("gather_kernel");

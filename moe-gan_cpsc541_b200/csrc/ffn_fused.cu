@@ -21,7 +21,7 @@
 //     a1_full[b] / a1_empty[b]  MMA -> epilogue, FFN1 accumulator    h_full[b] / h_empty[b]   epilogue -> MMA, GELU tile in smem
 //     a2_full / a2_empty        MMA -> epilogue, output accumulator
 // "full" barriers that the leader's MMA lane waits on collect arrivals from BOTH CTAs (TMA bytes via cta_group::2 loads, the peer's
-// epilogue warps through the cluster window with release.cluster semantics); "empty" barriers are signalled in both CTAs by
+// epilogue warps through the cluster window); "empty" barriers are signalled in both CTAs by
 // multicast tcgen05.commit.
 #include "umma_gemm.cuh"
 #include "ptx.cuh"
@@ -71,7 +71,25 @@ struct FusedParams {
     int out_bf16;
 };
 
-template <int D>
+// GELU epilogue arithmetic, two adjacent columns per call, entirely in packed fp16 (the tile is rounded to bf16 = 2^-9 anyway):
+//   gelu(x) * gate = (0.5 * gate * x) * (1 + erf(x / sqrt 2)),   erf(x / sqrt 2) ~= tanh(x * P(min(x^2, 5.5^2)))     (common.cuh: max |erf error| 1.3e-5)
+// 15 instructions per pair instead of the ~30 of the fp32 form (x0.5, (1 + t), gate and the bf16 pack each as separate fp32 ops): the
+// fused kernel's per-chunk time IS this epilogue's issue time (ncu / SASS: ~500 instructions per thread and chunk before), so the
+// instruction count is what sets the tensor-pipe utilisation.  Clamping x^2 (not x) keeps tanh's argument on the right side for any
+// |x|: P(30.25) > 0, so |x| > 5.5 gives tanh(+-large) = +-1 exactly as the clamped form does.  hg = 0.5 * gate in both halves.
+__device__ __forceinline__ uint32_t gelu_gate_pack(float x0, float x1, __half2 hg) {
+    const __half2 x = __floats2half2_rn(x0, x1);
+    const __half2 s = __hmin2(__hmul2(x, x), __float2half2_rn(30.25f));
+    __half2 p = __hfma2(s, __float2half2_rn(-1.3688055686176932e-05f), __float2half2_rn(-0.00019445275122756945f));
+    p = __hfma2(s, p, __float2half2_rn(0.036546657541717965f));
+    p = __hfma2(s, p, __float2half2_rn(0.797820262700123f));
+    const __half2 t = h2_tanh_approx(__hmul2(x, p));
+    const __half2 h = __hmul2(x, hg);
+    const float2 g = __half22float2(__hfma2(h, t, h));
+    return pack_bf16x2(g.x, g.y);
+}
+
+template <int D, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
                  const __grid_constant__ CUtensorMap mapW2, const FusedParams p) {
@@ -120,7 +138,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int mode = p.mode;
+    constexpr int mode = MODE;
     const int npt = mode == 1 ? (p.T + 2 * BM - 1) / (2 * BM) : __ldg(p.plan + 0) / 2;     // 256-row pair tiles
     const int n = mode == 1 ? p.E * C::CPE : C::CPE;                                         // chunks per tile
     const uint32_t w_base = smem_base + C::OFF_W;
@@ -207,7 +225,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         const int j = i - 1;
                         const int b = (int)(g2cnt & 1u);
                         if (j == 0) ptx::mbar_wait(a2_empty, ((uint32_t)xit & 1u) ^ 1u);   // previous tile's output has left TMEM
-                        ptx::mbar_wait_acquire_cluster(h_full(b), (g2cnt >> 1) & 1u);
+                        ptx::mbar_wait(h_full(b), (g2cnt >> 1) & 1u);
                         const int slot = (int)(wcnt % C::WS);
                         ptx::mbar_wait(w_full(slot), (wcnt / C::WS) & 1u);
                         ++wcnt;
@@ -254,6 +272,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const float4* bsrc = reinterpret_cast<const float4*>(p.b1s + (size_t)e * 4 * D + c * NC + cg * 32);
                 float gate = 1.0f;
                 if (mode == 1) gate = row_ok ? __ldg(p.gates + row * p.E + e) : 0.0f;
+                const __half2 hg = __float2half2_rn(0.5f * gate);
                 ptx::mbar_wait(a1_full(b), ph);
                 ptx::tc_fence_after();
                 uint32_t r[32];
@@ -261,31 +280,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(on_leader(a1_empty(b)));              // the FFN1 accumulator stage is free again
-                float v[32];
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {                                     // same address in every lane: one broadcast transaction
-                    const float4 b4 = __ldg(bsrc + i4);
-                    v[4 * i4 + 0] = __uint_as_float(r[4 * i4 + 0]) + b4.x; v[4 * i4 + 1] = __uint_as_float(r[4 * i4 + 1]) + b4.y;
-                    v[4 * i4 + 2] = __uint_as_float(r[4 * i4 + 2]) + b4.z; v[4 * i4 + 3] = __uint_as_float(r[4 * i4 + 3]) + b4.w;
-                }
-                float u0, u1;
-#pragma unroll
-                for (int k2 = 0; k2 < 32; k2 += 2) {
-                    gelu_pair_h2<false>(v[k2], v[k2 + 1], v[k2], v[k2 + 1], u0, u1);
-                    v[k2] *= gate; v[k2 + 1] *= gate;
-                }
+                if (lane == 0) ptx::mbar_arrive_cluster(on_leader(a1_empty(b)));      // the FFN1 accumulator stage is free again
                 ptx::mbar_wait(h_empty(b), ph ^ 1u);                                  // FFN2 of chunk i-2 has finished reading this buffer
                 const uint32_t hrow = smem_base + C::OFF_H + b * C::H_BYTES + h_row_off;
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
+                for (int i4 = 0; i4 < 4; ++i4) {                                     // 8 columns -> one 16-byte store
+                    const float4 ba = __ldg(bsrc + 2 * i4), bb = __ldg(bsrc + 2 * i4 + 1);   // same address in every lane: broadcast
+                    const uint32_t o0 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 0]) + ba.x, __uint_as_float(r[8 * i4 + 1]) + ba.y, hg);
+                    const uint32_t o1 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 2]) + ba.z, __uint_as_float(r[8 * i4 + 3]) + ba.w, hg);
+                    const uint32_t o2 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 4]) + bb.x, __uint_as_float(r[8 * i4 + 5]) + bb.y, hg);
+                    const uint32_t o3 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 6]) + bb.z, __uint_as_float(r[8 * i4 + 7]) + bb.w, hg);
                     const int chunk = (cg & 1) * 4 + i4;
-                    ptx::st_shared_v4(hrow + ((uint32_t)(chunk ^ sw) << 4), pack_bf16x2(v[8 * i4 + 0], v[8 * i4 + 1]), pack_bf16x2(v[8 * i4 + 2], v[8 * i4 + 3]),
-                                      pack_bf16x2(v[8 * i4 + 4], v[8 * i4 + 5]), pack_bf16x2(v[8 * i4 + 6], v[8 * i4 + 7]));
+                    ptx::st_shared_v4(hrow + ((uint32_t)(chunk ^ sw) << 4), o0, o1, o2, o3);
                 }
                 ptx::fence_proxy_async_smem();                                        // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_release_cluster(on_leader(h_full(b)));
+                // Plain (release.cta) remote arrive, as CUTLASS's ClusterBarrier::arrive(cta_id) does for cross-CTA buffer hand-offs: the tile
+                // is only ever read by THIS SM's tensor core (cta_group::2 reads each CTA's own half), and fence.proxy.async above has made
+                // the stores visible to it.  A release.cluster arrive compiles to MEMBAR.ALL.GPU + CGAERRBAR per warp and chunk, and an
+                // acquire.cluster wait to CCTL.IVALL (L1 invalidation) per poll: measured, that fixed cost - not the GELU arithmetic - set
+                // the per-chunk time of the first version of this kernel (2.6 us per chunk at d = 128 whatever the instruction count).
+                if (lane == 0) ptx::mbar_arrive_cluster(on_leader(h_full(b)));
                 ++a1cnt;
             }
             // ---- output epilogue of the tile ----
@@ -373,12 +388,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
 }
 
-template <int D>
+template <int D, int MODE>
 int launch_impl(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2, const FusedParams& p, int grid, cudaStream_t stream) {
     using C = FCfg<D>;
     static bool attr_set = false;
     if (!attr_set) {
-        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg;
@@ -394,7 +409,7 @@ int launch_impl(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<D>, mx, mw1, mw2, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<D, MODE>, mx, mw1, mw2, p);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(ffn_fused_kernel)");
     MOEGAN_CHECK_LAUNCH("ffn_fused_kernel");
     return MOEGAN_OK;
@@ -439,7 +454,8 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t stream) {
         const int dims[4] = {hid, d, a.mode == 1 ? a.rows * a.E : -1, a.E | (a.mode == 1 ? 0x20000 : 0)};
         profile_begin(stream, 3 * 1000 + NC + 100000 + (8 + a.mode) * 10000, nullptr, dims, &prof);
     }
-    rc = d == 128 ? launch_impl<128>(mx, mw1, mw2, p, 2 * pairs, stream) : launch_impl<256>(mx, mw1, mw2, p, 2 * pairs, stream);
+    if (a.mode == 1) rc = d == 128 ? launch_impl<128, 1>(mx, mw1, mw2, p, 2 * pairs, stream) : launch_impl<256, 1>(mx, mw1, mw2, p, 2 * pairs, stream);
+    else             rc = d == 128 ? launch_impl<128, 0>(mx, mw1, mw2, p, 2 * pairs, stream) : launch_impl<256, 0>(mx, mw1, mw2, p, 2 * pairs, stream);
     profile_end(stream, prof);
     return rc;
 }

@@ -37,7 +37,7 @@ int launch_balance_loss(const float* load, int E, int T, float bw, const float* 
 // ---- dispatch.cu ----------------------------------------------------------------------------------
 int launch_plan(const moegan_shape* s, const int32_t* chunk_counts, const float* chunk_colsum, int32_t* plan,
                 int32_t* chunk_base, float* load, cudaStream_t st);
-int launch_gather(const moegan_shape* s, const float* x, const int32_t* topk_idx, const float* gates, const int32_t* plan,
+int launch_gather(const moegan_shape* s, const float* x, const void* x_bf16, const int32_t* topk_idx, const float* gates, const int32_t* plan,
                   const int32_t* chunk_base, void* x_op, void* x_copy, int32_t* row_token, float* row_gate, int32_t* token_rows,
                   cudaStream_t st);
 int launch_to_operand(const float* src, int64_t rows, int64_t cols, int split, int sanitize, void* dst, cudaStream_t st);

@@ -209,9 +209,11 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         __syncthreads();
         const float* wsrc = Ws + buf * RT_KC * HID;
         const float* xsrc = xs + buf * RT_TOK * RT_KC + (q * 8) * RT_KC;
-        float part[8][4];
+        // packed fp32 FMA (fma.rn.f32x2, sm_100): two of the lane's four columns per instruction - the same two IEEE fused
+        // multiply-adds, bit for bit, in half the issue slots (ncu: this loop was 45 % FFMA and issue / latency bound)
+        float2 p01[8], p23[8];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) { part[a][0] = part[a][1] = part[a][2] = part[a][3] = 0.0f; }
+        for (int a = 0; a < 8; ++a) { p01[a] = make_float2(0.0f, 0.0f); p23[a] = make_float2(0.0f, 0.0f); }
 #pragma unroll
         for (int kq4 = 0; kq4 < RT_KC / 8; ++kq4) {
             const int kq = g * (RT_KC / 8) + kq4;       // this warp group's half of the chunk
@@ -221,19 +223,19 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const float4 wv = *reinterpret_cast<const float4*>(wsrc + (kq * 4 + kk) * HID + lane * 4);
+                const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const float xk = kk == 0 ? xv[a].x : kk == 1 ? xv[a].y : kk == 2 ? xv[a].z : xv[a].w;
-                    part[a][0] = fmaf(xk, wv.x, part[a][0]);
-                    part[a][1] = fmaf(xk, wv.y, part[a][1]);
-                    part[a][2] = fmaf(xk, wv.z, part[a][2]);
-                    part[a][3] = fmaf(xk, wv.w, part[a][3]);
+                    const float2 xx = make_float2(xk, xk);
+                    p01[a] = __ffma2_rn(xx, w01, p01[a]);
+                    p23[a] = __ffma2_rn(xx, w23, p23[a]);
                 }
             }
         }
         // blocked summation: per-chunk partials are added once -> error grows with sqrt(#chunks), not K
 #pragma unroll
-        for (int a = 0; a < 8; ++a) { acc[a][0] += part[a][0]; acc[a][1] += part[a][1]; acc[a][2] += part[a][2]; acc[a][3] += part[a][3]; }
+        for (int a = 0; a < 8; ++a) { acc[a][0] += p01[a].x; acc[a][1] += p01[a].y; acc[a][2] += p23[a].x; acc[a][3] += p23[a].y; }
         __syncthreads();
     }
 
@@ -257,11 +259,43 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         const float f0 = p0.x + p1.x, f1 = p0.y + p1.y, f2 = p0.z + p1.z, f3 = p0.w + p1.w;
         if (fp != nullptr) *reinterpret_cast<float4*>(fp + (size_t)t * HID + lane * 4) = make_float4(f0, f1, f2, f3);
         float my_raw = 0.0f;
-        for (int e = 0; e < E; ++e) {
-            const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
-            float part = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
-            part = warp_sum(part);
-            if (lane == e) my_raw = part;
+        if (E <= 8) {
+            // logits of up to 8 experts with ONE transposing butterfly (10 shuffles) instead of E full warp reductions (5 E): at every
+            // stage a lane keeps the half of its values that belongs to its side of the xor pair and hands over the other half.  The
+            // pairings are those of warp_sum (xor 16, 8, 4, 2, 1) and a + b == b + a, so every logit is bit-identical to the serial form.
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                v[e] = 0.0f;
+                if (e < E) {
+                    const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+                    v[e] = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
+                }
+            }
+#pragma unroll
+            for (int st = 0; st < 3; ++st) {
+                const int off = 16 >> st, half = 4 >> st;
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float keep = up ? v[i + half] : v[i];
+                    const float send = up ? v[i] : v[i + half];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            // lanes with (bit4, bit3, bit2) = (e>>2, e>>1, e) & 1 now hold expert e; lane e fetches its logit
+            const int src = (((lane >> 2) & 1) << 4) | (((lane >> 1) & 1) << 3) | ((lane & 1) << 2);
+            my_raw = __shfl_sync(0xffffffffu, v[0], src);
+            if (lane >= E) my_raw = 0.0f;
+        } else {
+            for (int e = 0; e < E; ++e) {
+                const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+                float part = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
+                part = warp_sum(part);
+                if (lane == e) my_raw = part;
+            }
         }
         const bool act = lane < E;
         if (act) my_raw += __ldg(tl + (size_t)(t / tps) * E + lane);

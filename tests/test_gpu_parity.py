@@ -357,6 +357,7 @@ def test_fused_ffn_forward(shape):
     k, hard = s.get("k"), s.get("hard", False)
     params, x, w, dout, gp, eps = _random_case(123 + s["d"] + s["E"], s["B"], s["H"], s["W"], s["d"], s["Dt"], s["E"], mu_scale=s.get("mu_scale", 30.0))
     m = G.build_module(params, s["d"], s["Dt"], s["E"], top_k=k, precision="bf16", training=not hard)
+    G.run_cuda(m, x, w, None if hard else eps, 1.0)                 # fills the expert-weight operand cache (its conversion is one more launch)
     n0 = pkg._cabi.lib().moegan_debug_launch_count()
     r = G.run_cuda(m, x, w, None if hard else eps, 1.0)
     n_fused = pkg._cabi.lib().moegan_debug_launch_count() - n0

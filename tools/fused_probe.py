@@ -24,6 +24,9 @@ def probe(name):
     torch.manual_seed(0)
     moe = pkg.SparseMoE(d, 512, E, top_k=k, precision="bf16").to(dev)
     moe.train(not ev)
+    moe.redraw_eps = False                # same eps for the fused and the separate run
+    for n in ("epsilon_f", "epsilon_t", "epsilon_c"):
+        getattr(moe.router, n).normal_()
     with torch.no_grad():
         for n in ("feature_mu", "text_mu", "combined_mu"):
             getattr(moe.router, n).mul_(8.0)
