@@ -14,8 +14,8 @@
 //   warp 16     TMA producer: the X tile (once per tile), then the weight tiles in the order the MMA warp consumes them
 //   warp 17     TMEM allocator; in the leader CTA one lane issues all tcgen05.mma of the pair
 // TMEM (512 columns): [0, d) output accumulator | [d, d+128), [d+128, d+256) double-buffered FFN1 accumulator.
-// MMA issue order (software pipelined so the tensor pipe works on chunk i+1 while the epilogue warps turn chunk i into H):
-//     G1(0), G1(1), G2(0), G1(2), G2(1), ..., G1(n-1), G2(n-2), G2(n-1)           n = chunks per tile (dense: E * 4d/128)
+// MMA issue order (FFN1 runs two chunks ahead, across tile boundaries, so the tensor pipe never waits for the epilogue of the chunk
+// it has just produced):  G1(0) G1(1) | G1(2) G2(0) | G1(3) G2(1) | ...           n = chunks per tile (dense: E * 4d/128)
 // mbarrier pipelines (all waits carry a watchdog that traps instead of hanging the GPU):
 //     x_full / x_empty          TMA -> MMA, per X stage              w_full[s] / w_empty[s]   TMA -> MMA, weight ring
 //     a1_full[b] / a1_empty[b]  MMA -> epilogue, FFN1 accumulator    h_full[b] / h_empty[b]   epilogue -> MMA, GELU tile in smem
@@ -51,7 +51,8 @@ template <int D> struct FCfg {
     static constexpr uint32_t OFF_H = OFF_W + WS * W_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_H + 2 * H_BYTES;
     static constexpr uint32_t BAR_BYTES = 256;
-    static constexpr uint32_t SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024 /* manual alignment */;
+    static constexpr uint32_t OFF_BIAS = OFF_BAR + BAR_BYTES;     // per epilogue warp: the 32 FFN1 bias values of its columns (128 B)
+    static constexpr uint32_t SMEM_BYTES = OFF_BIAS + NEW * 128;  // the dynamic shared window is declared (and checked) 1024-byte aligned
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr int CPE = 4 * D / NC;                        // chunks per expert
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -94,9 +95,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
                  const __grid_constant__ CUtensorMap mapW2, const FusedParams p) {
     using C = FCfg<D>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = ptx::smem_u32(smem_raw);
-    const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+    const uint32_t smem_base = smem_raw_u32;                      // SWIZZLE_128B atoms need 1024-byte alignment
+    if ((smem_base & 1023u) != 0u) { if (threadIdx.x == 0) printf("moegan: ffn_fused: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     const uint32_t bar_base = smem_base + C::OFF_BAR;
     auto x_full = [&](int s) { return bar_base + 8u * s; };
     auto x_empty = [&](int s) { return bar_base + 8u * (C::XS + s); };
@@ -143,49 +145,66 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int n = mode == 1 ? p.E * C::CPE : C::CPE;                                         // chunks per tile
     const uint32_t w_base = smem_base + C::OFF_W;
 
+    // The chunks of all tiles this CTA pair works on form ONE stream g = 0 .. total-1 (tile = g / n, chunk in tile = g % n; n is even, so
+    // the double-buffer index g & 1 is the same on all sides).  FFN1 runs TWO chunks ahead of FFN2:
+    //     G1(0) G1(1) | G1(2) G2(0) | G1(3) G2(1) | ... | G1(g+2) G2(g) | ...
+    // G1(g+2) only needs the FFN1 accumulator stage that the epilogue of chunk g has just emptied - it is issued at the START of that
+    // epilogue, so its result is waiting long before the epilogue warps get to chunk g+2, across tile boundaries too.  (Issuing G1(g+1)
+    // only after H(g-1) was complete, as the first version did, put two barrier round trips and the FFN1 MMA on the critical path of every
+    // chunk: ncu showed the epilogue warps polling a1_full 12 times per chunk.)
+    const int my_tiles = pair0 < npt ? (npt - pair0 + pair_stride - 1) / pair_stride : 0;
+    const int total = my_tiles * n;
     if (warp == WARP_TMA) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             uint32_t wcnt = 0;
-            int xit = 0;
-            for (int pt = pair0; pt < npt; pt += pair_stride, ++xit) {
-                const int xs = xit % C::XS;
-                const uint32_t xph = (uint32_t)(xit / C::XS) & 1u;
-                ptx::mbar_wait(x_empty(xs), xph ^ 1u);
+            int e_tile = 0;
+            auto load_x = [&](int tit) {                                             // tile tit of this pair: 128 rows x d of this CTA
+                const int pt = pair0 + tit * pair_stride;
+                const int xs = tit % C::XS;
+                ptx::mbar_wait(x_empty(xs), ((uint32_t)(tit / C::XS) & 1u) ^ 1u);
                 const uint32_t fbx = ptx::mapa_cluster(x_full(xs), 0);
                 ptx::mbar_arrive_expect_tx_cluster(fbx, C::X_BYTES);
                 const int row0 = pt * 2 * BM + rank * BM;
 #pragma unroll
                 for (int kb = 0; kb < D / 64; ++kb)
                     ptx::tma_load_2d_cta2(smem_base + C::OFF_X + xs * C::X_BYTES + kb * 16384u, &mapX, fbx, kb * 64, row0);
-                const int e_tile = mode == 1 ? 0 : __ldg(p.plan + PLAN_BLK + pt * 2);
-                auto load_w1 = [&](int i) {
-                    const int e = mode == 1 ? i / C::CPE : e_tile, c = i % C::CPE;
-                    const int slot = (int)(wcnt % C::WS);
-                    ptx::mbar_wait(w_empty(slot), ((wcnt / C::WS) & 1u) ^ 1u);
-                    const uint32_t fb = ptx::mapa_cluster(w_full(slot), 0);
-                    ptx::mbar_arrive_expect_tx_cluster(fb, C::W_BYTES);
-                    const int row = e * 4 * D + c * NC + rank * (NC / 2);           // this CTA's 64 hidden units of the chunk
+            };
+            auto expert_of = [&](int g) {                                            // expert of stream chunk g
+                if (mode == 1) return (g % n) / C::CPE;
+                return __ldg(p.plan + PLAN_BLK + (pair0 + (g / n) * pair_stride) * 2);
+            };
+            auto load_w1 = [&](int g) {
+                if (g % n == 0) load_x(g / n);
+                const int e = expert_of(g), c = (g % n) % C::CPE;
+                const int slot = (int)(wcnt % C::WS);
+                ptx::mbar_wait(w_empty(slot), ((wcnt / C::WS) & 1u) ^ 1u);
+                const uint32_t fb = ptx::mapa_cluster(w_full(slot), 0);
+                ptx::mbar_arrive_expect_tx_cluster(fb, C::W_BYTES);
+                const int row = e * 4 * D + c * NC + rank * (NC / 2);               // this CTA's 64 hidden units of the chunk
 #pragma unroll
-                    for (int kb = 0; kb < D / 64; ++kb)
-                        ptx::tma_load_2d_cta2(w_base + slot * C::W_BYTES + kb * 8192u, &mapW1, fb, kb * 64, row);
-                    ++wcnt;
-                };
-                auto load_w2 = [&](int i) {
-                    const int e = mode == 1 ? i / C::CPE : e_tile, c = i % C::CPE;
-                    const int slot = (int)(wcnt % C::WS);
-                    ptx::mbar_wait(w_empty(slot), ((wcnt / C::WS) & 1u) ^ 1u);
-                    const uint32_t fb = ptx::mapa_cluster(w_full(slot), 0);
-                    ptx::mbar_arrive_expect_tx_cluster(fb, C::W_BYTES);
-                    const int row = e * D + rank * (D / 2);                          // this CTA's d/2 output features
+                for (int kb = 0; kb < D / 64; ++kb)
+                    ptx::tma_load_2d_cta2(w_base + slot * C::W_BYTES + kb * 8192u, &mapW1, fb, kb * 64, row);
+                ++wcnt;
+            };
+            auto load_w2 = [&](int g) {
+                const int e = expert_of(g), c = (g % n) % C::CPE;
+                const int slot = (int)(wcnt % C::WS);
+                ptx::mbar_wait(w_empty(slot), ((wcnt / C::WS) & 1u) ^ 1u);
+                const uint32_t fb = ptx::mapa_cluster(w_full(slot), 0);
+                ptx::mbar_arrive_expect_tx_cluster(fb, C::W_BYTES);
+                const int row = e * D + rank * (D / 2);                              // this CTA's d/2 output features
 #pragma unroll
-                    for (int kb = 0; kb < NC / 64; ++kb)
-                        ptx::tma_load_2d_cta2(w_base + slot * C::W_BYTES + kb * (uint32_t)(D / 2 * 128), &mapW2, fb, c * NC + kb * 64, row);
-                    ++wcnt;
-                };
-                load_w1(0);
-                for (int i = 1; i < n; ++i) { load_w1(i); load_w2(i - 1); }
-                load_w2(n - 1);
+                for (int kb = 0; kb < NC / 64; ++kb)
+                    ptx::tma_load_2d_cta2(w_base + slot * C::W_BYTES + kb * (uint32_t)(D / 2 * 128), &mapW2, fb, c * NC + kb * 64, row);
+                ++wcnt;
+            };
+            (void)e_tile;
+            if (total > 0) load_w1(0);
+            if (total > 1) load_w1(1);
+            for (int g = 0; g < total; ++g) {                                        // the order the MMA lane consumes the tiles in
+                if (g + 2 < total) load_w1(g + 2);
+                load_w2(g);
             }
         }
     } else if (warp == WARP_MMA) {
@@ -193,58 +212,57 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(2 * BM, NC, 0, 0);
             constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(2 * BM, D, 0, 0);
-            uint32_t wcnt = 0, g1cnt = 0, g2cnt = 0;
-            int xit = 0;
-            for (int pt = pair0; pt < npt; pt += pair_stride, ++xit) {
-                const int xs = xit % C::XS;
-                ptx::mbar_wait(x_full(xs), (uint32_t)(xit / C::XS) & 1u);
+            uint32_t wcnt = 0;
+            auto issue_g1 = [&](int g) {                                             // acc1[g & 1] = X W1(g)^T
+                const int tit = g / n, i = g % n;
+                const int xs = tit % C::XS;
+                if (i == 0) { ptx::mbar_wait(x_full(xs), (uint32_t)(tit / C::XS) & 1u); }
+                const int b = g & 1;
+                ptx::mbar_wait(a1_empty(b), (((uint32_t)g >> 1) & 1u) ^ 1u);
+                const int slot = (int)(wcnt % C::WS);
+                ptx::mbar_wait(w_full(slot), (wcnt / C::WS) & 1u);
+                ++wcnt;
                 ptx::tc_fence_after();
                 const uint32_t x_addr = smem_base + C::OFF_X + xs * C::X_BYTES;
-                for (int i = 0; i <= n; ++i) {
-                    if (i < n) {                                                     // G1(i): acc1[b] = X W1(i)^T
-                        const int b = (int)(g1cnt & 1u);
-                        ptx::mbar_wait(a1_empty(b), ((g1cnt >> 1) & 1u) ^ 1u);
-                        const int slot = (int)(wcnt % C::WS);
-                        ptx::mbar_wait(w_full(slot), (wcnt / C::WS) & 1u);
-                        ++wcnt;
-                        ptx::tc_fence_after();
-                        const uint32_t w_addr = w_base + slot * C::W_BYTES;
-                        const uint32_t tmem_d = tmem_base + D + b * NC;
+                const uint32_t w_addr = w_base + slot * C::W_BYTES;
+                const uint32_t tmem_d = tmem_base + D + b * NC;
 #pragma unroll
-                        for (int kb = 0; kb < D / 64; ++kb)
+                for (int kb = 0; kb < D / 64; ++kb)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_cta2(tmem_d, ptx::umma_smem_desc(x_addr + kb * 16384u + k * 32u, 16u, 1024u),
-                                                    ptx::umma_smem_desc(w_addr + kb * 8192u + k * 32u, 16u, 1024u), idesc1, (kb | k) != 0 ? 1u : 0u);
-                        ptx::umma_commit_cta2(w_empty(slot), 3);
-                        ptx::umma_commit_cta2(a1_full(b), 3);
-                        if (i == n - 1) ptx::umma_commit_cta2(x_empty(xs), 3);       // the X stage is free once the last FFN1 chunk has retired
-                        ++g1cnt;
-                    }
-                    if (i >= 1) {                                                    // G2(j): acc2 (+)= H(j) W2(j)^T
-                        const int j = i - 1;
-                        const int b = (int)(g2cnt & 1u);
-                        if (j == 0) ptx::mbar_wait(a2_empty, ((uint32_t)xit & 1u) ^ 1u);   // previous tile's output has left TMEM
-                        ptx::mbar_wait(h_full(b), (g2cnt >> 1) & 1u);
-                        const int slot = (int)(wcnt % C::WS);
-                        ptx::mbar_wait(w_full(slot), (wcnt / C::WS) & 1u);
-                        ++wcnt;
-                        ptx::tc_fence_after();
-                        const uint32_t w_addr = w_base + slot * C::W_BYTES;
-                        const uint32_t h_addr = smem_base + C::OFF_H + b * C::H_BYTES;
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16_cta2(tmem_d, ptx::umma_smem_desc(x_addr + kb * 16384u + k * 32u, 16u, 1024u),
+                                            ptx::umma_smem_desc(w_addr + kb * 8192u + k * 32u, 16u, 1024u), idesc1, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit_cta2(w_empty(slot), 3);
+                ptx::umma_commit_cta2(a1_full(b), 3);
+                if (i == n - 1) ptx::umma_commit_cta2(x_empty(xs), 3);               // the X stage is free once the tile's last FFN1 chunk has retired
+            };
+            auto issue_g2 = [&](int g) {                                             // acc2 (+)= H(g) W2(g)^T
+                const int tit = g / n, j = g % n;
+                const int b = g & 1;
+                if (j == 0) ptx::mbar_wait(a2_empty, ((uint32_t)tit & 1u) ^ 1u);     // the previous tile's output has left TMEM
+                ptx::mbar_wait(h_full(b), ((uint32_t)g >> 1) & 1u);
+                const int slot = (int)(wcnt % C::WS);
+                ptx::mbar_wait(w_full(slot), (wcnt / C::WS) & 1u);
+                ++wcnt;
+                ptx::tc_fence_after();
+                const uint32_t w_addr = w_base + slot * C::W_BYTES;
+                const uint32_t h_addr = smem_base + C::OFF_H + b * C::H_BYTES;
 #pragma unroll
-                        for (int kb = 0; kb < NC / 64; ++kb)
+                for (int kb = 0; kb < NC / 64; ++kb)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_cta2(tmem_base, ptx::umma_smem_desc(h_addr + kb * 16384u + k * 32u, 16u, 1024u),
-                                                    ptx::umma_smem_desc(w_addr + kb * (uint32_t)(D / 2 * 128) + k * 32u, 16u, 1024u), idesc2,
-                                                    (j | kb | k) != 0 ? 1u : 0u);
-                        ptx::umma_commit_cta2(w_empty(slot), 3);
-                        ptx::umma_commit_cta2(h_empty(b), 3);
-                        if (j == n - 1) ptx::umma_commit_cta2(a2_full, 3);
-                        ++g2cnt;
-                    }
-                }
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16_cta2(tmem_base, ptx::umma_smem_desc(h_addr + kb * 16384u + k * 32u, 16u, 1024u),
+                                            ptx::umma_smem_desc(w_addr + kb * (uint32_t)(D / 2 * 128) + k * 32u, 16u, 1024u), idesc2,
+                                            (j | kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit_cta2(w_empty(slot), 3);
+                ptx::umma_commit_cta2(h_empty(b), 3);
+                if (j == n - 1) ptx::umma_commit_cta2(a2_full, 3);
+            };
+            if (total > 0) issue_g1(0);
+            if (total > 1) issue_g1(1);
+            for (int g = 0; g < total; ++g) {
+                if (g + 2 < total) issue_g1(g + 2);
+                issue_g2(g);
             }
         }
     } else {
@@ -265,14 +283,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const long long row = (long long)pt * 2 * BM + rank * BM + row_in;      // token (mode 1) / dispatched row (mode 0)
             const int e_tile = mode == 1 ? 0 : __ldg(p.plan + PLAN_BLK + pt * 2);
             const bool row_ok = row < (mode == 1 ? p.T : p.rows);
-            for (int i = 0; i < n; ++i) {
+            // The lane's FFN1 bias value and the row's gate of chunk i + 1 are fetched while chunk i is processed (ncu on the first version:
+            // long_scoreboard - the bias / gate loads issued right before their use - was 3.4 of 8.6 stalled warps per issue).
+            auto bias_of = [&](int i) {
                 const int e = mode == 1 ? i / C::CPE : e_tile, c = i % C::CPE;
+                return __ldg(p.b1s + (size_t)e * 4 * D + c * NC + cg * 32 + lane);
+            };
+            auto gate_of = [&](int i) { return (mode == 1 && row_ok) ? __ldg(p.gates + row * p.E + i / C::CPE) : (mode == 1 ? 0.0f : 1.0f); };
+            float bias_next = bias_of(0), gate_next = gate_of(0);
+            const uint32_t bias_slot = smem_base + C::OFF_BIAS + warp * 128u;
+            for (int i = 0; i < n; ++i) {
                 const int b = (int)(a1cnt & 1u);
                 const uint32_t ph = (a1cnt >> 1) & 1u;
-                const float4* bsrc = reinterpret_cast<const float4*>(p.b1s + (size_t)e * 4 * D + c * NC + cg * 32);
-                float gate = 1.0f;
-                if (mode == 1) gate = row_ok ? __ldg(p.gates + row * p.E + e) : 0.0f;
-                const __half2 hg = __float2half2_rn(0.5f * gate);
+                const __half2 hg = __float2half2_rn(0.5f * gate_next);
+                ptx::st_shared_b32(bias_slot + lane * 4u, __float_as_uint(bias_next));     // read back below as broadcast 16-byte loads
+                if (i + 1 < n) { bias_next = bias_of(i + 1); gate_next = gate_of(i + 1); }
                 ptx::mbar_wait(a1_full(b), ph);
                 ptx::tc_fence_after();
                 uint32_t r[32];
@@ -285,7 +310,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const uint32_t hrow = smem_base + C::OFF_H + b * C::H_BYTES + h_row_off;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {                                     // 8 columns -> one 16-byte store
-                    const float4 ba = __ldg(bsrc + 2 * i4), bb = __ldg(bsrc + 2 * i4 + 1);   // same address in every lane: broadcast
+                    const float4 ba = ptx::ld_shared_f4(bias_slot + (uint32_t)(8 * i4) * 4u), bb = ptx::ld_shared_f4(bias_slot + (uint32_t)(8 * i4 + 4) * 4u);
                     const uint32_t o0 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 0]) + ba.x, __uint_as_float(r[8 * i4 + 1]) + ba.y, hg);
                     const uint32_t o1 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 2]) + ba.z, __uint_as_float(r[8 * i4 + 3]) + ba.w, hg);
                     const uint32_t o2 = gelu_gate_pack(__uint_as_float(r[8 * i4 + 4]) + bb.x, __uint_as_float(r[8 * i4 + 5]) + bb.y, hg);
