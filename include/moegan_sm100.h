@@ -199,7 +199,8 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
  * combine, and its backward), enqueued by ONE call per direction with every intermediate carved out of ONE
  * caller-owned workspace: this is what SparseMoE.forward uses, so the host cost per step is two FFI calls.
  * Independent sub-chains (weight conversion in the forward, the router's backward in the backward) are forked onto a
- * library-owned side stream and joined before their results are needed (MOEGAN_DISABLE_SIDE_STREAM=1 turns this off).
+ * library-owned side stream (one set per CUDA device, created lazily) and joined before their results are needed
+ * (MOEGAN_DISABLE_SIDE_STREAM=1 turns this off).
  * Byte offsets of the intermediates inside the forward workspace (all 256-byte aligned): */
 typedef struct {
     int64_t Wf, Wt, Wc, Wf_op, Wt_op, tp, tl, fp, raw, topk_idx, gates, chunk_counts, chunk_colsum, plan, chunk_base,

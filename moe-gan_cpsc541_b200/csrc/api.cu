@@ -605,7 +605,10 @@ int moegan_balance_loss_bwd(const float* load, int32_t E, int32_t T, float balan
 // are cudaEventRecord / cudaStreamWaitEvent pairs, so the pattern is legal inside CUDA-graph capture too.
 struct SideStream { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, join2 = nullptr, dxr = nullptr;
                     bool ok = false, tried = false; };
-static SideStream g_side;
+// one set per device (a process that drives several GPUs gets streams / events on each of them, created lazily on the device that is
+// current when the block call arrives - the caller's stream belongs to that device)
+constexpr int MOEGAN_MAX_DEVICES = 64;
+static SideStream g_side_dev[MOEGAN_MAX_DEVICES];
 static std::mutex g_side_mu;
 static std::atomic<int> g_side_override{-1};     // moegan_debug_set_side_streams: -1 = environment / default
 static bool side_enabled() {
@@ -632,6 +635,9 @@ static bool side_pays(const moegan_shape* s) {
 static SideStream* side_stream() {
     if (!side_enabled()) return nullptr;
     std::lock_guard<std::mutex> lk(g_side_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MOEGAN_MAX_DEVICES) { cudaGetLastError(); return nullptr; }
+    SideStream& g_side = g_side_dev[dev];
     if (!g_side.tried) {
         g_side.tried = true;
         g_side.ok = cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) == cudaSuccess &&

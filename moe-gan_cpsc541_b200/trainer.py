@@ -46,7 +46,18 @@ class GradReducer:
     """
 
     def __init__(self, params: Sequence[nn.Parameter], group=None, bucket_bytes: int = 25 << 20, overlap: bool = True,
-                 tail_bytes: int = 8 << 20):
+                 tail_bytes: int = 8 << 20, comm_priority: Optional[int] = None):
+        import os
+        # MOEGAN_DP_MODE (bench / profiling): "overlap" (default) = buckets all-reduced on a communication stream while backward runs;
+        # "single" = ONE all-reduce of all gradients after backward, on the compute stream (no SM contention with the persistent
+        # 1-CTA-per-SM GEMMs of backward, which leave an overlapped NCCL kernel waiting for SMs: tools/dp_timeline.py)
+        mode = os.environ.get("MOEGAN_DP_MODE", "overlap")
+        if mode == "single":
+            overlap, bucket_bytes, tail_bytes = False, 1 << 62, 0
+        if comm_priority is None and os.environ.get("MOEGAN_DP_COMM_PRIORITY"):
+            comm_priority = int(os.environ["MOEGAN_DP_COMM_PRIORITY"])
+        self.comm_priority = comm_priority
+        self.defer = mode == "single"          # launch nothing from the hooks: finish() packs and reduces everything at once
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -103,14 +114,15 @@ class GradReducer:
             self.pending[bi] = len(b)
             self.launched[bi] = False
         if self.overlap and self.buckets and self.buckets[0][0].is_cuda and self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream()
+            # a high-priority stream lets the few CTAs of an NCCL kernel be placed ahead of the next compute kernel's CTAs
+            self.comm_stream = torch.cuda.Stream(priority=self.comm_priority) if self.comm_priority is not None else torch.cuda.Stream()
 
     def _on_grad(self, p: nn.Parameter) -> None:
         if not self.enabled:
             return
         bi = self.bucket_of[id(p)]
         self.pending[bi] -= 1
-        if self.pending[bi] == 0:
+        if self.pending[bi] == 0 and not self.defer:
             self._launch(bi)
 
     def _grad_view(self, p: nn.Parameter, flat_slice: torch.Tensor) -> Optional[torch.Tensor]:
