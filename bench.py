@@ -615,7 +615,7 @@ def bench_moe_block(args, T_, rank, world, dev, steps, warmup, use_graph, WL=Non
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n_before = lib.moegan_debug_launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):        # the stream the leaves' AccumulateGrad nodes were created on
                 step_device()
             launches_per_graph = int(lib.moegan_debug_launch_count() - n_before)
             step_value, launch_mode = graph.replay, "cuda_graph"
