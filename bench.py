@@ -685,7 +685,9 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     import torch
     pkg = importlib.import_module(PKG)
     lib = pkg._cabi.lib()
-    torch.backends.cudnn.benchmark = True          # autotune the (fixed-shape) convolutions of the host model, incl. R1's double backward
+    # autotune the (fixed-shape) convolutions of the host model, incl. R1's double backward.  MOEGAN_BENCH_CUDNN_BENCHMARK=0: cuDNN's
+    # heuristic choice instead (identical on every rank and every run; the autotuner's pick varies from process to process)
+    torch.backends.cudnn.benchmark = os.environ.get("MOEGAN_BENCH_CUDNN_BENCHMARK", "1") == "1"
     G, D = build_models(pkg, dev)
     B = TRAIN_BATCH
     torch.manual_seed(1234 + rank)                # rank-offset data

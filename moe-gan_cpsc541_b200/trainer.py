@@ -58,6 +58,7 @@ class GradReducer:
             comm_priority = int(os.environ["MOEGAN_DP_COMM_PRIORITY"])
         self.comm_priority = comm_priority
         self.defer = mode == "single"          # launch nothing from the hooks: finish() packs and reduces everything at once
+        self.skip_collective = False
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -152,6 +153,8 @@ class GradReducer:
                    "begin": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
             rec["ready"].record()
             self.trace.append(rec)
+        if self.skip_collective:
+            return
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
