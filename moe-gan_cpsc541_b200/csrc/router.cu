@@ -152,8 +152,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // Warp-per-token epilogue of the router forward (4 tokens per warp): logits from the 128 projection columns held 4 per lane, temperature,
 // clamps, softmax, clamp + renormalise, top-k by warp argmax (ties -> lowest index), histogram into cnt_s.  P = split-K exchange buffer
-// [2 (g)][4 (q)][8 (a)][128].  Returns this lane's share of the probability column sums.  Shared by the streaming and the weight-resident
-// kernel, so both produce bit-identical routing.
+// [2 (g)][4 (q)][8 (a)][128].  Returns this lane's share of the probability column sums.  // kernel of earlier experiments; kept as a function so that variants of the contraction share one epilogue.
 __device__ __forceinline__ float router_epilogue_tokens(const float* __restrict__ P, const float* __restrict__ WcT, const float* __restrict__ tl,
                                                        const float* __restrict__ temperature, float af, int g, int q, int lane, int t0, int T,
                                                        int E, int k, int tps, int dense, int hard, float* __restrict__ fp, float* __restrict__ raw,
@@ -369,128 +368,6 @@ router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, con
         chunk_colsum[(size_t)chunk * E + tid] = cs;
         chunk_counts[(size_t)chunk * E + tid] = cnt_s[tid];
     }
-}
-
-// =====================================================================================================
-// K2 (d = 128 / 256, large T): the same router with Wf RESIDENT in shared memory and a persistent CTA per SM.
-// The streaming kernel above re-reads Wf (64 / 128 KB) and re-transposes Wc for every 32-token chunk and pays two block barriers plus a
-// full global-load round trip per 32-row k chunk: at T = 65 536, d = 128 that is 2 048 CTAs of ~16 us each for 0.5 MFLOP of work apiece
-// (113 us, 0.26 of the fp32 FMA roof, 134 MB of L2 traffic for a 64 KB matrix).  Here a CTA loads Wf / Wc^T once, then walks its
-// chunks with a double-buffered cp.async prefetch of the next [32, d] token tile: one barrier pair per chunk, no global latency inside the
-// contraction.  The arithmetic - per-lane columns, 32-row blocked partial sums, split-K halves, epilogue - is the streaming kernel's,
-// instruction for instruction, so logits and routing are bit-identical.
-// =====================================================================================================
-template <int D>
-__global__ void __launch_bounds__(RT_THREADS, 1)
-router_fwd_resident_kernel(const float* __restrict__ x, const float* __restrict__ Wf, const float* __restrict__ Wc,
-                           const float* __restrict__ tl, const float* __restrict__ temperature, float af,
-                           int T, int E, int k, int tps, int dense, int hard, int nchunks,
-                           float* __restrict__ fp, float* __restrict__ raw, float* __restrict__ probs,
-                           int* __restrict__ topk_idx, float* __restrict__ gates,
-                           int* __restrict__ chunk_counts, float* __restrict__ chunk_colsum) {
-    extern __shared__ __align__(16) uint8_t rsm[];
-    constexpr int PD = (D == 128) ? 2 * 4 * 8 * HID : 0;          // d = 128: dedicated split-K exchange; d = 256: aliases the consumed x tile (32 KB)
-    float* Wfs = reinterpret_cast<float*>(rsm);                   // [D][128]
-    float* xs = Wfs + D * HID;                                    // [2][RT_TOK][D]
-    float* Pd = xs + 2 * RT_TOK * D;
-    float* WcT = Pd + PD;                                         // [E][128]
-    float* colsum_s = WcT + E * HID;                              // [8][32]
-    int* cnt_s = reinterpret_cast<int*>(colsum_s + 8 * 32);       // [32]
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int g = wid >> 2, q = wid & 3;
-
-    for (int i = tid; i < D * HID / 4; i += RT_THREADS) cp_async16(Wfs + i * 4, Wf + (size_t)i * 4, true);
-    for (int i = tid; i < HID * E; i += RT_THREADS) {             // WcT[e][j] = Wc[j][e], top 128 rows only
-        const int j = i / E, e = i - j * E;
-        WcT[e * HID + j] = Wc[i];
-    }
-    constexpr int XV = D / 32;                                    // 16-byte pieces of a [32, D] tile per thread
-    auto load_x = [&](int chunk, int buf) {
-#pragma unroll
-        for (int i = 0; i < XV; ++i) {
-            const int idx = tid + i * RT_THREADS;
-            const int tok = idx / (D / 4), c4 = idx - tok * (D / 4);
-            const bool ok = (chunk * RT_TOK + tok) < T;
-            cp_async16(xs + ((size_t)buf * RT_TOK + tok) * D + c4 * 4, x + (size_t)(ok ? chunk * RT_TOK + tok : 0) * D + c4 * 4, ok);
-        }
-    };
-    int chunk = blockIdx.x;
-    if (chunk < nchunks) load_x(chunk, 0);
-    cp_async_commit();
-    for (int it = 0; chunk < nchunks; chunk += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int t0 = chunk * RT_TOK;
-        if (chunk + (int)gridDim.x < nchunks) load_x(chunk + gridDim.x, buf ^ 1);     // buffer buf^1 was released by the barrier that ended iteration it-1
-        cp_async_commit();
-        cp_async_wait<1>();                                       // this chunk's tile (and, at it == 0, Wf) has landed for this thread
-#pragma unroll
-        for (int i = 0; i < XV; ++i) {                            // nan_to_num on the elements this thread staged (identity on finite input, :338-340)
-            const int idx = tid + i * RT_THREADS;
-            const int tok = idx / (D / 4), c4 = idx - tok * (D / 4);
-            float4* p4 = reinterpret_cast<float4*>(xs + ((size_t)buf * RT_TOK + tok) * D + c4 * 4);
-            float4 v = *p4;
-            v.x = nan_to_num_router(v.x); v.y = nan_to_num_router(v.y); v.z = nan_to_num_router(v.z); v.w = nan_to_num_router(v.w);
-            *p4 = v;
-        }
-        if (tid < 32) cnt_s[tid] = 0;
-        __syncthreads();
-
-        float acc[8][4];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
-        const float* xrow = xs + ((size_t)buf * RT_TOK + q * 8) * D;
-#pragma unroll 1
-        for (int c = 0; c < D / RT_KC; ++c) {
-            const float* wsrc = Wfs + (size_t)c * RT_KC * HID;
-            float2 p01[8], p23[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) { p01[a] = make_float2(0.0f, 0.0f); p23[a] = make_float2(0.0f, 0.0f); }
-#pragma unroll
-            for (int kq4 = 0; kq4 < RT_KC / 8; ++kq4) {
-                const int kq = g * (RT_KC / 8) + kq4;           // this warp group's half of the 32-row block
-                float4 xv[8];
-#pragma unroll
-                for (int a = 0; a < 8; ++a) xv[a] = *reinterpret_cast<const float4*>(xrow + (size_t)a * D + c * RT_KC + kq * 4);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wsrc + (kq * 4 + kk) * HID + lane * 4);
-                    const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        const float xk = kk == 0 ? xv[a].x : kk == 1 ? xv[a].y : kk == 2 ? xv[a].z : xv[a].w;
-                        const float2 xx = make_float2(xk, xk);
-                        p01[a] = __ffma2_rn(xx, w01, p01[a]);
-                        p23[a] = __ffma2_rn(xx, w23, p23[a]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 8; ++a) { acc[a][0] += p01[a].x; acc[a][1] += p01[a].y; acc[a][2] += p23[a].x; acc[a][3] += p23[a].y; }
-        }
-        __syncthreads();                                          // every warp is done reading the x tile (d = 256: it becomes the exchange buffer)
-        float* P = (D == 128) ? Pd : xs + (size_t)buf * RT_TOK * D;
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-            *reinterpret_cast<float4*>(P + ((g * 4 + q) * 8 + a) * HID + lane * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-        __syncthreads();
-        const float my_colsum = router_epilogue_tokens(P, WcT, tl, temperature, af, g, q, lane, t0, T, E, k, tps, dense, hard, fp, raw, probs,
-                                                       topk_idx, gates, cnt_s);
-        colsum_s[wid * 32 + lane] = my_colsum;
-        __syncthreads();
-        if (tid < E) {
-            float cs = 0.0f;
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) cs += colsum_s[w8 * 32 + tid];   // fixed order -> deterministic
-            chunk_colsum[(size_t)chunk * E + tid] = cs;
-            chunk_counts[(size_t)chunk * E + tid] = cnt_s[tid];
-        }
-        __syncthreads();                                          // cnt_s / colsum_s / the exchange buffer are reused by the next chunk
-    }
-    cp_async_wait<0>();
-}
-static size_t router_fwd_resident_smem(int D, int E) {
-    return ((size_t)D * HID + 2 * RT_TOK * D + (D == 128 ? 2 * 4 * 8 * HID : 0) + (size_t)E * HID + 8 * 32 + 32) * sizeof(float);
 }
 
 // =====================================================================================================
@@ -905,29 +782,6 @@ int launch_router_fwd(const moegan_shape* s, const float* x, const float* Wf, co
         attr = true;
     }
     const int chunks = ceil_div(s->T, RT_TOK);
-    static int resident = -1;
-    if (resident < 0) { const char* e = getenv("MOEGAN_DISABLE_RESIDENT_ROUTER"); resident = (e != nullptr && e[0] == '1') ? 0 : 1; }
-    if (resident == 1 && (s->d == 128 || s->d == 256) && chunks >= num_sms()) {     // enough chunks per CTA to amortise loading Wf once
-        static bool attr_r = false;
-        if (!attr_r) {
-            MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(router_fwd_resident_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)router_fwd_resident_smem(128, MOEGAN_MAX_EXPERTS)));
-            MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(router_fwd_resident_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)router_fwd_resident_smem(256, MOEGAN_MAX_EXPERTS)));
-            attr_r = true;
-        }
-        const int grid = chunks < num_sms() ? chunks : num_sms();
-        if (s->d == 128)
-            router_fwd_resident_kernel<128><<<grid, RT_THREADS, router_fwd_resident_smem(128, s->E), st>>>(
-                x, Wf, Wc, tl, temperature, af, s->T, s->E, s->k, s->tokens_per_sample, s->dense, s->hard, chunks, fp, raw, probs, topk_idx, gates,
-                chunk_counts, chunk_colsum);
-        else
-            router_fwd_resident_kernel<256><<<grid, RT_THREADS, router_fwd_resident_smem(256, s->E), st>>>(
-                x, Wf, Wc, tl, temperature, af, s->T, s->E, s->k, s->tokens_per_sample, s->dense, s->hard, chunks, fp, raw, probs, topk_idx, gates,
-                chunk_counts, chunk_colsum);
-        MOEGAN_CHECK_LAUNCH("router_fwd_resident_kernel");
-        return MOEGAN_OK;
-    }
     router_fwd_kernel<<<chunks, RT_THREADS, router_fwd_smem(s->E), st>>>(x, Wf, Wc, tl, temperature, af, s->T, s->d, s->E, s->k,
                                                                         s->tokens_per_sample, s->dense, s->hard, fp, raw, probs,
                                                                         topk_idx, gates, chunk_counts, chunk_colsum);
