@@ -760,13 +760,16 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     auto F = [&](int64_t off) -> float* { return reinterpret_cast<float*>(P(off)); };
     auto I = [&](int64_t off) -> int32_t* { return reinterpret_cast<int32_t*>(P(off)); };
     if (s->T == 0) return MOEGAN_OK;
-    // weight conversion (only when the caller's cache is stale) overlaps the router / dispatch kernels
+    // Weight conversion (only when the caller's cache is stale).  On small blocks it runs on the side stream, forked AFTER the router
+    // kernel has been enqueued: the router's CTAs (one per SM at T = 4096) are dispatched first and the conversion's blocks co-reside with
+    // them.  Forked at the top of the call (as in round 1) its many blocks were dispatched ahead of the single-block kl_finalize and the
+    // 8-block text kernel of the main chain, which then sat behind it for ~10 us (profiles/r02o_timeline_moe_block.log).
     SideStream* ss = (a->prep_w1 != nullptr && side_pays(s)) ? side_stream() : nullptr;
-    if (a->prep_w1 != nullptr) {
-        if (ss != nullptr) RUN(side_fork(ss, (cudaStream_t)stream));
-        RUN(moegan_prep_weights(s, a->prep_w1, a->prep_b1, a->prep_w2, a->prep_b2, const_cast<void*>(a->W1_op), const_cast<float*>(a->b1s),
-                                const_cast<void*>(a->W2_op), const_cast<float*>(a->b2s), ss != nullptr ? (void*)ss->s : stream));
-    }
+    auto prep = [&](void* st_) -> int {
+        return moegan_prep_weights(s, a->prep_w1, a->prep_b1, a->prep_w2, a->prep_b2, const_cast<void*>(a->W1_op), const_cast<float*>(a->b1s),
+                                   const_cast<void*>(a->W2_op), const_cast<float*>(a->b2s), st_);
+    };
+    if (a->prep_w1 != nullptr && ss == nullptr) RUN(prep(stream));
     REQ_PTR(a->mu_f); REQ_PTR(a->rho_f); REQ_PTR(a->mu_t); REQ_PTR(a->rho_t); REQ_PTR(a->mu_c); REQ_PTR(a->rho_c);
     if (a->sampled) { REQ_PTR(a->eps_f); REQ_PTR(a->eps_t); REQ_PTR(a->eps_c); }
     const bool keep_eps = a->need_backward && a->sampled;      // the eps consumed here, kept inside the workspace for the backward
@@ -776,6 +779,10 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
     RUN(moegan_router_text_fwd(s, a->w, F(L.Wt), F(L.Wc), F(L.tp), F(L.tl), stream));
     RUN(moegan_router_fwd(s, a->x, F(L.Wf), F(L.Wc), F(L.tl), a->temperature, a->annealing_factor, F(L.fp), F(L.raw), a->probs,
                           I(L.topk_idx), F(L.gates), I(L.chunk_counts), F(L.chunk_colsum), stream));
+    if (ss != nullptr) {
+        RUN(side_fork(ss, (cudaStream_t)stream));
+        RUN(prep(ss->s));
+    }
     RUN(moegan_dispatch_plan(s, I(L.chunk_counts), F(L.chunk_colsum), I(L.plan), I(L.chunk_base), a->load, stream));
     // a->x_op: the caller already holds the bf16 operand copy of x (emitted by moegan_layernorm_fwd_dual in the same pass as the fp32
     // rows): no conversion kernel here, and the backward pass reads that tensor too (moegan_block_bwd_args.x_op)
