@@ -777,10 +777,13 @@ int moegan_block_fwd(const moegan_shape* s, const moegan_block_fwd_args* a, void
                          F(L.Wf), F(L.Wt), F(L.Wc), P(L.Wf_op), P(L.Wt_op), a->kl_out,
                          keep_eps ? F(L.eps_f) : nullptr, keep_eps ? F(L.eps_t) : nullptr, keep_eps ? F(L.eps_c) : nullptr, (cudaStream_t)stream));
     RUN(moegan_router_text_fwd(s, a->w, F(L.Wt), F(L.Wc), F(L.tp), F(L.tl), stream));
+    // the fork EVENT is recorded before the router kernel (so the conversion depends only on what precedes it), the conversion is
+    // ENQUEUED after it (so the router's CTAs, one per SM, are dispatched first and the conversion's blocks fill in beside them)
+    if (ss != nullptr) MOEGAN_CHECK_CUDA(cudaEventRecord(ss->fork, (cudaStream_t)stream));
     RUN(moegan_router_fwd(s, a->x, F(L.Wf), F(L.Wc), F(L.tl), a->temperature, a->annealing_factor, F(L.fp), F(L.raw), a->probs,
                           I(L.topk_idx), F(L.gates), I(L.chunk_counts), F(L.chunk_colsum), stream));
     if (ss != nullptr) {
-        RUN(side_fork(ss, (cudaStream_t)stream));
+        MOEGAN_CHECK_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
         RUN(prep(ss->s));
     }
     RUN(moegan_dispatch_plan(s, I(L.chunk_counts), F(L.chunk_colsum), I(L.plan), I(L.chunk_base), a->load, stream));

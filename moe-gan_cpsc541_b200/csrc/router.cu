@@ -150,110 +150,164 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Warp-per-token epilogue of the router forward (4 tokens per warp): logits from the 128 projection columns held 4 per lane, temperature,
+// Epilogue of the router forward: each warp finishes 4 tokens - logits from the 128 projection columns held 4 per lane, temperature,
 // clamps, softmax, clamp + renormalise, top-k by warp argmax (ties -> lowest index), histogram into cnt_s.  P = split-K exchange buffer
-// [2 (g)][4 (q)][8 (a)][128].  Returns this lane's share of the probability column sums.  // kernel of earlier experiments; kept as a function so that variants of the contraction share one epilogue.
+// [2 (g)][4 (q)][8 (a)][128].  Returns this lane's share of the probability column sums.
+// The 4 tokens are processed SIDE BY SIDE: every stage (logit butterfly, max, two sums, the k argmax rounds) is a chain of dependent warp
+// shuffles, ~40 deep per token; one token after the other (round 1: `#pragma unroll 1` over the tokens) that chain - not the
+// contraction - was most of a CTA's life (~2 000 cycles per token, 4 tokens per warp, against ~2 500 cycles for the whole [32, d] x
+// [d, 128] contraction at d = 128).  Interleaved, the four chains hide each other's shuffle latency.  Per-token arithmetic and the
+// order of every reduction are unchanged, so logits, probabilities and routing are bit-identical.
+template <int U>
+__device__ __forceinline__ void warp_sum_n(float (&v)[U]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+}
+template <int U>
+__device__ __forceinline__ void warp_max_n(float (&v)[U]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = fmaxf(v[u], __shfl_xor_sync(0xffffffffu, v[u], o));
+}
 __device__ __forceinline__ float router_epilogue_tokens(const float* __restrict__ P, const float* __restrict__ WcT, const float* __restrict__ tl,
                                                        const float* __restrict__ temperature, float af, int g, int q, int lane, int t0, int T,
                                                        int E, int k, int tps, int dense, int hard, float* __restrict__ fp, float* __restrict__ raw,
                                                        float* __restrict__ probs, int* __restrict__ topk_idx, float* __restrict__ gates,
                                                        int* __restrict__ cnt_s) {
+    constexpr int U = 4;
     const float tau = clampf(__ldg(temperature) * af, 0.5f, 5.0f);   // (:375)
-    float my_colsum = 0.0f;
-#pragma unroll 1
-    for (int a4 = 0; a4 < 4; ++a4) {
-        const int a = g * 4 + a4;
+    const bool act = lane < E;
+    int tt[U]; bool ok[U];
+    float f[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int a = g * 4 + u;
         const int t = t0 + q * 8 + a;
-        if (t >= T) break;   // warp-uniform
+        ok[u] = t < T;                       // warp-uniform; tokens past the end are computed on zero rows and never stored
+        tt[u] = ok[u] ? t : T - 1;
         const float4 p0 = *reinterpret_cast<const float4*>(P + ((0 * 4 + q) * 8 + a) * HID + lane * 4);
         const float4 p1 = *reinterpret_cast<const float4*>(P + ((1 * 4 + q) * 8 + a) * HID + lane * 4);
-        const float f0 = p0.x + p1.x, f1 = p0.y + p1.y, f2 = p0.z + p1.z, f3 = p0.w + p1.w;
-        if (fp != nullptr) *reinterpret_cast<float4*>(fp + (size_t)t * HID + lane * 4) = make_float4(f0, f1, f2, f3);
-        float my_raw = 0.0f;
-        if (E <= 8) {
-            // logits of up to 8 experts with ONE transposing butterfly (10 shuffles) instead of E full warp reductions (5 E): at every
-            // stage a lane keeps the half of its values that belongs to its side of the xor pair and hands over the other half.  The
-            // pairings are those of warp_sum (xor 16, 8, 4, 2, 1) and a + b == b + a, so every logit is bit-identical to the serial form.
-            float v[8];
+        f[u][0] = p0.x + p1.x; f[u][1] = p0.y + p1.y; f[u][2] = p0.z + p1.z; f[u][3] = p0.w + p1.w;
+        if (fp != nullptr && ok[u]) *reinterpret_cast<float4*>(fp + (size_t)t * HID + lane * 4) = make_float4(f[u][0], f[u][1], f[u][2], f[u][3]);
+    }
+    float rw[U];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                v[e] = 0.0f;
-                if (e < E) {
-                    const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
-                    v[e] = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
-                }
-            }
+    for (int u = 0; u < U; ++u) rw[u] = 0.0f;
+    if (E <= 8) {
+        // logits of up to 8 experts with ONE transposing butterfly (10 shuffles) instead of E full warp reductions (5 E): at every
+        // stage a lane keeps the half of its values that belongs to its side of the xor pair and hands over the other half.  The
+        // pairings are those of warp_sum (xor 16, 8, 4, 2, 1) and a + b == b + a, so every logit is bit-identical to the serial form.
+        float v[U][8];
 #pragma unroll
-            for (int st = 0; st < 3; ++st) {
-                const int off = 16 >> st, half = 4 >> st;
-                const bool up = (lane & off) != 0;
+        for (int e = 0; e < 8; ++e) {
+            float4 wc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < E) wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
 #pragma unroll
-                for (int i = 0; i < half; ++i) {
-                    const float keep = up ? v[i + half] : v[i];
-                    const float send = up ? v[i] : v[i + half];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-            // lanes with (bit4, bit3, bit2) = (e>>2, e>>1, e) & 1 now hold expert e; lane e fetches its logit
-            const int src = (((lane >> 2) & 1) << 4) | (((lane >> 1) & 1) << 3) | ((lane & 1) << 2);
-            my_raw = __shfl_sync(0xffffffffu, v[0], src);
-            if (lane >= E) my_raw = 0.0f;
-        } else {
-            for (int e = 0; e < E; ++e) {
-                const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
-                float part = fmaf(f3, wc.w, fmaf(f2, wc.z, fmaf(f1, wc.y, f0 * wc.x)));
-                part = warp_sum(part);
-                if (lane == e) my_raw = part;
-            }
+            for (int u = 0; u < U; ++u) v[u][e] = e < E ? fmaf(f[u][3], wc.w, fmaf(f[u][2], wc.z, fmaf(f[u][1], wc.y, f[u][0] * wc.x))) : 0.0f;
         }
-        const bool act = lane < E;
-        if (act) my_raw += __ldg(tl + (size_t)(t / tps) * E + lane);
-        const float z = my_raw / tau;                              // (:378)
-        const float l = clampf(z, -20.0f, 20.0f);                  // (:381)
-        const float m = warp_max(act ? l : -INFINITY);
-        const float ex = act ? expf(l - m) : 0.0f;
-        const float s = ex / warp_sum(ex);                         // (:384)
-        const float cl = act ? clampf(s, 1e-6f, 1.0f) : 0.0f;      // (:387)
-        const float p = cl / warp_sum(cl);                         // (:389)
-        my_colsum += act ? p : 0.0f;
-        if (act) raw[(size_t)t * E + lane] = my_raw;
-        if (dense) {
-            if (act) {
-                probs[(size_t)t * E + lane] = p;
-                gates[(size_t)t * E + lane] = p;
-                topk_idx[(size_t)t * E + lane] = lane;
-            }
-        } else {
-            bool taken = false;
-            int sel_i[MOEGAN_MAX_TOPK]; float sel_p[MOEGAN_MAX_TOPK];
-            float gsum = 0.0f;
 #pragma unroll
-            for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) {
-                if (j < k) {
-                    float bv = (act && !taken) ? p : -1.0f;
-                    int bi = lane;
+        for (int st = 0; st < 3; ++st) {
+            const int off = 16 >> st, half = 4 >> st;
+            const bool up = (lane & off) != 0;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                    }
-                    if (lane == bi) taken = true;
-                    sel_i[j] = bi; sel_p[j] = bv;
-                    gsum += bv;
-                } else { sel_i[j] = 0; sel_p[j] = 0.0f; }
-            }
+            for (int i = 0; i < half; ++i)
 #pragma unroll
-            for (int j = 0; j < MOEGAN_MAX_TOPK; ++j) {
-                if (j < k && lane == j) {
-                    topk_idx[(size_t)t * k + j] = sel_i[j];
-                    gates[(size_t)t * k + j] = hard ? 1.0f : sel_p[j] / gsum;
-                    atomicAdd(&cnt_s[sel_i[j]], 1);
+                for (int u = 0; u < U; ++u) {
+                    const float keep = up ? v[u][i + half] : v[u][i];
+                    const float send = up ? v[u][i] : v[u][i + half];
+                    v[u][i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
+        }
+        // lanes with (bit4, bit3, bit2) = (e>>2, e>>1, e) & 1 hold expert e after the last two steps; lane e fetches its logit
+        const int src = (((lane >> 2) & 1) << 4) | (((lane >> 1) & 1) << 3) | ((lane & 1) << 2);
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u][0] += __shfl_xor_sync(0xffffffffu, v[u][0], 2);
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u][0] += __shfl_xor_sync(0xffffffffu, v[u][0], 1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float r = __shfl_sync(0xffffffffu, v[u][0], src);
+            rw[u] = act ? r : 0.0f;
+        }
+    } else {
+        for (int e = 0; e < E; ++e) {
+            const float4 wc = *reinterpret_cast<const float4*>(WcT + e * HID + lane * 4);
+            float part[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) part[u] = fmaf(f[u][3], wc.w, fmaf(f[u][2], wc.z, fmaf(f[u][1], wc.y, f[u][0] * wc.x)));
+            warp_sum_n<U>(part);
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (lane == e) rw[u] = part[u];
+        }
+    }
+    float l[U], m[U], ex[U], sm[U], cl[U], cs[U], p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (act) rw[u] += __ldg(tl + (size_t)(tt[u] / tps) * E + lane);
+        const float z = rw[u] / tau;                               // (:378)
+        l[u] = clampf(z, -20.0f, 20.0f);                           // (:381)
+        m[u] = act ? l[u] : -INFINITY;
+    }
+    warp_max_n<U>(m);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ex[u] = act ? expf(l[u] - m[u]) : 0.0f; sm[u] = ex[u]; }
+    warp_sum_n<U>(sm);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const float sft = ex[u] / sm[u]; cl[u] = act ? clampf(sft, 1e-6f, 1.0f) : 0.0f; cs[u] = cl[u]; }   // (:384, :387)
+    warp_sum_n<U>(cs);
+    float my_colsum = 0.0f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        p[u] = cl[u] / cs[u];                                      // (:389)
+        my_colsum += (act && ok[u]) ? p[u] : 0.0f;
+        if (act && ok[u]) raw[(size_t)tt[u] * E + lane] = rw[u];
+    }
+    if (dense) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (act && ok[u]) {
+                probs[(size_t)tt[u] * E + lane] = p[u];
+                gates[(size_t)tt[u] * E + lane] = p[u];
+                topk_idx[(size_t)tt[u] * E + lane] = lane;
             }
-            if (act) probs[(size_t)t * E + lane] = hard ? (lane == sel_i[0] ? 1.0f : 0.0f) : p;   // (:392-400)
+        return my_colsum;
+    }
+    // top-k: k rounds of warp argmax (ties -> lowest index); lane j keeps the j-th selection of every token
+    bool taken[U]; float gsum[U], my_p[U]; int my_i[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { taken[u] = false; gsum[u] = 0.0f; my_p[u] = 0.0f; my_i[u] = 0; }
+    for (int j = 0; j < k; ++j) {
+        float bv[U]; int bi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { bv[u] = (act && !taken[u]) ? p[u] : -1.0f; bi[u] = lane; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[u], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[u], o);
+                if (ov > bv[u] || (ov == bv[u] && oi < bi[u])) { bv[u] = ov; bi[u] = oi; }
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (lane == bi[u]) taken[u] = true;
+            if (lane == j) { my_i[u] = bi[u]; my_p[u] = bv[u]; }
+            gsum[u] += bv[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int first = __shfl_sync(0xffffffffu, my_i[u], 0);
+        if (ok[u]) {
+            if (lane < k) {
+                topk_idx[(size_t)tt[u] * k + lane] = my_i[u];
+                gates[(size_t)tt[u] * k + lane] = hard ? 1.0f : my_p[u] / gsum[u];
+                atomicAdd(&cnt_s[my_i[u]], 1);
+            }
+            if (act) probs[(size_t)tt[u] * E + lane] = hard ? (lane == first ? 1.0f : 0.0f) : p[u];   // (:392-400)
         }
     }
     return my_colsum;
