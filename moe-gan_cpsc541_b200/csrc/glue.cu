@@ -9,7 +9,9 @@
 //     activations: grid = clamp(base + 0.05 * off, -1, 1), F.grid_sample(bilinear, zeros, align_corners=False).
 // All of them are HBM-bound: every tensor is read or written exactly once per pass, with 8- or 16-byte accesses along the
 // contiguous channel dimension.
+#include <cstdlib>
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace moegan {
 
@@ -237,6 +239,240 @@ partial_sum_tall_kernel(const float* __restrict__ part, int n, int nparts, float
 // column sums of a tall matrix: out[c] = sum_r x[r, c]  (bias gradient of a Linear applied to [T, d] tokens; ATen's generic
 // reduction needs ~80 us for a bf16 [65 536, 128] input).  CTA = 128 columns x one row split; thread = 4 columns, 8 row lanes,
 // 4 rows in flight; partials [nsplit][cols] are summed in a fixed order -> deterministic.
+// ---- LayerNorm backward, bulk-copy pipelined (d = 128 / 256 / 512) ------------------------------------------------------------------
+// The register-pipelined kernel above is latency-bound (ncu, rows = 65 536, d = 128: 24.8 us = 2.1 TB/s, long_scoreboard 7.2 of 11 stalled
+// warps per issue, 30 % of the warps resident): a warp issues the 8-byte loads of four rows, waits for them, reduces, stores, and only
+// then issues the next loads; 80 registers allow three CTAs per SM.  Here the x / grad rows of a tile (32 / 16 / 8 rows = 8 .. 16 KB per
+// tensor, contiguous in memory) are brought in by cp.async.bulk (one elected thread, no tensor map needed) into a 4-stage shared-memory
+// ring with full / empty mbarriers, three tiles ahead of the warps that consume them; mean / rstd of the next rows are fetched before the
+// wait.  Arithmetic per row and the dgamma / dbeta reduction order are those of the kernel above.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <typename T> __device__ __forceinline__ float4 lds_vec4(const T* p);
+template <> __device__ __forceinline__ float4 lds_vec4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 lds_vec4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
+}
+constexpr int LNB_STAGES = 4;
+template <typename TG, typename TIN, int NSEG> struct LnBulk {
+    static constexpr int D = NSEG * 128;
+    static constexpr int TR = 32 / NSEG;                 // rows per tile
+    static constexpr int RW = TR / 8;                    // rows per warp and tile (4 / 2 / 1)
+    static constexpr uint32_t XB = TR * D * sizeof(TIN), GB = TR * D * sizeof(TG), SB = XB + GB;
+    static constexpr uint32_t SMEM = LNB_STAGES * SB + 2 * LNB_STAGES * 8;
+};
+template <typename TG, typename TIN, int NSEG>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows,
+                          TIN* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
+    using L = LnBulk<TG, TIN, NSEG>;
+    constexpr int D = L::D, TR = L::TR, RW = L::RW, ST = LNB_STAGES;
+    extern __shared__ __align__(128) uint8_t lsm[];
+    __shared__ float4 red[8][NSEG * 32];
+    const uint32_t sm0 = ptx::smem_u32(lsm);
+    const uint32_t bar0 = sm0 + ST * L::SB;
+    auto full = [&](int s_) { return bar0 + 8u * s_; };
+    auto empty = [&](int s_) { return bar0 + 8u * (ST + s_); };
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s_ = 0; s_ < ST; ++s_) { ptx::mbar_init(full(s_), 1); ptx::mbar_init(empty(s_), 8); }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    const long long ntiles = (rows + TR - 1) / TR;
+    const int my_n = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto tile_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
+    auto issue = [&](int i) {                                    // thread 0: rows of local tile i -> ring slot i % ST
+        const int slot = i % ST;
+        if (i >= ST) ptx::mbar_wait(empty(slot), (((uint32_t)(i / ST)) & 1u) ^ 1u);      // all 8 warps have left the slot's previous tile
+        const long long r0 = tile_of(i) * TR;
+        const uint32_t vr = (uint32_t)((rows - r0) < TR ? (rows - r0) : TR);
+        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)(sizeof(TIN) + sizeof(TG)));
+        bulk_g2s(sm0 + slot * L::SB, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
+        bulk_g2s(sm0 + slot * L::SB + L::XB, g + r0 * D, vr * D * (uint32_t)sizeof(TG), full(slot));
+    };
+    if (tid == 0)
+        for (int i = 0; i < ST - 1 && i < my_n; ++i) issue(i);
+
+    float4 gam[NSEG], dg[NSEG], db[NSEG];
+#pragma unroll
+    for (int s_ = 0; s_ < NSEG; ++s_) {
+        dg[s_] = make_float4(0.f, 0.f, 0.f, 0.f); db[s_] = dg[s_];
+        gam[s_] = __ldg(reinterpret_cast<const float4*>(gamma + s_ * 128 + lane * 4));
+    }
+    const float inv_d = 1.0f / (float)D;
+    for (int i = 0; i < my_n; ++i) {
+        const int slot = i % ST;
+        if (tid == 0 && i + ST - 1 < my_n) issue(i + ST - 1);
+        const long long r0 = tile_of(i) * TR + wid * RW;
+        float mean[RW], rs[RW];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {                           // issued before the wait: their latency hides behind it
+            const bool ok = r0 + r < rows;
+            mean[r] = ok ? __ldg(mean_in + r0 + r) : 0.f;
+            rs[r] = ok ? __ldg(rstd_in + r0 + r) : 0.f;
+        }
+        ptx::mbar_wait(full(slot), ((uint32_t)(i / ST)) & 1u);
+        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * L::SB) + (size_t)wid * RW * D;
+        const TG* gs_ = reinterpret_cast<const TG*>(lsm + (size_t)slot * L::SB + L::XB) + (size_t)wid * RW * D;
+        float4 xh[RW][NSEG], gg[RW][NSEG];
+        float s1[RW], s2[RW];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+            const bool ok = r0 + r < rows;
+            s1[r] = 0.f; s2[r] = 0.f;
+#pragma unroll
+            for (int s_ = 0; s_ < NSEG; ++s_) {
+                xh[r][s_] = make_float4(0.f, 0.f, 0.f, 0.f); gg[r][s_] = xh[r][s_];
+                if (ok) {
+                    const float4 xv = lds_vec4<TIN>(xs_ + (size_t)r * D + s_ * 128 + lane * 4);
+                    const float4 gv = lds_vec4<TG>(gs_ + (size_t)r * D + s_ * 128 + lane * 4);
+                    xh[r][s_] = make_float4((xv.x - mean[r]) * rs[r], (xv.y - mean[r]) * rs[r], (xv.z - mean[r]) * rs[r], (xv.w - mean[r]) * rs[r]);
+                    dg[s_].x += gv.x * xh[r][s_].x; dg[s_].y += gv.y * xh[r][s_].y; dg[s_].z += gv.z * xh[r][s_].z; dg[s_].w += gv.w * xh[r][s_].w;
+                    db[s_].x += gv.x; db[s_].y += gv.y; db[s_].z += gv.z; db[s_].w += gv.w;
+                    gg[r][s_] = make_float4(gv.x * gam[s_].x, gv.y * gam[s_].y, gv.z * gam[s_].z, gv.w * gam[s_].w);
+                    s1[r] += (gg[r][s_].x + gg[r][s_].y) + (gg[r][s_].z + gg[r][s_].w);
+                    s2[r] += (gg[r][s_].x * xh[r][s_].x + gg[r][s_].y * xh[r][s_].y) + (gg[r][s_].z * xh[r][s_].z + gg[r][s_].w * xh[r][s_].w);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty(slot));            // this warp has read its rows of the slot
+#pragma unroll
+        for (int r = 0; r < RW; ++r) { s1[r] = warp_sum(s1[r]) * inv_d; s2[r] = warp_sum(s2[r]) * inv_d; }
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+            if (r0 + r < rows) {
+#pragma unroll
+                for (int s_ = 0; s_ < NSEG; ++s_) {
+                    float4 o;
+                    o.x = rs[r] * (gg[r][s_].x - s1[r] - xh[r][s_].x * s2[r]); o.y = rs[r] * (gg[r][s_].y - s1[r] - xh[r][s_].y * s2[r]);
+                    o.z = rs[r] * (gg[r][s_].z - s1[r] - xh[r][s_].z * s2[r]); o.w = rs[r] * (gg[r][s_].w - s1[r] - xh[r][s_].w * s2[r]);
+                    Vec4<TIN>::store(dx + (r0 + r) * D + s_ * 128 + lane * 4, o);
+                }
+            }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int s_ = 0; s_ < NSEG; ++s_) red[wid][s_ * 32 + lane] = pass == 0 ? dg[s_] : db[s_];
+        __syncthreads();
+        for (int j = threadIdx.x; j < NSEG * 32; j += 256) {
+            float4 a = red[0][j];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { const float4 b = red[w][j]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+            reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * 2 + pass) * D)[j] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// LayerNorm forward with the same ring: x tiles arrive by cp.async.bulk three tiles ahead; per-row arithmetic is that of
+// layernorm_fwd_kernel (two-pass mean / variance on the registers of the row).
+template <typename TIN, int NSEG> struct LnFwdBulk {
+    static constexpr int D = NSEG * 128;
+    static constexpr int TR = 32 / NSEG;
+    static constexpr int RW = TR / 8;
+    static constexpr uint32_t SB = TR * D * sizeof(TIN);
+    static constexpr uint32_t SMEM = LNB_STAGES * SB + 2 * LNB_STAGES * 8;
+};
+template <typename TIN, typename TOUT, int NSEG>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
+                          float eps, TOUT* __restrict__ y, __nv_bfloat16* __restrict__ y_op, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out) {
+    using L = LnFwdBulk<TIN, NSEG>;
+    constexpr int D = L::D, TR = L::TR, RW = L::RW, ST = LNB_STAGES;
+    extern __shared__ __align__(128) uint8_t lsm[];
+    const uint32_t sm0 = ptx::smem_u32(lsm);
+    const uint32_t bar0 = sm0 + ST * L::SB;
+    auto full = [&](int s_) { return bar0 + 8u * s_; };
+    auto empty = [&](int s_) { return bar0 + 8u * (ST + s_); };
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s_ = 0; s_ < ST; ++s_) { ptx::mbar_init(full(s_), 1); ptx::mbar_init(empty(s_), 8); }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    const long long ntiles = (rows + TR - 1) / TR;
+    const int my_n = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto tile_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
+    auto issue = [&](int i) {
+        const int slot = i % ST;
+        if (i >= ST) ptx::mbar_wait(empty(slot), (((uint32_t)(i / ST)) & 1u) ^ 1u);
+        const long long r0 = tile_of(i) * TR;
+        const uint32_t vr = (uint32_t)((rows - r0) < TR ? (rows - r0) : TR);
+        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)sizeof(TIN));
+        bulk_g2s(sm0 + slot * L::SB, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
+    };
+    if (tid == 0)
+        for (int i = 0; i < ST - 1 && i < my_n; ++i) issue(i);
+    float4 gam[NSEG], bet[NSEG];
+#pragma unroll
+    for (int s_ = 0; s_ < NSEG; ++s_) {
+        gam[s_] = __ldg(reinterpret_cast<const float4*>(gamma + s_ * 128 + lane * 4));
+        bet[s_] = __ldg(reinterpret_cast<const float4*>(beta + s_ * 128 + lane * 4));
+    }
+    const float inv_d = 1.0f / (float)D;
+    for (int i = 0; i < my_n; ++i) {
+        const int slot = i % ST;
+        if (tid == 0 && i + ST - 1 < my_n) issue(i + ST - 1);
+        const long long r0 = tile_of(i) * TR + wid * RW;
+        ptx::mbar_wait(full(slot), ((uint32_t)(i / ST)) & 1u);
+        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * L::SB) + (size_t)wid * RW * D;
+        float4 v[RW][NSEG];
+        float sum[RW], mean[RW], rstd[RW];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+            sum[r] = 0.f;
+#pragma unroll
+            for (int s_ = 0; s_ < NSEG; ++s_) {
+                v[r][s_] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + r < rows) v[r][s_] = lds_vec4<TIN>(xs_ + (size_t)r * D + s_ * 128 + lane * 4);
+                sum[r] += (v[r][s_].x + v[r][s_].y) + (v[r][s_].z + v[r][s_].w);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty(slot));
+#pragma unroll
+        for (int r = 0; r < RW; ++r) mean[r] = warp_sum(sum[r]) * inv_d;
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+            float sq = 0.f;
+#pragma unroll
+            for (int s_ = 0; s_ < NSEG; ++s_) {
+                const float a = v[r][s_].x - mean[r], b = v[r][s_].y - mean[r], c = v[r][s_].z - mean[r], e = v[r][s_].w - mean[r];
+                sq += (a * a + b * b) + (c * c + e * e);
+            }
+            sum[r] = sq;
+        }
+#pragma unroll
+        for (int r = 0; r < RW; ++r) rstd[r] = rsqrtf(warp_sum(sum[r]) * inv_d + eps);
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+            if (r0 + r < rows) {
+#pragma unroll
+                for (int s_ = 0; s_ < NSEG; ++s_) {
+                    const int c = s_ * 128 + lane * 4;
+                    float4 o;
+                    o.x = (v[r][s_].x - mean[r]) * rstd[r] * gam[s_].x + bet[s_].x; o.y = (v[r][s_].y - mean[r]) * rstd[r] * gam[s_].y + bet[s_].y;
+                    o.z = (v[r][s_].z - mean[r]) * rstd[r] * gam[s_].z + bet[s_].z; o.w = (v[r][s_].w - mean[r]) * rstd[r] * gam[s_].w + bet[s_].w;
+                    Vec4<TOUT>::store(y + (r0 + r) * D + c, o);
+                    if (y_op != nullptr) Vec4<__nv_bfloat16>::store(y_op + (r0 + r) * D + c, o);
+                }
+            }
+        if (lane < RW && r0 + lane < rows) {
+            float m = mean[0], q = rstd[0];
+#pragma unroll
+            for (int r = 1; r < RW; ++r) if (lane == r) { m = mean[r]; q = rstd[r]; }
+            mean_out[r0 + lane] = m; rstd_out[r0 + lane] = q;
+        }
+    }
+}
+
 // =====================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -613,6 +849,9 @@ inline int grid_cap(long long blocks) {
 }  // namespace
 
 // ---- launchers ------------------------------------------------------------------------------------------------
+// A/B switches for tools/ln_probe.py (read once): MOEGAN_LN_BULK=0 selects the register-pipelined kernels
+static bool ln_bulk_env_off() { static const bool off = [] { const char* e = getenv("MOEGAN_LN_BULK"); return e != nullptr && e[0] == '0'; }(); return off; }
+static bool ln_fwd_bulk_disabled() { return ln_bulk_env_off(); }
 int ln_bwd_blocks(long long rows) {
     long long b = (rows + 7) / 8;
     const long long cap = (long long)num_sms() * 4;
@@ -626,6 +865,28 @@ int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const fl
     if (rows == 0) return MOEGAN_OK;
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
+    if ((nseg == 1 || nseg == 2 || nseg == 4) && rows >= 4096 && !ln_fwd_bulk_disabled()) {
+#define MOEGAN_LN_FBULK3(TI, TO, NS)                                                                                            \
+        do {                                                                                                                    \
+            typedef LnFwdBulk<TI, NS> LB;                                                                                       \
+            static bool attr = false;                                                                                           \
+            if (!attr) {                                                                                                        \
+                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_fwd_bulk_kernel<TI, TO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB::SMEM)); \
+                attr = true;                                                                                                    \
+            }                                                                                                                   \
+            const long long nt = (rows + LB::TR - 1) / LB::TR;                                                                  \
+            const long long cap = (long long)num_sms() * 3;                                                                     \
+            layernorm_fwd_bulk_kernel<TI, TO, NS><<<(int)(nt < cap ? nt : cap), 256, LB::SMEM, st>>>(                           \
+                reinterpret_cast<const TI*>(x), gamma, beta, rows, eps, reinterpret_cast<TO*>(y), reinterpret_cast<__nv_bfloat16*>(y_op), mean, rstd); \
+        } while (0)
+#define MOEGAN_LN_FBULK(TI, TO) do { if (nseg == 1) MOEGAN_LN_FBULK3(TI, TO, 1); else if (nseg == 2) MOEGAN_LN_FBULK3(TI, TO, 2); else MOEGAN_LN_FBULK3(TI, TO, 4); } while (0)
+        if (x_bf16) { if (y_bf16) MOEGAN_LN_FBULK(bf, bf); else MOEGAN_LN_FBULK(bf, float); }
+        else        { if (y_bf16) MOEGAN_LN_FBULK(float, bf); else MOEGAN_LN_FBULK(float, float); }
+#undef MOEGAN_LN_FBULK
+#undef MOEGAN_LN_FBULK3
+        MOEGAN_CHECK_LAUNCH("layernorm_fwd_bulk_kernel");
+        return MOEGAN_OK;
+    }
 #define MOEGAN_LN_FWD2(TI, TO, NS, RR)                                                                                         \
     layernorm_fwd_kernel<TI, TO, NS, RR><<<(int)((rows + 8 * RR - 1) / (8 * RR)), 256, 0, st>>>(                              \
         reinterpret_cast<const TI*>(x), gamma, beta, rows, d, eps, reinterpret_cast<TO*>(y), reinterpret_cast<__nv_bfloat16*>(y_op), mean, rstd)
@@ -652,6 +913,33 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
     const int blocks = ln_bwd_blocks(rows);
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
+    if ((nseg == 1 || nseg == 2 || nseg == 4) && !ln_bulk_env_off()) {
+        // bulk-copy pipelined kernel; same partial layout ([nb][2][d], nb <= blocks) and finishing pass as the register-pipelined one below
+        int nb = blocks;
+#define MOEGAN_LN_BULK3(TG, TI, NS)                                                                                             \
+        do {                                                                                                                    \
+            typedef LnBulk<TG, TI, NS> LB;                                                                                      \
+            static bool attr = false;                                                                                           \
+            if (!attr) {                                                                                                        \
+                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_bulk_kernel<TG, TI, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB::SMEM)); \
+                attr = true;                                                                                                    \
+            }                                                                                                                   \
+            const long long nt = (rows + LB::TR - 1) / LB::TR;                                                                  \
+            const long long cap = (long long)num_sms() * (LB::SMEM > 100 * 1024 ? 1 : 2);    /* persistent: CTAs resident per SM */ \
+            nb = (int)(nt < cap ? nt : cap);                                                                                    \
+            layernorm_bwd_bulk_kernel<TG, TI, NS><<<nb, 256, LB::SMEM, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, \
+                                                                                 mean, rstd, rows, reinterpret_cast<TI*>(dx), scratch);    \
+        } while (0)
+#define MOEGAN_LN_BULK(TG, TI) do { if (nseg == 1) MOEGAN_LN_BULK3(TG, TI, 1); else if (nseg == 2) MOEGAN_LN_BULK3(TG, TI, 2); else MOEGAN_LN_BULK3(TG, TI, 4); } while (0)
+        if (g_bf16) { if (x_bf16) MOEGAN_LN_BULK(bf, bf); else MOEGAN_LN_BULK(bf, float); }
+        else        { if (x_bf16) MOEGAN_LN_BULK(float, bf); else MOEGAN_LN_BULK(float, float); }
+#undef MOEGAN_LN_BULK
+#undef MOEGAN_LN_BULK3
+        MOEGAN_CHECK_LAUNCH("layernorm_bwd_bulk_kernel");
+        partial_sum_tall_kernel<<<ceil_div(2 * d, 32), 256, 0, st>>>(scratch, 2 * d, nb, dgamma_dbeta);
+        MOEGAN_CHECK_LAUNCH("partial_sum_tall_kernel");
+        return MOEGAN_OK;
+    }
 #define MOEGAN_LN_BWD2(TG, TI, NS, RR)                                                                                         \
     layernorm_bwd_kernel<TG, TI, NS, RR><<<blocks, 256, 0, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, mean, \
                                                                  rstd, rows, d, reinterpret_cast<TI*>(dx), scratch)

@@ -16,7 +16,7 @@ def _rel(a, b):
     return G_.rel_err(a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy())
 
 
-@pytest.mark.parametrize("rows,d", [(4099, 128), (1024, 256), (333, 512), (5, 1024), (70001, 128)])
+@pytest.mark.parametrize("rows,d", [(4099, 128), (1024, 256), (333, 512), (5, 1024), (70001, 128), (4100, 256), (16385, 256), (4097, 512), (9, 384)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layernorm_matches_torch(rows, d, dtype):
     glue = G_.pkg().glue
@@ -144,12 +144,13 @@ def test_modulated_transformation_module_matches_torch_ops(monkeypatch):
         assert _rel(p.grad, ref[n]) < 2e-4, n
 
 
-def test_layernorm_bf16_output_and_bf16_gradient():
+@pytest.mark.parametrize("rows", [2050, 8201])            # register-pipelined forward (< 4096 rows) and the bulk-copy ring
+def test_layernorm_bf16_output_and_bf16_gradient(rows):
     """norm1 / norm2 under autocast: bf16 in, bf16 out (= the rounding the consuming matmul applies), bf16 upstream gradient."""
     glue = G_.pkg().glue
     g = torch.Generator().manual_seed(7)
-    x = torch.randn(2050, 256, generator=g).bfloat16(); w = torch.rand(256, generator=g) + 0.5; b = torch.randn(256, generator=g) * 0.1
-    gy = torch.randn(2050, 256, generator=g).bfloat16()
+    x = torch.randn(rows, 256, generator=g).bfloat16(); w = torch.rand(256, generator=g) + 0.5; b = torch.randn(256, generator=g) * 0.1
+    gy = torch.randn(rows, 256, generator=g).bfloat16()
     xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
     yr = F.layer_norm(xr, (256,), wr, br, 1e-5); yr.backward(gy.double())
     xc = x.cuda().requires_grad_(True); wc = w.cuda().requires_grad_(True); bc = b.cuda().requires_grad_(True)
