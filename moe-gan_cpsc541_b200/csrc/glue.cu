@@ -506,33 +506,34 @@ colsum_rows_kernel(const T* __restrict__ x, long long rows, int cols, int nsplit
 // =====================================================================================================
 // channel_scale: out[b, p, c] = lrelu(x[b, p, c] * s[b, c], slope)      x: [B, P, C] (NHWC), s: [B, C] fp32
 // =====================================================================================================
-// forward: flat over groups of 8 channels, CS_U groups (256 apart) per thread, all loads issued before the first use
+// forward: grid.y = sample, flat over the sample's groups of 8 channels, CS_U groups (256 apart) per thread, all loads issued before
+// the first use.  Index arithmetic is 32-bit and per sample: the first version decoded (b, p, c) from a flat 64-bit index with two
+// 64-bit divisions per group - ~200 instructions next to two 16-byte loads.
 constexpr int CS_U = 2;
 template <typename T, typename TS>
 __global__ void __launch_bounds__(256)
-channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, long long n8, int P, int C, float slope, T* __restrict__ out) {
-    const int c8 = C / 8;
-    const long long i0 = (long long)blockIdx.x * (256 * CS_U) + threadIdx.x;
+channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, unsigned n8s /* P * C / 8 */, int C, float slope, T* __restrict__ out) {
+    const unsigned c8 = (unsigned)C / 8u;
+    const unsigned j0 = blockIdx.x * (256u * CS_U) + threadIdx.x;
+    const size_t base = (size_t)blockIdx.y * n8s;
+    const TS* sb = s + (size_t)blockIdx.y * C;
     float v[CS_U][8], sc[CS_U][8];
 #pragma unroll
     for (int u = 0; u < CS_U; ++u) {
-        const long long i = i0 + u * 256;
-        if (i < n8) {
-            const long long bp = i / c8;
-            const int c = (int)(i - bp * c8) * 8;
-            const long long b = bp / P;
-            Vec8<T>::load(x + i * 8, v[u]);
-            Vec8<TS>::load(s + b * C + c, sc[u]);
+        const unsigned j = j0 + u * 256u;
+        if (j < n8s) {
+            Vec8<T>::load(x + (base + j) * 8, v[u]);
+            Vec8<TS>::load(sb + (j % c8) * 8u, sc[u]);
         }
     }
 #pragma unroll
     for (int u = 0; u < CS_U; ++u) {
-        const long long i = i0 + u * 256;
-        if (i < n8) {
+        const unsigned j = j0 + u * 256u;
+        if (j < n8s) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float t = v[u][e] * sc[u][e]; o[e] = t > 0.f ? t : t * slope; }
-            Vec8<T>::store(out + i * 8, o);
+            Vec8<T>::store(out + (base + j) * 8, o);
         }
     }
 }
@@ -619,132 +620,233 @@ __device__ __forceinline__ Tap make_tap(float offx, float offy, int i, int j, in
     return t;
 }
 
-// forward: warp per output pixel, lanes over channels (4 per lane and 128-channel segment)
-template <typename T>
-__global__ void __launch_bounds__(256)
-offset_sample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ off, long long npix, int H, int W, int C, T* __restrict__ out) {
-    const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (p >= npix) return;
+// All three kernels were issue-bound in their first form (ncu, B = 256, 16 x 16, C = 128: 61 - 76 % issue-active at 1.3 - 2 TB/s): a
+// warp per pixel recomputed the taps in all 32 lanes (~300 warp instructions for 256 bytes of output) and moved 8 bytes per lane.
+// Now: CTA = a tile of OS_TP pixels of one sample (grid.y = sample); one THREAD per pixel computes the taps into shared memory, then
+// the CTA's threads walk (pixel, 8-channel group) items with 16-byte accesses, two items in flight.
+constexpr int OS_TP = 64;
+struct TapTile {
+    int4 idx[OS_TP];        // pixel index of the 4 taps inside the sample, -1 = outside
+    float4 w[OS_TP];        // bilinear weights
+    float4 f[OS_TP];        // wx, wy, sx, sy
+};
+__device__ __forceinline__ int tap_tile_fill(TapTile& tt, const float* __restrict__ off, int b, int p0, int H, int W) {
     const int HW = H * W;
-    const long long b = p / HW;
-    const int ij = (int)(p - b * HW);
-    const Tap t = make_tap(__ldg(off + p * 2), __ldg(off + p * 2 + 1), ij / W, ij % W, H, W);
-    const T* xb = x + (size_t)b * HW * C;
-    for (int c = lane * 4; c < C; c += 128) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int np = min(OS_TP, HW - p0);
+    if ((int)threadIdx.x < np) {
+        const int p = p0 + threadIdx.x;
+        const float2 o = __ldg(reinterpret_cast<const float2*>(off + ((size_t)b * HW + p) * 2));
+        const Tap t = make_tap(o.x, o.y, p / W, p % W, H, W);
+        tt.idx[threadIdx.x] = make_int4(t.idx[0], t.idx[1], t.idx[2], t.idx[3]);
+        tt.w[threadIdx.x] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+        tt.f[threadIdx.x] = make_float4(t.wx, t.wy, t.sx, t.sy);
+    }
+    __syncthreads();
+    return np;
+}
+template <typename T>
+__device__ __forceinline__ void load_taps(const T* __restrict__ xc, int C, const int4 id, float (&v)[4][8]) {
+    const int ids[4] = {id.x, id.y, id.z, id.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (t.idx[k] >= 0) {
-                const float4 v = Vec4<T>::load(xb + (size_t)t.idx[k] * C + c);
-                a.x = fmaf(t.w[k], v.x, a.x); a.y = fmaf(t.w[k], v.y, a.y); a.z = fmaf(t.w[k], v.z, a.z); a.w = fmaf(t.w[k], v.w, a.w);
+    for (int k = 0; k < 4; ++k) {
+        if (ids[k] >= 0) Vec8<T>::load(xc + (size_t)ids[k] * C, v[k]);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+        }
+    }
+}
+// forward: out[p, c] = sum_k w_k * x[tap_k, c]   (fma chain over the taps in order, as before).  U = items in flight per thread:
+// U = 2 needs 94 registers (2 CTAs per SM), U = 1 fits 4 CTAs per SM.
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U == 1 ? 4 : 2)
+offset_sample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ off, int H, int W, int C, T* __restrict__ out) {
+    __shared__ TapTile tt;
+    const int b = blockIdx.y, p0 = blockIdx.x * OS_TP, HW = H * W;
+    const int np = tap_tile_fill(tt, off, b, p0, H, W);
+    const unsigned c8 = (unsigned)C / 8u, n_items = (unsigned)np * c8;
+    const T* xb = x + (size_t)b * HW * C;
+    T* ob = out + ((size_t)b * HW + p0) * C;
+    for (unsigned it0 = threadIdx.x; it0 < n_items; it0 += 256 * U) {
+        float v[U][4][8];
+        unsigned pl[U], cg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned it = it0 + 256u * u;
+            if (it < n_items) {
+                pl[u] = it / c8; cg[u] = it - pl[u] * c8;
+                load_taps<T>(xb + cg[u] * 8, C, tt.idx[pl[u]], v[u]);
             }
-        Vec4<T>::store(out + (size_t)p * C + c, a);
-    }
-}
-// backward w.r.t. the offsets: warp per output pixel, reduction over channels
-template <typename T>
-__global__ void __launch_bounds__(256)
-offset_sample_bwd_off_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ off, long long npix, int H, int W, int C,
-                             float* __restrict__ doff) {
-    const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (p >= npix) return;
-    const int HW = H * W;
-    const long long b = p / HW;
-    const int ij = (int)(p - b * HW);
-    const Tap t = make_tap(__ldg(off + p * 2), __ldg(off + p * 2 + 1), ij / W, ij % W, H, W);
-    const T* xb = x + (size_t)b * HW * C;
-    float gix = 0.f, giy = 0.f;
-    for (int c = lane * 4; c < C; c += 128) {
-        const float4 gv = Vec4<T>::load(g + (size_t)p * C + c);
-        float4 v[4];
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = t.idx[k] >= 0 ? Vec4<T>::load(xb + (size_t)t.idx[k] * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float omy = 1.0f - t.wy, omx = 1.0f - t.wx;
-#define MOEGAN_TAPGRAD(f)                                                                                   \
-        gix += gv.f * ((v[1].f - v[0].f) * omy + (v[3].f - v[2].f) * t.wy);                               \
-        giy += gv.f * ((v[2].f - v[0].f) * omx + (v[3].f - v[1].f) * t.wx);
-        MOEGAN_TAPGRAD(x) MOEGAN_TAPGRAD(y) MOEGAN_TAPGRAD(z) MOEGAN_TAPGRAD(w)
-#undef MOEGAN_TAPGRAD
+        for (int u = 0; u < U; ++u) {
+            const unsigned it = it0 + 256u * u;
+            if (it < n_items) {
+                const float4 w = tt.w[pl[u]];
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(w.w, v[u][3][e], fmaf(w.z, v[u][2][e], fmaf(w.y, v[u][1][e], w.x * v[u][0][e])));
+                Vec8<T>::store(ob + (size_t)pl[u] * C + cg[u] * 8, o);
+            }
+        }
     }
-    gix = warp_sum(gix); giy = warp_sum(giy);
-    if (lane == 0) { doff[p * 2] = gix * t.sx; doff[p * 2 + 1] = giy * t.sy; }
 }
-// backward w.r.t. the input, as a deterministic GATHER.  CTA = one sample.  The scatter pattern (which output pixels touch
-// which input pixel, with which weight) is the same for every channel, so it is inverted once per sample in shared memory:
-//   1. every output pixel p computes its 4 taps;  2. per-input-pixel counts (integer atomics: order-free) and an exclusive scan;
-//   3. input pixel q scans the tap table in (p, tap) order and writes its contributor list -> fixed accumulation order;
-//   4. warp per input pixel, lanes over channels: dx[q, :] = sum_e w_e * g[p_e, :]  (coalesced row reads, no atomics).
+// backward w.r.t. the offsets: the 16 lanes that share a pixel (C / 8 is a multiple of 16) reduce their 8-channel partial sums with
+// shuffles, the C / 128 partials of a pixel are summed in order by the pixel's thread.
 template <typename T>
 __global__ void __launch_bounds__(256)
-offset_sample_bwd_in_kernel(const T* __restrict__ g, const float* __restrict__ off, int H, int W, int C, T* __restrict__ dx) {
-    extern __shared__ float smem[];
+offset_sample_bwd_off_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ off, int H, int W, int C,
+                             float* __restrict__ doff) {
+    __shared__ TapTile tt;
+    __shared__ float2 part[OS_TP][8];                    // [pixel][C / 128 <= 8]
+    const int b = blockIdx.y, p0 = blockIdx.x * OS_TP, HW = H * W;
+    const int np = tap_tile_fill(tt, off, b, p0, H, W);
+    const unsigned c8 = (unsigned)C / 8u, n_items = (unsigned)np * c8;       // a multiple of 16
+    const T* xb = x + (size_t)b * HW * C;
+    const T* gb = g + ((size_t)b * HW + p0) * C;
+    for (unsigned base = 0; base < n_items; base += 256) {                   // warp-uniform trip count (shuffles below)
+        const unsigned it = base + threadIdx.x;
+        const bool ok = it < n_items;
+        const unsigned pl = ok ? it / c8 : 0, cg = ok ? it - pl * c8 : 0;
+        float gix = 0.f, giy = 0.f;
+        if (ok) {
+            float gv[8], v[4][8];
+            Vec8<T>::load(gb + (size_t)pl * C + cg * 8, gv);
+            load_taps<T>(xb + cg * 8, C, tt.idx[pl], v);
+            const float4 f = tt.f[pl];
+            const float omx = 1.0f - f.x, omy = 1.0f - f.y;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                gix += gv[e] * ((v[1][e] - v[0][e]) * omy + (v[3][e] - v[2][e]) * f.y);
+                giy += gv[e] * ((v[2][e] - v[0][e]) * omx + (v[3][e] - v[1][e]) * f.x);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            gix += __shfl_xor_sync(0xffffffffu, gix, o);
+            giy += __shfl_xor_sync(0xffffffffu, giy, o);
+        }
+        if (ok && (threadIdx.x & 15) == 0) part[pl][cg >> 4] = make_float2(gix, giy);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < np) {
+        const int nparts = C / 128;
+        float gix = 0.f, giy = 0.f;
+        for (int j = 0; j < nparts; ++j) { gix += part[threadIdx.x][j].x; giy += part[threadIdx.x][j].y; }
+        const float4 f = tt.f[threadIdx.x];
+        *reinterpret_cast<float2*>(doff + ((size_t)b * HW + p0 + threadIdx.x) * 2) = make_float2(gix * f.z, giy * f.w);
+    }
+}
+// backward w.r.t. the input, as a deterministic GATHER.  The scatter pattern (which output pixels touch which input pixel, with
+// which weight) is the same for every channel, so it is inverted in shared memory.  A sample's input pixels are split over S CTAs
+// (slices of QS <= 64 pixels):
+//   1. every output pixel p of the sample computes its 4 taps (each CTA of the sample repeats this: one thread per pixel);
+//   2. thread (q, r) - input pixel q of the slice, quarter r of the output pixels - compares the taps of its <= 64 output pixels
+//      with q and keeps the matches as a 256-bit mask in registers; the per-(q, r) counts are scanned into list offsets;
+//   3. the same thread expands its mask into the contributor list of q, in (p, tap) order -> fixed accumulation order;
+//   4. (input pixel, 8-channel group) items: dx[q, c..c+7] = sum_e w_e * g[p_e, c..c+7]  (16-byte row reads, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(256)
+offset_sample_bwd_in_kernel(const T* __restrict__ g, const float* __restrict__ off, int H, int W, int C, int S, int QS, T* __restrict__ dx) {
+    extern __shared__ __align__(16) float smem[];
     const int HW = H * W;                                 // <= 256
     int* tidx = reinterpret_cast<int*>(smem);             // [HW][4]
     float* tw = smem + HW * 4;                            // [HW][4]
-    int* cnt = reinterpret_cast<int*>(smem + HW * 8);     // [HW]
-    int* start = cnt + HW;                                // [HW + 1] (+ padding to a multiple of 4 ints)
-    int* ent_p = start + ((HW + 1 + 3) & ~3);             // [4 * HW]
-    float* ent_w = reinterpret_cast<float*>(ent_p + 4 * HW);
-    const int b = blockIdx.x, tid = threadIdx.x;
+    int* ent_p = reinterpret_cast<int*>(smem + HW * 8);   // [4 * HW] (every tap of the sample may land in one slice)
+    float* ent_w = smem + HW * 12;                        // [4 * HW]
+    __shared__ int cnt[4][64];
+    __shared__ int start[65];
+    const int b = blockIdx.x / S, q0 = (blockIdx.x % S) * QS, tid = threadIdx.x;
+    const int nq = min(QS, HW - q0);                      // input pixels of this slice (<= 64)
     if (tid < HW) {
-        const Tap t = make_tap(__ldg(off + ((size_t)b * HW + tid) * 2), __ldg(off + ((size_t)b * HW + tid) * 2 + 1), tid / W, tid % W, H, W);
+        const float2 o = __ldg(reinterpret_cast<const float2*>(off + ((size_t)b * HW + tid) * 2));
+        const Tap t = make_tap(o.x, o.y, tid / W, tid % W, H, W);
+        *reinterpret_cast<int4*>(tidx + tid * 4) = make_int4(t.idx[0], t.idx[1], t.idx[2], t.idx[3]);
+        *reinterpret_cast<float4*>(tw + tid * 4) = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+    }
+    __syncthreads();
+    const int ql = tid & 63, r = tid >> 6;                // a warp has one r: the tap reads below are broadcasts
+    const int PR = (HW + 3) / 4;                          // output pixels per quarter (<= 64)
+    const int pr0 = r * PR;
+    const int me = ql < nq ? q0 + ql : -2;                // -2 matches nothing (-1 = outside tap)
+    unsigned m[8];                                        // 4 bits per output pixel of the quarter
+    int n = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { tidx[tid * 4 + k] = t.idx[k]; tw[tid * 4 + k] = t.w[k]; }
-        cnt[tid] = 0;
-    }
-    __syncthreads();
-    if (tid < HW) {
+    for (int wd = 0; wd < 8; ++wd) {
+        m[wd] = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const int q = tidx[tid * 4 + k]; if (q >= 0) atomicAdd(&cnt[q], 1); }
+        for (int j = 0; j < 8; ++j) {
+            const int pp = wd * 8 + j;
+            if (pp < PR && pr0 + pp < HW) {               // warp-uniform
+                const int4 id = *reinterpret_cast<const int4*>(tidx + (pr0 + pp) * 4);
+                const unsigned bits = (id.x == me ? 1u : 0u) | (id.y == me ? 2u : 0u) | (id.z == me ? 4u : 0u) | (id.w == me ? 8u : 0u);
+                m[wd] |= bits << (4 * j);
+            }
+        }
+        n += __popc(m[wd]);
+    }
+    cnt[r][ql] = n;
+    __syncthreads();
+    if (tid < 32) {                                       // exclusive scan of the 64 per-pixel totals by one warp
+        const int t0 = cnt[0][tid] + cnt[1][tid] + cnt[2][tid] + cnt[3][tid];
+        const int t1 = cnt[0][tid + 32] + cnt[1][tid + 32] + cnt[2][tid + 32] + cnt[3][tid + 32];
+        int i0 = t0, i1 = t1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a0 = __shfl_up_sync(0xffffffffu, i0, o), a1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (tid >= o) { i0 += a0; i1 += a1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        start[tid] = i0 - t0;
+        start[tid + 32] = tot0 + i1 - t1;
+        if (tid == 31) start[64] = tot0 + i1;
     }
     __syncthreads();
-    // exclusive scan of cnt (Hillis-Steele over 256 slots, in place in start[1..])
-    __shared__ int scan[256];
-    scan[tid] = tid < HW ? cnt[tid] : 0;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-        const int add = tid >= o ? scan[tid - o] : 0;
-        __syncthreads();
-        scan[tid] += add;
-        __syncthreads();
-    }
-    if (tid == 0) start[0] = 0;
-    if (tid < HW) start[tid + 1] = scan[tid];
-    __syncthreads();
-    if (tid < HW) {
-        int pos = start[tid];
-        for (int p = 0; p < HW; ++p) {
-            const int4 id = *reinterpret_cast<const int4*>(tidx + p * 4);     // broadcast read
-            if (id.x == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 0]; ++pos; }
-            if (id.y == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 1]; ++pos; }
-            if (id.z == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 2]; ++pos; }
-            if (id.w == tid) { ent_p[pos] = p; ent_w[pos] = tw[p * 4 + 3]; ++pos; }
+    {
+        int pos = start[ql];
+        for (int rr = 0; rr < r; ++rr) pos += cnt[rr][ql];
+#pragma unroll
+        for (int wd = 0; wd < 8; ++wd) {
+            unsigned w = m[wd];
+            while (w) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                const int key = (pr0 + wd * 8) * 4 + bit;         // = p * 4 + tap
+                ent_p[pos] = key >> 2;
+                ent_w[pos] = tw[key];
+                ++pos;
+            }
         }
     }
     __syncthreads();
-    const int wid = tid >> 5, lane = tid & 31;
+    const unsigned c8 = (unsigned)C / 8u, n_items = (unsigned)nq * c8;
     const T* gb = g + (size_t)b * HW * C;
-    T* db = dx + (size_t)b * HW * C;
-    for (int q = wid; q < HW; q += 8) {
+    T* db = dx + ((size_t)b * HW + q0) * C;
+    for (unsigned it = tid; it < n_items; it += 256) {
+        const unsigned q = it / c8, cg = it - q * c8;
         const int e0 = start[q], e1 = start[q + 1];
-        for (int c = lane * 4; c < C; c += 128) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            int e = e0;
-            for (; e + 1 < e1; e += 2) {                  // two rows in flight
-                const float4 v0 = Vec4<T>::load(gb + (size_t)ent_p[e] * C + c), v1 = Vec4<T>::load(gb + (size_t)ent_p[e + 1] * C + c);
-                const float w0 = ent_w[e], w1 = ent_w[e + 1];
-                a.x = fmaf(w0, v0.x, a.x); a.y = fmaf(w0, v0.y, a.y); a.z = fmaf(w0, v0.z, a.z); a.w = fmaf(w0, v0.w, a.w);
-                a.x = fmaf(w1, v1.x, a.x); a.y = fmaf(w1, v1.y, a.y); a.z = fmaf(w1, v1.z, a.z); a.w = fmaf(w1, v1.w, a.w);
-            }
-            if (e < e1) {
-                const float4 v0 = Vec4<T>::load(gb + (size_t)ent_p[e] * C + c);
-                const float w0 = ent_w[e];
-                a.x = fmaf(w0, v0.x, a.x); a.y = fmaf(w0, v0.y, a.y); a.z = fmaf(w0, v0.z, a.z); a.w = fmaf(w0, v0.w, a.w);
-            }
-            Vec4<T>::store(db + (size_t)q * C + c, a);
+        const T* gc = gb + cg * 8;
+        float a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.f;
+        int e = e0;
+        for (; e + 3 < e1; e += 4) {                      // four rows in flight; the accumulation order stays e0, e0 + 1, ...
+            float v[4][8], w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { Vec8<T>::load(gc + (size_t)ent_p[e + j] * C, v[j]); w[j] = ent_w[e + j]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[c] = fmaf(w[j], v[j][c], a[c]);
         }
+        for (; e < e1; ++e) {
+            float v[8];
+            Vec8<T>::load(gc + (size_t)ent_p[e] * C, v);
+            const float w = ent_w[e];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = fmaf(w, v[c], a[c]);
+        }
+        Vec8<T>::store(db + (size_t)q * C + cg * 8, a);
     }
 }
 
@@ -763,23 +865,23 @@ __device__ __forceinline__ void up2_src(int dst, int n_in, int& i0, int& i1, flo
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
-upsample2x_fwd_kernel(const T* __restrict__ x, long long n8, int H, int W, int C, T* __restrict__ out) {
-    const int c8 = C / 8, OW = 2 * W, OH = 2 * H;
-    const long long i0 = (long long)blockIdx.x * (256 * CS_U) + threadIdx.x;
+upsample2x_fwd_kernel(const T* __restrict__ x, unsigned n8s /* 4 * H * W * C / 8 */, int H, int W, int C, T* __restrict__ out) {
+    const unsigned c8 = (unsigned)C / 8u, OW = 2u * W;
+    const unsigned j0 = blockIdx.x * (256u * CS_U) + threadIdx.x;          // grid.y = sample; 32-bit index inside the sample
+    const T* xs = x + (size_t)blockIdx.y * H * W * C;
+    T* os = out + (size_t)blockIdx.y * n8s * 8;
     float v[CS_U][4][8], ly[CS_U], lx[CS_U];
 #pragma unroll
     for (int u = 0; u < CS_U; ++u) {
-        const long long i = i0 + u * 256;
-        if (i < n8) {
-            long long pix = i / c8;
-            const int c = (int)(i - pix * c8) * 8;
-            const int ox = (int)(pix % OW); pix /= OW;
-            const int oy = (int)(pix % OH);
-            const long long b = pix / OH;
+        const unsigned j = j0 + u * 256u;
+        if (j < n8s) {
+            const unsigned pix = j / c8;
+            const int c = (int)(j - pix * c8) * 8;
+            const int oy = (int)(pix / OW), ox = (int)(pix - (unsigned)oy * OW);
             int y0, y1, x0, x1;
             up2_src(oy, H, y0, y1, ly[u]);
             up2_src(ox, W, x0, x1, lx[u]);
-            const T* xb = x + (size_t)b * H * W * C + c;
+            const T* xb = xs + c;
             Vec8<T>::load(xb + ((size_t)y0 * W + x0) * C, v[u][0]);
             Vec8<T>::load(xb + ((size_t)y0 * W + x1) * C, v[u][1]);
             Vec8<T>::load(xb + ((size_t)y1 * W + x0) * C, v[u][2]);
@@ -788,13 +890,13 @@ upsample2x_fwd_kernel(const T* __restrict__ x, long long n8, int H, int W, int C
     }
 #pragma unroll
     for (int u = 0; u < CS_U; ++u) {
-        const long long i = i0 + u * 256;
-        if (i < n8) {
+        const unsigned j = j0 + u * 256u;
+        if (j < n8s) {
             const float h1 = ly[u], h0 = 1.f - h1, w1 = lx[u], w0 = 1.f - w1;
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = h0 * (w0 * v[u][0][e] + w1 * v[u][1][e]) + h1 * (w0 * v[u][2][e] + w1 * v[u][3][e]);
-            Vec8<T>::store(out + i * 8, o);
+            Vec8<T>::store(os + (size_t)j * 8, o);
         }
     }
 }
@@ -808,19 +910,18 @@ __device__ __forceinline__ void up2_adj(int i, int n_in, float (&w)[4]) {
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
-upsample2x_bwd_kernel(const T* __restrict__ g, long long n8, int H, int W, int C, T* __restrict__ dx) {
-    const int c8 = C / 8, OW = 2 * W;
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n8) return;
-    long long pix = i / c8;
-    const int c = (int)(i - pix * c8) * 8;
-    const int ix = (int)(pix % W); pix /= W;
-    const int iy = (int)(pix % H);
-    const long long b = pix / H;
+upsample2x_bwd_kernel(const T* __restrict__ g, unsigned n8s /* H * W * C / 8 */, int H, int W, int C, T* __restrict__ dx) {
+    const unsigned c8 = (unsigned)C / 8u;
+    const int OW = 2 * W;
+    const unsigned j = blockIdx.x * 256u + threadIdx.x;                   // grid.y = sample
+    if (j >= n8s) return;
+    const unsigned pix = j / c8;
+    const int c = (int)(j - pix * c8) * 8;
+    const int iy = (int)(pix / (unsigned)W), ix = (int)(pix - (unsigned)iy * (unsigned)W);
     float wy[4], wx[4];
     up2_adj(iy, H, wy);
     up2_adj(ix, W, wx);
-    const T* gb = g + (size_t)b * 4 * H * W * C + c;
+    const T* gb = g + (size_t)blockIdx.y * 4 * H * W * C + c;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -838,7 +939,7 @@ upsample2x_bwd_kernel(const T* __restrict__ g, long long n8, int H, int W, int C
                 for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[q][e], acc[e]);
             }
     }
-    Vec8<T>::store(dx + i * 8, acc);
+    Vec8<T>::store(dx + ((size_t)blockIdx.y * n8s + j) * 8, acc);
 }
 
 inline int grid_cap(long long blocks) {
@@ -961,11 +1062,12 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
 
 int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_CHANNEL_SCALE_FWD, (long long)B, P, C, (bf16 ? 1 : 0) | (s_bf16 ? 2 : 0));
-    const long long n8 = (long long)B * P * C / 8;
-    if (n8 == 0) return MOEGAN_OK;
-    const unsigned blocks = (unsigned)((n8 + 256 * CS_U - 1) / (256 * CS_U));
+    const long long n8s = (long long)P * C / 8;
+    if (n8s == 0 || B == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(n8s < (1ll << 31) && B <= 65535, MOEGAN_ERR_BAD_SHAPE, "channel_scale_fwd: P * C / 8 = %lld must be < 2^31 and B = %d <= 65535", n8s, B);
+    const dim3 grid((unsigned)((n8s + 256 * CS_U - 1) / (256 * CS_U)), (unsigned)B);
     typedef __nv_bfloat16 bf;
-#define MOEGAN_CS_FWD(T, TS) channel_scale_fwd_kernel<T, TS><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), n8, P, C, slope, reinterpret_cast<T*>(out))
+#define MOEGAN_CS_FWD(T, TS) channel_scale_fwd_kernel<T, TS><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const TS*>(s), (unsigned)n8s, C, slope, reinterpret_cast<T*>(out))
     if (bf16) { if (s_bf16) MOEGAN_CS_FWD(bf, bf); else MOEGAN_CS_FWD(bf, float); }
     else      { if (s_bf16) MOEGAN_CS_FWD(float, bf); else MOEGAN_CS_FWD(float, float); }
 #undef MOEGAN_CS_FWD
@@ -1031,32 +1133,40 @@ int launch_colsum(const void* x, int bf16, long long rows, int cols, float* out,
 
 int launch_upsample2x_fwd(const void* x, int bf16, int B, int H, int W, int C, void* out, cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_UPSAMPLE2X_FWD, (long long)B, H * W, C, bf16 ? 1 : 0);
-    const long long n8 = (long long)B * 4 * H * W * C / 8;
-    if (n8 == 0) return MOEGAN_OK;
-    const unsigned blocks = (unsigned)((n8 + 256 * CS_U - 1) / (256 * CS_U));
-    if (bf16) upsample2x_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n8, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
-    else      upsample2x_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), n8, H, W, C, reinterpret_cast<float*>(out));
+    const long long n8s = (long long)4 * H * W * C / 8;
+    if (n8s == 0 || B == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(n8s < (1ll << 31) && B <= 65535, MOEGAN_ERR_BAD_SHAPE, "upsample2x_fwd: 4 * H * W * C / 8 = %lld must be < 2^31 and B = %d <= 65535", n8s, B);
+    const dim3 grid((unsigned)((n8s + 256 * CS_U - 1) / (256 * CS_U)), (unsigned)B);
+    if (bf16) upsample2x_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), (unsigned)n8s, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+    else      upsample2x_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), (unsigned)n8s, H, W, C, reinterpret_cast<float*>(out));
     MOEGAN_CHECK_LAUNCH("upsample2x_fwd_kernel");
     return MOEGAN_OK;
 }
 int launch_upsample2x_bwd(const void* g, int bf16, int B, int H, int W, int C, void* dx, cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_UPSAMPLE2X_BWD, (long long)B, H * W, C, bf16 ? 1 : 0);
-    const long long n8 = (long long)B * H * W * C / 8;
-    if (n8 == 0) return MOEGAN_OK;
-    const unsigned blocks = (unsigned)((n8 + 255) / 256);
-    if (bf16) upsample2x_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), n8, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx));
-    else      upsample2x_bwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), n8, H, W, C, reinterpret_cast<float*>(dx));
+    const long long n8s = (long long)H * W * C / 8;
+    if (n8s == 0 || B == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(n8s < (1ll << 31) && B <= 65535, MOEGAN_ERR_BAD_SHAPE, "upsample2x_bwd: H * W * C / 8 = %lld must be < 2^31 and B = %d <= 65535", n8s, B);
+    const dim3 grid((unsigned)((n8s + 255) / 256), (unsigned)B);
+    if (bf16) upsample2x_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), (unsigned)n8s, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx));
+    else      upsample2x_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g), (unsigned)n8s, H, W, C, reinterpret_cast<float*>(dx));
     MOEGAN_CHECK_LAUNCH("upsample2x_bwd_kernel");
     return MOEGAN_OK;
 }
 
 int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, int H, int W, int C, void* out, cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_OFFSET_SAMPLE_FWD, (long long)B, H * W, C, bf16 ? 1 : 0);
-    const long long npix = (long long)B * H * W;
-    if (npix == 0) return MOEGAN_OK;
-    const int blocks = (int)((npix + 7) / 8);
-    if (bf16) offset_sample_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), off, npix, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
-    else      offset_sample_fwd_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), off, npix, H, W, C, reinterpret_cast<float*>(out));
+    if ((long long)B * H * W == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(B <= 65535, MOEGAN_ERR_BAD_SHAPE, "offset_sample: B = %d must be <= 65535", B);
+    const dim3 grid((unsigned)((H * W + OS_TP - 1) / OS_TP), (unsigned)B);
+    static const bool u2 = [] { const char* e = getenv("MOEGAN_OS_FWD_U"); return e != nullptr && e[0] == '2'; }();     // A/B switch (tools/glue_probe.py)
+    if (bf16) {
+        if (u2) offset_sample_fwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), off, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+        else    offset_sample_fwd_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), off, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+    } else {
+        if (u2) offset_sample_fwd_kernel<float, 2><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), off, H, W, C, reinterpret_cast<float*>(out));
+        else    offset_sample_fwd_kernel<float, 1><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), off, H, W, C, reinterpret_cast<float*>(out));
+    }
     MOEGAN_CHECK_LAUNCH("offset_sample_fwd_kernel");
     return MOEGAN_OK;
 }
@@ -1064,8 +1174,10 @@ int launch_offset_sample_fwd(const void* x, int bf16, const float* off, int B, i
 template <typename T>
 static int launch_bwd_in(const T* g, const float* off, int B, int H, int W, int C, T* dx, cudaStream_t st) {
     const int HW = H * W;
-    const size_t smem = (size_t)4 * (HW * 8 + HW + ((HW + 1 + 3) & ~3) + HW * 8);
-    offset_sample_bwd_in_kernel<T><<<B, 256, smem, st>>>(g, off, H, W, C, dx);
+    const int S = HW >= 128 ? 4 : (HW >= 32 ? 2 : 1);       // CTAs per sample; slices of QS <= 64 input pixels
+    const int QS = (HW + S - 1) / S;
+    const size_t smem = (size_t)4 * HW * 16;
+    offset_sample_bwd_in_kernel<T><<<B * S, 256, smem, st>>>(g, off, H, W, C, S, QS, dx);
     MOEGAN_CHECK_LAUNCH("offset_sample_bwd_in_kernel");
     return MOEGAN_OK;
 }
@@ -1073,15 +1185,15 @@ static int launch_bwd_in(const T* g, const float* off, int B, int H, int W, int 
 int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float* off, int B, int H, int W, int C, void* dx, float* doff,
                              cudaStream_t st) {
     ProfScope _ps(st, MOEGAN_PROF_OFFSET_SAMPLE_BWD, (long long)B, H * W, C, bf16 ? 1 : 0);
-    const long long npix = (long long)B * H * W;
-    if (npix == 0) return MOEGAN_OK;
-    const int blocks = (int)((npix + 7) / 8);
+    if ((long long)B * H * W == 0) return MOEGAN_OK;
+    MOEGAN_REQUIRE(B <= 65535 && C <= 1024, MOEGAN_ERR_BAD_SHAPE, "offset_sample_bwd: B = %d must be <= 65535 and C = %d <= 1024", B, C);
+    const dim3 grid((unsigned)((H * W + OS_TP - 1) / OS_TP), (unsigned)B);
     if (bf16) {
-        offset_sample_bwd_off_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), off, npix, H, W, C, doff);
+        offset_sample_bwd_off_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), off, H, W, C, doff);
         MOEGAN_CHECK_LAUNCH("offset_sample_bwd_off_kernel");
         return launch_bwd_in<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(g), off, B, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx), st);
     }
-    offset_sample_bwd_off_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), off, npix, H, W, C, doff);
+    offset_sample_bwd_off_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), off, H, W, C, doff);
     MOEGAN_CHECK_LAUNCH("offset_sample_bwd_off_kernel");
     return launch_bwd_in<float>(reinterpret_cast<const float*>(g), off, B, H, W, C, reinterpret_cast<float*>(dx), st);
 }

@@ -87,7 +87,8 @@ def test_channel_scale_nchw_input_and_small_channels():
 
 
 @pytest.mark.parametrize("B,C,H,W,scale", [(2, 128, 16, 16, 1.0), (3, 256, 8, 8, 10.0), (2, 512, 4, 4, 30.0), (4, 128, 16, 16, 60.0),
-                                           (2, 128, 4, 4, 0.0)])
+                                           (2, 128, 4, 4, 0.0), (2, 128, 5, 7, 8.0), (3, 384, 3, 3, 10.0), (2, 128, 16, 16, 400.0),
+                                           (2, 1024, 2, 2, 5.0), (130, 128, 16, 15, 3.0), (1, 256, 1, 1, 2.0)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_offset_sample_matches_grid_sample(B, C, H, W, scale, dtype):
     """scale stretches the raw offsets so that taps cross pixel borders (10), leave the image (zero padding) and hit the
