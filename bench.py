@@ -82,10 +82,29 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = self._handle(pynvml, index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
+
+    @staticmethod
+    def _handle(pynvml, index):
+        """NVML handle of CUDA device `index` of THIS process: NVML numbers the physical GPUs, CUDA numbers the ones CUDA_VISIBLE_DEVICES
+        leaves visible - look the device up by UUID (else through CUDA_VISIBLE_DEVICES, else by the same index)."""
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if ids and ids[index].isdigit():
+                return pynvml.nvmlDeviceGetHandleByIndex(int(ids[index]))
+        except Exception:
+            pass
+        return pynvml.nvmlDeviceGetHandleByIndex(index)
 
     def _run(self):
         while not self._stop.is_set():
@@ -700,7 +719,8 @@ def bench_train_step(args, T_, rank, world, dev, steps, warmup, use_graph):
     bucket_mb = float(os.environ.get("MOEGAN_BENCH_BUCKET_MB", "25"))
 
     def make_trainer(graph):
-        return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph, bucket_bytes=int(bucket_mb * (1 << 20)))
+        return pkg.MoEGANTrainer(G, D, amp_dtype=torch.bfloat16, use_cuda_graph=graph, bucket_bytes=int(bucket_mb * (1 << 20)),
+                                 exact_dp_balance=os.environ.get("MOEGAN_BENCH_LOCAL_BALANCE", "0") != "1")     # profiling switch only
 
     launch_mode = "eager"
     trainer = make_trainer(False)

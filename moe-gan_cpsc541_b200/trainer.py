@@ -58,7 +58,9 @@ class GradReducer:
             comm_priority = int(os.environ["MOEGAN_DP_COMM_PRIORITY"])
         self.comm_priority = comm_priority
         self.defer = mode == "single"          # launch nothing from the hooks: finish() packs and reduces everything at once
-        self.skip_collective = False
+        # profiling only (tools/dp_diag3.sh): pack the buckets but launch no collective - the result is NOT a data-parallel step
+        self.skip_collective = os.environ.get("MOEGAN_DP_SKIP_COLLECTIVE", "0") == "1"
+        self._comm_used = False
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -156,6 +158,7 @@ class GradReducer:
         if self.skip_collective:
             return
         if self.comm_stream is not None:
+            self._comm_used = True
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 if rec is not None:
@@ -178,8 +181,9 @@ class GradReducer:
         for bi in range(len(self.buckets)):
             if not self.launched[bi]:
                 self._launch(bi)          # parameters that received no gradient this step
-        if self.comm_stream is not None:
+        if self.comm_stream is not None and self._comm_used:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._comm_used = False
         for bi, b in enumerate(self.buckets):
             views = self._flat(bi).split([p.numel() for p in b])
             for p, v in zip(b, views):
