@@ -419,7 +419,7 @@ PROF_NAMES = {1: "sample_kl(+kl_finalize)", 2: "text_fwd", 3: "router_fwd", 4: "
               8: "combine_fwd", 9: "combine_bwd", 10: "slab_sum", 11: "uncombine", 12: "router_bwd_logits(+dtl)", 13: "router_bwd_small",
               14: "router_bwd_text", 15: "reparam_kl_bwd", 16: "sum_partials", 17: "colsum_grouped", 18: "balance_loss",
               20: "layernorm_fwd", 21: "layernorm_bwd", 22: "channel_scale_fwd", 23: "channel_scale_bwd", 24: "offset_sample_fwd",
-              25: "offset_sample_bwd", 26: "colsum", 27: "upsample2x_fwd", 28: "upsample2x_bwd"}
+              25: "offset_sample_bwd", 26: "colsum", 27: "upsample2x_fwd", 28: "upsample2x_bwd", 29: "demod_coef_fwd", 30: "demod_coef_bwd"}
 GEMM_KINDS = {0: "rows x W^T (K-major B)", 1: "rows x W (MN-major B)", 2: "wgrad A^T B"}
 GEMM_EPI = {0: "f32", 1: "bf16", 2: "bias+bf16", 3: "bias+f32", 4: "bias+GELU", 5: "bias+GELU fp32x3", 6: "xGELU'", 7: "xGELU' fp32x3"}
 NOMINAL_HBM_GBS = 8000.0     # the figure north_star quotes
@@ -471,6 +471,9 @@ def kernel_model(tag, meta, Dt=512):
         if kid == 25: return name, f"B={a} P={b} C={c}", float(a * b * c * 3 * sz(1) + 2 * a * b * 8), None, "hbm"
         if kid == 26: return name, f"rows={a} cols={b}", float(a * b * sz(1)), None, "hbm"
         if kid in (27, 28): return name, f"B={a} P={b} C={c}", float(5 * a * b * c * sz(1)), None, "hbm"
+        if kid in (29, 30):                                      # a = B, b = Cin, c = Cout, taps in bits 8..: weights (+ dw) dominate
+            taps = bits >> 8
+            return name, f"B={a} Cin={b} Cout={c} taps={taps}", float(b * c * taps * 4 * (1 if kid == 29 else 2) + b * c * 4 * 2 + a * (b + c) * 4), None, "latency"
         if kid == 6:  return name, f"rows={a} cols={b}", float(a * b * (4 + (4 if bits & 0x400 else 2))), None, "hbm"
         if kid == 10: return name, f"m_cap={a} cols={b}", float(a // 32 * b * 4 + c * b * 4), None, "hbm"
         if kid == 16: return name, f"n={a} splits={b}", float(a * (b + 1) * 4), None, "hbm"

@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define MOEGAN_ABI_VERSION 5
+#define MOEGAN_ABI_VERSION 6
 #define MOEGAN_ROUTER_HID 128 /* t2i_moe_gan.py:279,286 */
 #define MOEGAN_MAX_EXPERTS 32
 #define MOEGAN_MAX_TOPK 8     /* sparse (non-dense) mode */
@@ -309,6 +309,20 @@ int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, cons
 int moegan_upsample2x_fwd(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* out, void* stream);
 int moegan_upsample2x_bwd(const void* g, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* dx, void* stream);
 
+/* replaces: the demodulation coefficients of ModulatedConv.forward (t2i_moe_gan.py:165-170), in the "scale the activations" form the
+ * host model uses (the reference scales a per-sample copy of the weight and normalises it; this is the same factor per (sample, output
+ * channel)):   wsq[o,i] = sum_{ky,kx} w[o,i,ky,kx]^2,   d[b,o] = rsqrt( sum_i s[b,i]^2 * wsq[o,i] + eps ).
+ * s [B,Cin] fp32 or bf16 (the modulation Linear's output); w fp32 [Cout,Cin,KH,KW] with ELEMENT strides w_so / w_si / w_sh / w_sw
+ * (contiguous or channels-last); wsq [Cout,Cin] and d [B,Cout] fp32 outputs (wsq is kept for the backward); compute_wsq = 0: wsq is an
+ * INPUT (the caller computed it for the same weights earlier - the generator runs twice per train step between optimizer steps).
+ * Backward: dd [B,Cout] fp32 -> ds [B,Cin] in s's dtype and dw fp32 in w's strides (every element written).  Deterministic. */
+int moegan_demod_coef_fwd(const void* s, int32_t s_is_bf16, const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw,
+                          int32_t B, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, float eps, int32_t compute_wsq, float* wsq, float* d,
+                          void* stream);
+int moegan_demod_coef_bwd(const float* dd, const float* d, const void* s, int32_t s_is_bf16, const float* w, int64_t w_so, int64_t w_si,
+                          int64_t w_sh, int64_t w_sw, const float* wsq, int32_t B, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW,
+                          void* ds, float* dw, void* stream);
+
 /* ---- test / bench hook ---------------------------------------------------------------------- */
 /* Plain (ungrouped) GEMM on the same tcgen05 kernel, fp32 out:  C[M,N] = op(A) * op(B).
  * kind 0: A [M,S*K] K-major, B [N,S*K] K-major.   kind 1: A [M,S*K] K-major, B [K,S*N] (N contiguous).
@@ -338,7 +352,7 @@ enum {
     MOEGAN_PROF_BALANCE = 18,
     MOEGAN_PROF_LAYERNORM_FWD = 20, MOEGAN_PROF_LAYERNORM_BWD = 21, MOEGAN_PROF_CHANNEL_SCALE_FWD = 22, MOEGAN_PROF_CHANNEL_SCALE_BWD = 23,
     MOEGAN_PROF_OFFSET_SAMPLE_FWD = 24, MOEGAN_PROF_OFFSET_SAMPLE_BWD = 25, MOEGAN_PROF_COLSUM = 26,
-    MOEGAN_PROF_UPSAMPLE2X_FWD = 27, MOEGAN_PROF_UPSAMPLE2X_BWD = 28
+    MOEGAN_PROF_UPSAMPLE2X_FWD = 27, MOEGAN_PROF_UPSAMPLE2X_BWD = 28, MOEGAN_PROF_DEMOD_COEF_FWD = 29, MOEGAN_PROF_DEMOD_COEF_BWD = 30
 };
 int moegan_debug_profile_enable(int32_t level);
 int moegan_debug_profile_read(float* ms_out, int32_t* tag_out, int32_t max_n);

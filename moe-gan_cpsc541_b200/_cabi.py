@@ -17,7 +17,7 @@ MAX_EXPERTS = 32
 MAX_TOPK = 8
 CHUNK = 32
 KL_OUT_FLOATS = 2 + 256
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Shape(ctypes.Structure):
@@ -96,6 +96,8 @@ SIGNATURES = {
     "moegan_channel_scale_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),
     "moegan_colsum_scratch_bytes": (c_int64, [c_int64, c_int32]),
     "moegan_colsum": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, c_int64, _P]),
+    "moegan_demod_coef_fwd": (c_int32, [_P, c_int32, _P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P, _P, _P]),
+    "moegan_demod_coef_bwd": (c_int32, [_P, _P, _P, c_int32, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "moegan_offset_sample_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "moegan_offset_sample_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "moegan_upsample2x_fwd": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),

@@ -983,6 +983,24 @@ int moegan_offset_sample_bwd(const void* g, const void* x, int32_t is_bf16, cons
     return launch_offset_sample_bwd(g, x, is_bf16, off, B, H, W, C, dx, doff, (cudaStream_t)stream);
 }
 
+int moegan_demod_coef_fwd(const void* sv, int32_t s_is_bf16, const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t B,
+                          int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, float eps, int32_t compute_wsq, float* wsq, float* d, void* stream) {
+    MOEGAN_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1 && KH >= 1 && KW >= 1 && (int64_t)Cin * Cout < (1ll << 31), MOEGAN_ERR_BAD_SHAPE,
+                   "demod_coef_fwd: bad shape B %d Cin %d Cout %d kernel %d x %d", B, Cin, Cout, KH, KW);
+    REQ_PTR(w); REQ_PTR(wsq);
+    if (B > 0) { REQ_PTR(sv); REQ_PTR(d); }
+    return launch_demod_coef_fwd(sv, s_is_bf16, w, w_so, w_si, w_sh, w_sw, B, Cin, Cout, KH, KW, eps, compute_wsq, wsq, d, (cudaStream_t)stream);
+}
+int moegan_demod_coef_bwd(const float* dd, const float* d, const void* sv, int32_t s_is_bf16, const float* w, int64_t w_so, int64_t w_si,
+                          int64_t w_sh, int64_t w_sw, const float* wsq, int32_t B, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, void* ds,
+                          float* dw, void* stream) {
+    MOEGAN_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1 && KH >= 1 && KW >= 1 && (int64_t)Cin * Cout < (1ll << 31), MOEGAN_ERR_BAD_SHAPE,
+                   "demod_coef_bwd: bad shape B %d Cin %d Cout %d kernel %d x %d", B, Cin, Cout, KH, KW);
+    REQ_PTR(w); REQ_PTR(wsq); REQ_PTR(dw);
+    if (B > 0) { REQ_PTR(dd); REQ_PTR(d); REQ_PTR(sv); REQ_PTR(ds); }
+    return launch_demod_coef_bwd(dd, d, sv, s_is_bf16, w, w_so, w_si, w_sh, w_sw, wsq, B, Cin, Cout, KH, KW, ds, dw, (cudaStream_t)stream);
+}
+
 int moegan_upsample2x_fwd(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
     MOEGAN_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, MOEGAN_ERR_BAD_SHAPE,
                    "upsample2x: B (%d) >= 0, H x W (%d x %d) >= 1, C (%d) a positive multiple of 8", B, H, W, C);

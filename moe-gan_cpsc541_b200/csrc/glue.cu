@@ -591,6 +591,124 @@ channel_scale_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const
 }
 
 // =====================================================================================================
+// demod_coef: the demodulation coefficients of ModulatedConv (t2i_moe_gan.py:165-170) in "scale the activations" form,
+//     wsq[o, i] = sum_taps w[o, i, ky, kx]^2        d[b, o] = rsqrt( sum_i s[b, i]^2 * wsq[o, i] + eps )
+// In torch ops this is ~7 launches forward (float, pow, sum, pow, an fp32 SIMT sgemm, add, rsqrt) and ~12 backward per layer - 32 + 16
+// times per train step, ~1.5 ms of 3 us kernels.  Here: one pass over the weights + one small tiled fp32 GEMM forward; two GEMMs
+// backward whose epilogues write ds (in s's dtype) and dw (in the weight's own strides, contiguous or channels-last).
+//     t[b, o]  = -0.5 * dd[b, o] * d[b, o]^3
+//     ds[b, i] = 2 s[b, i] * sum_o t[b, o] wsq[o, i]        dw[o, i, tap] = 2 w[o, i, tap] * sum_b t[b, o] s[b, i]^2
+// =====================================================================================================
+struct DemodArgs {
+    const void* s; int s_bf16;                 // [B, Cin]
+    const float* w; long long so, si, sh, sw;  // [Cout, Cin, KH, KW] with element strides
+    const float* wsq;                          // [Cout, Cin]
+    const float* d; const float* dd;           // [B, Cout]
+    float* d_out; void* ds; float* dw;
+    int B, Cin, Cout, KH, KW; float eps;
+};
+__device__ __forceinline__ float demod_s(const DemodArgs& a, int b, int i) {
+    return a.s_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.s)[(size_t)b * a.Cin + i])
+                    : __ldg(reinterpret_cast<const float*>(a.s) + (size_t)b * a.Cin + i);
+}
+__global__ void __launch_bounds__(256)
+demod_wsq_kernel(const float* __restrict__ w, long long so, long long si, long long sh, long long sw, int Cout, int Cin, int KH, int KW,
+                 float* __restrict__ wsq) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Cout * Cin) return;
+    const int o = idx / Cin, i = idx - o * Cin;
+    const float* p = w + o * so + i * si;
+    float acc = 0.f;
+    for (int ky = 0; ky < KH; ++ky)
+        for (int kx = 0; kx < KW; ++kx) { const float v = __ldg(p + ky * sh + kx * sw); acc = fmaf(v, v, acc); }
+    wsq[idx] = acc;
+}
+// C[M, N] = A[M, K] * B[K, N], 32 x 32 tiles, K in chunks of 64, 256 threads (4 rows x 1 column each), fp32 FMA in k order.  The
+// operands are a few hundred KB (L2-resident) and the grid is 64 - 256 CTAs, so what matters is latency: the next chunk's 16 operand
+// values per thread are fetched into registers before the current chunk is multiplied.
+//   MODE 0 (forward):  M = B,    N = Cout, K = Cin:  A = s^2, B = wsq^T      -> d  = rsqrt(C + eps)
+//   MODE 1 (ds):       M = B,    N = Cin,  K = Cout: A = t,   B = wsq        -> ds = 2 s C
+//   MODE 2 (dw):       M = Cout, N = Cin,  K = B:    A = t^T, B = s^2        -> dw = 2 w C   (all taps)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+demod_gemm_kernel(const DemodArgs a) {
+    constexpr int BK = 64, LDK = BK + 4;        // row stride 68 floats: 16-byte aligned rows, a quarter-warp's LDS.128 hits 32 distinct banks
+    __shared__ __align__(16) float As[32][LDK], Bs[32][LDK];      // both [row][k]: the inner loop reads 4 k values per LDS.128
+    const int M = MODE == 2 ? a.Cout : a.B, N = MODE == 0 ? a.Cout : a.Cin, K = MODE == 0 ? a.Cin : (MODE == 1 ? a.Cout : a.B);
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    auto tval = [&](int b, int o) { const float dv = __ldg(a.d + (size_t)b * a.Cout + o); return -0.5f * __ldg(a.dd + (size_t)b * a.Cout + o) * dv * dv * dv; };
+    // element j (of 8) of this thread in the A / B tile of the chunk at k0: value + where it goes in shared memory
+    auto fetchA = [&](int j, int k0) -> float {
+        const int e = threadIdx.x + 256 * j;
+        if (MODE == 2) { const int m = m0 + (e & 31), k = k0 + (e >> 5); return (m < M && k < K) ? tval(k, m) : 0.f; }     // t[b, o]: o fastest
+        const int m = m0 + (e >> 6), k = k0 + (e & 63);
+        if (!(m < M && k < K)) return 0.f;
+        if (MODE == 0) { const float v = demod_s(a, m, k); return v * v; }                                                  // s^2: i fastest
+        return tval(m, k);                                                                                                  // t[b, o]: o fastest
+    };
+    auto storeA = [&](int j, float v) {
+        const int e = threadIdx.x + 256 * j;
+        if (MODE == 2) As[e & 31][e >> 5] = v; else As[e >> 6][e & 63] = v;
+    };
+    auto fetchB = [&](int j, int k0) -> float {
+        const int e = threadIdx.x + 256 * j;
+        if (MODE == 0) { const int n = n0 + (e >> 6), k = k0 + (e & 63); return (n < N && k < K) ? __ldg(a.wsq + (size_t)n * a.Cin + k) : 0.f; }   // wsq[o, i]: i fastest
+        const int n = n0 + (e & 31), k = k0 + (e >> 5);
+        if (!(n < N && k < K)) return 0.f;
+        if (MODE == 1) return __ldg(a.wsq + (size_t)k * a.Cin + n);                                                         // wsq[o, i]: i fastest
+        const float v = demod_s(a, k, n); return v * v;                                                                     // s^2: i fastest
+    };
+    auto storeB = [&](int j, float v) {
+        const int e = threadIdx.x + 256 * j;
+        if (MODE == 0) Bs[e >> 6][e & 63] = v; else Bs[e & 31][e >> 5] = v;
+    };
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float ra[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ra[j] = fetchA(j, 0); rb[j] = fetchB(j, 0); }
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { storeA(j, ra[j]); storeB(j, rb[j]); }
+        __syncthreads();
+        if (k0 + BK < K) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ra[j] = fetchA(j, k0 + BK); rb[j] = fetchB(j, k0 + BK); }
+        }
+        // one shared-memory load per FMA (the first version) made this loop LSU-bound; 5 LDS.128 now feed 16 FMAs
+#pragma unroll 4
+        for (int kk = 0; kk < BK; kk += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[tx][kk]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[ty + 8 * j][kk]);      // same address in the whole warp: broadcast
+                acc[j] = fmaf(a4.w, b4.w, fmaf(a4.z, b4.z, fmaf(a4.y, b4.y, fmaf(a4.x, b4.x, acc[j]))));
+            }
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx;
+    if (n >= N) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int m = m0 + ty + 8 * j;
+        if (m >= M) continue;
+        if (MODE == 0) {
+            a.d_out[(size_t)m * a.Cout + n] = rsqrtf(acc[j] + a.eps);
+        } else if (MODE == 1) {
+            const float v = 2.0f * demod_s(a, m, n) * acc[j];
+            if (a.s_bf16) reinterpret_cast<__nv_bfloat16*>(a.ds)[(size_t)m * a.Cin + n] = __float2bfloat16_rn(v);
+            else          reinterpret_cast<float*>(a.ds)[(size_t)m * a.Cin + n] = v;
+        } else {
+            const float v = 2.0f * acc[j];
+            const long long base = m * a.so + n * a.si;
+            for (int ky = 0; ky < a.KH; ++ky)
+                for (int kx = 0; kx < a.KW; ++kx) { const long long off = base + ky * a.sh + kx * a.sw; a.dw[off] = v * __ldg(a.w + off); }
+        }
+    }
+}
+
+// =====================================================================================================
 // offset_sample (NHWC): out[b, i, j, :] = bilinear(x[b], grid(b, i, j)),  grid = clamp(base + 0.05 * off, -1, 1)
 // =====================================================================================================
 struct Tap {            // the 4 bilinear taps of one output pixel
@@ -1196,6 +1314,40 @@ int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float
     offset_sample_bwd_off_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g), reinterpret_cast<const float*>(x), off, H, W, C, doff);
     MOEGAN_CHECK_LAUNCH("offset_sample_bwd_off_kernel");
     return launch_bwd_in<float>(reinterpret_cast<const float*>(g), off, B, H, W, C, reinterpret_cast<float*>(dx), st);
+}
+
+int launch_demod_coef_fwd(const void* sv, int s_bf16, const float* w, long long so, long long si, long long sh, long long sw, int B, int Cin,
+                          int Cout, int KH, int KW, float eps, int compute_wsq, float* wsq, float* d, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_DEMOD_COEF_FWD, (long long)B, Cin, Cout, (s_bf16 ? 1 : 0) | (compute_wsq ? 2 : 0) | (KH * KW) << 8);
+    if ((long long)Cout * Cin == 0) return MOEGAN_OK;
+    if (compute_wsq) {
+        demod_wsq_kernel<<<ceil_div(Cout * Cin, 256), 256, 0, st>>>(w, so, si, sh, sw, Cout, Cin, KH, KW, wsq);
+        MOEGAN_CHECK_LAUNCH("demod_wsq_kernel");
+    }
+    if (B == 0) return MOEGAN_OK;
+    DemodArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = sv; a.s_bf16 = s_bf16; a.w = w; a.so = so; a.si = si; a.sh = sh; a.sw = sw; a.wsq = wsq; a.d_out = d;
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.eps = eps;
+    demod_gemm_kernel<0><<<dim3(ceil_div(Cout, 32), ceil_div(B, 32)), 256, 0, st>>>(a);
+    MOEGAN_CHECK_LAUNCH("demod_gemm_kernel<fwd>");
+    return MOEGAN_OK;
+}
+int launch_demod_coef_bwd(const float* dd, const float* d, const void* sv, int s_bf16, const float* w, long long so, long long si, long long sh,
+                          long long sw, const float* wsq, int B, int Cin, int Cout, int KH, int KW, void* ds, float* dw, cudaStream_t st) {
+    ProfScope _ps(st, MOEGAN_PROF_DEMOD_COEF_BWD, (long long)B, Cin, Cout, (s_bf16 ? 1 : 0) | (KH * KW) << 8);
+    if ((long long)Cout * Cin == 0) return MOEGAN_OK;
+    DemodArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = sv; a.s_bf16 = s_bf16; a.w = w; a.so = so; a.si = si; a.sh = sh; a.sw = sw; a.wsq = wsq; a.d = d; a.dd = dd; a.ds = ds; a.dw = dw;
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW;
+    if (B > 0) {
+        demod_gemm_kernel<1><<<dim3(ceil_div(Cin, 32), ceil_div(B, 32)), 256, 0, st>>>(a);
+        MOEGAN_CHECK_LAUNCH("demod_gemm_kernel<ds>");
+    }
+    demod_gemm_kernel<2><<<dim3(ceil_div(Cin, 32), ceil_div(Cout, 32)), 256, 0, st>>>(a);     // B == 0: K loop empty, dw = 0
+    MOEGAN_CHECK_LAUNCH("demod_gemm_kernel<dw>");
+    return MOEGAN_OK;
 }
 
 }  // namespace moegan

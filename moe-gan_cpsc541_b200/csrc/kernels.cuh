@@ -75,6 +75,11 @@ int launch_offset_sample_bwd(const void* g, const void* x, int bf16, const float
 int launch_upsample2x_fwd(const void* x, int bf16, int B, int H, int W, int C, void* out, cudaStream_t st);
 int launch_upsample2x_bwd(const void* g, int bf16, int B, int H, int W, int C, void* dx, cudaStream_t st);
 
+int launch_demod_coef_fwd(const void* s, int s_bf16, const float* w, long long so, long long si, long long sh, long long sw, int B, int Cin,
+                          int Cout, int KH, int KW, float eps, int compute_wsq, float* wsq, float* d, cudaStream_t st);
+int launch_demod_coef_bwd(const float* dd, const float* d, const void* s, int s_bf16, const float* w, long long so, long long si, long long sh,
+                          long long sw, const float* wsq, int B, int Cin, int Cout, int KH, int KW, void* ds, float* dw, cudaStream_t st);
+
 int launch_sum_partials(const float* part, long long n, int nsplit, float* out, cudaStream_t st);
 
 }  // namespace moegan

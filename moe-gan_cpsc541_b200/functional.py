@@ -87,6 +87,10 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 _WEIGHT_GENERATION = 0
 
 
+def weight_generation() -> int:
+    return _WEIGHT_GENERATION
+
+
 def bump_weight_generation() -> None:
     """Invalidate every WeightCache.  Call after anything that changes expert weights WITHOUT bumping `Parameter._version` -
     i.e. a CUDA-graph replay whose captured optimizer step writes the parameters from inside the graph (MoEGANTrainer.step does)."""

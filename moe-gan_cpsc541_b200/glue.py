@@ -150,6 +150,85 @@ def channel_scale(x: torch.Tensor, s: torch.Tensor, slope: float = 1.0) -> torch
 
 
 # --------------------------------------------------------------------------------------------------
+# demodulation coefficients of ModulatedConv (t2i_moe_gan.py:165-170)
+# --------------------------------------------------------------------------------------------------
+class _DemodCoefFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, weight, eps, cache):
+        B, Cin = s.shape
+        Cout, _, KH, KW = weight.shape
+        sc = s.detach()
+        sc = (sc if sc.dtype in (torch.float32, torch.bfloat16) else sc.float()).contiguous()
+        w = weight.detach()
+        so, si, sh, sw = w.stride()
+        # wsq depends on the weights only: the generator runs twice per train step between optimizer steps (the D-step's no_grad pass and
+        # the G-step), the second pass reuses the first one's.  Key as for the expert-weight cache (functional.WeightCache): storage,
+        # autograd version, and the generation counter the trainer bumps after every CUDA-graph replay.
+        # While a CUDA graph is being captured only entries made inside the SAME capture are served (a replay must recompute from the
+        # then-current weights; an eager entry would be baked into the graph as a stale pointer), and capture entries are never served
+        # to eager calls.
+        wsq, compute = None, 1
+        if cache is not None:
+            from .functional import weight_generation
+            capturing = torch.cuda.is_current_stream_capturing()
+            cid = int(C.lib().moegan_stream_capture_id(C.c_void_p(torch.cuda.current_stream().cuda_stream))) if capturing else 0
+            slot = "capture" if capturing else "eager"
+            key = (cid, w.data_ptr(), weight._version, weight_generation(), tuple(w.shape), tuple(w.stride()))
+            entry = cache.get(slot)
+            if entry is not None and entry[0] == key and (not capturing or cid > 0):
+                wsq, compute = entry[1], 0
+        if wsq is None:
+            wsq = torch.empty((Cout, Cin), device=w.device, dtype=torch.float32)
+        d = torch.empty((B, Cout), device=w.device, dtype=torch.float32)
+        C.check(C.lib().moegan_demod_coef_fwd(C.ptr(sc), _is_bf16(sc), C.ptr(w), so, si, sh, sw, B, Cin, Cout, KH, KW, float(eps), compute,
+                                              C.ptr(wsq), C.ptr(d), _stream()), "moegan_demod_coef_fwd")
+        if cache is not None and compute:
+            cache[slot] = (key, wsq)
+        ctx.save_for_backward(sc, w, wsq, d)
+        ctx.s_dtype = s.dtype
+        return d
+
+    @staticmethod
+    def backward(ctx, dd):
+        sc, w, wsq, d = ctx.saved_tensors
+        B, Cin = sc.shape
+        Cout, _, KH, KW = w.shape
+        so, si, sh, sw = w.stride()
+        ddc = dd.float().contiguous()
+        ds = torch.empty_like(sc)
+        dw = torch.empty_like(w)                      # same strides as the weight (contiguous or channels-last); every element is written
+        C.check(C.lib().moegan_demod_coef_bwd(C.ptr(ddc), C.ptr(d), C.ptr(sc), _is_bf16(sc), C.ptr(w), so, si, sh, sw, C.ptr(wsq), B, Cin, Cout,
+                                              KH, KW, C.ptr(ds), C.ptr(dw), _stream()), "moegan_demod_coef_bwd")
+        return ds.to(ctx.s_dtype), dw, None, None
+
+
+_TORCH_DEMOD = __import__("os").environ.get("MOEGAN_TORCH_DEMOD", "0") == "1"
+
+
+def demod_coef_reference(s: torch.Tensor, weight: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """The definition in torch ops (fp32): d[b,o] = rsqrt(sum_i s[b,i]^2 * sum_taps w[o,i]^2 + eps)."""
+    wsq = weight.float().pow(2).sum(dim=(2, 3))
+    with torch.autocast(s.device.type, enabled=False):
+        return torch.rsqrt(s.float().pow(2) @ wsq.t() + eps)
+
+
+def demod_coef(s: torch.Tensor, weight: torch.Tensor, eps: float = 1e-8, cache: dict = None) -> torch.Tensor:
+    """Demodulation coefficients [B, Cout] (fp32) of a ModulatedConv with modulation s [B, Cin] and weight [Cout, Cin, KH, KW]: what the
+    reference computes as `rsqrt(sum((weight * s)^2) + 1e-8)` per sample and output channel (t2i_moe_gan.py:165-170).  `cache`: a dict
+    owned by the calling module in which the weight-only factor sum_taps(w^2) is kept between calls with unchanged weights."""
+    if _TORCH_DEMOD:                     # A/B switch for bench runs: the torch-op definition instead of the kernels
+        return demod_coef_reference(s, weight, eps)
+    if s.is_cuda and weight.is_cuda and weight.dtype == torch.float32 and weight.dim() == 4 and s.dim() == 2:
+        dense = weight.is_contiguous() or weight.is_contiguous(memory_format=torch.channels_last)
+        if dense:
+            return _DemodCoefFn.apply(s, weight, eps, cache)
+        _torch_path("demod_coef", f"weight strides {weight.stride()} are neither contiguous nor channels-last")
+    elif s.is_cuda:
+        _torch_path("demod_coef", f"weight dtype {weight.dtype} / shape {tuple(weight.shape)}")
+    return demod_coef_reference(s, weight, eps)
+
+
+# --------------------------------------------------------------------------------------------------
 # Linear over all tokens with a fast bias gradient; nn.MultiheadAttention evaluated through it (t2i_moe_gan.py:516-517,:545,:557)
 # --------------------------------------------------------------------------------------------------
 def colsum(x2: torch.Tensor) -> torch.Tensor:

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(pkg._cabi.SIGNATURES) == decl, "ctypes signature table and header disagree"
-    assert lib.moegan_version() == pkg._cabi.ABI_VERSION == 5
+    assert lib.moegan_version() == pkg._cabi.ABI_VERSION == 6
 
 
 def test_sizes_and_error_reporting(pkg):

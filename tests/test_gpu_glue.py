@@ -54,6 +54,69 @@ def test_layernorm_3d_input_and_autocast():
     assert _rel(y, ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,Cin,Cout,k", [(5, 128, 256, 3), (256, 512, 512, 3), (33, 256, 3, 1), (7, 100, 70, 3), (2, 512, 128, 1), (64, 32, 32, 5)])
+@pytest.mark.parametrize("s_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_demod_coef_matches_torch(B, Cin, Cout, k, s_dtype, channels_last):
+    """Demodulation coefficients of ModulatedConv (t2i_moe_gan.py:165-170), d = rsqrt(s^2 @ sum_taps(w^2)^T + 1e-8), and their
+    gradients w.r.t. the modulation and the weight against the same expression in fp64 torch ops; weights contiguous and channels-last
+    (dw must come back in the weight's own strides); bf16 modulation as under autocast; ragged sizes (to_rgb: Cout = 3)."""
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(B + Cin + Cout + k)
+    s = (torch.randn(B, Cin, generator=g) * 0.5 + 1.0).to(s_dtype)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    gd = torch.randn(B, Cout, generator=g)
+    sr = s.double().requires_grad_(True); wr = w.double().requires_grad_(True)
+    dr = torch.rsqrt(sr.pow(2) @ wr.pow(2).sum(dim=(2, 3)).t() + 1e-8)
+    dr.backward(gd.double())
+    sc = s.cuda().requires_grad_(True)
+    wc = w.cuda()
+    if channels_last:
+        wc = wc.contiguous(memory_format=torch.channels_last)
+    wc.requires_grad_(True)
+    dc = glue.demod_coef(sc, wc)
+    assert dc.dtype == torch.float32 and dc.shape == (B, Cout)
+    dc.backward(gd.cuda())
+    assert wc.grad.stride() == wc.stride() and sc.grad.dtype == s_dtype
+    assert _rel(dc, dr) < 2e-6
+    assert _rel(wc.grad, wr.grad) < 1e-5
+    assert _rel(sc.grad, sr.grad) < (1e-5 if s_dtype == torch.float32 else 1e-2)
+    with torch.no_grad():                                   # the torch-op definition the CPU path uses
+        assert _rel(dc, glue.demod_coef_reference(s.cuda(), w.cuda())) < 2e-6
+    sc2 = s.cuda().requires_grad_(True); wc2 = wc.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+    d2 = glue.demod_coef(sc2, wc2); d2.backward(gd.cuda())
+    assert torch.equal(d2, dc) and torch.equal(sc2.grad, sc.grad) and torch.equal(wc2.grad, wc.grad)
+
+
+def test_demod_coef_weight_factor_cache():
+    """sum_taps(w^2) is kept between calls while the weights are unchanged (the generator runs twice per train step between optimizer
+    steps): the second call launches one kernel less and returns the same coefficients; an in-place weight update or a bumped weight
+    generation (CUDA-graph replay of an optimizer step) invalidates it."""
+    pkg = G_.pkg(); glue = pkg.glue
+    lib = pkg._cabi.lib()
+    torch.manual_seed(3)
+    w = torch.nn.Parameter(torch.randn(256, 128, 3, 3, device="cuda") * 0.05)
+    s = torch.randn(9, 128, device="cuda")
+    cache = {}
+
+    def call():
+        n0 = lib.moegan_debug_launch_count()
+        d = glue.demod_coef(s, w, cache=cache)
+        return d, lib.moegan_debug_launch_count() - n0
+
+    d1, n1 = call(); d2, n2 = call()
+    assert (n1, n2) == (2, 1) and torch.equal(d1, d2)
+    with torch.no_grad():
+        w.mul_(1.5)                                          # bumps Parameter._version
+    d3, n3 = call()
+    assert n3 == 2 and _rel(d3, d1 / 1.5) < 1e-6
+    w.data.mul_(2.0)                                         # no version bump: what a captured optimizer step does ...
+    pkg.functional.bump_weight_generation()                  # ... and what the trainer calls after every replay
+    d4, n4 = call()
+    assert n4 == 2 and _rel(d4, d3 / 2.0) < 1e-6
+    assert _rel(d4, glue.demod_coef_reference(s, w.detach())) < 2e-6
+
+
 @pytest.mark.parametrize("B,C,H,W", [(3, 128, 16, 16), (2, 256, 8, 8), (5, 512, 4, 4), (300, 128, 4, 4), (2, 128, 64, 64)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("slope", [1.0, 0.2])
