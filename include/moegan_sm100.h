@@ -268,6 +268,17 @@ int moegan_layernorm_fwd(const void* x, int32_t x_is_bf16, const float* gamma, c
  * (y [rows,d] fp32) and their bf16 GEMM-operand copy (y_op [rows,d] bf16) in one pass over x. */
 int moegan_layernorm_fwd_dual(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
                               float* y, void* y_op, float* mean, float* rstd, void* stream);
+/* The residual add in front of norm2 / norm3 fused into the LayerNorm (t2i_moe_gan.py:545 + :553, :557 + :561:
+ * `t = t + attn(...)`, then `norm(t)`): sum_out = x + addend (rounded to their common dtype, as the torch add), y = LayerNorm(sum_out);
+ * y_op: optional bf16 copy of y (may be NULL; needs y fp32).  d = 128 / 256 / 512.  One pass over the rows and one launch less. */
+int moegan_add_layernorm_fwd(const void* x, const void* addend, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows,
+                             int32_t d, float eps, void* sum_out, void* y, int32_t y_is_bf16, void* y_op, float* mean, float* rstd,
+                             void* stream);
+/* moegan_layernorm_bwd with dx = LayerNorm-backward(dy) + gadd: gadd [rows,d] in x's dtype is the gradient reaching the LayerNorm's
+ * INPUT along the residual path (the summed rows are also consumed by the next residual add).  d = 128 / 256 / 512. */
+int moegan_layernorm_bwd_add(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
+                             const float* rstd, int64_t rows, int32_t d, const void* gadd, void* dx, float* dgamma_dbeta, void* scratch,
+                             int64_t scratch_bytes, void* stream);
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d);
 /* dy fp32 or bf16; dx [rows,d] in x's dtype; dgamma_dbeta fp32 [2,d] (row 0 = weight gradient, row 1 = bias gradient),
  * deterministic. */

@@ -91,6 +91,8 @@ SIGNATURES = {
     "moegan_layernorm_fwd_dual": (c_int32, [_P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, _P, _P, _P, _P]),
     "moegan_layernorm_bwd_scratch_bytes": (c_int64, [c_int64, c_int32]),
     "moegan_layernorm_bwd": (c_int32, [_P, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
+    "moegan_add_layernorm_fwd": (c_int32, [_P, _P, c_int32, _P, _P, c_int64, c_int32, c_float, _P, _P, c_int32, _P, _P, _P, _P]),
+    "moegan_layernorm_bwd_add": (c_int32, [_P, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int64, _P]),
     "moegan_channel_scale_fwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "moegan_channel_scale_bwd_scratch_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "moegan_channel_scale_bwd": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),

@@ -910,6 +910,29 @@ int moegan_layernorm_fwd_dual(const void* x, int32_t x_is_bf16, const float* gam
                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0, MOEGAN_ERR_MISALIGNED, "layernorm_fwd_dual: pointers must be 16-byte aligned");
     return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, 0, y_op, mean, rstd, (cudaStream_t)stream);
 }
+int moegan_add_layernorm_fwd(const void* x, const void* addend, int32_t x_is_bf16, const float* gamma, const float* beta, int64_t rows, int32_t d,
+                             float eps, void* sum_out, void* y, int32_t y_is_bf16, void* y_op, float* mean, float* rstd, void* stream) {
+    RUN(check_ln(rows, d));
+    MOEGAN_REQUIRE(d == 128 || d == 256 || d == 512, MOEGAN_ERR_BAD_SHAPE, "add_layernorm_fwd: d = %d must be 128, 256 or 512", d);
+    REQ_PTR(x); REQ_PTR(addend); REQ_PTR(sum_out); REQ_PTR(gamma); REQ_PTR(beta); REQ_PTR(y); REQ_PTR(mean); REQ_PTR(rstd);
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(sum_out) | reinterpret_cast<uintptr_t>(y) |
+                     reinterpret_cast<uintptr_t>(y_op) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+                   MOEGAN_ERR_MISALIGNED, "add_layernorm_fwd: pointers must be 16-byte aligned");
+    return launch_layernorm_fwd(x, x_is_bf16, gamma, beta, rows, d, eps, y, y_is_bf16, y_op, mean, rstd, (cudaStream_t)stream, addend, sum_out);
+}
+int moegan_layernorm_bwd_add(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
+                             const float* rstd, int64_t rows, int32_t d, const void* gadd, void* dx, float* dgamma_dbeta, void* scratch,
+                             int64_t scratch_bytes, void* stream) {
+    RUN(check_ln(rows, d));
+    MOEGAN_REQUIRE(d == 128 || d == 256 || d == 512, MOEGAN_ERR_BAD_SHAPE, "layernorm_bwd_add: d = %d must be 128, 256 or 512", d);
+    REQ_PTR(dy); REQ_PTR(x); REQ_PTR(gamma); REQ_PTR(mean); REQ_PTR(rstd); REQ_PTR(gadd); REQ_PTR(dx); REQ_PTR(dgamma_dbeta); REQ_PTR(scratch);
+    MOEGAN_REQUIRE(scratch_bytes >= moegan_layernorm_bwd_scratch_bytes(rows, d), MOEGAN_ERR_BAD_SHAPE, "layernorm_bwd_add: scratch too small");
+    MOEGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gadd) |
+                     reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0, MOEGAN_ERR_MISALIGNED,
+                   "layernorm_bwd_add: pointers must be 16-byte aligned");
+    return launch_layernorm_bwd(dy, dy_is_bf16, x, x_is_bf16, gamma, mean, rstd, rows, d, dx, dgamma_dbeta, reinterpret_cast<float*>(scratch),
+                                (cudaStream_t)stream, gadd);
+}
 int64_t moegan_layernorm_bwd_scratch_bytes(int64_t rows, int32_t d) { return (int64_t)ln_bwd_blocks(rows) * 2 * d * 4 + 256; }
 int moegan_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const void* x, int32_t x_is_bf16, const float* gamma, const float* mean,
                          const float* rstd, int64_t rows, int32_t d, void* dx, float* dgamma_dbeta, void* scratch, int64_t scratch_bytes,

@@ -256,6 +256,9 @@ template <> __device__ __forceinline__ float4 lds_vec4<__nv_bfloat16>(const __nv
     const uint2 u = *reinterpret_cast<const uint2*>(p);
     return make_float4(bf16_lo_to_float(u.x), bf16_hi_to_float(u.x), bf16_lo_to_float(u.y), bf16_hi_to_float(u.y));
 }
+template <typename T> __device__ __forceinline__ float round_as(float v);          // v rounded to storage type T, as fp32
+template <> __device__ __forceinline__ float round_as<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_as<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 constexpr int LNB_STAGES = 4;
 template <typename TG, typename TIN, int NSEG> struct LnBulk {
     static constexpr int D = NSEG * 128;
@@ -268,13 +271,16 @@ template <typename TG, typename TIN, int NSEG>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, const float* __restrict__ gamma,
                           const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows,
-                          TIN* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
+                          const TIN* __restrict__ gadd, TIN* __restrict__ dx, float* __restrict__ part /* [gridDim.x][2][d] */) {
+    // gadd != nullptr: the gradient that reaches the LayerNorm's INPUT along the residual path (the rows were also consumed by the next
+    // residual add) is added into dx here instead of by a separate add kernel; it rides in the ring as a third tile.
     using L = LnBulk<TG, TIN, NSEG>;
     constexpr int D = L::D, TR = L::TR, RW = L::RW, ST = LNB_STAGES;
     extern __shared__ __align__(128) uint8_t lsm[];
     __shared__ float4 red[8][NSEG * 32];
     const uint32_t sm0 = ptx::smem_u32(lsm);
-    const uint32_t bar0 = sm0 + ST * L::SB;
+    const uint32_t SBk = gadd != nullptr ? L::SB + L::XB : L::SB;       // stage = [x tile | g tile | gadd tile]
+    const uint32_t bar0 = sm0 + ST * SBk;
     auto full = [&](int s_) { return bar0 + 8u * s_; };
     auto empty = [&](int s_) { return bar0 + 8u * (ST + s_); };
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -291,9 +297,10 @@ layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, c
         if (i >= ST) ptx::mbar_wait(empty(slot), (((uint32_t)(i / ST)) & 1u) ^ 1u);      // all 8 warps have left the slot's previous tile
         const long long r0 = tile_of(i) * TR;
         const uint32_t vr = (uint32_t)((rows - r0) < TR ? (rows - r0) : TR);
-        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)(sizeof(TIN) + sizeof(TG)));
-        bulk_g2s(sm0 + slot * L::SB, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
-        bulk_g2s(sm0 + slot * L::SB + L::XB, g + r0 * D, vr * D * (uint32_t)sizeof(TG), full(slot));
+        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)(sizeof(TIN) * (gadd != nullptr ? 2 : 1) + sizeof(TG)));
+        bulk_g2s(sm0 + slot * SBk, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
+        bulk_g2s(sm0 + slot * SBk + L::XB, g + r0 * D, vr * D * (uint32_t)sizeof(TG), full(slot));
+        if (gadd != nullptr) bulk_g2s(sm0 + slot * SBk + L::SB, gadd + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
     };
     if (tid == 0)
         for (int i = 0; i < ST - 1 && i < my_n; ++i) issue(i);
@@ -317,8 +324,9 @@ layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, c
             rs[r] = ok ? __ldg(rstd_in + r0 + r) : 0.f;
         }
         ptx::mbar_wait(full(slot), ((uint32_t)(i / ST)) & 1u);
-        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * L::SB) + (size_t)wid * RW * D;
-        const TG* gs_ = reinterpret_cast<const TG*>(lsm + (size_t)slot * L::SB + L::XB) + (size_t)wid * RW * D;
+        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * SBk) + (size_t)wid * RW * D;
+        const TG* gs_ = reinterpret_cast<const TG*>(lsm + (size_t)slot * SBk + L::XB) + (size_t)wid * RW * D;
+        const TIN* as_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * SBk + L::SB) + (size_t)wid * RW * D;
         float4 xh[RW][NSEG], gg[RW][NSEG];
         float s1[RW], s2[RW];
 #pragma unroll
@@ -341,7 +349,7 @@ layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, c
             }
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty(slot));            // this warp has read its rows of the slot
+        if (gadd == nullptr && lane == 0) ptx::mbar_arrive(empty(slot));      // this warp has read its rows of the slot
 #pragma unroll
         for (int r = 0; r < RW; ++r) { s1[r] = warp_sum(s1[r]) * inv_d; s2[r] = warp_sum(s2[r]) * inv_d; }
 #pragma unroll
@@ -352,9 +360,17 @@ layernorm_bwd_bulk_kernel(const TG* __restrict__ g, const TIN* __restrict__ x, c
                     float4 o;
                     o.x = rs[r] * (gg[r][s_].x - s1[r] - xh[r][s_].x * s2[r]); o.y = rs[r] * (gg[r][s_].y - s1[r] - xh[r][s_].y * s2[r]);
                     o.z = rs[r] * (gg[r][s_].z - s1[r] - xh[r][s_].z * s2[r]); o.w = rs[r] * (gg[r][s_].w - s1[r] - xh[r][s_].w * s2[r]);
+                    if (gadd != nullptr) {
+                        const float4 av = lds_vec4<TIN>(as_ + (size_t)r * D + s_ * 128 + lane * 4);
+                        o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
+                    }
                     Vec4<TIN>::store(dx + (r0 + r) * D + s_ * 128 + lane * 4, o);
                 }
             }
+        if (gadd != nullptr) {                                   // the gadd tile was read last: hand the slot back only now
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty(slot));
+        }
     }
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -381,14 +397,17 @@ template <typename TIN, int NSEG> struct LnFwdBulk {
 };
 template <typename TIN, typename TOUT, int NSEG>
 __global__ void __launch_bounds__(256)
-layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
-                          float eps, TOUT* __restrict__ y, __nv_bfloat16* __restrict__ y_op, float* __restrict__ mean_out,
-                          float* __restrict__ rstd_out) {
+layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const TIN* __restrict__ addend, TIN* __restrict__ sum_out, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, long long rows, float eps, TOUT* __restrict__ y, __nv_bfloat16* __restrict__ y_op,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    // addend != nullptr: the residual add in front of the LayerNorm (t = t + attn(...); n = norm(t), t2i_moe_gan.py:545-561) happens here:
+    // v = round_TIN(x + addend) is written to sum_out and normalised - one pass over the rows less than add + LayerNorm, one launch less.
     using L = LnFwdBulk<TIN, NSEG>;
     constexpr int D = L::D, TR = L::TR, RW = L::RW, ST = LNB_STAGES;
     extern __shared__ __align__(128) uint8_t lsm[];
     const uint32_t sm0 = ptx::smem_u32(lsm);
-    const uint32_t bar0 = sm0 + ST * L::SB;
+    const uint32_t SBk = addend != nullptr ? 2 * L::SB : L::SB;           // stage = [x tile | addend tile]
+    const uint32_t bar0 = sm0 + ST * SBk;
     auto full = [&](int s_) { return bar0 + 8u * s_; };
     auto empty = [&](int s_) { return bar0 + 8u * (ST + s_); };
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -405,8 +424,9 @@ layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const float* __restrict__ g
         if (i >= ST) ptx::mbar_wait(empty(slot), (((uint32_t)(i / ST)) & 1u) ^ 1u);
         const long long r0 = tile_of(i) * TR;
         const uint32_t vr = (uint32_t)((rows - r0) < TR ? (rows - r0) : TR);
-        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)sizeof(TIN));
-        bulk_g2s(sm0 + slot * L::SB, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
+        ptx::mbar_arrive_expect_tx(full(slot), vr * D * (uint32_t)sizeof(TIN) * (addend != nullptr ? 2u : 1u));
+        bulk_g2s(sm0 + slot * SBk, x + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
+        if (addend != nullptr) bulk_g2s(sm0 + slot * SBk + L::SB, addend + r0 * D, vr * D * (uint32_t)sizeof(TIN), full(slot));
     };
     if (tid == 0)
         for (int i = 0; i < ST - 1 && i < my_n; ++i) issue(i);
@@ -422,7 +442,8 @@ layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const float* __restrict__ g
         if (tid == 0 && i + ST - 1 < my_n) issue(i + ST - 1);
         const long long r0 = tile_of(i) * TR + wid * RW;
         ptx::mbar_wait(full(slot), ((uint32_t)(i / ST)) & 1u);
-        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * L::SB) + (size_t)wid * RW * D;
+        const TIN* xs_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * SBk) + (size_t)wid * RW * D;
+        const TIN* as_ = reinterpret_cast<const TIN*>(lsm + (size_t)slot * SBk + L::SB) + (size_t)wid * RW * D;
         float4 v[RW][NSEG];
         float sum[RW], mean[RW], rstd[RW];
 #pragma unroll
@@ -431,7 +452,15 @@ layernorm_fwd_bulk_kernel(const TIN* __restrict__ x, const float* __restrict__ g
 #pragma unroll
             for (int s_ = 0; s_ < NSEG; ++s_) {
                 v[r][s_] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r0 + r < rows) v[r][s_] = lds_vec4<TIN>(xs_ + (size_t)r * D + s_ * 128 + lane * 4);
+                if (r0 + r < rows) {
+                    v[r][s_] = lds_vec4<TIN>(xs_ + (size_t)r * D + s_ * 128 + lane * 4);
+                    if (addend != nullptr) {
+                        const float4 av = lds_vec4<TIN>(as_ + (size_t)r * D + s_ * 128 + lane * 4);
+                        v[r][s_] = make_float4(round_as<TIN>(v[r][s_].x + av.x), round_as<TIN>(v[r][s_].y + av.y),
+                                               round_as<TIN>(v[r][s_].z + av.z), round_as<TIN>(v[r][s_].w + av.w));
+                        Vec4<TIN>::store(sum_out + (r0 + r) * D + s_ * 128 + lane * 4, v[r][s_]);
+                    }
+                }
                 sum[r] += (v[r][s_].x + v[r][s_].y) + (v[r][s_].z + v[r][s_].w);
             }
         }
@@ -637,44 +666,65 @@ demod_gemm_kernel(const DemodArgs a) {
     const int M = MODE == 2 ? a.Cout : a.B, N = MODE == 0 ? a.Cout : a.Cin, K = MODE == 0 ? a.Cin : (MODE == 1 ? a.Cout : a.B);
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    auto tval = [&](int b, int o) { const float dv = __ldg(a.d + (size_t)b * a.Cout + o); return -0.5f * __ldg(a.dd + (size_t)b * a.Cout + o) * dv * dv * dv; };
-    // element j (of 8) of this thread in the A / B tile of the chunk at k0: value + where it goes in shared memory
-    auto fetchA = [&](int j, int k0) -> float {
-        const int e = threadIdx.x + 256 * j;
-        if (MODE == 2) { const int m = m0 + (e & 31), k = k0 + (e >> 5); return (m < M && k < K) ? tval(k, m) : 0.f; }     // t[b, o]: o fastest
-        const int m = m0 + (e >> 6), k = k0 + (e & 63);
-        if (!(m < M && k < K)) return 0.f;
-        if (MODE == 0) { const float v = demod_s(a, m, k); return v * v; }                                                  // s^2: i fastest
-        return tval(m, k);                                                                                                  // t[b, o]: o fastest
+    // Operand fetch in two halves: LOAD (raw values from clamped, always-valid addresses - no arithmetic, no branches, so the 16 - 24 loads
+    // of a chunk are all in flight together) and, one chunk later, CONVERT + store to shared memory (square / t = -0.5 dd d^3, zero outside
+    // the matrix).  With the arithmetic inside the fetch (first version) every load was followed by its use and the chunk's loads ran one
+    // after the other: 5.7 us per 64-wide chunk at every size.
+    const float* sf = reinterpret_cast<const float*>(a.s);
+    const unsigned short* sh = reinterpret_cast<const unsigned short*>(a.s);
+    auto load_s = [&](int b, int i) -> float {          // raw: the fp32 value, or the bf16 bits in the low half (widened by s_val below)
+        const size_t off = (size_t)b * a.Cin + i;
+        return a.s_bf16 ? __uint_as_float((unsigned)sh[off]) : __ldg(sf + off);
     };
-    auto storeA = [&](int j, float v) {
-        const int e = threadIdx.x + 256 * j;
-        if (MODE == 2) As[e & 31][e >> 5] = v; else As[e >> 6][e & 63] = v;
-    };
-    auto fetchB = [&](int j, int k0) -> float {
-        const int e = threadIdx.x + 256 * j;
-        if (MODE == 0) { const int n = n0 + (e >> 6), k = k0 + (e & 63); return (n < N && k < K) ? __ldg(a.wsq + (size_t)n * a.Cin + k) : 0.f; }   // wsq[o, i]: i fastest
-        const int n = n0 + (e & 31), k = k0 + (e >> 5);
-        if (!(n < N && k < K)) return 0.f;
-        if (MODE == 1) return __ldg(a.wsq + (size_t)k * a.Cin + n);                                                         // wsq[o, i]: i fastest
-        const float v = demod_s(a, k, n); return v * v;                                                                     // s^2: i fastest
-    };
-    auto storeB = [&](int j, float v) {
-        const int e = threadIdx.x + 256 * j;
-        if (MODE == 0) Bs[e >> 6][e & 63] = v; else Bs[e & 31][e >> 5] = v;
-    };
+    auto s_val = [&](float raw) -> float { return a.s_bf16 ? __uint_as_float(__float_as_uint(raw) << 16) : raw; };
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float ra[8], rb[8];
+    float ra[8], ra2[8], rb[8];
+    auto load_chunk = [&](int k0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ra[j] = fetchA(j, 0); rb[j] = fetchB(j, 0); }
-    for (int k0 = 0; k0 < K; k0 += BK) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { storeA(j, ra[j]); storeB(j, rb[j]); }
-        __syncthreads();
-        if (k0 + BK < K) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { ra[j] = fetchA(j, k0 + BK); rb[j] = fetchB(j, k0 + BK); }
+        for (int j = 0; j < 8; ++j) {
+            const int e = threadIdx.x + 256 * j;
+            if (MODE == 0) {            // A(b, i) = s^2 (i fastest);  B(i, o) = wsq[o, i] (i fastest)
+                const int m = min(m0 + (e >> 6), M - 1), k = min(k0 + (e & 63), K - 1), n = min(n0 + (e >> 6), N - 1);
+                ra[j] = load_s(m, k);
+                rb[j] = __ldg(a.wsq + (size_t)n * a.Cin + k);
+            } else if (MODE == 1) {     // A(b, o) = t (o fastest);  B(o, i) = wsq[o, i] (i fastest)
+                const int m = min(m0 + (e >> 6), M - 1), k = min(k0 + (e & 63), K - 1);
+                ra[j] = __ldg(a.d + (size_t)m * a.Cout + k); ra2[j] = __ldg(a.dd + (size_t)m * a.Cout + k);
+                const int kk = min(k0 + (e >> 5), K - 1), n = min(n0 + (e & 31), N - 1);
+                rb[j] = __ldg(a.wsq + (size_t)kk * a.Cin + n);
+            } else {                    // A(o, b) = t[b, o] (o fastest);  B(b, i) = s^2 (i fastest)
+                const int m = min(m0 + (e & 31), M - 1), kk = min(k0 + (e >> 5), K - 1), n = min(n0 + (e & 31), N - 1);
+                ra[j] = __ldg(a.d + (size_t)kk * a.Cout + m); ra2[j] = __ldg(a.dd + (size_t)kk * a.Cout + m);
+                rb[j] = load_s(kk, n);
+            }
         }
+    };
+    auto store_chunk = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = threadIdx.x + 256 * j;
+            if (MODE == 0) {
+                const bool oka = m0 + (e >> 6) < M && k0 + (e & 63) < K, okb = n0 + (e >> 6) < N && k0 + (e & 63) < K;
+                const float sv = s_val(ra[j]);
+                As[e >> 6][e & 63] = oka ? sv * sv : 0.f;
+                Bs[e >> 6][e & 63] = okb ? rb[j] : 0.f;
+            } else if (MODE == 1) {
+                const bool oka = m0 + (e >> 6) < M && k0 + (e & 63) < K, okb = k0 + (e >> 5) < K && n0 + (e & 31) < N;
+                As[e >> 6][e & 63] = oka ? -0.5f * ra2[j] * ra[j] * ra[j] * ra[j] : 0.f;
+                Bs[e & 31][e >> 5] = okb ? rb[j] : 0.f;
+            } else {
+                const bool oka = m0 + (e & 31) < M && k0 + (e >> 5) < K, okb = k0 + (e >> 5) < K && n0 + (e & 31) < N;
+                As[e & 31][e >> 5] = oka ? -0.5f * ra2[j] * ra[j] * ra[j] * ra[j] : 0.f;
+                const float sv = s_val(rb[j]);
+                Bs[e & 31][e >> 5] = okb ? sv * sv : 0.f;
+            }
+        }
+    };
+    if (K > 0) load_chunk(0);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        store_chunk(k0);
+        __syncthreads();
+        if (k0 + BK < K) load_chunk(k0 + BK);
         // one shared-memory load per FMA (the first version) made this loop LSU-bound; 5 LDS.128 now feed 16 FMAs
 #pragma unroll 4
         for (int kk = 0; kk < BK; kk += 4) {
@@ -689,6 +739,31 @@ demod_gemm_kernel(const DemodArgs a) {
     }
     const int n = n0 + tx;
     if (n >= N) return;
+    if (MODE == 2 && a.KH * a.KW <= 9) {
+        // all weight taps of the thread's 4 outputs are loaded before the first product (a load-multiply-store loop over the taps ran its
+        // 36 global loads one after the other: 12 us of the 25 us this launch took at 128 x 128 x 3 x 3)
+        const int taps = a.KH * a.KW;
+        float wv[4][9];
+        long long toff[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { const int ky = t / a.KW, kx = t - ky * a.KW; toff[t] = t < taps ? ky * a.sh + kx * a.sw : 0; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = min(m0 + ty + 8 * j, M - 1);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[j][t] = __ldg(a.w + m * a.so + n * a.si + toff[t]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty + 8 * j;
+            if (m >= M) continue;
+            const float v = 2.0f * acc[j];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (t < taps) a.dw[m * a.so + n * a.si + toff[t]] = v * wv[j][t];
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int m = m0 + ty + 8 * j;
@@ -1079,24 +1154,28 @@ int ln_bwd_blocks(long long rows) {
 
 // (NSEG, R) by segment count: 1 -> (1, 4), 2 -> (2, 2), 3..4 -> (4, 1), 5..8 -> (8, 1)
 int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
-                         int y_bf16, void* y_op, float* mean, float* rstd, cudaStream_t st) {
-    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_FWD, rows, d, 0, (x_bf16 ? 1 : 0) | (y_bf16 ? 2 : 0) | (y_op != nullptr ? 4 : 0));
+                         int y_bf16, void* y_op, float* mean, float* rstd, cudaStream_t st, const void* addend, void* sum_out) {
+    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_FWD, rows, d, 0, (x_bf16 ? 1 : 0) | (y_bf16 ? 2 : 0) | (y_op != nullptr ? 4 : 0) | (addend != nullptr ? 8 : 0));
     if (rows == 0) return MOEGAN_OK;
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
-    if ((nseg == 1 || nseg == 2 || nseg == 4) && rows >= 4096 && !ln_fwd_bulk_disabled()) {
+    const bool bulk_ok = nseg == 1 || nseg == 2 || nseg == 4;
+    MOEGAN_REQUIRE(addend == nullptr || bulk_ok, MOEGAN_ERR_BAD_SHAPE, "add_layernorm_fwd: d = %d must be 128, 256 or 512", d);
+    if (bulk_ok && (addend != nullptr || (rows >= 4096 && !ln_fwd_bulk_disabled()))) {
+        const uint32_t smem_mul = addend != nullptr ? 2u : 1u;
 #define MOEGAN_LN_FBULK3(TI, TO, NS)                                                                                            \
         do {                                                                                                                    \
             typedef LnFwdBulk<TI, NS> LB;                                                                                       \
             static bool attr = false;                                                                                           \
             if (!attr) {                                                                                                        \
-                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_fwd_bulk_kernel<TI, TO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB::SMEM)); \
+                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_fwd_bulk_kernel<TI, TO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * LNB_STAGES * LB::SB + 2 * LNB_STAGES * 8))); \
                 attr = true;                                                                                                    \
             }                                                                                                                   \
             const long long nt = (rows + LB::TR - 1) / LB::TR;                                                                  \
             const long long cap = (long long)num_sms() * 3;                                                                     \
-            layernorm_fwd_bulk_kernel<TI, TO, NS><<<(int)(nt < cap ? nt : cap), 256, LB::SMEM, st>>>(                           \
-                reinterpret_cast<const TI*>(x), gamma, beta, rows, eps, reinterpret_cast<TO*>(y), reinterpret_cast<__nv_bfloat16*>(y_op), mean, rstd); \
+            layernorm_fwd_bulk_kernel<TI, TO, NS><<<(int)(nt < cap ? nt : cap), 256, smem_mul * LNB_STAGES * LB::SB + 2 * LNB_STAGES * 8, st>>>(  \
+                reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(addend), reinterpret_cast<TI*>(sum_out), gamma, beta, rows, eps,   \
+                reinterpret_cast<TO*>(y), reinterpret_cast<__nv_bfloat16*>(y_op), mean, rstd);                                         \
         } while (0)
 #define MOEGAN_LN_FBULK(TI, TO) do { if (nseg == 1) MOEGAN_LN_FBULK3(TI, TO, 1); else if (nseg == 2) MOEGAN_LN_FBULK3(TI, TO, 2); else MOEGAN_LN_FBULK3(TI, TO, 4); } while (0)
         if (x_bf16) { if (y_bf16) MOEGAN_LN_FBULK(bf, bf); else MOEGAN_LN_FBULK(bf, float); }
@@ -1123,8 +1202,8 @@ int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const fl
 }
 
 int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd,
-                         long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st) {
-    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_BWD, rows, d, 0, (g_bf16 ? 1 : 0) | (x_bf16 ? 2 : 0));
+                         long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st, const void* gadd) {
+    ProfScope _ps(st, MOEGAN_PROF_LAYERNORM_BWD, rows, d, 0, (g_bf16 ? 1 : 0) | (x_bf16 ? 2 : 0) | (gadd != nullptr ? 4 : 0));
     if (rows == 0) {
         MOEGAN_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, (size_t)2 * d * 4, st));
         return MOEGAN_OK;
@@ -1132,7 +1211,8 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
     const int blocks = ln_bwd_blocks(rows);
     typedef __nv_bfloat16 bf;
     const int nseg = d / 128;
-    if ((nseg == 1 || nseg == 2 || nseg == 4) && !ln_bulk_env_off()) {
+    MOEGAN_REQUIRE(gadd == nullptr || nseg == 1 || nseg == 2 || nseg == 4, MOEGAN_ERR_BAD_SHAPE, "layernorm_bwd_add: d = %d must be 128, 256 or 512", d);
+    if ((nseg == 1 || nseg == 2 || nseg == 4) && (gadd != nullptr || !ln_bulk_env_off())) {
         // bulk-copy pipelined kernel; same partial layout ([nb][2][d], nb <= blocks) and finishing pass as the register-pipelined one below
         int nb = blocks;
 #define MOEGAN_LN_BULK3(TG, TI, NS)                                                                                             \
@@ -1140,14 +1220,15 @@ int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, c
             typedef LnBulk<TG, TI, NS> LB;                                                                                      \
             static bool attr = false;                                                                                           \
             if (!attr) {                                                                                                        \
-                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_bulk_kernel<TG, TI, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB::SMEM)); \
+                MOEGAN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_bulk_kernel<TG, TI, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LNB_STAGES * (LB::SB + LB::XB) + 2 * LNB_STAGES * 8))); \
                 attr = true;                                                                                                    \
             }                                                                                                                   \
             const long long nt = (rows + LB::TR - 1) / LB::TR;                                                                  \
-            const long long cap = (long long)num_sms() * (LB::SMEM > 100 * 1024 ? 1 : 2);    /* persistent: CTAs resident per SM */ \
+            const uint32_t smem = LNB_STAGES * (LB::SB + (gadd != nullptr ? LB::XB : 0u)) + 2 * LNB_STAGES * 8;                   \
+            const long long cap = (long long)num_sms() * (smem > 100 * 1024 ? 1 : 2);        /* persistent: CTAs resident per SM */ \
             nb = (int)(nt < cap ? nt : cap);                                                                                    \
-            layernorm_bwd_bulk_kernel<TG, TI, NS><<<nb, 256, LB::SMEM, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, \
-                                                                                 mean, rstd, rows, reinterpret_cast<TI*>(dx), scratch);    \
+            layernorm_bwd_bulk_kernel<TG, TI, NS><<<nb, 256, smem, st>>>(reinterpret_cast<const TG*>(g), reinterpret_cast<const TI*>(x), gamma, \
+                                                                         mean, rstd, rows, reinterpret_cast<const TI*>(gadd), reinterpret_cast<TI*>(dx), scratch); \
         } while (0)
 #define MOEGAN_LN_BULK(TG, TI) do { if (nseg == 1) MOEGAN_LN_BULK3(TG, TI, 1); else if (nseg == 2) MOEGAN_LN_BULK3(TG, TI, 2); else MOEGAN_LN_BULK3(TG, TI, 4); } while (0)
         if (g_bf16) { if (x_bf16) MOEGAN_LN_BULK(bf, bf); else MOEGAN_LN_BULK(bf, float); }

@@ -59,9 +59,9 @@ int launch_colsum_grouped(const moegan_shape* s, const int32_t* plan, const void
 // ---- glue.cu (layers around the block: SURVEY 8(f) N1 / N3) ----------------------------------------
 int ln_bwd_blocks(long long rows);
 int launch_layernorm_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, long long rows, int d, float eps, void* y,
-                         int y_bf16, void* y_op, float* mean, float* rstd, cudaStream_t st);
+                         int y_bf16, void* y_op, float* mean, float* rstd, cudaStream_t st, const void* addend = nullptr, void* sum_out = nullptr);
 int launch_layernorm_bwd(const void* g, int g_bf16, const void* x, int x_bf16, const float* gamma, const float* mean, const float* rstd,
-                         long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st);
+                         long long rows, int d, void* dx, float* dgamma_dbeta, float* scratch, cudaStream_t st, const void* gadd = nullptr);
 int channel_scale_psplit(int B, int P, int C);
 int launch_channel_scale_fwd(const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* out, cudaStream_t st);
 int launch_channel_scale_bwd(const void* g, const void* x, int bf16, const void* s, int s_bf16, int B, int P, int C, float slope, void* dx,

@@ -89,6 +89,72 @@ class _LayerNormFn(torch.autograd.Function):
         return dx.view(ctx.x_shape).to(ctx.x_dtype), dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None, None, None
 
 
+class _AddLayerNormFn(torch.autograd.Function):
+    """(t, a) -> (t + a, LayerNorm(t + a)[, bf16 copy]) in one kernel; backward: d(t + a) = LayerNorm-backward(g_n) + g_sum, also fused."""
+
+    @staticmethod
+    def forward(ctx, x, addend, weight, bias, eps, out_dtype, with_operand):
+        d = x.shape[-1]
+        x2, a2 = x.reshape(-1, d).contiguous(), addend.reshape(-1, d).contiguous()
+        rows = x2.shape[0]
+        wf, bf = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        s = torch.empty_like(x2)
+        y = torch.empty(rows, d, device=x.device, dtype=out_dtype)
+        y_op = torch.empty(rows, d, device=x.device, dtype=torch.bfloat16) if with_operand else None
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        C.check(C.lib().moegan_add_layernorm_fwd(C.ptr(x2), C.ptr(a2), _is_bf16(x2), C.ptr(wf), C.ptr(bf), rows, d, float(eps), C.ptr(s), C.ptr(y),
+                                                 _is_bf16(y), C.ptr(y_op) if with_operand else None, C.ptr(mean), C.ptr(rstd), _stream()),
+                "moegan_add_layernorm_fwd")
+        ctx.save_for_backward(s, wf, mean, rstd)
+        ctx.x_shape, ctx.w_dtype = x.shape, weight.dtype
+        outs = (s.view(x.shape), y.view(x.shape))
+        if with_operand:
+            y_op = y_op.view(x.shape)
+            ctx.mark_non_differentiable(y_op)
+            outs = outs + (y_op,)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_sum, gy, *unused):
+        s, wf, mean, rstd = ctx.saved_tensors
+        rows, d = s.shape
+        lib = C.lib()
+        if gy is None:                                   # the normalised rows were not used: only the residual path carries gradient
+            return g_sum, g_sum, None, None, None, None, None
+        g = gy.reshape(rows, d)
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        g = g.contiguous()
+        dx = torch.empty_like(s)
+        dgb = torch.empty(2, d, device=g.device, dtype=torch.float32)
+        nbytes = int(lib.moegan_layernorm_bwd_scratch_bytes(rows, d))
+        scratch = torch.empty(nbytes, device=g.device, dtype=torch.uint8)
+        if g_sum is None:
+            C.check(lib.moegan_layernorm_bwd(C.ptr(g), _is_bf16(g), C.ptr(s), _is_bf16(s), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d,
+                                             C.ptr(dx), C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd")
+        else:
+            ga = g_sum.reshape(rows, d).to(s.dtype).contiguous()
+            C.check(lib.moegan_layernorm_bwd_add(C.ptr(g), _is_bf16(g), C.ptr(s), _is_bf16(s), C.ptr(wf), C.ptr(mean), C.ptr(rstd), rows, d,
+                                                 C.ptr(ga), C.ptr(dx), C.ptr(dgb), C.ptr(scratch), nbytes, _stream()), "moegan_layernorm_bwd_add")
+        dxv = dx.view(ctx.x_shape)
+        return dxv, dxv, dgb[0].to(ctx.w_dtype), dgb[1].to(ctx.w_dtype), None, None, None
+
+
+def add_layer_norm(x: torch.Tensor, addend: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=torch.float32,
+                   with_operand: bool = False):
+    """`t = x + addend; n = nn.LayerNorm(d)(t)` -> `(t, n)` (with_operand=True: `(t, n fp32, n rounded to bf16)`): the residual adds in
+    front of norm2 / norm3 of AttentionBlock (t2i_moe_gan.py:545 + :553, :557 + :561).  On CUDA, for d = 128 / 256 / 512 and operands of
+    one dtype (fp32 / bf16), one kernel forward and one backward; anything else is the add followed by `layer_norm`."""
+    d = x.shape[-1]
+    if (not _NO_ADD_LN and x.is_cuda and addend.is_cuda and d in (128, 256, 512) and x.dtype == addend.dtype and x.dtype in (torch.float32, torch.bfloat16)
+            and x.shape == addend.shape and (not with_operand or out_dtype == torch.float32)):
+        return _AddLayerNormFn.apply(x, addend, weight, bias, eps, out_dtype, with_operand)
+    t = x + addend
+    n = layer_norm(t, weight, bias, eps, out_dtype, with_operand)
+    return (t,) + n if with_operand else (t, n)
+
+
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=torch.float32, with_operand: bool = False):
     """`nn.LayerNorm(d)(x)` over the last dimension.  Result fp32 (what autocast's LayerNorm returns), or bf16 when the
     only consumer is an autocast matmul that would round it to bf16 first thing anyway (same values, one pass less).
@@ -203,6 +269,7 @@ class _DemodCoefFn(torch.autograd.Function):
 
 
 _TORCH_DEMOD = __import__("os").environ.get("MOEGAN_TORCH_DEMOD", "0") == "1"
+_NO_ADD_LN = __import__("os").environ.get("MOEGAN_NO_ADD_LN", "0") == "1"      # A/B switch: residual add and LayerNorm as two kernels
 
 
 def demod_coef_reference(s: torch.Tensor, weight: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:

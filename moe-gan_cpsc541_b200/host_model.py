@@ -109,17 +109,19 @@ class AttentionBlock(nn.Module):
         ln = lambda m, v, dt=torch.float32: glue.layer_norm(v, m.weight, m.bias, m.eps, dt)
         t = self.proj_in(x, w).permute(0, 2, 3, 1).reshape(B, H * W, C)
         n = ln(self.norm1, t, mm)
-        t = t + glue.multihead_attention(self.self_attn, n, n)            # = self.self_attn(n, n, n, need_weights=False)[0]
+        a1 = glue.multihead_attention(self.self_attn, n, n)               # = self.self_attn(n, n, n, need_weights=False)[0]
+        # `t = t + attn; norm(t)` (:545 + :553, :557 + :561): the residual add rides in the LayerNorm kernel (glue.add_layer_norm)
+        t, n2 = glue.add_layer_norm(t, a1.to(t.dtype), self.norm2.weight, self.norm2.bias, self.norm2.eps, mm)
         tp = self.text_proj(text_seq)
-        t = t + glue.multihead_attention(self.cross_attn, ln(self.norm2, t, mm), tp)
-        x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        a2 = glue.multihead_attention(self.cross_attn, n2, tp)
         # norm3 (:561): the fp32 rows the router reads and - when the block runs its bf16 tensor-core path - their bf16 operand copy
         # from the same pass, so the block has no conversion kernel of its own
         bf16_block = t.is_cuda and getattr(self.moe, "takes_operand", False) and self.moe._precision_code() == 0
         if bf16_block:
-            x_n, x_op = glue.layer_norm(t, self.norm3.weight, self.norm3.bias, self.norm3.eps, torch.float32, with_operand=True)
+            t, x_n, x_op = glue.add_layer_norm(t, a2.to(t.dtype), self.norm3.weight, self.norm3.bias, self.norm3.eps, torch.float32, with_operand=True)
         else:
-            x_n, x_op = ln(self.norm3, t), None
+            (t, x_n), x_op = glue.add_layer_norm(t, a2.to(t.dtype), self.norm3.weight, self.norm3.bias, self.norm3.eps, torch.float32), None
+        x_spatial = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
         x_norm = x_n.reshape(B, H, W, C).permute(0, 3, 1, 2)                # NCHW view of NHWC memory (:561)
         if getattr(self.moe, "fuses_residual", False):
             # B200 block: `x_spatial + moe_out` (:571) happens in the combine kernel, in x_spatial's dtype

@@ -43,6 +43,45 @@ def test_layernorm_matches_torch(rows, d, dtype):
     assert torch.equal(wc2.grad, wc.grad) and torch.equal(bc2.grad, bc.grad) and torch.equal(xc2.grad, xc.grad)
 
 
+@pytest.mark.parametrize("rows,d", [(4099, 128), (16385, 256), (4097, 512), (33, 128), (70001, 128)])
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_add_layer_norm_matches_torch(rows, d, dtype, out_dtype):
+    """The residual add in front of norm2 / norm3 fused into the LayerNorm kernel (t2i_moe_gan.py:545 + :553, :557 + :561): the sum is
+    bit-identical to the torch add in the operands' dtype, the normalised rows and all gradients (the sum's consumer and the
+    LayerNorm's consumer both send gradient back) match fp64 torch ops; with_operand returns the rounded copy too."""
+    glue = G_.pkg().glue
+    g = torch.Generator().manual_seed(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 2 + 0.5).to(dtype); a = torch.randn(rows, d, generator=g).to(dtype)
+    w = torch.randn(d, generator=g) * 0.5 + 1.0; b = torch.randn(d, generator=g) * 0.1
+    g_sum = torch.randn(rows, d, generator=g).to(dtype); g_n = torch.randn(rows, d, generator=g).to(out_dtype)
+    tr = (x + a).double().requires_grad_(True)              # the reference starts from the SAME rounded sum
+    wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    nr = F.layer_norm(tr, (d,), wr, br, 1e-5)
+    torch.autograd.backward([tr * 1.0, nr], [g_sum.double(), g_n.double()])
+    xc = x.cuda().requires_grad_(True); ac = a.cuda().requires_grad_(True); wc = w.cuda().requires_grad_(True); bc = b.cuda().requires_grad_(True)
+    with_op = out_dtype == torch.float32
+    outs = glue.add_layer_norm(xc, ac, wc, bc, 1e-5, out_dtype, with_operand=with_op)
+    tc, nc = outs[0], outs[1]
+    assert tc.dtype == dtype and nc.dtype == out_dtype
+    assert torch.equal(tc, (x + a).cuda())
+    if with_op:
+        assert torch.equal(outs[2], nc.detach().bfloat16())
+    torch.autograd.backward([tc, nc], [g_sum.cuda(), g_n.cuda()])
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert _rel(nc, nr) < (2e-5 if out_dtype == torch.float32 else 1e-2)
+    assert torch.equal(xc.grad, ac.grad)
+    assert _rel(xc.grad, tr.grad) < tol
+    assert _rel(wc.grad, wr.grad) < (2e-5 if out_dtype == torch.float32 else 2e-3)
+    assert _rel(bc.grad, br.grad) < (2e-5 if out_dtype == torch.float32 else 2e-3)
+    # only one of the two outputs used downstream
+    xc2 = x.cuda().requires_grad_(True); ac2 = a.cuda().requires_grad_(True)
+    t2, n2 = glue.add_layer_norm(xc2, ac2, wc, bc, 1e-5, out_dtype)[:2]
+    n2.backward(g_n.cuda())
+    tr2 = (x + a).double().requires_grad_(True)
+    F.layer_norm(tr2, (d,), w.double(), b.double(), 1e-5).backward(g_n.double())
+    assert _rel(xc2.grad, tr2.grad) < tol
+
+
 def test_layernorm_3d_input_and_autocast():
     glue = G_.pkg().glue
     x = torch.randn(4, 64, 256, device="cuda")
