@@ -837,17 +837,35 @@ __device__ __forceinline__ int tap_tile_fill(TapTile& tt, const float* __restric
     __syncthreads();
     return np;
 }
-template <typename T>
-__device__ __forceinline__ void load_taps(const T* __restrict__ xc, int C, const int4 id, float (&v)[4][8]) {
-    const int ids[4] = {id.x, id.y, id.z, id.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (ids[k] >= 0) Vec8<T>::load(xc + (size_t)ids[k] * C, v[k]);
-        else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
-        }
+// 8 channels as loaded (no arithmetic): a load whose result is converted right away inside a branch cannot be overlapped with the next
+// load - the four tap loads of an item then run one after the other (seen in the SASS of the first version: @!P BRA; LDG.128;
+// IMAD.U32 ... per tap).  Taps outside the image read pixel 0 (a valid address) and are zeroed in the conversion.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
+        f[0] = ok ? a.x : 0.f; f[1] = ok ? a.y : 0.f; f[2] = ok ? a.z : 0.f; f[3] = ok ? a.w : 0.f;
+        f[4] = ok ? b.x : 0.f; f[5] = ok ? b.y : 0.f; f[6] = ok ? b.z : 0.f; f[7] = ok ? b.w : 0.f;
     }
+};
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
+        const uint4 v = ok ? u : make_uint4(0u, 0u, 0u, 0u);
+        f[0] = bf16_lo_to_float(v.x); f[1] = bf16_hi_to_float(v.x); f[2] = bf16_lo_to_float(v.y); f[3] = bf16_hi_to_float(v.y);
+        f[4] = bf16_lo_to_float(v.z); f[5] = bf16_hi_to_float(v.z); f[6] = bf16_lo_to_float(v.w); f[7] = bf16_hi_to_float(v.w);
+    }
+};
+template <typename T>
+__device__ __forceinline__ void load_taps_raw(const T* __restrict__ xc, int C, const int4 id, Raw8<T> (&r)[4]) {
+    r[0].load(xc + (size_t)max(id.x, 0) * C); r[1].load(xc + (size_t)max(id.y, 0) * C);
+    r[2].load(xc + (size_t)max(id.z, 0) * C); r[3].load(xc + (size_t)max(id.w, 0) * C);
+}
+template <typename T>
+__device__ __forceinline__ void taps_to_float(const Raw8<T> (&r)[4], const int4 id, float (&v)[4][8]) {
+    r[0].get(id.x >= 0, v[0]); r[1].get(id.y >= 0, v[1]); r[2].get(id.z >= 0, v[2]); r[3].get(id.w >= 0, v[3]);
 }
 // forward: out[p, c] = sum_k w_k * x[tap_k, c]   (fma chain over the taps in order, as before).  U = items in flight per thread:
 // U = 2 needs 94 registers (2 CTAs per SM), U = 1 fits 4 CTAs per SM.
@@ -861,24 +879,24 @@ offset_sample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ off,
     const T* xb = x + (size_t)b * HW * C;
     T* ob = out + ((size_t)b * HW + p0) * C;
     for (unsigned it0 = threadIdx.x; it0 < n_items; it0 += 256 * U) {
-        float v[U][4][8];
+        Raw8<T> raw[U][4];
         unsigned pl[U], cg[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const unsigned it = it0 + 256u * u;
-            if (it < n_items) {
-                pl[u] = it / c8; cg[u] = it - pl[u] * c8;
-                load_taps<T>(xb + cg[u] * 8, C, tt.idx[pl[u]], v[u]);
-            }
+            const unsigned it = min(it0 + 256u * u, n_items - 1);         // clamped: the loads carry no branch
+            pl[u] = it / c8; cg[u] = it - pl[u] * c8;
+            load_taps_raw<T>(xb + cg[u] * 8, C, tt.idx[pl[u]], raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const unsigned it = it0 + 256u * u;
             if (it < n_items) {
+                float v[4][8];
+                taps_to_float<T>(raw[u], tt.idx[pl[u]], v);
                 const float4 w = tt.w[pl[u]];
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = fmaf(w.w, v[u][3][e], fmaf(w.z, v[u][2][e], fmaf(w.y, v[u][1][e], w.x * v[u][0][e])));
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(w.w, v[3][e], fmaf(w.z, v[2][e], fmaf(w.y, v[1][e], w.x * v[0][e])));
                 Vec8<T>::store(ob + (size_t)pl[u] * C + cg[u] * 8, o);
             }
         }
@@ -904,8 +922,11 @@ offset_sample_bwd_off_kernel(const T* __restrict__ g, const T* __restrict__ x, c
         float gix = 0.f, giy = 0.f;
         if (ok) {
             float gv[8], v[4][8];
-            Vec8<T>::load(gb + (size_t)pl * C + cg * 8, gv);
-            load_taps<T>(xb + cg * 8, C, tt.idx[pl], v);
+            Raw8<T> graw, raw[4];
+            graw.load(gb + (size_t)pl * C + cg * 8);
+            load_taps_raw<T>(xb + cg * 8, C, tt.idx[pl], raw);
+            graw.get(true, gv);
+            taps_to_float<T>(raw, tt.idx[pl], v);
             const float4 f = tt.f[pl];
             const float omx = 1.0f - f.x, omy = 1.0f - f.y;
 #pragma unroll
@@ -1118,19 +1139,25 @@ upsample2x_bwd_kernel(const T* __restrict__ g, unsigned n8s /* H * W * C / 8 */,
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const int OH = 2 * H;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        float v[4][8];
+        // the 4 loads of a row carry no branch (clamped coordinates; taps with zero weight are zeroed in the conversion)
+        Raw8<T> raw[4];
+        const int oy = min(max(2 * iy - 1 + a, 0), OH - 1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (wy[a] != 0.f && wx[q] != 0.f) Vec8<T>::load(gb + ((size_t)(2 * iy - 1 + a) * OW + (2 * ix - 1 + q)) * C, v[q]);
+        for (int q = 0; q < 4; ++q) raw[q].load(gb + ((size_t)oy * OW + min(max(2 * ix - 1 + q, 0), OW - 1)) * C);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (wy[a] != 0.f && wx[q] != 0.f) {
+        for (int q = 0; q < 4; ++q) {
+            const bool on = wy[a] != 0.f && wx[q] != 0.f;
+            float v[8];
+            raw[q].get(on, v);
+            if (on) {
                 const float wgt = wy[a] * wx[q];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[q][e], acc[e]);
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
             }
+        }
     }
     Vec8<T>::store(dx + ((size_t)blockIdx.y * n8s + j) * 8, acc);
 }
