@@ -34,3 +34,31 @@ def test_glue_cpu_definitions(pkg):
     t = torch.randn(7, 128)
     w, b = torch.randn(128), torch.randn(128)
     assert torch.allclose(glue.layer_norm(t, w, b, 1e-5), F.layer_norm(t, (128,), w, b, 1e-5))
+    # residual add + LayerNorm (AttentionBlock :545 + :553, :557 + :561)
+    a = torch.randn(7, 128)
+    t2, n2 = glue.add_layer_norm(t, a, w, b, 1e-5)
+    assert torch.equal(t2, t + a) and torch.allclose(n2, F.layer_norm(t + a, (128,), w, b, 1e-5))
+    t3, n3, op3 = glue.add_layer_norm(t, a, w, b, 1e-5, with_operand=True)
+    assert torch.equal(t3, t2) and torch.equal(n3, n2) and op3.dtype == torch.bfloat16 and torch.equal(op3, n2.bfloat16())
+
+
+def test_demod_coef_equals_the_weight_space_formula(pkg):
+    """glue.demod_coef's definition, d = rsqrt(s^2 @ sum_taps(w^2)^T + 1e-8), is the factor the reference computes in weight space
+    (t2i_moe_gan.py:161-166: weight = W[None] * style; d = rsqrt((weight ** 2).sum(dim=(2, 3, 4)) + 1e-8)) - values and both gradients,
+    fp64."""
+    glue = pkg.glue
+    torch.manual_seed(2)
+    B, Cin, Cout, k = 3, 6, 5, 3
+    s = torch.randn(B, Cin, dtype=torch.float64, requires_grad=True)
+    W = torch.randn(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    gd = torch.randn(B, Cout, dtype=torch.float64)
+    weight = W.unsqueeze(0) * s.view(B, 1, Cin, 1, 1)
+    d_ref = torch.rsqrt((weight ** 2).sum(dim=(2, 3, 4)) + 1e-8)
+    g_ref = torch.autograd.grad(d_ref, (s, W), gd)
+    d = torch.rsqrt(s.pow(2) @ W.pow(2).sum(dim=(2, 3)).t() + 1e-8)          # = glue.demod_coef_reference in fp64
+    assert torch.allclose(d, d_ref, rtol=1e-12, atol=1e-12)
+    for a_, r_ in zip(torch.autograd.grad(d, (s, W), gd), g_ref):
+        assert torch.allclose(a_, r_, rtol=1e-10, atol=1e-12)
+    # the fp32 CPU path of glue.demod_coef is that expression
+    d32 = glue.demod_coef(s.detach().float(), W.detach().float())
+    assert d32.dtype == torch.float32 and torch.allclose(d32.double(), d_ref, rtol=1e-5, atol=1e-6)
