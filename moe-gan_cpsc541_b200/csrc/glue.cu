@@ -63,6 +63,28 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 
+// 8 channels as loaded (no arithmetic): a load whose result is converted right away inside a branch cannot be overlapped with the next
+// load - the four tap loads of an item then run one after the other (seen in the SASS of the first version: @!P BRA; LDG.128;
+// IMAD.U32 ... per tap).  Taps outside the image read pixel 0 (a valid address) and are zeroed in the conversion.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
+        f[0] = ok ? a.x : 0.f; f[1] = ok ? a.y : 0.f; f[2] = ok ? a.z : 0.f; f[3] = ok ? a.w : 0.f;
+        f[4] = ok ? b.x : 0.f; f[5] = ok ? b.y : 0.f; f[6] = ok ? b.z : 0.f; f[7] = ok ? b.w : 0.f;
+    }
+};
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
+        const uint4 v = ok ? u : make_uint4(0u, 0u, 0u, 0u);
+        f[0] = bf16_lo_to_float(v.x); f[1] = bf16_hi_to_float(v.x); f[2] = bf16_lo_to_float(v.y); f[3] = bf16_hi_to_float(v.y);
+        f[4] = bf16_lo_to_float(v.z); f[5] = bf16_hi_to_float(v.z); f[6] = bf16_lo_to_float(v.w); f[7] = bf16_hi_to_float(v.w);
+    }
+};
+
 // =====================================================================================================
 // LayerNorm over the last dimension (d = 128 * nseg <= 1024), eps inside the sqrt (nn.LayerNorm)
 // =====================================================================================================
@@ -546,19 +568,20 @@ channel_scale_fwd_kernel(const T* __restrict__ x, const TS* __restrict__ s, unsi
     const unsigned j0 = blockIdx.x * (256u * CS_U) + threadIdx.x;
     const size_t base = (size_t)blockIdx.y * n8s;
     const TS* sb = s + (size_t)blockIdx.y * C;
-    float v[CS_U][8], sc[CS_U][8];
+    Raw8<T> rx[CS_U];
+    Raw8<TS> rs[CS_U];
 #pragma unroll
-    for (int u = 0; u < CS_U; ++u) {
-        const unsigned j = j0 + u * 256u;
-        if (j < n8s) {
-            Vec8<T>::load(x + (base + j) * 8, v[u]);
-            Vec8<TS>::load(sb + (j % c8) * 8u, sc[u]);
-        }
+    for (int u = 0; u < CS_U; ++u) {                       // raw loads from clamped indices: no branch, no conversion between them
+        const unsigned j = min(j0 + u * 256u, n8s - 1u);
+        rx[u].load(x + (base + j) * 8);
+        rs[u].load(sb + (j % c8) * 8u);
     }
 #pragma unroll
     for (int u = 0; u < CS_U; ++u) {
         const unsigned j = j0 + u * 256u;
         if (j < n8s) {
+            float v[CS_U][8], sc[CS_U][8];
+            rx[u].get(true, v[u]); rs[u].get(true, sc[u]);
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float t = v[u][e] * sc[u][e]; o[e] = t > 0.f ? t : t * slope; }
@@ -837,27 +860,6 @@ __device__ __forceinline__ int tap_tile_fill(TapTile& tt, const float* __restric
     __syncthreads();
     return np;
 }
-// 8 channels as loaded (no arithmetic): a load whose result is converted right away inside a branch cannot be overlapped with the next
-// load - the four tap loads of an item then run one after the other (seen in the SASS of the first version: @!P BRA; LDG.128;
-// IMAD.U32 ... per tap).  Taps outside the image read pixel 0 (a valid address) and are zeroed in the conversion.
-template <typename T> struct Raw8;
-template <> struct Raw8<float> {
-    float4 a, b;
-    __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
-    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
-        f[0] = ok ? a.x : 0.f; f[1] = ok ? a.y : 0.f; f[2] = ok ? a.z : 0.f; f[3] = ok ? a.w : 0.f;
-        f[4] = ok ? b.x : 0.f; f[5] = ok ? b.y : 0.f; f[6] = ok ? b.z : 0.f; f[7] = ok ? b.w : 0.f;
-    }
-};
-template <> struct Raw8<__nv_bfloat16> {
-    uint4 u;
-    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
-    __device__ __forceinline__ void get(bool ok, float (&f)[8]) const {
-        const uint4 v = ok ? u : make_uint4(0u, 0u, 0u, 0u);
-        f[0] = bf16_lo_to_float(v.x); f[1] = bf16_hi_to_float(v.x); f[2] = bf16_lo_to_float(v.y); f[3] = bf16_hi_to_float(v.y);
-        f[4] = bf16_lo_to_float(v.z); f[5] = bf16_hi_to_float(v.z); f[6] = bf16_lo_to_float(v.w); f[7] = bf16_hi_to_float(v.w);
-    }
-};
 template <typename T>
 __device__ __forceinline__ void load_taps_raw(const T* __restrict__ xc, int C, const int4 id, Raw8<T> (&r)[4]) {
     r[0].load(xc + (size_t)max(id.x, 0) * C); r[1].load(xc + (size_t)max(id.y, 0) * C);
