@@ -54,3 +54,35 @@ def test_reference_arm_sets_threads_under_a_launcher_env():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_clock_sampler_maps_cuda_device_to_nvml_handle(monkeypatch):
+    """NVML numbers the physical GPUs, CUDA the visible ones: with CUDA_VISIBLE_DEVICES=1 the sampler must not read GPU 0 (an idle GPU's
+    120 MHz would look like a stuck clock to the driver).  Lookup order: UUID of the torch device, then CUDA_VISIBLE_DEVICES, then index."""
+    import bench
+
+    class FakeNvml:
+        def __init__(self, by_uuid=True):
+            self.calls, self.by_uuid = [], by_uuid
+
+        def nvmlDeviceGetHandleByUUID(self, u):
+            if not self.by_uuid:
+                raise RuntimeError("no such uuid")
+            self.calls.append(("uuid", u)); return "h-" + u
+
+        def nvmlDeviceGetHandleByIndex(self, i):
+            self.calls.append(("index", i)); return f"h-idx{i}"
+
+    import torch
+
+    class Props:
+        uuid = "12345678-aaaa-bbbb-cccc-1234567890ab"
+
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: Props())
+    nv = FakeNvml()
+    assert bench.ClockSampler._handle(nv, 0) == "h-GPU-" + Props.uuid and nv.calls[0][0] == "uuid"
+    nv = FakeNvml(by_uuid=False)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,1")
+    assert bench.ClockSampler._handle(nv, 1) == "h-idx1" and bench.ClockSampler._handle(nv, 0) == "h-idx3"
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-deadbeef")            # UUID form: fall through to the plain index
+    assert bench.ClockSampler._handle(nv, 0) == "h-idx0"
