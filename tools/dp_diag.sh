@@ -1,3 +1,4 @@
+# per-GPU single-process step (GPU 0, GPU 1, both at once) next to the 2-GPU data-parallel step on the same box
 one() { python -c "
 import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[1], round(d['value']), round(d['ms_per_step'],3), d['clocks'])" $1; }
 B="python bench.py --steps 30 --warmup 5 --skip-cpu --skip-extras"

@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""offset_sample forward + backward at the 16x16 / C = 128 layer of the train step, twice - the target of
+    ncu --set full -k regex:offset_sample -s 3 -c 3 -o out python tools/offset_sample_probe.py"""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
